@@ -1,0 +1,113 @@
+"""ctypes binding of libclc_b200.so (the C ABI declared in include/clc_b200.h).
+
+There is no fallback: if the shared library is missing the import of any op fails loudly
+with the build instruction.  Every call goes through `call()`, which turns a negative
+status into a RuntimeError carrying clc_strerror / clc_last_cuda_error.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclc_b200.so")
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f = C.c_float
+_sz = C.c_size_t
+
+
+class PatchView(C.Structure):
+    """struct clc_patch_view (include/clc_b200.h)."""
+    _fields_ = [("q", _p), ("q_sn", _i64), ("q_spy", _i64), ("q_spx", _i64), ("q_sc", _i64),
+                ("q_sy", _i64), ("npx", _i32), ("q_repeat", _i32)]
+
+
+_PTR5 = _p * 5
+_PTR4 = _p * 4
+
+# name -> (restype, argtypes); mirrors include/clc_b200.h one to one.
+PROTOTYPES = {
+    "clc_version": (C.c_int, []),
+    "clc_strerror": (C.c_char_p, [C.c_int]),
+    "clc_last_cuda_error": (C.c_char_p, []),
+    "clc_gc_fwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p,
+                             _i64, _i64, _f, _f, _p]),
+    "clc_gc_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f, _p, _i64,
+                             _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _f, _f, _p]),
+    "clc_lrp_add_fwd": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),
+    "clc_lrp_add_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p]),
+    "clc_gc_symbols_indexes": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, C.c_int, _p, _i64, _p, _i64,
+                                         _i64, _i64, _f, _p]),
+    "clc_eb_fwd": (C.c_int, [_p, _p, _PTR5, _PTR5, _PTR4, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p]),
+    "clc_eb_bwd": (C.c_int, [_p, _p, _PTR5, _PTR5, _PTR4, _p, _p, _p, _f, _p, _p, _p, _p, _p,
+                             _i64, _i64, _i64, _f, _p]),
+    "clc_log2_sum_fwd": (C.c_int, [_p, _i64, _p, _p]),
+    "clc_log2_sum_bwd": (C.c_int, [_p, _f, _p, _p, _i64, _p]),
+    "clc_pearson_corr": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
+                                   _p, _sz, _p]),
+    "clc_pearson_corr_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "clc_topk_rows": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p]),
+    "clc_gaussian_mask": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
+    "clc_match_topk_tc": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                    _p, _sz, _p]),
+    "clc_match_topk_tc_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "clc_gather_blend_fwd": (C.c_int, [_p, _p, _p, _f, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                       _i32, _p]),
+    "clc_gather_blend_bwd": (C.c_int, [_p, _p, _p, _f, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
+                                       _i32, _i32, _p]),
+    "clc_pearson_topk_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
+                                       _i32, _i32, _i32, _i32, _p]),
+    "clc_clm_fuse_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
+    "clc_clm_fuse_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
+}
+
+_lib = None
+_launches = 0  # number of C-ABI kernel-enqueueing calls made by this process (bench.py reads it)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; fail loudly if the extension is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"clc_b200: {LIB_PATH} is missing -- the CUDA extension is not built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                "There is no CPU or PyTorch fallback.")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(h, name)  # AttributeError if the library does not export the symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; raise RuntimeError on a negative status."""
+    global _launches
+    h = lib()
+    rc = getattr(h, name)(*args)
+    _launches += 1
+    if rc != 0:
+        msg = h.clc_strerror(rc).decode()
+        cuda = h.clc_last_cuda_error().decode()
+        raise RuntimeError(f"{name} failed: {msg}" + (f" [{cuda}]" if cuda and rc == -4 else ""))
+    return rc
+
+
+def launches():
+    return _launches
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL for None)."""
+    return None if t is None else t.data_ptr()
+
+
+def ptr_array(tensors, n):
+    arr = (_p * n)()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

@@ -1,0 +1,74 @@
+// Shared helpers for libclc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/clc_b200.h"
+
+namespace clc {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// Thread-local text of the last CUDA failure, surfaced through clc_last_cuda_error().
+extern thread_local char g_last_cuda_error[256];
+
+inline int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", where, cudaGetErrorString(e));
+  return CLC_ERR_CUDA;
+}
+
+#define CLC_CHECK_LAUNCH(where)                                  \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return ::clc::cuda_fail(e__, where); \
+  } while (0)
+
+#define CLC_CUDA(call)                                           \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return ::clc::cuda_fail(e__, #call); \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` against a previous use
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// Streaming (read-once / write-once) variants: do not pollute L1.
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+  __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Grid size for a grid-stride elementwise kernel: enough CTAs for `work_items` at `per_block`
+// items per pass, capped at `waves` full waves of the 148 SMs x `ctas_per_sm` resident CTAs.
+inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8, int waves = 1) {
+  int64_t need = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)kNumSMs * ctas_per_sm * waves;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace clc

@@ -1,0 +1,723 @@
+// Entropy stage of the CLC latent path: GaussianConditional (+STE round, +bpp partial),
+// LRP add, symbols/indexes, EntropyBottleneck (factorised prior) and the log2-sum of
+// RateDistortionLoss -- forward and backward.  All kernels are HBM-bandwidth bound:
+// float4 coalesced streaming accesses, grid-stride over a grid sized in multiples of the
+// 148 SMs, warp-shuffle + one double atomic per CTA for the bpp partial sums.
+//
+// Reference arithmetic followed (file:line into the reference tree):
+//   likelihood ............ models/CLC_run.py:718-736 (in-tree restatement of GaussianConditional)
+//   ste_round ............. models/CLC_run.py:35-36, :571, :528-530
+//   LRP add ............... models/CLC_run.py:582-583
+//   bpp ................... train_CLC.py:48-51
+//   EntropyBottleneck ..... compressai (un-vendored) as called at models/CLC_run.py:526
+#include "common.cuh"
+
+namespace clc {
+
+constexpr float kNegInvSqrt2 = -0.70710678118654752440f;  // const = -(2 ** -0.5)
+constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
+
+// ------------------------------------------------------------------------------------------
+// GaussianConditional
+// ------------------------------------------------------------------------------------------
+struct GcOut {
+  float lik_raw, lik, y_hat, outputs;
+};
+
+// One element of GaussianConditional.forward + ste_round.  Argument formation order follows
+// the reference exactly: values = outputs - means; (half - |values|) / scales as a true
+// division; const * inputs; half * erfc(.); upper - lower  (CLC_run.py:720-736).
+__device__ __forceinline__ GcOut gc_elem(float y, float s, float m, float n, bool train,
+                                         float scale_bound, float lik_bound) {
+  GcOut o;
+  const float q = rintf(y - m);  // torch.round: half-to-even
+  o.y_hat = q + m;
+  o.outputs = train ? (y + n) : o.y_hat;
+  // values = outputs - means, formed literally in fp32 in both modes (in eval mode
+  // (round(y-m)+m)-m is not always exactly round(y-m)).
+  const float values = o.outputs - m;
+  const float sc = fmaxf(s, scale_bound);
+  const float v = fabsf(values);
+  const float up = (0.5f - v) / sc;
+  const float lo = (-0.5f - v) / sc;
+  const float U = 0.5f * erfcf(kNegInvSqrt2 * up);
+  const float L = 0.5f * erfcf(kNegInvSqrt2 * lo);
+  o.lik_raw = U - L;
+  o.lik = fmaxf(o.lik_raw, lik_bound);
+  return o;
+}
+
+struct GcFwdParams {
+  const float *y, *scale, *mean, *noise;
+  float *lik, *y_hat, *outputs;
+  double* log2_sum;
+  int64_t y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs;
+  int64_t B, CS;
+  float scale_bound, lik_bound;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) gc_fwd_kernel(const GcFwdParams p) {
+  __shared__ float red[32];
+  const bool train = p.noise != nullptr;
+  constexpr int W = VEC ? 4 : 1;
+  const int64_t per_b = p.CS / W;
+  const int64_t total = p.B * per_b;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_b;
+    const int64_t j = (i - b * per_b) * W;
+    if constexpr (VEC) {
+      const float4 y4 = ld4_stream(p.y + b * p.y_bs + j);
+      const float4 s4 = ld4_stream(p.scale + b * p.scale_bs + j);
+      const float4 m4 = p.mean ? ld4_stream(p.mean + b * p.mean_bs + j) : make_float4(0, 0, 0, 0);
+      const float4 n4 = train ? ld4_stream(p.noise + b * p.noise_bs + j) : make_float4(0, 0, 0, 0);
+      const GcOut o0 = gc_elem(y4.x, s4.x, m4.x, n4.x, train, p.scale_bound, p.lik_bound);
+      const GcOut o1 = gc_elem(y4.y, s4.y, m4.y, n4.y, train, p.scale_bound, p.lik_bound);
+      const GcOut o2 = gc_elem(y4.z, s4.z, m4.z, n4.z, train, p.scale_bound, p.lik_bound);
+      const GcOut o3 = gc_elem(y4.w, s4.w, m4.w, n4.w, train, p.scale_bound, p.lik_bound);
+      st4_stream(p.lik + b * p.lik_bs + j, make_float4(o0.lik, o1.lik, o2.lik, o3.lik));
+      if (p.y_hat)
+        st4(p.y_hat + b * p.y_hat_bs + j, make_float4(o0.y_hat, o1.y_hat, o2.y_hat, o3.y_hat));
+      if (p.outputs)
+        st4_stream(p.outputs + b * p.outputs_bs + j,
+                   make_float4(o0.outputs, o1.outputs, o2.outputs, o3.outputs));
+      if (p.log2_sum) acc += (log2f(o0.lik) + log2f(o1.lik)) + (log2f(o2.lik) + log2f(o3.lik));
+    } else {
+      const float y = p.y[b * p.y_bs + j];
+      const float s = p.scale[b * p.scale_bs + j];
+      const float m = p.mean ? p.mean[b * p.mean_bs + j] : 0.f;
+      const float n = train ? p.noise[b * p.noise_bs + j] : 0.f;
+      const GcOut o = gc_elem(y, s, m, n, train, p.scale_bound, p.lik_bound);
+      p.lik[b * p.lik_bs + j] = o.lik;
+      if (p.y_hat) p.y_hat[b * p.y_hat_bs + j] = o.y_hat;
+      if (p.outputs) p.outputs[b * p.outputs_bs + j] = o.outputs;
+      if (p.log2_sum) acc += log2f(o.lik);
+    }
+  }
+  if (p.log2_sum) {
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(p.log2_sum, (double)tot);
+  }
+}
+
+struct GcBwdParams {
+  const float *y, *scale, *mean, *noise, *lik, *g_lik, *g_y_hat;
+  float *g_y, *g_scale, *g_mean;
+  int64_t y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs;
+  int64_t B, CS;
+  float bpp_coef, scale_bound, lik_bound;
+};
+
+struct GcGrad {
+  float g_y, g_scale, g_mean;
+};
+
+// Analytic backward of gc_elem.  lik = Phi(up) - Phi(lo); dPhi(t)/dt = phi(t).
+//   dlik/dv = (phi(lo) - phi(up)) / sc;  dlik/dsc = (lo*phi(lo) - up*phi(up)) / sc
+// LowerBound gates (compressai.ops.LowerBound): pass iff x >= bound or grad < 0, for both the
+// likelihood floor and the scale floor.  Eval mode: round() has zero gradient, so only the
+// scale receives gradient through the likelihood.
+__device__ __forceinline__ GcGrad gc_elem_bwd(float y, float s, float m, float n, bool train,
+                                              float lik, float g_lik, bool has_g_lik, float bpp_coef,
+                                              float g_y_hat, float scale_bound, float lik_bound) {
+  GcGrad g;
+  float values;
+  if (train) {
+    values = (y + n) - m;
+  } else {
+    const float q = rintf(y - m);
+    values = (q + m) - m;
+  }
+  const float sc = fmaxf(s, scale_bound);
+  const float v = fabsf(values);
+  const float up = (0.5f - v) / sc;
+  const float lo = (-0.5f - v) / sc;
+  const float pu = kInvSqrt2Pi * expf(-0.5f * up * up);
+  const float pl = kInvSqrt2Pi * expf(-0.5f * lo * lo);
+  float gl = has_g_lik ? g_lik : (bpp_coef / lik);
+  // likelihood LowerBound gate: lik > bound means the raw value was above the floor.
+  const bool pass_l = (lik > lik_bound) || (gl < 0.f);
+  gl = pass_l ? gl : 0.f;
+  const float inv = 1.0f / sc;
+  const float dv = (pl - pu) * inv;
+  const float ds = (lo * pl - up * pu) * inv;
+  const float sgn = (values > 0.f) ? 1.f : ((values < 0.f) ? -1.f : 0.f);
+  const float gv = gl * dv * sgn;
+  g.g_y = g_y_hat + (train ? gv : 0.f);
+  g.g_mean = train ? -gv : 0.f;
+  const float gs = gl * ds;
+  g.g_scale = ((s >= scale_bound) || (gs < 0.f)) ? gs : 0.f;
+  return g;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) gc_bwd_kernel(const GcBwdParams p) {
+  const bool train = p.noise != nullptr;
+  const bool has_gl = p.g_lik != nullptr;
+  constexpr int W = VEC ? 4 : 1;
+  const int64_t per_b = p.CS / W;
+  const int64_t total = p.B * per_b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_b;
+    const int64_t j = (i - b * per_b) * W;
+    if constexpr (VEC) {
+      const float4 z4 = make_float4(0, 0, 0, 0);
+      const float4 y4 = ld4_stream(p.y + b * p.y_bs + j);
+      const float4 s4 = ld4_stream(p.scale + b * p.scale_bs + j);
+      const float4 m4 = p.mean ? ld4_stream(p.mean + b * p.mean_bs + j) : z4;
+      const float4 n4 = train ? ld4_stream(p.noise + b * p.noise_bs + j) : z4;
+      const float4 l4 = ld4_stream(p.lik + b * p.lik_bs + j);
+      const float4 gl4 = has_gl ? ld4_stream(p.g_lik + b * p.g_lik_bs + j) : z4;
+      const float4 gy4 = p.g_y_hat ? ld4_stream(p.g_y_hat + b * p.g_y_hat_bs + j) : z4;
+      const GcGrad g0 = gc_elem_bwd(y4.x, s4.x, m4.x, n4.x, train, l4.x, gl4.x, has_gl, p.bpp_coef, gy4.x, p.scale_bound, p.lik_bound);
+      const GcGrad g1 = gc_elem_bwd(y4.y, s4.y, m4.y, n4.y, train, l4.y, gl4.y, has_gl, p.bpp_coef, gy4.y, p.scale_bound, p.lik_bound);
+      const GcGrad g2 = gc_elem_bwd(y4.z, s4.z, m4.z, n4.z, train, l4.z, gl4.z, has_gl, p.bpp_coef, gy4.z, p.scale_bound, p.lik_bound);
+      const GcGrad g3 = gc_elem_bwd(y4.w, s4.w, m4.w, n4.w, train, l4.w, gl4.w, has_gl, p.bpp_coef, gy4.w, p.scale_bound, p.lik_bound);
+      st4_stream(p.g_y + b * p.g_y_bs + j, make_float4(g0.g_y, g1.g_y, g2.g_y, g3.g_y));
+      st4_stream(p.g_scale + b * p.g_scale_bs + j, make_float4(g0.g_scale, g1.g_scale, g2.g_scale, g3.g_scale));
+      if (p.g_mean)
+        st4_stream(p.g_mean + b * p.g_mean_bs + j, make_float4(g0.g_mean, g1.g_mean, g2.g_mean, g3.g_mean));
+    } else {
+      const float y = p.y[b * p.y_bs + j];
+      const float s = p.scale[b * p.scale_bs + j];
+      const float m = p.mean ? p.mean[b * p.mean_bs + j] : 0.f;
+      const float n = train ? p.noise[b * p.noise_bs + j] : 0.f;
+      const float l = p.lik[b * p.lik_bs + j];
+      const float gl = has_gl ? p.g_lik[b * p.g_lik_bs + j] : 0.f;
+      const float gy = p.g_y_hat ? p.g_y_hat[b * p.g_y_hat_bs + j] : 0.f;
+      const GcGrad g = gc_elem_bwd(y, s, m, n, train, l, gl, has_gl, p.bpp_coef, gy, p.scale_bound, p.lik_bound);
+      p.g_y[b * p.g_y_bs + j] = g.g_y;
+      p.g_scale[b * p.g_scale_bs + j] = g.g_scale;
+      if (p.g_mean) p.g_mean[b * p.g_mean_bs + j] = g.g_mean;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LRP add
+// ------------------------------------------------------------------------------------------
+template <bool VEC, bool BWD>
+__global__ void __launch_bounds__(256)
+lrp_kernel(float* __restrict__ io, int64_t io_bs, const float* __restrict__ lrp, int64_t lrp_bs,
+           const float* __restrict__ g, int64_t g_bs, int64_t B, int64_t CS) {
+  constexpr int W = VEC ? 4 : 1;
+  const int64_t per_b = CS / W;
+  const int64_t total = B * per_b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_b;
+    const int64_t j = (i - b * per_b) * W;
+    if constexpr (VEC) {
+      const float4 l4 = ld4_stream(lrp + b * lrp_bs + j);
+      const float t0 = tanhf(l4.x), t1 = tanhf(l4.y), t2 = tanhf(l4.z), t3 = tanhf(l4.w);
+      if constexpr (!BWD) {
+        float4 v = ld4(io + b * io_bs + j);
+        v.x += 0.5f * t0; v.y += 0.5f * t1; v.z += 0.5f * t2; v.w += 0.5f * t3;
+        st4(io + b * io_bs + j, v);
+      } else {
+        const float4 g4 = ld4_stream(g + b * g_bs + j);
+        st4_stream(io + b * io_bs + j,
+                   make_float4(g4.x * (0.5f * (1.f - t0 * t0)), g4.y * (0.5f * (1.f - t1 * t1)),
+                               g4.z * (0.5f * (1.f - t2 * t2)), g4.w * (0.5f * (1.f - t3 * t3))));
+      }
+    } else {
+      const float t = tanhf(lrp[b * lrp_bs + j]);
+      if constexpr (!BWD) io[b * io_bs + j] += 0.5f * t;
+      else io[b * io_bs + j] = g[b * g_bs + j] * (0.5f * (1.f - t * t));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// symbols + scale-table indexes
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gc_symbols_indexes_kernel(const float* __restrict__ y, int64_t y_bs, const float* __restrict__ scale,
+                          int64_t scale_bs, const float* __restrict__ mean, int64_t mean_bs,
+                          const float* __restrict__ table, int T, int32_t* __restrict__ symbols,
+                          int64_t symbols_bs, int32_t* __restrict__ indexes, int64_t indexes_bs,
+                          int64_t B, int64_t CS, float scale_bound) {
+  __shared__ float tab[256];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) tab[t] = table[t];
+  __syncthreads();
+  const int64_t total = B * CS;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / CS, j = i - b * CS;
+    if (symbols) {
+      const float m = mean ? mean[b * mean_bs + j] : 0.f;
+      symbols[b * symbols_bs + j] = (int32_t)rintf(y[b * y_bs + j] - m);
+    }
+    if (indexes) {
+      const float sc = fmaxf(scale[b * scale_bs + j], scale_bound);
+      // index = (T-1) - #{t < T-1 : sc <= tab[t]}.  The table ascends, so the count is
+      // (T-1) - first t in [0, T-1] with sc <= tab[t] (T-1 if none): a binary search
+      // instead of the reference's T-1 full-tensor passes.
+      int lo = 0, hi = T - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sc <= tab[mid]) hi = mid; else lo = mid + 1;
+      }
+      indexes[b * indexes_bs + j] = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// EntropyBottleneck, filters (3,3,3,3).  Per-channel parameter pack in shared memory:
+//   [0..2]   softplus(M0) (3x1)   [3..11]  softplus(M1) (3x3) [12..20] M2 [21..29] M3 [30..32] M4 (1x3)
+//   [33..35] b0 [36..38] b1 [39..41] b2 [42..44] b3 [45] b4
+//   [46..48] tanh(f0) [49..51] tanh(f1) [52..54] tanh(f2) [55..57] tanh(f3)
+// ------------------------------------------------------------------------------------------
+constexpr int kEbPack = 58;
+
+struct EbPtrs {
+  const float* matrix[5];
+  const float* bias[5];
+  const float* factor[4];
+};
+struct EbGradPtrs {
+  float* matrix[5];
+  float* bias[5];
+  float* factor[4];
+};
+
+__device__ __forceinline__ float softplusf(float x) {
+  // torch.nn.functional.softplus, beta=1, threshold=20
+  return x > 20.f ? x : log1pf(expf(x));
+}
+
+__device__ __forceinline__ void eb_load_pack(const EbPtrs& P, int c, float* pk) {
+  // raw -> transformed parameters of channel c (58 values), done by the first 58 threads
+  const int t = threadIdx.x;
+  if (t < 3) pk[t] = softplusf(P.matrix[0][c * 3 + t]);
+  else if (t < 12) pk[t] = softplusf(P.matrix[1][c * 9 + (t - 3)]);
+  else if (t < 21) pk[t] = softplusf(P.matrix[2][c * 9 + (t - 12)]);
+  else if (t < 30) pk[t] = softplusf(P.matrix[3][c * 9 + (t - 21)]);
+  else if (t < 33) pk[t] = softplusf(P.matrix[4][c * 3 + (t - 30)]);
+  else if (t < 36) pk[t] = P.bias[0][c * 3 + (t - 33)];
+  else if (t < 39) pk[t] = P.bias[1][c * 3 + (t - 36)];
+  else if (t < 42) pk[t] = P.bias[2][c * 3 + (t - 39)];
+  else if (t < 45) pk[t] = P.bias[3][c * 3 + (t - 42)];
+  else if (t < 46) pk[t] = P.bias[4][c];
+  else if (t < 49) pk[t] = tanhf(P.factor[0][c * 3 + (t - 46)]);
+  else if (t < 52) pk[t] = tanhf(P.factor[1][c * 3 + (t - 49)]);
+  else if (t < 55) pk[t] = tanhf(P.factor[2][c * 3 + (t - 52)]);
+  else if (t < 58) pk[t] = tanhf(P.factor[3][c * 3 + (t - 55)]);
+}
+
+// logits = _logits_cumulative(x) for one scalar input.  Operation order follows upstream:
+// matmul(softplus(M), x) accumulated left to right, + bias, + tanh(factor) * tanh(logits).
+// When KEEP, the pre-gate activations a[l][j] (after bias) of layers 0..3 are kept for backward.
+template <bool KEEP>
+__device__ __forceinline__ float eb_logits(const float* pk, float x, float (*a)[3], float (*in)[3]) {
+  float h[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float t = pk[j] * x + pk[33 + j];
+    if (KEEP) a[0][j] = t;
+    h[j] = t + pk[46 + j] * tanhf(t);
+  }
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+    float o[3];
+    if (KEEP) { in[l][0] = h[0]; in[l][1] = h[1]; in[l][2] = h[2]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float* mrow = pk + 3 + (l - 1) * 9 + j * 3;
+      float t = mrow[0] * h[0];
+      t = fmaf(mrow[1], h[1], t);
+      t = fmaf(mrow[2], h[2], t);
+      t += pk[33 + 3 * l + j];
+      if (KEEP) a[l][j] = t;
+      o[j] = t + pk[46 + 3 * l + j] * tanhf(t);
+    }
+    h[0] = o[0]; h[1] = o[1]; h[2] = o[2];
+  }
+  if (KEEP) { in[4][0] = h[0]; in[4][1] = h[1]; in[4][2] = h[2]; }
+  float t = pk[30] * h[0];
+  t = fmaf(pk[31], h[1], t);
+  t = fmaf(pk[32], h[2], t);
+  return t + pk[45];
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+struct EbFwdParams {
+  const float *z, *noise, *quantiles;
+  float *lik, *z_hat, *outputs;
+  double* log2_sum;
+  int64_t B, C, S;
+  float lik_bound;
+  EbPtrs P;
+};
+
+// grid = (C, chunks): CTA (c, k) handles elements k, k+chunks, ... of channel c's B*S values.
+__global__ void __launch_bounds__(128) eb_fwd_kernel(const EbFwdParams p) {
+  __shared__ float pk[64];
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  eb_load_pack(p.P, c, pk);
+  __syncthreads();
+  const float med = p.quantiles[c * 3 + 1];
+  const bool train = p.noise != nullptr;
+  const int64_t n = p.B * p.S;
+  float acc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t b = e / p.S, s = e - b * p.S;
+    const int64_t off = (b * p.C + c) * p.S + s;
+    const float z = p.z[off];
+    const float zh = rintf(z - med) + med;
+    const float x = train ? (z + p.noise[off]) : zh;
+    const float lo = eb_logits<false>(pk, x - 0.5f, nullptr, nullptr);
+    const float up = eb_logits<false>(pk, x + 0.5f, nullptr, nullptr);
+    const float t = lo + up;
+    const float sg = (t > 0.f) ? -1.f : ((t < 0.f) ? 1.f : 0.f);  // -sign(lower + upper)
+    const float lik = fmaxf(fabsf(sigmoidf_(sg * up) - sigmoidf_(sg * lo)), p.lik_bound);
+    p.lik[off] = lik;
+    if (p.z_hat) p.z_hat[off] = zh;
+    if (p.outputs) p.outputs[off] = x;
+    acc += log2f(lik);
+  }
+  if (p.log2_sum) {
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(p.log2_sum, (double)tot);
+  }
+}
+
+struct EbBwdParams {
+  const float *z, *noise, *quantiles, *lik, *g_lik, *g_z_hat;
+  float* g_z;
+  int64_t B, C, S;
+  float bpp_coef, lik_bound;
+  bool param_grads;
+  EbPtrs P;
+  EbGradPtrs G;
+};
+
+// Reverse-mode through one logits chain.  g_out = dL/dlogit.  Accumulates transformed-parameter
+// gradients into gp[58] (w.r.t. softplus(M), b, tanh(f)) and returns dL/dx.
+__device__ __forceinline__ float eb_logits_bwd(const float* pk, float x, const float (*a)[3],
+                                               const float (*in)[3], float g_out, float* gp) {
+  float gh[3];
+  // layer 4: out = M4 . in4 + b4
+  gp[45] += g_out;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gp[30 + i] += g_out * in[4][i];
+    gh[i] = g_out * pk[30 + i];
+  }
+#pragma unroll
+  for (int l = 3; l >= 1; --l) {
+    float gin[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float th = tanhf(a[l][j]);
+      const float tf = pk[46 + 3 * l + j];
+      gp[46 + 3 * l + j] += gh[j] * th;                 // d/d tanh(f)
+      const float ga = gh[j] * (1.f + tf * (1.f - th * th));  // through h = a + tf*tanh(a)
+      gp[33 + 3 * l + j] += ga;                         // bias
+      const float* mrow = pk + 3 + (l - 1) * 9 + j * 3;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        gp[3 + (l - 1) * 9 + j * 3 + i] += ga * in[l][i];
+        gin[i] = fmaf(ga, mrow[i], gin[i]);
+      }
+    }
+    gh[0] = gin[0]; gh[1] = gin[1]; gh[2] = gin[2];
+  }
+  float gx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float th = tanhf(a[0][j]);
+    const float tf = pk[46 + j];
+    gp[46 + j] += gh[j] * th;
+    const float ga = gh[j] * (1.f + tf * (1.f - th * th));
+    gp[33 + j] += ga;
+    gp[j] += ga * x;
+    gx = fmaf(ga, pk[j], gx);
+  }
+  return gx;
+}
+
+__global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
+  __shared__ float pk[64];
+  __shared__ float gsum[64];
+  const int c = blockIdx.x;
+  eb_load_pack(p.P, c, pk);
+  if (threadIdx.x < 64) gsum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const float med = p.quantiles[c * 3 + 1];
+  const bool train = p.noise != nullptr;
+  const int64_t n = p.B * p.S;
+  float gp[kEbPack];
+#pragma unroll
+  for (int i = 0; i < kEbPack; ++i) gp[i] = 0.f;
+  for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t b = e / p.S, s = e - b * p.S;
+    const int64_t off = (b * p.C + c) * p.S + s;
+    const float z = p.z[off];
+    const float x = train ? (z + p.noise[off]) : (rintf(z - med) + med);
+    float a_lo[4][3], in_lo[5][3], a_up[4][3], in_up[5][3];
+    const float lo = eb_logits<true>(pk, x - 0.5f, a_lo, in_lo);
+    const float up = eb_logits<true>(pk, x + 0.5f, a_up, in_up);
+    const float t = lo + up;
+    const float sg = (t > 0.f) ? -1.f : ((t < 0.f) ? 1.f : 0.f);
+    const float su = sigmoidf_(sg * up), sl = sigmoidf_(sg * lo);
+    const float D = su - sl;
+    const float lik = p.lik[off];
+    float gl = p.g_lik ? p.g_lik[off] : (p.bpp_coef / lik);
+    gl = ((lik > p.lik_bound) || (gl < 0.f)) ? gl : 0.f;
+    const float sd = (D > 0.f) ? 1.f : ((D < 0.f) ? -1.f : 0.f);  // d|D|/dD
+    const float g_up = gl * sd * su * (1.f - su) * sg;
+    const float g_lo = -gl * sd * sl * (1.f - sl) * sg;
+    float gx = eb_logits_bwd(pk, x + 0.5f, a_up, in_up, g_up, gp);
+    gx += eb_logits_bwd(pk, x - 0.5f, a_lo, in_lo, g_lo, gp);
+    const float gzh = p.g_z_hat ? p.g_z_hat[off] : 0.f;  // STE: d z_hat / d z = 1
+    p.g_z[off] = gzh + (train ? gx : 0.f);
+  }
+  if (!p.param_grads) return;
+  // CTA reduction of the 58 transformed-parameter gradients: warp shuffle, then shared atomics.
+#pragma unroll
+  for (int i = 0; i < kEbPack; ++i) {
+    const float v = warp_sum(gp[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&gsum[i], v);
+  }
+  __syncthreads();
+  // Chain through softplus / tanh of the raw parameters and add to global (one atomic each).
+  const int t = threadIdx.x;
+  if (t < kEbPack) {
+    const float g = gsum[t];
+    if (t < 33) {
+      int l, k;
+      if (t < 3) { l = 0; k = t; } else if (t < 12) { l = 1; k = t - 3; } else if (t < 21) { l = 2; k = t - 12; }
+      else if (t < 30) { l = 3; k = t - 21; } else { l = 4; k = t - 30; }
+      const int per = (l == 0 || l == 4) ? 3 : 9;
+      const float raw = p.P.matrix[l][c * per + k];
+      atomicAdd(&p.G.matrix[l][c * per + k], g * sigmoidf_(raw));  // d softplus = sigmoid
+    } else if (t < 46) {
+      const int l = (t - 33) / 3, k = (t - 33) % 3;
+      if (t == 45) atomicAdd(&p.G.bias[4][c], g);
+      else atomicAdd(&p.G.bias[l][c * 3 + k], g);
+    } else {
+      const int l = (t - 46) / 3, k = (t - 46) % 3;
+      const float tf = pk[t];
+      atomicAdd(&p.G.factor[l][c * 3 + k], g * (1.f - tf * tf));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// log2-sum (rate term) forward / backward
+// ------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+log2_sum_kernel(const float* __restrict__ lik, int64_t n, double* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  if constexpr (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = ld4_stream(lik + 4 * i);
+      acc += (log2f(v.x) + log2f(v.y)) + (log2f(v.z) + log2f(v.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) acc += log2f(lik[(n4 << 2) + threadIdx.x]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+      acc += log2f(lik[i]);
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, (double)tot);
+}
+
+__global__ void __launch_bounds__(256)
+log2_sum_bwd_kernel(const float* __restrict__ lik, float coef, const double* __restrict__ coef_dev,
+                    float* __restrict__ g, int64_t n) {
+  if (coef_dev) coef *= (float)(*coef_dev);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    g[i] = coef / lik[i];
+}
+
+}  // namespace clc
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace clc;
+
+static bool vec_ok(int64_t CS, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> strides) {
+  if (CS % 4) return false;
+  for (const void* q : ptrs) if (q && !aligned16(q)) return false;
+  for (int64_t s : strides) if (s % 4) return false;
+  return true;
+}
+
+extern "C" int clc_gc_fwd(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                          const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs,
+                          float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
+                          float* outputs, int64_t outputs_bs, double* log2_sum,
+                          int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+  if (!y || !scale || !lik || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || CS == 0) return CLC_OK;
+  GcFwdParams p{y, scale, mean, noise, lik, y_hat, outputs, log2_sum,
+                y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs, B, CS, scale_bound, lik_bound};
+  const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, y_hat, outputs},
+                          {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs});
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) gc_fwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
+  else gc_fwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
+  CLC_CHECK_LAUNCH("clc_gc_fwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_gc_bwd(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                          const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs,
+                          const float* lik, int64_t lik_bs, const float* g_lik, int64_t g_lik_bs,
+                          float bpp_coef, const float* g_y_hat, int64_t g_y_hat_bs,
+                          float* g_y, int64_t g_y_bs, float* g_scale, int64_t g_scale_bs,
+                          float* g_mean, int64_t g_mean_bs,
+                          int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+  if (!y || !scale || !lik || !g_y || !g_scale || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (mean && !g_mean) return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || CS == 0) return CLC_OK;
+  GcBwdParams p{y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean,
+                y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs,
+                B, CS, bpp_coef, scale_bound, lik_bound};
+  const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean},
+                          {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs});
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) gc_bwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
+  else gc_bwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
+  CLC_CHECK_LAUNCH("clc_gc_bwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_lrp_add_fwd(float* y_hat, int64_t y_hat_bs, const float* lrp, int64_t lrp_bs,
+                               int64_t B, int64_t CS, void* stream) {
+  if (!y_hat || !lrp || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || CS == 0) return CLC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_ok(CS, {y_hat, lrp}, {y_hat_bs, lrp_bs}))
+    lrp_kernel<true, false><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(y_hat, y_hat_bs, lrp, lrp_bs, nullptr, 0, B, CS);
+  else
+    lrp_kernel<false, false><<<grid_for(B * CS, 256), 256, 0, st>>>(y_hat, y_hat_bs, lrp, lrp_bs, nullptr, 0, B, CS);
+  CLC_CHECK_LAUNCH("clc_lrp_add_fwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_lrp_add_bwd(const float* g, int64_t g_bs, const float* lrp, int64_t lrp_bs,
+                               float* g_lrp, int64_t g_lrp_bs, int64_t B, int64_t CS, void* stream) {
+  if (!g || !lrp || !g_lrp || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || CS == 0) return CLC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_ok(CS, {g, lrp, g_lrp}, {g_bs, lrp_bs, g_lrp_bs}))
+    lrp_kernel<true, true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(g_lrp, g_lrp_bs, lrp, lrp_bs, g, g_bs, B, CS);
+  else
+    lrp_kernel<false, true><<<grid_for(B * CS, 256), 256, 0, st>>>(g_lrp, g_lrp_bs, lrp, lrp_bs, g, g_bs, B, CS);
+  CLC_CHECK_LAUNCH("clc_lrp_add_bwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_gc_symbols_indexes(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                                      const float* mean, int64_t mean_bs, const float* scale_table, int T,
+                                      int32_t* symbols, int64_t symbols_bs, int32_t* indexes, int64_t indexes_bs,
+                                      int64_t B, int64_t CS, float scale_bound, void* stream) {
+  if (B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (symbols && !y) return CLC_ERR_INVALID_ARGUMENT;
+  if (indexes && (!scale || !scale_table || T < 1)) return CLC_ERR_INVALID_ARGUMENT;
+  if (T > 256) return CLC_ERR_UNSUPPORTED;
+  if (B == 0 || CS == 0 || (!symbols && !indexes)) return CLC_OK;
+  gc_symbols_indexes_kernel<<<grid_for(B * CS, 256), 256, 0, (cudaStream_t)stream>>>(
+      y, y_bs, scale, scale_bs, mean, mean_bs, scale_table, T, symbols, symbols_bs, indexes, indexes_bs,
+      B, CS, scale_bound);
+  CLC_CHECK_LAUNCH("clc_gc_symbols_indexes");
+  return CLC_OK;
+}
+
+static int eb_grid_y(int64_t C, int64_t n) {
+  // enough CTAs per channel to cover n elements at 128 threads, but keep the whole grid
+  // near 148 x 8 CTAs so per-channel parameter packs are not re-derived needlessly.
+  int64_t chunks = (n + 127) / 128;
+  int64_t cap = ((int64_t)kNumSMs * 16 + C - 1) / C;
+  if (cap < 1) cap = 1;
+  if (chunks > cap) chunks = cap;
+  if (chunks > 65535) chunks = 65535;
+  return (int)(chunks < 1 ? 1 : chunks);
+}
+
+extern "C" int clc_eb_fwd(const float* z, const float* noise, const float* const matrix[5],
+                          const float* const bias[5], const float* const factor[4], const float* quantiles,
+                          float* lik, float* z_hat, float* outputs, double* log2_sum,
+                          int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+  if (!z || !matrix || !bias || !factor || !quantiles || !lik || B < 0 || C < 0 || S < 0)
+    return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || C == 0 || S == 0) return CLC_OK;
+  if (C > 2147483647LL) return CLC_ERR_UNSUPPORTED;
+  EbFwdParams p;
+  p.z = z; p.noise = noise; p.quantiles = quantiles; p.lik = lik; p.z_hat = z_hat; p.outputs = outputs;
+  p.log2_sum = log2_sum; p.B = B; p.C = C; p.S = S; p.lik_bound = lik_bound;
+  for (int i = 0; i < 5; ++i) { p.P.matrix[i] = matrix[i]; p.P.bias[i] = bias[i]; if (!matrix[i] || !bias[i]) return CLC_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < 4; ++i) { p.P.factor[i] = factor[i]; if (!factor[i]) return CLC_ERR_INVALID_ARGUMENT; }
+  dim3 grid((unsigned)C, (unsigned)eb_grid_y(C, B * S));
+  eb_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  CLC_CHECK_LAUNCH("clc_eb_fwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_eb_bwd(const float* z, const float* noise, const float* const matrix[5],
+                          const float* const bias[5], const float* const factor[4], const float* quantiles,
+                          const float* lik, const float* g_lik, float bpp_coef, const float* g_z_hat,
+                          float* g_z, float* const g_matrix[5], float* const g_bias[5], float* const g_factor[4],
+                          int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+  if (!z || !matrix || !bias || !factor || !quantiles || !lik || !g_z || B < 0 || C < 0 || S < 0)
+    return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || C == 0 || S == 0) return CLC_OK;
+  EbBwdParams p;
+  p.z = z; p.noise = noise; p.quantiles = quantiles; p.lik = lik; p.g_lik = g_lik; p.g_z_hat = g_z_hat;
+  p.g_z = g_z; p.B = B; p.C = C; p.S = S; p.bpp_coef = bpp_coef; p.lik_bound = lik_bound;
+  p.param_grads = g_matrix && g_bias && g_factor;
+  for (int i = 0; i < 5; ++i) {
+    p.P.matrix[i] = matrix[i]; p.P.bias[i] = bias[i];
+    if (!matrix[i] || !bias[i]) return CLC_ERR_INVALID_ARGUMENT;
+    p.G.matrix[i] = p.param_grads ? g_matrix[i] : nullptr;
+    p.G.bias[i] = p.param_grads ? g_bias[i] : nullptr;
+    if (p.param_grads && (!g_matrix[i] || !g_bias[i])) return CLC_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 0; i < 4; ++i) {
+    p.P.factor[i] = factor[i];
+    if (!factor[i]) return CLC_ERR_INVALID_ARGUMENT;
+    p.G.factor[i] = p.param_grads ? g_factor[i] : nullptr;
+    if (p.param_grads && !g_factor[i]) return CLC_ERR_INVALID_ARGUMENT;
+  }
+  dim3 grid((unsigned)C, (unsigned)eb_grid_y(C, B * S));
+  eb_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  CLC_CHECK_LAUNCH("clc_eb_bwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_log2_sum_fwd(const float* lik, int64_t n, double* log2_sum, void* stream) {
+  if (!lik || !log2_sum || n < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (n == 0) return CLC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (aligned16(lik)) log2_sum_kernel<true><<<grid_for(n / 4 + 1, 256, 4), 256, 0, st>>>(lik, n, log2_sum);
+  else log2_sum_kernel<false><<<grid_for(n, 256, 4), 256, 0, st>>>(lik, n, log2_sum);
+  CLC_CHECK_LAUNCH("clc_log2_sum_fwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_log2_sum_bwd(const float* lik, float coef, const double* coef_dev, float* g_lik,
+                                int64_t n, void* stream) {
+  if (!lik || !g_lik || n < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (n == 0) return CLC_OK;
+  log2_sum_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(lik, coef, coef_dev, g_lik, n);
+  CLC_CHECK_LAUNCH("clc_log2_sum_bwd");
+  return CLC_OK;
+}

@@ -1,0 +1,595 @@
+// Reference matching, exact-fp32 path ("fp32 mode"): Pearson correlation map on CUDA cores
+// with sequential fp32 FMA accumulation, warp-shuffle top-k, Gaussian mask, gather/blend and
+// the backward kernels.  The tcgen05 screening path lives in match_tc.cu and shares the
+// statistics / re-scoring helpers declared in match.cuh.
+//
+// Reference arithmetic followed (file:line into the reference tree):
+//   L2_or_pearson_corr ........ models/Patch_Matching.py:854-910
+//   create_gaussian_masks ..... models/Patch_Matching.py:779-807
+//   SI_Wraper ................. models/Patch_Matching.py:218-240
+#include "match.cuh"
+
+namespace clc {
+
+// ------------------------------------------------------------------------------------------
+// Per-pixel channel sums of the reference-side features: S1 = sum_c r, S2 = sum_c r^2.
+// One thread per pixel, looping over channels (coalesced across pixels).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+channel_sums_kernel(const float* __restrict__ r, float* __restrict__ s1, float* __restrict__ s2,
+                    int64_t NP, int C, int64_t HW) {
+  const int64_t total = NP * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, px = i - n * HW;
+    const float* p = r + n * C * HW + px;
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = p[(int64_t)c * HW];
+      a += v;
+      b = fmaf(v, v, b);
+    }
+    s1[i] = a;
+    s2[i] = b;
+  }
+}
+
+// Per-patch query statistics: xs = sum q, sxx = sum q^2 over the C*ph*pw patch elements.
+// One warp per (problem-query, patch).
+__global__ void __launch_bounds__(256)
+patch_stats_kernel(PatchAddr qa, float* __restrict__ xs, float* __restrict__ sxx, int64_t NQ, int P,
+                   int C, int ph, int pw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= NQ * P) return;
+  const int64_t nq = w / P;
+  const int patch = (int)(w - nq * P);
+  const float* base = qa.q + nq * qa.sn + qa.patch_off(patch);
+  const int K = C * ph * pw, pp = ph * pw;
+  float a = 0.f, b = 0.f;
+  for (int e = lane; e < K; e += 32) {
+    const int c = e / pp, rem = e - c * pp;
+    const int dy = rem / pw, dx = rem - dy * pw;
+    const float v = base[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+    a += v;
+    b = fmaf(v, v, b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { xs[w] = a; sxx[w] = b; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Correlation GEMM (fp32 FMA, 64x64 tile, 4x4 micro-tile) with the Pearson epilogue.
+//   xy[patch, pos] = sum_{c,dy,dx} q[patch,c,dy,dx] * r[c, oy+dy, ox+dx]
+// accumulated in ascending k = (c, dy, dx) order with one fp32 FMA chain per output.
+// ------------------------------------------------------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+pearson_corr_kernel(PatchAddr qa, const float* __restrict__ r, const float* __restrict__ s1,
+                    const float* __restrict__ s2, const float* __restrict__ xs,
+                    const float* __restrict__ sxx, const float* __restrict__ mask,
+                    float* __restrict__ corr, int P, int C, int ph, int pw, int fh, int fw) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int ch = fh - ph + 1, cw = fw - pw + 1, L = ch * cw;
+  const int pp = ph * pw, K = C * pp;
+  const int64_t HW = (int64_t)fh * fw;
+  const int n = blockIdx.z;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int nq = n / qa.repeat;
+  const float* qbase = qa.q + (int64_t)nq * qa.sn;
+  const float* rbase = r + (int64_t)n * C * HW;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // Per-thread load coordinates (fixed across the K loop).
+  //   A: 4 elements, e = tid + i*256 -> k_local = e % 16, patch_local = e / 16
+  //   B: 4 elements, e = tid + i*256 -> pos_local = e % 64, k_local = e / 64
+  int64_t a_off[4];
+  bool a_ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * 256;
+    const int pl = e >> 4;
+    a_ok[i] = (m0 + pl) < P;
+    a_off[i] = a_ok[i] ? qa.patch_off(m0 + pl) : 0;
+  }
+  int64_t b_off[4];
+  bool b_ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * 256;
+    const int pos = n0 + (e & 63);
+    b_ok[i] = pos < L;
+    const int oy = b_ok[i] ? pos / cw : 0, ox = b_ok[i] ? pos - oy * cw : 0;
+    b_off[i] = (int64_t)oy * fw + ox;
+  }
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      {  // A
+        const int kl = e & 15, pl = e >> 4;
+        const int k = k0 + kl;
+        float v = 0.f;
+        if (a_ok[i] && k < K) {
+          const int c = k / pp, rem = k - c * pp;
+          const int dy = rem / pw, dx = rem - dy * pw;
+          v = qbase[a_off[i] + (int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+        }
+        As[kl][pl] = v;
+      }
+      {  // B
+        const int kl = e >> 6, pl = e & 63;
+        const int k = k0 + kl;
+        float v = 0.f;
+        if (b_ok[i] && k < K) {
+          const int c = k / pp, rem = k - c * pp;
+          const int dy = rem / pw, dx = rem - dy * pw;
+          v = rbase[(int64_t)c * HW + b_off[i] + (int64_t)dy * fw + dx];
+        }
+        Bs[kl][pl] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // Pearson epilogue, in the reference's operation order (Patch_Matching.py:880-905).
+  const float inv_k = 1.0f / (float)K;  // kernel_mean = ones / patch_size
+  const float* s1n = s1 + (int64_t)n * HW;
+  const float* s2n = s2 + (int64_t)n * HW;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pos = n0 + tx * 4 + j;
+    if (pos >= L) continue;
+    const int oy = pos / cw, ox = pos - oy * cw;
+    float b1 = 0.f, b2 = 0.f;
+    for (int dy = 0; dy < ph; ++dy)
+      for (int dx = 0; dx < pw; ++dx) {
+        b1 += s1n[(oy + dy) * fw + ox + dx];
+        b2 += s2n[(oy + dy) * fw + ox + dx];
+      }
+    const PosStat ps = pos_stat(b1, b2, inv_k, (float)K);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int patch = m0 + ty * 4 + i;
+      if (patch >= P) continue;
+      const int64_t qi = (int64_t)nq * P + patch;
+      float v = pearson(acc[i][j], ps, xs[qi], sxx[qi], (float)K);
+      if (mask) v *= mask[(int64_t)patch * L + pos];
+      corr[((int64_t)n * P + patch) * L + pos] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-wise top-k by k passes of a warp-shuffle arg-max, each pass excluding everything at or
+// above the previous winner in (value desc, index asc) order.  Deterministic; ties resolve to
+// the lowest index; NaN ranks above every number (as torch.topk).  One warp per row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool key_before(float av, int ai, float bv, int bi) {
+  // true if (av, ai) ranks strictly before (bv, bi)
+  const bool an = av != av, bn = bv != bv;
+  if (an != bn) return an;
+  if (!an && av != bv) return av > bv;
+  return ai < bi;
+}
+
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const float* __restrict__ x, int64_t R, int64_t L, int k, float* __restrict__ val,
+                 int32_t* __restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= R) return;
+  const float* xr = x + row * L;
+  float pv = 0.f;
+  int pi = -1;  // previous winner; pi < 0 means none yet
+  for (int t = 0; t < k; ++t) {
+    float bv = 0.f;
+    int bi = -1;
+    for (int64_t i = lane; i < L; i += 32) {
+      const float v = xr[i];
+      if (pi >= 0 && !key_before(pv, pi, v, (int)i)) continue;  // not after the previous winner
+      if (bi < 0 || key_before(v, (int)i, bv, bi)) { bv = v; bi = (int)i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || key_before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      val[row * k + t] = bv;
+      idx[row * k + t] = bi;
+    }
+    pv = bv;
+    pi = bi;
+    if (bi < 0) break;  // fewer than k elements
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// create_gaussian_masks, fp64 on the device, rounded to fp32 (the reference builds it in
+// numpy float64 and casts).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gaussian_mask_kernel(float* __restrict__ mask, int img_h, int img_w, int ph, int pw) {
+  const int ch = img_h - ph + 1, cw = img_w - pw + 1;
+  const int P = (img_h * img_w) / (ph * pw);
+  const int64_t total = (int64_t)P * ch * cw;
+  const double patch_img_w = (double)img_w / (double)pw;
+  const double sig_h = 0.5 * img_h, sig_w = 0.5 * img_w;
+  const int r0 = (ph + 1) / 2 - 1, c0 = (pw + 1) / 2 - 1;
+  const double kNeg4Ln2 = -4.0 * 0.693147180559945309417232121458;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i / ((int64_t)ch * cw));
+    const int rem = (int)(i - (int64_t)p * ch * cw);
+    const int ii = rem / cw, jj = rem - ii * cw;
+    const double center_h = (floor((double)p / patch_img_w) + 0.5) * ph;
+    const double center_w = (fmod((double)p, patch_img_w) + 0.5) * pw;
+    const double hv = (double)(ii + r0 + 1) - (double)(ph % 2) / 2.0;
+    const double wv = (double)(jj + c0 + 1) - (double)(pw % 2) / 2.0;
+    const double rg = ((hv - center_h) * (hv - center_h)) / (sig_h * sig_h);
+    const double cg = ((wv - center_w) * (wv - center_w)) / (sig_w * sig_w);
+    mask[i] = (float)exp(kNeg4Ln2 * (rg + cg));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gather + blend (SI_Wraper :226-238).  One thread per output element (n, c, y, x); weights =
+// softmax(val * T) recomputed per thread (k exps) and written once per patch.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxK = 32;
+
+__global__ void __launch_bounds__(256)
+gather_blend_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
+                        const float* __restrict__ val, float temperature, float* __restrict__ out,
+                        float* __restrict__ weights, int64_t NP, int C, int fh, int fw, int gh, int gw,
+                        int corr_w, int k, int is_stack) {
+  const int npx = fw / gw, P = (fh / gh) * npx;
+  const int64_t HW = (int64_t)fh * fw;
+  const int64_t total = NP * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % fw);
+    const int y = (int)((i / fw) % fh);
+    const int c = (int)((i / HW) % C);
+    const int64_t n = i / (HW * C);
+    const int py = y / gh, px = x / gw, dy = y - py * gh, dx = x - px * gw;
+    const int patch = py * npx + px;
+    const int32_t* ip = idx + (n * P + patch) * k;
+    const float* fp = feat + (n * C + c) * HW;
+    if (is_stack) {
+      for (int j = 0; j < k; ++j) {
+        const int id = ip[j];
+        const int sy = id / corr_w, sx = id - sy * corr_w;
+        out[((n * k + j) * C + c) * HW + (int64_t)y * fw + x] = fp[(sy + dy) * fw + sx + dx];
+      }
+    } else {
+      const float* vp = val + (n * P + patch) * k;
+      float mx = -INFINITY;
+      for (int j = 0; j < k; ++j) mx = fmaxf(mx, vp[j] * temperature);
+      float den = 0.f;
+      for (int j = 0; j < k; ++j) den += expf(vp[j] * temperature - mx);
+      float acc = 0.f;
+      const bool writer = weights && c == 0 && dy == 0 && dx == 0;
+      for (int j = 0; j < k; ++j) {
+        const float wj = expf(vp[j] * temperature - mx) / den;
+        const int id = ip[j];
+        const int sy = id / corr_w, sx = id - sy * corr_w;
+        // torch.sum over the k axis: sequential left-to-right accumulation of y_patch * weight
+        acc += fp[(sy + dy) * fw + sx + dx] * wj;
+        if (writer) weights[(n * P + patch) * k + j] = wj;
+      }
+      out[i] = acc;
+    }
+  }
+}
+
+// Backward: one CTA per (n, patch).  g_feat scatter-add (windows overlap -> atomics);
+// g_w[j] = sum g_out * patch_j reduced over the CTA; g_val through the softmax.
+__global__ void __launch_bounds__(128)
+gather_blend_bwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
+                        const float* __restrict__ weights, float temperature,
+                        const float* __restrict__ g_out, float* __restrict__ g_feat,
+                        float* __restrict__ g_val, int C, int fh, int fw, int gh, int gw, int corr_w,
+                        int k, int is_stack) {
+  __shared__ float red[32];
+  __shared__ float gw_s[kMaxK];
+  const int npx = fw / gw, P = (fh / gh) * npx;
+  const int64_t HW = (int64_t)fh * fw;
+  const int64_t n = blockIdx.x / P;
+  const int patch = blockIdx.x - (int)(n * P);
+  const int py = patch / npx, px = patch - py * npx;
+  const int pp = gh * gw, K = C * pp;
+  const int32_t* ip = idx + (n * P + patch) * k;
+  for (int j = 0; j < k; ++j) {
+    const int id = ip[j];
+    const int sy = id / corr_w, sx = id - sy * corr_w;
+    const float wj = is_stack ? 1.f : weights[(n * P + patch) * k + j];
+    float part = 0.f;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+      const int c = e / pp, rem = e - c * pp;
+      const int dy = rem / gw, dx = rem - dy * gw;
+      const int64_t o = (int64_t)(py * gh + dy) * fw + px * gw + dx;
+      const float g = is_stack ? g_out[((n * k + j) * C + c) * HW + o] : g_out[(n * C + c) * HW + o];
+      const int64_t f = (n * C + c) * HW + (int64_t)(sy + dy) * fw + sx + dx;
+      if (!is_stack) part = fmaf(g, feat[f], part);
+      atomicAdd(&g_feat[f], wj * g);
+    }
+    if (!is_stack) {
+      const float tot = block_sum(part, red);
+      if (threadIdx.x == 0) gw_s[j] = tot;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* gv = g_val + (n * P + patch) * k;
+    if (is_stack) {
+      for (int j = 0; j < k; ++j) gv[j] = 0.f;
+    } else {
+      // w = softmax(v*T): dL/dv_j = T * w_j * (g_w_j - sum_i w_i g_w_i)
+      const float* w = weights + (n * P + patch) * k;
+      float dot = 0.f;
+      for (int j = 0; j < k; ++j) dot = fmaf(w[j], gw_s[j], dot);
+      for (int j = 0; j < k; ++j) gv[j] = temperature * w[j] * (gw_s[j] - dot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of the masked Pearson value at the k selected positions.  One CTA per (n, patch).
+// out = num / sqrt(D), num = xy - ym*xs, D = dY*dX, dY = syy - ym^2 K, dX = sxx - xm*xs.
+// xy's query operand is detached in the reference (conv2d weights = x.data), every other use
+// of x (xs, sxx, xm) is attached.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pearson_topk_bwd_kernel(PatchAddr qa, const float* __restrict__ r, const float* __restrict__ mask,
+                        const int32_t* __restrict__ idx, const float* __restrict__ g_val,
+                        float* __restrict__ g_r, float* __restrict__ g_q, int P, int C, int ph, int pw,
+                        int fh, int fw, int k) {
+  __shared__ float red[32];
+  __shared__ float bc[4];
+  const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
+  const int64_t HW = (int64_t)fh * fw;
+  const int64_t n = blockIdx.x / P;
+  const int patch = blockIdx.x - (int)(n * P);
+  const int64_t nq = n / qa.repeat;
+  const float* qb = qa.q + nq * qa.sn + qa.patch_off(patch);
+  const float* rb = r + n * C * HW;
+  const int pp = ph * pw, K = C * pp;
+  const float Kf = (float)K, inv_k = 1.0f / Kf;
+
+  // patch statistics
+  float a = 0.f, b = 0.f;
+  for (int e = threadIdx.x; e < K; e += blockDim.x) {
+    const int c = e / pp, rem = e - c * pp;
+    const int dy = rem / pw, dx = rem - dy * pw;
+    const float v = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+    a += v;
+    b = fmaf(v, v, b);
+  }
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) bc[0] = a;
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) bc[1] = b;
+  __syncthreads();
+  const float xs = bc[0], sxx = bc[1];
+  const float xm = xs / Kf;
+  const float dX = sxx - xm * xs;
+
+  float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;  // accumulated over the k positions
+  for (int j = 0; j < k; ++j) {
+    const int id = idx[(n * P + patch) * k + j];
+    const int oy = id / cw, ox = id - oy * cw;
+    float s1 = 0.f, s2 = 0.f, xy = 0.f;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+      const int c = e / pp, rem = e - c * pp;
+      const int dy = rem / pw, dx = rem - dy * pw;
+      const float qv = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+      const float rv = rb[(int64_t)c * HW + (int64_t)(oy + dy) * fw + ox + dx];
+      s1 += rv;
+      s2 = fmaf(rv, rv, s2);
+      xy = fmaf(qv, rv, xy);
+    }
+    s1 = block_sum(s1, red);
+    if (threadIdx.x == 0) bc[0] = s1;
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) bc[1] = s2;
+    xy = block_sum(xy, red);
+    if (threadIdx.x == 0) bc[2] = xy;
+    __syncthreads();
+    s1 = bc[0]; s2 = bc[1]; xy = bc[2];
+    __syncthreads();
+    const float ym = s1 * inv_k;
+    const float dY = s2 - ym * ym * Kf;
+    const float D = dY * dX;
+    const float num = xy - ym * xs;
+    const float rs = rsqrtf(D);
+    float g = g_val[(n * P + patch) * k + j];
+    if (mask) g *= mask[(int64_t)patch * L + id];
+    const float g_num = g * rs;
+    const float g_D = -0.5f * g * num * rs / D;
+    const float g_dY = g_D * dX, g_dX = g_D * dY;
+    const float g_ym = -g_num * xs - 2.f * g_dY * ym * Kf;
+    const float g_xy = g_num;
+    t_gxs += -g_num * ym - g_dX * xm;
+    t_gsxx += g_dX;
+    t_gxm += -g_dX * xs;
+    const float c_mean = g_ym * inv_k;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+      const int c = e / pp, rem = e - c * pp;
+      const int dy = rem / pw, dx = rem - dy * pw;
+      const float qv = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+      const int64_t ro = (int64_t)c * HW + (int64_t)(oy + dy) * fw + ox + dx;
+      const float rv = rb[ro];
+      atomicAdd(&g_r[n * C * HW + ro], fmaf(g_xy, qv, fmaf(2.f * g_dY, rv, c_mean)));
+    }
+  }
+  if (g_q) {
+    float* gqb = g_q + nq * qa.sn + qa.patch_off(patch);
+    const float cst = t_gxs + t_gxm * inv_k;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+      const int c = e / pp, rem = e - c * pp;
+      const int dy = rem / pw, dx = rem - dy * pw;
+      const int64_t o = (int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx;
+      atomicAdd(&gqb[o], fmaf(2.f * t_gsxx, qb[o], cst));
+    }
+  }
+}
+
+// Host helpers shared with match_tc.cu --------------------------------------------------------
+int launch_channel_sums(const float* r, float* s1, float* s2, int64_t NP, int C, int64_t HW,
+                        cudaStream_t st) {
+  channel_sums_kernel<<<grid_for(NP * HW, 256), 256, 0, st>>>(r, s1, s2, NP, C, HW);
+  CLC_CHECK_LAUNCH("channel_sums");
+  return CLC_OK;
+}
+
+int launch_patch_stats(const PatchAddr& qa, float* xs, float* sxx, int64_t NQ, int P, int C, int ph,
+                       int pw, cudaStream_t st) {
+  const int64_t warps = NQ * P;
+  patch_stats_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(qa, xs, sxx, NQ, P, C, ph, pw);
+  CLC_CHECK_LAUNCH("patch_stats");
+  return CLC_OK;
+}
+
+}  // namespace clc
+
+using namespace clc;
+
+static bool view_ok(const clc_patch_view* v) { return v && v->q && v->npx >= 1 && v->q_repeat >= 1; }
+
+static PatchAddr make_addr(const clc_patch_view* v) {
+  PatchAddr a;
+  a.q = v->q; a.sn = v->q_sn; a.spy = v->q_spy; a.spx = v->q_spx; a.sc = v->q_sc; a.sy = v->q_sy;
+  a.npx = v->npx; a.repeat = v->q_repeat;
+  return a;
+}
+
+extern "C" size_t clc_pearson_corr_workspace_bytes(int64_t NP, int32_t P, int32_t C, int32_t ph,
+                                                   int32_t pw, int32_t fh, int32_t fw) {
+  (void)C; (void)ph; (void)pw;
+  // s1, s2: NP*fh*fw each;  xs, sxx: NP*P each (upper bound: one query per problem)
+  return sizeof(float) * (size_t)(2 * NP * (int64_t)fh * fw + 2 * NP * (int64_t)P) + 256;
+}
+
+extern "C" int clc_pearson_corr(const clc_patch_view* qv, const float* r, const float* mask, float* corr,
+                                int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
+                                int32_t fh, int32_t fw, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (!view_ok(qv) || !r || !corr || NP < 0 || P < 1 || C < 1 || ph < 1 || pw < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (fh < ph || fw < pw) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  if (NP > 65535) return CLC_ERR_UNSUPPORTED;
+  if (NP % qv->q_repeat) return CLC_ERR_INVALID_ARGUMENT;
+  if (!workspace || workspace_bytes < clc_pearson_corr_workspace_bytes(NP, P, C, ph, pw, fh, fw))
+    return CLC_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t HW = (int64_t)fh * fw;
+  const int64_t NQ = NP / qv->q_repeat;
+  float* s1 = (float*)workspace;
+  float* s2 = s1 + NP * HW;
+  float* xs = s2 + NP * HW;
+  float* sxx = xs + NQ * P;
+  const PatchAddr qa = make_addr(qv);
+  int rc;
+  if ((rc = launch_channel_sums(r, s1, s2, NP, C, HW, st))) return rc;
+  if ((rc = launch_patch_stats(qa, xs, sxx, NQ, P, C, ph, pw, st))) return rc;
+  const int L = (fh - ph + 1) * (fw - pw + 1);
+  dim3 grid((L + TN - 1) / TN, (P + TM - 1) / TM, (unsigned)NP);
+  pearson_corr_kernel<<<grid, 256, 0, st>>>(qa, r, s1, s2, xs, sxx, mask, corr, P, C, ph, pw, fh, fw);
+  CLC_CHECK_LAUNCH("clc_pearson_corr");
+  return CLC_OK;
+}
+
+extern "C" int clc_topk_rows(const float* x, int64_t R, int64_t L, int32_t k, float* val, int32_t* idx,
+                             void* stream) {
+  if (!x || !val || !idx || R < 0 || L < 1 || k < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (k > L || L > 2147483647LL) return CLC_ERR_INVALID_ARGUMENT;
+  if (k > kMaxK) return CLC_ERR_UNSUPPORTED;
+  if (R == 0) return CLC_OK;
+  topk_rows_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, R, L, k, val, idx);
+  CLC_CHECK_LAUNCH("clc_topk_rows");
+  return CLC_OK;
+}
+
+extern "C" int clc_gaussian_mask(float* mask, int32_t img_h, int32_t img_w, int32_t ph, int32_t pw,
+                                 void* stream) {
+  if (!mask || ph < 1 || pw < 1 || img_h < ph || img_w < pw) return CLC_ERR_INVALID_ARGUMENT;
+  if (img_w % pw) return CLC_ERR_UNSUPPORTED;  // patch_img_w must be integral (as in the reference use)
+  const int64_t total = (int64_t)((img_h * img_w) / (ph * pw)) * (img_h - ph + 1) * (img_w - pw + 1);
+  gaussian_mask_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mask, img_h, img_w, ph, pw);
+  CLC_CHECK_LAUNCH("clc_gaussian_mask");
+  return CLC_OK;
+}
+
+static bool gather_args_ok(int64_t NP, int C, int fh, int fw, int gh, int gw, int corr_w, int k) {
+  return NP >= 0 && C >= 1 && gh >= 1 && gw >= 1 && fh >= gh && fw >= gw && fh % gh == 0 &&
+         fw % gw == 0 && corr_w >= 1 && k >= 1 && k <= kMaxK;
+}
+
+extern "C" int clc_gather_blend_fwd(const float* feat, const int32_t* idx, const float* val, float temperature,
+                                    float* out, float* weights, int64_t NP, int32_t C, int32_t fh, int32_t fw,
+                                    int32_t gh, int32_t gw, int32_t corr_w, int32_t k, int32_t is_stack,
+                                    void* stream) {
+  if (!feat || !idx || !out || (!is_stack && !val)) return CLC_ERR_INVALID_ARGUMENT;
+  if (!gather_args_ok(NP, C, fh, fw, gh, gw, corr_w, k)) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  const int64_t total = NP * C * (int64_t)fh * fw;
+  gather_blend_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      feat, idx, val, temperature, out, weights, NP, C, fh, fw, gh, gw, corr_w, k, is_stack);
+  CLC_CHECK_LAUNCH("clc_gather_blend_fwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_gather_blend_bwd(const float* feat, const int32_t* idx, const float* weights,
+                                    float temperature, const float* g_out, float* g_feat, float* g_val,
+                                    int64_t NP, int32_t C, int32_t fh, int32_t fw, int32_t gh, int32_t gw,
+                                    int32_t corr_w, int32_t k, int32_t is_stack, void* stream) {
+  if (!feat || !idx || !g_out || !g_feat || !g_val || (!is_stack && !weights)) return CLC_ERR_INVALID_ARGUMENT;
+  if (!gather_args_ok(NP, C, fh, fw, gh, gw, corr_w, k)) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  const int64_t blocks = NP * (fh / gh) * (fw / gw);
+  if (blocks > 2147483647LL) return CLC_ERR_UNSUPPORTED;
+  gather_blend_bwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+      feat, idx, weights, temperature, g_out, g_feat, g_val, C, fh, fw, gh, gw, corr_w, k, is_stack);
+  CLC_CHECK_LAUNCH("clc_gather_blend_bwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const float* mask,
+                                    const int32_t* idx, const float* g_val, float* g_r, float* g_q,
+                                    int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
+                                    int32_t fh, int32_t fw, int32_t k, void* stream) {
+  if (!view_ok(qv) || !r || !idx || !g_val || !g_r) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP < 0 || P < 1 || C < 1 || ph < 1 || pw < 1 || fh < ph || fw < pw || k < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  if (NP * P > 2147483647LL) return CLC_ERR_UNSUPPORTED;
+  pearson_topk_bwd_kernel<<<(unsigned)(NP * P), 128, 0, (cudaStream_t)stream>>>(
+      make_addr(qv), r, mask, idx, g_val, g_r, g_q, P, C, ph, pw, fh, fw, k);
+  CLC_CHECK_LAUNCH("clc_pearson_topk_bwd");
+  return CLC_OK;
+}

@@ -1,0 +1,245 @@
+/*
+ * clc_b200.h -- C ABI of libclc_b200.so: the CLC conditional-latent hot path
+ * (match + CLM fusion + ChARM entropy stage + bpp) as hand-written sm_100a kernels.
+ *
+ * The reference (ydchen0806/CLC) is pure Python; it has no FFI.  Each entry point
+ * below replaces the PyTorch operator sequence of one reference function (cited
+ * per function as file:line into the reference tree) and is what a ctypes/cffi
+ * binding on the reference side would bind.
+ *
+ * Conventions:
+ *   - plain pointers + sizes, no torch types; all tensors are fp32, NCHW, device memory
+ *     on the calling thread's current CUDA device; index tensors are int32.
+ *   - every call returns 0 on success or a negative clc_status; nothing throws.
+ *   - no allocation, no host synchronisation, no global mutable state: the caller passes
+ *     outputs and workspace; kernels are enqueued on `stream` (a cudaStream_t).
+ *   - "bs" arguments are batch strides in ELEMENTS, so channel-slice views of a
+ *     [B, 320, h, w] tensor (CLC_run.py:535 `y.chunk(5, 1)`) are accepted without copies.
+ *   - accumulator outputs (`double* log2_sum`, parameter gradients, g_ref) are ADDED to;
+ *     the caller zero-initialises them.
+ */
+#ifndef CLC_B200_H_
+#define CLC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CLC_API __attribute__((visibility("default")))
+#else
+#define CLC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum clc_status {
+  CLC_OK = 0,
+  CLC_ERR_INVALID_ARGUMENT = -1, /* NULL where required, non-positive size, bad mode      */
+  CLC_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels implement               */
+  CLC_ERR_WORKSPACE = -3,        /* workspace too small (see *_workspace_bytes)            */
+  CLC_ERR_CUDA = -4,             /* a CUDA runtime / driver call failed (launch error)     */
+  CLC_ERR_ARCH = -5              /* device is not sm_100 (tcgen05 / TMA path unavailable)  */
+} clc_status;
+
+CLC_API int clc_version(void);                 /* ABI version, currently 1 */
+CLC_API const char* clc_strerror(int status);  /* static string */
+/* Text of the last CUDA error seen by the calling thread (empty if none). */
+CLC_API const char* clc_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * Entropy stage
+ * ---------------------------------------------------------------------------------- */
+
+/* GaussianConditional.forward + ste_round, fused.
+ * Replaces: compressai GaussianConditional.forward as called at CLC_run.py:569
+ *           (restated in-tree at CLC_run.py:718-736), ste_round CLC_run.py:35-36,:571,
+ *           and (optionally) the bpp reduction of train_CLC.py:48-51 for this tensor.
+ * Tensors are [B, CS] with CS contiguous elements per batch item and the given batch strides.
+ *   noise == NULL : eval,  outputs = round(y-mean)+mean          ("dequantize")
+ *   noise != NULL : train, outputs = y + noise                   ("noise"; noise ~ U(-.5,.5))
+ *   lik      = max( .5erfc(-(.5-v)/(s*sqrt2)) - .5erfc(-(-.5-v)/(s*sqrt2)), lik_bound ),
+ *              v = |outputs - mean|, s = max(scale, scale_bound)
+ *   y_hat    = round(y-mean)+mean        (optional, may be NULL)
+ *   outputs  = first return value of GaussianConditional.forward (optional, may be NULL)
+ *   log2_sum += sum(log2(lik))           (optional, may be NULL)
+ * mean may be NULL (zero mean). */
+CLC_API int clc_gc_fwd(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+               const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs,
+               float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
+               float* outputs, int64_t outputs_bs, double* log2_sum,
+               int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream);
+
+/* Backward of clc_gc_fwd (autograd semantics of the reference incl. both LowerBound gates:
+ * gradient passes iff x >= bound or grad < 0; ste_round: d/dy = 1, d/dmean = 0).
+ *   lik     : the likelihood tensor written by clc_gc_fwd (required)
+ *   g_lik   : dL/dlik, or NULL -> dL/dlik = bpp_coef / lik  (bpp loss formed analytically,
+ *             bpp_coef = dL/dbpp * 1/(-ln2 * num_pixels), train_CLC.py:48-51)
+ *   g_y_hat : dL/dy_hat, may be NULL
+ *   g_mean  : may be NULL when mean == NULL. */
+CLC_API int clc_gc_bwd(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+               const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs,
+               const float* lik, int64_t lik_bs, const float* g_lik, int64_t g_lik_bs,
+               float bpp_coef, const float* g_y_hat, int64_t g_y_hat_bs,
+               float* g_y, int64_t g_y_bs, float* g_scale, int64_t g_scale_bs,
+               float* g_mean, int64_t g_mean_bs,
+               int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream);
+
+/* Latent residual prediction add:  y_hat += 0.5 * tanh(lrp)   (CLC_run.py:582-583). */
+CLC_API int clc_lrp_add_fwd(float* y_hat, int64_t y_hat_bs, const float* lrp, int64_t lrp_bs,
+                    int64_t B, int64_t CS, void* stream);
+/* g_lrp = g * 0.5 * (1 - tanh(lrp)^2);  (g_y_hat = g, no kernel needed). */
+CLC_API int clc_lrp_add_bwd(const float* g, int64_t g_bs, const float* lrp, int64_t lrp_bs,
+                    float* g_lrp, int64_t g_lrp_bs, int64_t B, int64_t CS, void* stream);
+
+/* Quantised symbols + scale-table indexes for the entropy coder.
+ * Replaces: GaussianConditional.quantize(y, "symbols", mean) CLC_run.py:690 and
+ *           GaussianConditional.build_indexes(scale) CLC_run.py:689 (63 passes upstream).
+ *   symbols = int32(round(y - mean));
+ *   indexes = (T-1) - #{ t in table[0..T-2] : max(scale, scale_bound) <= t }
+ * `scale_table` is a device pointer to T ascending floats (T <= 256). */
+CLC_API int clc_gc_symbols_indexes(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                           const float* mean, int64_t mean_bs, const float* scale_table, int T,
+                           int32_t* symbols, int64_t symbols_bs, int32_t* indexes, int64_t indexes_bs,
+                           int64_t B, int64_t CS, float scale_bound, void* stream);
+
+/* EntropyBottleneck.forward (factorised prior, filters (3,3,3,3)) + z STE round, fused.
+ * Replaces: compressai EntropyBottleneck.forward called at CLC_run.py:526, `_get_medians`
+ *           :528 and the z straight-through round :529-530.
+ * z is [B, C, S] contiguous.  matrix[i]/bias[i]/factor[i] are device pointers to the module's
+ * _matrix{i} [C,f(i+1),f(i)], _bias{i} [C,f(i+1),1], _factor{i} [C,f(i+1),1] with f=(1,3,3,3,3,1);
+ * quantiles is [C,1,3] (median = quantiles[c][1]).
+ *   noise == NULL : eval, outputs = round(z-med)+med;  else outputs = z + noise
+ *   lik = max(|sigmoid(s*u) - sigmoid(s*l)|, lik_bound), l,u = logits(outputs -/+ .5),
+ *         s = -sign(l+u)
+ *   z_hat = round(z-med)+med (optional);  outputs optional;  log2_sum += sum(log2 lik). */
+CLC_API int clc_eb_fwd(const float* z, const float* noise, const float* const matrix[5],
+               const float* const bias[5], const float* const factor[4], const float* quantiles,
+               float* lik, float* z_hat, float* outputs, double* log2_sum,
+               int64_t B, int64_t C, int64_t S, float lik_bound, void* stream);
+
+/* Backward of clc_eb_fwd.  g_lik may be NULL -> bpp_coef / lik.  g_z_hat may be NULL.
+ * Parameter gradients are ACCUMULATED into g_matrix/g_bias/g_factor (same shapes as the
+ * parameters; any of the three arrays may be NULL to skip parameter gradients). */
+CLC_API int clc_eb_bwd(const float* z, const float* noise, const float* const matrix[5],
+               const float* const bias[5], const float* const factor[4], const float* quantiles,
+               const float* lik, const float* g_lik, float bpp_coef, const float* g_z_hat,
+               float* g_z, float* const g_matrix[5], float* const g_bias[5], float* const g_factor[4],
+               int64_t B, int64_t C, int64_t S, float lik_bound, void* stream);
+
+/* Rate term of RateDistortionLoss for an arbitrary likelihood tensor.
+ * Replaces: `torch.log(likelihoods).sum()` train_CLC.py:48-51, eval.py:27-31.
+ *   fwd: *log2_sum += sum_i log2(lik[i]);
+ *   bwd: g_lik[i] = coef * (coef_dev ? *coef_dev : 1) / lik[i]   (coef_dev: optional DEVICE
+ *        float64 scalar, so an upstream autograd scalar never needs a host read). */
+CLC_API int clc_log2_sum_fwd(const float* lik, int64_t n, double* log2_sum, void* stream);
+CLC_API int clc_log2_sum_bwd(const float* lik, float coef, const double* coef_dev, float* g_lik,
+                             int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Reference matching (Patch_Matching.py)
+ * ---------------------------------------------------------------------------------- */
+
+/* Addressing of query patches: element (patch, c, dy, dx) of problem n lives at
+ *   q + (n / q_repeat) * q_sn + (patch / npx) * q_spy + (patch % npx) * q_spx
+ *     + c * q_sc + dy * q_sy + dx
+ * which covers both an extracted [P, C, ph, pw] patch tensor (npx = P, q_spx = C*ph*pw,
+ * q_sc = ph*pw, q_sy = pw) and patches addressed in place inside an NCHW image
+ * (q_spy = ph*W, q_spx = pw, q_sc = H*W, q_sy = W) -- the reshape/permute copy of
+ * Patch_Matching.py:172 is never made. */
+typedef struct clc_patch_view {
+  const float* q;
+  int64_t q_sn, q_spy, q_spx, q_sc, q_sy;
+  int32_t npx;      /* patches per row of the patch grid                                   */
+  int32_t q_repeat; /* consecutive problems sharing one query image (= n_refs when the refs
+                       of an image are stacked along the problem axis), >= 1              */
+} clc_patch_view;
+
+/* Pearson correlation map, materialised (exact fp32 FMA path; "fp32 mode").
+ * Replaces: L2_or_pearson_corr Patch_Matching.py:854-910 (+ `cross_corr * mask` :182-183).
+ *   r    : [NP, C, fh, fw] reference-side features, one per problem
+ *   mask : NULL or [P, fh-ph+1, fw-pw+1] (shared by all problems)
+ *   corr : out [NP, P, fh-ph+1, fw-pw+1] */
+CLC_API int clc_pearson_corr(const clc_patch_view* qv, const float* r, const float* mask, float* corr,
+                     int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
+                     int32_t fh, int32_t fw, void* workspace, size_t workspace_bytes, void* stream);
+CLC_API size_t clc_pearson_corr_workspace_bytes(int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
+                                        int32_t fh, int32_t fw);
+
+/* Row-wise top-k (values descending, ties -> lowest index), warp-shuffle selection.
+ * Replaces: torch.topk(cross_corr, k, dim=2) Patch_Matching.py:224.  k <= 32.
+ *   x [R, L] -> val [R, k], idx [R, k] (int32 position in the row). */
+CLC_API int clc_topk_rows(const float* x, int64_t R, int64_t L, int32_t k, float* val, int32_t* idx,
+                  void* stream);
+
+/* create_gaussian_masks Patch_Matching.py:779-807, evaluated in fp64 on the device and
+ * rounded to fp32 like the reference's numpy path.  mask: out [P, img_h-ph+1, img_w-pw+1]. */
+CLC_API int clc_gaussian_mask(float* mask, int32_t img_h, int32_t img_w, int32_t ph, int32_t pw, void* stream);
+
+/* Fused match: correlation GEMM on tcgen05 tensor cores (bf16 operands staged by TMA,
+ * fp32 accumulate in TMEM) with the Pearson normalisation, Gaussian mask and a per-patch
+ * candidate top-KC selection fused into the epilogue (the P x L map is never written),
+ * followed by exact fp32 FMA re-scoring of the candidates and the final warp-shuffle top-k.
+ * Replaces: L2_or_pearson_corr + mask + torch.topk (Patch_Matching.py:181-183,:224).
+ *   q_img : [NQ, C, H, W] query latents, problem n uses image n / q_repeat
+ *   r     : [NP, C, H, W] reference latents (same spatial size as the query)
+ *   gaussian_mask : 0 = no mask, 1 = create_gaussian_masks(H, W, ph, pw)
+ *   val, idx : out [NP, P, k], P = (H/ph)*(W/pw); idx = oy*(W-pw+1)+ox
+ *   n_uncertified : optional device int32 counter += patches whose candidate set could not be
+ *                   certified to contain the exact top-k (screening error bound), may be NULL */
+CLC_API int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
+                      int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                      int32_t gaussian_mask, float* val, int32_t* idx, int32_t* n_uncertified,
+                      void* workspace, size_t workspace_bytes, void* stream);
+CLC_API size_t clc_match_topk_tc_workspace_bytes(int64_t NP, int32_t q_repeat, int32_t C, int32_t H,
+                                         int32_t W, int32_t ph, int32_t pw, int32_t k);
+
+/* softmax(value*T) weights + gather of the k matched patches + weighted sum + tile
+ * reassembly (or channel stacking).
+ * Replaces: SI_Wraper Patch_Matching.py:226-238.
+ *   feat : [NP, C, fh, fw] features gathered from; fh = npy*gh, fw = npx*gw where (gh, gw) is
+ *          the patch size at this feature scale.  idx indexes a correlation map of width
+ *          corr_w (oy = idx / corr_w, ox = idx % corr_w).  For the multi-scale reuse
+ *          (:198-208) the caller passes indices of the sub-sampled map, its width, and the
+ *          scaled patch size.
+ *   out  : [NP, C, fh, fw] (is_stack = 0) or [NP, k*C, fh, fw] (is_stack = 1)
+ *   weights : out [NP, P, k] softmax weights (needed by the backward), may be NULL if is_stack */
+CLC_API int clc_gather_blend_fwd(const float* feat, const int32_t* idx, const float* val, float temperature,
+                         float* out, float* weights, int64_t NP, int32_t C, int32_t fh, int32_t fw,
+                         int32_t gh, int32_t gw, int32_t corr_w, int32_t k, int32_t is_stack,
+                         void* stream);
+/* Backward: g_feat (ACCUMULATED, zero-init by caller) and g_val [NP, P, k]. */
+CLC_API int clc_gather_blend_bwd(const float* feat, const int32_t* idx, const float* weights,
+                         float temperature, const float* g_out, float* g_feat, float* g_val,
+                         int64_t NP, int32_t C, int32_t fh, int32_t fw, int32_t gh, int32_t gw,
+                         int32_t corr_w, int32_t k, int32_t is_stack, void* stream);
+
+/* Backward of the (masked) Pearson correlation at the k selected positions only, with the
+ * reference's autograd semantics: the conv2d weights are detached query patches
+ * (Patch_Matching.py:869) so d(xy)/dq is dropped, while the query still receives gradient
+ * through x_sum / sum_x_square / x_mean (:880-887) and the reference side through all terms.
+ *   g_val : [NP, P, k] dL/d(masked corr value);  g_r ACCUMULATED [NP, C, fh, fw];
+ *   g_q   : ACCUMULATED, addressed like the query through `gqv` (same strides as qv), may be NULL */
+CLC_API int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const float* mask,
+                         const int32_t* idx, const float* g_val, float* g_r, float* g_q,
+                         int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
+                         int32_t fh, int32_t fw, int32_t k, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * CLM conditional fusion (elementwise part; the 1x1 / 3x3 convolutions stay nn.Conv2d)
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces: SimpleCLM.forward CLM.py:170-182 (sigmoid gate, softmax over refs, weighted sum, +y).
+ *   ref_t [R, B, C, S], att [R, B, 1, S], y [B, C, S] -> out [B, C, S]
+ *   out = sum_r softmax_r(att) * ref_t[r] * sigmoid(att[r]) + y */
+CLC_API int clc_clm_fuse_fwd(const float* ref_t, const float* att, const float* y, float* out,
+                     int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
+/* g_ref_t [R,B,C,S], g_att [R,B,1,S]; g_y = g_out (no kernel). */
+CLC_API int clc_clm_fuse_bwd(const float* ref_t, const float* att, const float* g_out, float* g_ref_t,
+                     float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLC_B200_H_ */

@@ -1,0 +1,264 @@
+"""GPU parity: entropy stage (C ABI through the drop-in modules) vs the CPU oracle and the
+reference-generated golden vectors.  Bars (BASELINE.json north_star): symbols bit-exact,
+likelihoods within 1e-4 relative, bpp within 1e-3."""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+LIK_RTOL = 1e-4   # north_star: likelihoods within 1e-4 relative
+GRAD_RTOL = 2e-4  # analytic backward vs fp32 autograd of the oracle
+BPP_ATOL = 1e-3   # north_star: bpp within 1e-3
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _operator_inputs(shape, seed, halves=True):
+    """SURVEY 8d operator-level distribution: y~N(0,9), mu~N(0,1), scale log-uniform [0.05,300],
+    1% exact-half residues, |y-mu| in {8,12,40} outliers."""
+    g = torch.Generator().manual_seed(seed)
+    y = 3 * torch.randn(shape, generator=g)
+    mu = torch.randn(shape, generator=g)
+    sc = torch.exp(torch.empty(shape).uniform_(math.log(0.05), math.log(300.0), generator=g))
+    sc.view(-1)[::97] *= -1  # some negative raw scales (the model's raw output can be <= 0)
+    if halves:
+        n = y.numel()
+        idx = torch.randperm(n, generator=g)[: max(n // 100, 4)]
+        kk = torch.randint(-6, 7, (idx.numel(),), generator=g).float()
+        # mu on a coarse binary grid so that (mu + k + 0.5) - mu is exactly k + 0.5 in fp32
+        mu.view(-1)[idx] = torch.round(mu.view(-1)[idx] * 8) / 8
+        y.view(-1)[idx] = mu.view(-1)[idx] + kk + 0.5
+        out = torch.randperm(n, generator=g)[:3]
+        y.view(-1)[out] = mu.view(-1)[out] + torch.tensor([8.0, 12.0, 40.0])
+    noise = torch.rand(shape, generator=g) - 0.5
+    return y, mu, sc, noise
+
+
+def _rel(a, b, mask):
+    return ((a.double() - b.double()).abs() / b.double().abs())[mask].max().item()
+
+
+def test_gc_golden_reference_vectors():
+    import clc_b200
+    g = load_golden("gaussian.npz")
+    gc = clc_b200.GaussianConditional(None).to(_dev()).eval()
+    d = _dev()
+    # KATs: 8 elements -> exercises the scalar (non-vectorised) kernel on an odd shape
+    y, mu, sc = g["kat_y"].view(1, -1), g["kat_mu"].view(1, -1), g["kat_scale"].view(1, -1)
+    out, lik, y_hat = gc(y.to(d), sc.to(d), mu.to(d), ste=True)
+    assert torch.equal(y_hat.cpu().view(-1), g["kat_y_hat"])
+    assert torch.equal(out.cpu().view(-1), g["kat_y_hat"])
+    ref = g["kat_lik"].clamp_min(1e-9)
+    assert _rel(lik.cpu().view(-1), ref, ref > 1e-9) < LIK_RTOL
+    assert torch.equal(lik.cpu().view(-1)[ref <= 1e-9], ref[ref <= 1e-9])
+    # random sweep produced by the reference's own _likelihood
+    y, mu, sc, noise = (g[k].view(4, -1) for k in ("y", "mu", "scale", "noise"))
+    _, lik, y_hat = gc(y.to(d), sc.to(d), mu.to(d), ste=True, want_outputs=False)
+    assert torch.equal(y_hat.cpu().view(-1), g["y_hat"])
+    ref = g["lik_eval"].clamp_min(1e-9)
+    assert _rel(lik.cpu().view(-1), ref, ref > 1e-9) < LIK_RTOL
+    gc.train()
+    out, lik = gc(y.to(d), sc.to(d), mu.to(d), noise=noise.to(d))
+    assert torch.equal(out.cpu().view(-1), g["y"] + g["noise"])
+    ref = g["lik_train"].clamp_min(1e-9)
+    assert _rel(lik.cpu().view(-1), ref, ref > 1e-9) < LIK_RTOL
+    # against fp64: the CUDA fp32 result must be no further from the truth than the bar
+    ref64 = g["lik_eval64"]
+    gc.eval()
+    _, lik = gc(y.to(d), sc.to(d), mu.to(d))
+    assert _rel(lik.cpu().view(-1), ref64, ref64 > 1e-9) < 2e-4
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 16, 16), (3, 64, 32, 48), (2, 5, 3, 7), (1, 64, 80, 128)])
+@pytest.mark.parametrize("train", [False, True])
+def test_gc_forward_backward_vs_oracle(shape, train):
+    import clc_b200
+    from oracle import clc_oracle as O
+    d = _dev()
+    y, mu, sc, noise = _operator_inputs(shape, seed=sum(shape) + int(train))
+    # oracle (CPU fp32 autograd)
+    yo, muo, sco = (t.clone().requires_grad_(True) for t in (y, mu, sc))
+    out_o, lik_o, yhat_o = O.gc_forward(yo, sco, muo, noise=noise if train else None)
+    g = torch.Generator().manual_seed(5)
+    w_hat = torch.randn(shape, generator=g)
+    bpp_o = torch.log(lik_o).sum() / (-math.log(2) * 1000.0)
+    (bpp_o + (yhat_o * w_hat).sum()).backward()
+    # CUDA
+    gc = clc_b200.GaussianConditional(None).to(d).train(train)
+    yc, muc, scc = (t.to(d).requires_grad_(True) for t in (y, mu, sc))
+    out_c, lik_c, yhat_c = gc(yc, scc, muc, noise=noise.to(d) if train else None, ste=True)
+    assert torch.equal(yhat_c.detach().cpu(), yhat_o.detach()), "quantised symbols must be bit-exact"
+    assert torch.equal(out_c.detach().cpu(), out_o.detach())
+    big = lik_o.detach() > 1e-9
+    assert _rel(lik_c.detach().cpu(), lik_o.detach(), big) < LIK_RTOL
+    assert torch.equal(lik_c.detach().cpu()[~big], lik_o.detach()[~big])
+    crit = clc_b200.RateDistortionLoss()
+    bpp_c = clc_b200.ops.log2_sum(lik_c) / (-1000.0)
+    assert abs(bpp_c.item() - bpp_o.item()) < BPP_ATOL * max(1.0, abs(bpp_o.item()) * 1e-3)
+    (bpp_c.float() + (yhat_c * w_hat.to(d)).sum()).backward()
+    for name, a, b in (("y", yc.grad, yo.grad), ("mu", muc.grad, muo.grad), ("scale", scc.grad, sco.grad)):
+        a, b = a.cpu(), b
+        scale = b.abs().max().item() + 1e-30
+        err = (a - b).abs().max().item() / scale
+        assert err < GRAD_RTOL, (name, err)
+        # LowerBound gates: zero-gradient pattern must agree wherever the oracle is exactly zero
+        assert ((b == 0) & (a.abs() > 1e-6 * scale)).sum().item() == 0, name
+
+
+def test_gc_channel_slice_views_no_copy():
+    """y.chunk(5, 1) views (batch stride 320*h*w) go straight to the kernel."""
+    import clc_b200
+    from oracle import clc_oracle as O
+    d = _dev()
+    y, mu, sc, _ = _operator_inputs((4, 320, 16, 16), seed=3)
+    gc = clc_b200.GaussianConditional(None).to(d).eval()
+    yc, muc, scc = y.to(d), mu.to(d), sc.to(d)
+    for i, (ys, ms, ss) in enumerate(zip(yc.chunk(5, 1), muc.chunk(5, 1), scc.chunk(5, 1))):
+        assert not ys.is_contiguous()
+        _, lik, y_hat = gc(ys, ss, ms, ste=True, want_outputs=False)
+        sl = slice(64 * i, 64 * (i + 1))
+        _, lik_o, yhat_o = O.gc_forward(y[:, sl], sc[:, sl], mu[:, sl])
+        assert torch.equal(y_hat.cpu(), yhat_o)
+        big = lik_o > 1e-9
+        assert _rel(lik.cpu(), lik_o, big) < LIK_RTOL
+
+
+def test_gc_no_means_and_empty():
+    import clc_b200
+    from oracle import clc_oracle as O
+    d = _dev()
+    y, _, sc, _ = _operator_inputs((2, 8, 4, 4), seed=9)
+    gc = clc_b200.GaussianConditional(None).to(d).eval()
+    out, lik = gc(y.to(d), sc.to(d))
+    out_o, lik_o, _ = O.gc_forward(y, sc)
+    assert torch.equal(out.cpu(), out_o)
+    assert _rel(lik.cpu(), lik_o, lik_o > 1e-9) < LIK_RTOL
+    e = torch.empty(0, 8, 4, 4, device=d)
+    out, lik = gc(e, e, e)
+    assert out.shape == e.shape and lik.shape == e.shape
+
+
+def test_lrp_add_and_symbols_indexes():
+    import clc_b200
+    from clc_b200 import ops
+    from oracle import clc_oracle as O
+    d = _dev()
+    y, mu, sc, _ = _operator_inputs((3, 64, 16, 16), seed=21)
+    g = torch.Generator().manual_seed(2)
+    lrp = 2 * torch.randn(y.shape, generator=g)
+    # forward/backward of y_hat += 0.5*tanh(lrp)
+    base_o = y.clone().requires_grad_(True)
+    lrp_o = lrp.clone().requires_grad_(True)
+    res_o = O.lrp_add(base_o * 1.0, lrp_o)
+    w = torch.randn(y.shape, generator=g)
+    (res_o * w).sum().backward()
+    base_c = y.to(d).requires_grad_(True)
+    lrp_c = lrp.to(d).requires_grad_(True)
+    res_c = ops.lrp_add_(base_c * 1.0, lrp_c)
+    (res_c * w.to(d)).sum().backward()
+    assert torch.allclose(res_c.detach().cpu(), res_o.detach(), rtol=0, atol=2e-7)
+    assert torch.allclose(lrp_c.grad.cpu(), lrp_o.grad, rtol=1e-5, atol=1e-7)
+    assert torch.equal(base_c.grad.cpu(), base_o.grad)
+    # symbols / indexes: bit-exact integers
+    gc = clc_b200.GaussianConditional(None).to(d)
+    table = O.get_scale_table()
+    gc.update_scale_table(table)
+    sym_o, idx_o = O.gc_symbols_indexes(y, sc, mu, table)
+    assert torch.equal(gc.quantize(y.to(d), "symbols", mu.to(d)).cpu(), sym_o)
+    assert torch.equal(gc.build_indexes(sc.to(d)).cpu(), idx_o)
+    edge = torch.cat([table, table * (1 + 1e-6), table * (1 - 1e-6), torch.tensor([0.0, -1.0, 1e9])]).view(1, -1)
+    assert torch.equal(gc.build_indexes(edge.to(d)).cpu(), O.gc_symbols_indexes(edge, edge, edge, table)[1])
+    assert torch.equal(gc.quantize(y.to(d), "dequantize", mu.to(d)).cpu(), torch.round(y - mu) + mu)
+    with pytest.raises(ValueError):
+        gc.quantize(y.to(d), "nope")
+
+
+@pytest.mark.parametrize("shape", [(8, 192, 4, 4), (3, 192, 8, 12), (1, 7, 5, 3)])
+@pytest.mark.parametrize("train", [False, True])
+@pytest.mark.parametrize("perturb", [False, True])
+def test_entropy_bottleneck_vs_oracle(shape, train, perturb):
+    import clc_b200
+    from oracle import clc_oracle as O
+    d = _dev()
+    C = shape[1]
+    torch.manual_seed(4)
+    eb_o = O.EntropyBottleneck(C)
+    if perturb:
+        with torch.no_grad():
+            for n, p in eb_o.named_parameters():
+                p.add_(0.1 * torch.randn_like(p))
+    eb_c = clc_b200.EntropyBottleneck(C)
+    eb_c.load_state_dict(eb_o.state_dict())
+    eb_c = eb_c.to(d).train(train)
+    g = torch.Generator().manual_seed(8)
+    z = 2 * torch.randn(shape, generator=g)
+    z.view(-1)[:5] = torch.tensor([0.5, 1.5, -2.5, 30.0, -30.0])[: min(5, z.numel())]
+    noise = torch.rand(shape, generator=g) - 0.5
+    w = torch.randn(shape, generator=g)
+    zo = z.clone().requires_grad_(True)
+    out_o, lik_o, zhat_o = O.eb_forward(eb_o, zo, noise=noise if train else None)
+    (torch.log(lik_o).sum() / (-math.log(2) * 500.0) + (zhat_o * w).sum()).backward()
+    zc = z.to(d).requires_grad_(True)
+    out_c, lik_c, zhat_c = eb_c(zc, noise=noise.to(d) if train else None, ste=True)
+    assert torch.equal(zhat_c.detach().cpu(), zhat_o.detach())
+    assert torch.equal(out_c.detach().cpu(), out_o.detach())
+    big = lik_o.detach() > 1e-9
+    assert _rel(lik_c.detach().cpu(), lik_o.detach(), big) < LIK_RTOL
+    (clc_b200.ops.log2_sum(lik_c).float() / (-500.0) + (zhat_c * w.to(d)).sum()).backward()
+    sc_ = zo.grad.abs().max().item()
+    assert (zc.grad.cpu() - zo.grad).abs().max().item() / sc_ < GRAD_RTOL
+    for (n, po), (_, pc) in zip(eb_o.named_parameters(), eb_c.named_parameters()):
+        if n == "quantiles":
+            continue
+        if po.grad is None:
+            assert pc.grad is None or pc.grad.abs().max() == 0, n
+            continue
+        s = po.grad.abs().max().item() + 1e-12
+        assert (pc.grad.cpu() - po.grad).abs().max().item() / s < 5e-4, n
+    # aux loss (torch) agrees
+    assert torch.allclose(eb_c.loss().cpu(), eb_o.loss(), rtol=1e-6)
+
+
+def test_rate_distortion_loss_golden_and_bpp():
+    import clc_b200
+    g = load_golden("rd_loss.npz")
+    d = _dev()
+    crit = clc_b200.RateDistortionLoss(lmbda=0.013)
+    lik_y = g["lik_y"].to(d).requires_grad_(True)
+    out = crit({"likelihoods": {"y": lik_y, "z": g["lik_z"].to(d)}, "x_hat": g["x_hat"].to(d)}, g["x"].to(d))
+    assert abs(out["bpp_loss"].item() - g["bpp_loss"].item()) < BPP_ATOL
+    assert abs(out["bpp_loss"].item() - g["bpp_loss"].item()) < 1e-5 * abs(g["bpp_loss"].item())
+    assert torch.allclose(out["mse_loss"].cpu(), g["mse_loss"], rtol=1e-5)
+    assert torch.allclose(out["loss"].cpu(), g["loss"], rtol=1e-5)
+    out["loss"].backward()
+    ref = 1.0 / (g["lik_y"] * (-math.log(2) * 2 * 64 * 64))
+    assert torch.allclose(lik_y.grad.cpu(), ref, rtol=1e-5)
+    assert abs(clc_b200.compute_bpp({"x_hat": g["x_hat"].to(d), "likelihoods": {"y": g["lik_y"].to(d), "z": g["lik_z"].to(d)}})
+               - g["bpp_loss"].item()) < 1e-4
+
+
+def test_full_size_properties_cfg4():
+    """At BASELINE cfg4 size (1 x 320 x 80 x 128 latent) use size-independent properties:
+    idempotence of the quantiser, likelihood symmetry in the residual sign, bounds, and the
+    fused bpp accumulator equal to the stand-alone log2-sum kernel."""
+    import clc_b200
+    d = _dev()
+    y, mu, sc, _ = _operator_inputs((1, 320, 80, 128), seed=77, halves=False)
+    gc = clc_b200.GaussianConditional(None).to(d).eval()
+    yc, muc, scc = y.to(d), mu.to(d), sc.to(d)
+    acc = torch.zeros(1, dtype=torch.float64, device=d)
+    _, lik, y_hat = gc(yc, scc, muc, ste=True, want_outputs=False, log2_acc=acc)
+    _, lik2, y_hat2 = gc(y_hat, scc, muc, ste=True, want_outputs=False)
+    assert torch.equal(y_hat2, y_hat) and torch.equal(lik2, lik)          # idempotent
+    _, lik3, _ = gc(2 * muc - y_hat, scc, muc, ste=True, want_outputs=False)
+    assert torch.allclose(lik3, lik, rtol=1e-5, atol=0)                     # even in (y - mu)
+    assert lik.min().item() >= 1e-9 and lik.max().item() <= 1.0
+    s2 = clc_b200.ops.log2_sum(lik)
+    assert abs(acc.item() - s2.item()) < 1e-6 * abs(s2.item())
+    assert abs(s2.item() - torch.log2(lik.double()).sum().item()) < 1e-5 * abs(s2.item())
