@@ -1,0 +1,323 @@
+"""Drop-in `CLC` and `TCM` models (reference: models/CLC_run.py:316-814, models/tcm.py:310-626).
+
+Same constructor signature, submodule names (=> identical state_dict keys, checked by
+tests/test_model_cpu.py against the reference itself) and `forward` contract
+    forward(x, ref_frames=None) -> {"x_hat", "likelihoods": {"y", "z"}, "para": {"means", "scales", "y"}}
+The analysis / synthesis / hyper transforms and the per-slice parameter networks are plain
+PyTorch modules (clc_b200.layers); the latent hot path inside `forward` runs in the fused
+sm_100a kernels:
+    entropy_bottleneck(z) + z STE round  -> one launch   (CLC_run.py:526-530)
+    per slice: gaussian_conditional + ste_round -> one launch (:569,:571); 0.5*tanh(lrp) add -> one (:582-583)
+Opt-in extended wiring (`match_refs=True`, SURVEY.md 7.1 level C): each reference latent is first
+aligned to y by Pearson patch matching + top-k gather (Patch_Matching.py) before entering
+`ref_feature_adapter`.  The default (False) is the shipped reference forward.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .entropy_models import EntropyBottleneck, GaussianConditional
+from .layers import (CLMAlign, ConvTransBlock, ReferenceEncoder, ResidualBlockUpsample,
+                     ResidualBlockWithStride, SWAtten, conv, conv1x1, conv3x3, subpel_conv3x3)
+from .matching import match_and_gather
+
+SCALES_MIN = 0.11
+SCALES_MAX = 256
+SCALES_LEVELS = 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+def _update_registered_buffers(module, module_name, buffer_names, state_dict, policy="resize_if_empty"):
+    """Resize the (empty) CDF buffers so a checkpoint's tables can be loaded (CLC_run.py:46-97)."""
+    valid = dict(module.named_buffers())
+    for name in buffer_names:
+        if name not in valid:
+            raise ValueError(f'Invalid buffer name "{name}"')
+    for name in buffer_names:
+        key = f"{module_name}.{name}"
+        if key not in state_dict:
+            continue
+        buf = valid[name]
+        if policy in ("resize_if_empty", "resize"):
+            if policy == "resize" or buf.numel() == 0:
+                buf.resize_(state_dict[key].size())
+        else:
+            raise ValueError(f'Invalid policy "{policy}"')
+
+
+class CompressionModel(nn.Module):
+    def __init__(self, entropy_bottleneck_channels=None):
+        super().__init__()
+        if entropy_bottleneck_channels is not None:
+            self.entropy_bottleneck = EntropyBottleneck(entropy_bottleneck_channels)
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def update(self, force=False):
+        updated = False
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                updated |= bool(m.update(force=force))
+        return updated
+
+
+def _stage(dim, head_dim, n, window=8):
+    return [ConvTransBlock(dim, dim, head_dim, window, 0, "W" if i % 2 == 0 else "SW") for i in range(n)]
+
+
+def _param_net(cin, cout=64):
+    return nn.Sequential(conv(cin, 224, stride=1, kernel_size=3), nn.GELU(),
+                         conv(224, 128, stride=1, kernel_size=3), nn.GELU(),
+                         conv(128, cout, stride=1, kernel_size=3))
+
+
+class _ChARMBase(CompressionModel):
+    """Everything TCM and CLC share: transforms, slice attention, and the fused slice loop."""
+
+    def _build_common(self, config, head_dim, drop_path_rate, N, M, num_slices, max_support_slices):
+        if drop_path_rate:
+            raise NotImplementedError("drop_path_rate > 0 is not used by the reference configs")
+        self.config, self.head_dim, self.window_size = config, head_dim, 8
+        self.num_slices, self.max_support_slices, self.M = num_slices, max_support_slices, M
+        ws = self.window_size
+        self.g_a = nn.Sequential(
+            ResidualBlockWithStride(3, 2 * N, 2),
+            *_stage(N, head_dim[0], config[0], ws), ResidualBlockWithStride(2 * N, 2 * N, stride=2),
+            *_stage(N, head_dim[1], config[1], ws), ResidualBlockWithStride(2 * N, 2 * N, stride=2),
+            *_stage(N, head_dim[2], config[2], ws), conv3x3(2 * N, M, stride=2))
+        self.g_s = nn.Sequential(
+            ResidualBlockUpsample(M, 2 * N, 2),
+            *_stage(N, head_dim[3], config[3], ws), ResidualBlockUpsample(2 * N, 2 * N, 2),
+            *_stage(N, head_dim[4], config[4], ws), ResidualBlockUpsample(2 * N, 2 * N, 2),
+            *_stage(N, head_dim[5], config[5], ws), subpel_conv3x3(2 * N, 3, 2))
+
+    def _build_hyper(self, config, N):
+        self.h_a = nn.Sequential(ResidualBlockWithStride(320, 2 * N, 2), *_stage(N, 32, config[0], 4),
+                                 conv3x3(2 * N, 192, stride=2))
+        self.h_mean_s = nn.Sequential(ResidualBlockUpsample(192, 2 * N, 2), *_stage(N, 32, config[3], 4),
+                                      subpel_conv3x3(2 * N, 320, 2))
+        self.h_scale_s = nn.Sequential(ResidualBlockUpsample(192, 2 * N, 2), *_stage(N, 32, config[3], 4),
+                                       subpel_conv3x3(2 * N, 320, 2))
+
+    def _slice_width(self):
+        return 320 // self.num_slices
+
+    def _support_ch(self, i, extra=0):
+        return 320 + self._slice_width() * min(i + extra, 5 + extra)
+
+    def update(self, scale_table=None, force=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
+
+    # -- fused latent path ---------------------------------------------------------------------
+    def _hyper(self, y, noise):
+        z = self.h_a(y)
+        _, z_lik, z_hat = self.entropy_bottleneck(z, noise=None if noise is None else noise.get("z"),
+                                                  ste=True, want_outputs=False)
+        return z_lik, self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+
+    def _slice_loop(self, y, latent_means, latent_scales, ref_features, noise):
+        """CLC_run.py:535-590 / tcm.py:440-475.  `transforms(i)` picks the per-slice networks."""
+        y_shape = y.shape[2:]
+        y_hat_slices, liks, mus, scales = [], [], [], []
+        use_ref = ref_features is not None
+        for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
+            support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[:self.max_support_slices]
+            mean_support = self.atten_mean[i](torch.cat([latent_means] + support, dim=1))
+            scale_support = self.atten_scale[i](torch.cat([latent_scales] + support, dim=1))
+            if use_ref:
+                mu = self.ref_cc_mean_transforms[i](torch.cat([mean_support, ref_features], dim=1))
+                scale = self.ref_cc_scale_transforms[i](torch.cat([scale_support, ref_features], dim=1))
+            else:
+                mu = self.cc_mean_transforms[i](mean_support)
+                scale = self.cc_scale_transforms[i](scale_support)
+            mu = mu[:, :, :y_shape[0], :y_shape[1]]
+            scale = scale[:, :, :y_shape[0], :y_shape[1]]
+            mus.append(mu)
+            scales.append(scale)
+            # one launch: likelihood (train: y + U(-.5,.5); eval: round) AND ste_round(y - mu) + mu
+            n_i = None if noise is None else noise["y"][:, i * y_slice.shape[1]:(i + 1) * y_slice.shape[1]]
+            _, lik_i, y_hat_i = self.gaussian_conditional(y_slice, scale, mu, noise=n_i, ste=True,
+                                                          want_outputs=False)
+            liks.append(lik_i)
+            if use_ref:
+                lrp = self.ref_lrp_transforms[i](torch.cat([mean_support, y_hat_i, ref_features], dim=1))
+            else:
+                lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_i], dim=1))
+            y_hat_i = self._lrp_add(y_hat_i, lrp)  # y_hat += 0.5 * tanh(lrp), in place
+            y_hat_slices.append(y_hat_i)
+        return (torch.cat(y_hat_slices, dim=1), torch.cat(mus, dim=1), torch.cat(scales, dim=1),
+                torch.cat(liks, dim=1))
+
+    @staticmethod
+    def _lrp_add(y_hat, lrp):
+        return ops.lrp_add_(y_hat, lrp)
+
+    def compress(self, *a, **k):
+        raise NotImplementedError("rANS bitstream coding is the next scope row (SURVEY.md 8f-1); "
+                                  "use symbols_and_indexes() for the coder inputs")
+
+    def decompress(self, *a, **k):
+        raise NotImplementedError("rANS bitstream decoding is the next scope row (SURVEY.md 8f-1)")
+
+
+class TCM(_ChARMBase):
+    def __init__(self, config=[2, 2, 2, 2, 2, 2], head_dim=[8, 16, 32, 32, 16, 8], drop_path_rate=0, N=128, M=320,
+                 num_slices=5, max_support_slices=5, **kwargs):
+        super().__init__(entropy_bottleneck_channels=N)
+        self._build_common(config, head_dim, drop_path_rate, N, M, num_slices, max_support_slices)
+        self._build_hyper(config, N)
+        ws, sw = self.window_size, self._slice_width()
+        self.atten_mean = nn.ModuleList(nn.Sequential(SWAtten(self._support_ch(i), self._support_ch(i), 16, ws, 0, inter_dim=128))
+                                        for i in range(num_slices))
+        self.atten_scale = nn.ModuleList(nn.Sequential(SWAtten(self._support_ch(i), self._support_ch(i), 16, ws, 0, inter_dim=128))
+                                         for i in range(num_slices))
+        self.cc_mean_transforms = nn.ModuleList(_param_net(self._support_ch(i), sw) for i in range(num_slices))
+        self.cc_scale_transforms = nn.ModuleList(_param_net(self._support_ch(i), sw) for i in range(num_slices))
+        self.lrp_transforms = nn.ModuleList(_param_net(self._support_ch(i, 1), sw) for i in range(num_slices))
+        self.entropy_bottleneck = EntropyBottleneck(192)
+        self.gaussian_conditional = GaussianConditional(None)
+
+    def forward(self, x, noise=None):
+        y = self.g_a(x)
+        z_lik, latent_scales, latent_means = self._hyper(y, noise)
+        y_hat, means, scales, y_lik = self._slice_loop(y, latent_means, latent_scales, None, noise)
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik},
+                "para": {"means": means, "scales": scales, "y": y}}
+
+    def load_state_dict(self, state_dict, strict=True):
+        _update_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
+                                   ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        _update_registered_buffers(self.entropy_bottleneck, "entropy_bottleneck",
+                                   ["_quantized_cdf", "_offset", "_cdf_length"], state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        N = state_dict["g_a.0.weight"].size(0)
+        M = state_dict["g_a.6.weight"].size(0)
+        net = cls(N, M)
+        net.load_state_dict(state_dict)
+        return net
+
+
+class CLC(_ChARMBase):
+    def __init__(self, config=[2, 2, 2, 2, 2, 2], head_dim=[8, 16, 32, 32, 16, 8], drop_path_rate=0, N=128, M=320,
+                 num_slices=5, max_support_slices=5, num_ref_frames=3, use_ref=True, match_refs=False,
+                 match_patch=4, match_k=4, match_temperature=15.0, match_mode="tc", **kwargs):
+        super().__init__(entropy_bottleneck_channels=N)
+        self.num_ref_frames, self.use_ref = num_ref_frames, use_ref
+        self.match_refs, self.match_patch, self.match_k = match_refs, match_patch, match_k
+        self.match_temperature, self.match_mode = match_temperature, match_mode
+        self._build_common(config, head_dim, drop_path_rate, N, M, num_slices, max_support_slices)
+        self.ref_encoder = ReferenceEncoder(N, M)
+        # Instantiated-but-unused in the reference forward (CLC_run.py:359-369); kept for key parity.
+        self.feature_alignment = nn.ModuleList(CLMAlign(192, head_dim=32, window_size=4) for _ in range(num_ref_frames))
+        self.multi_ref_fusion = nn.Sequential(conv1x1(192 * (num_ref_frames + 1), 256), nn.GELU(), conv1x1(256, 192))
+        self._build_hyper(config, N)
+        ws, sw = self.window_size, self._slice_width()
+        self.atten_mean = nn.ModuleList(nn.Sequential(SWAtten(self._support_ch(i), self._support_ch(i), 16, ws, 0, inter_dim=128))
+                                        for i in range(num_slices))
+        self.atten_scale = nn.ModuleList(nn.Sequential(SWAtten(self._support_ch(i), self._support_ch(i), 16, ws, 0, inter_dim=128))
+                                         for i in range(num_slices))
+        self.ref_cc_mean_transforms = nn.ModuleList(_param_net(self._support_ch(i) + 64, sw) for i in range(num_slices))
+        self.ref_cc_scale_transforms = nn.ModuleList(_param_net(self._support_ch(i) + 64, sw) for i in range(num_slices))
+        self.cc_mean_transforms = nn.ModuleList(_param_net(self._support_ch(i), sw) for i in range(num_slices))
+        self.cc_scale_transforms = nn.ModuleList(_param_net(self._support_ch(i), sw) for i in range(num_slices))
+        self.lrp_transforms = nn.ModuleList(_param_net(self._support_ch(i, 1), sw) for i in range(num_slices))
+        self.ref_lrp_transforms = nn.ModuleList(_param_net(self._support_ch(i, 1) + 64, sw) for i in range(num_slices))
+        self.ref_feature_adapter = nn.Sequential(conv1x1(M * num_ref_frames, 128), nn.GELU(), conv1x1(128, 64))
+        self.entropy_bottleneck = EntropyBottleneck(192)
+        self.gaussian_conditional = GaussianConditional(None)
+
+    def extract_ref_features(self, ref_frames, y=None):
+        """CLC_run.py:493-510; with match_refs the reference latents are aligned to y first."""
+        if ref_frames is None or not self.use_ref:
+            return None
+        B = ref_frames[0].size(0)
+        # one encoder pass over all references instead of a Python loop of n_refs passes
+        feats = self.ref_encoder(torch.cat(list(ref_frames), dim=0))
+        R = len(ref_frames)
+        feats = feats.view(R, B, *feats.shape[1:]).transpose(0, 1)  # [B, R, M, h, w]
+        if self.match_refs:
+            if y is None:
+                raise ValueError("match_refs needs the image latent y")
+            feats = match_and_gather(y, feats.contiguous(), self.match_patch, self.match_patch, self.match_k,
+                                     self.match_temperature, True, False, self.match_mode)
+        return self.ref_feature_adapter(feats.reshape(B, R * feats.shape[2], *feats.shape[3:]))
+
+    def forward(self, x, ref_frames=None, noise=None):
+        """`noise` (optional dict {"y": [B,320,h,w], "z": [B,192,h/4,w/4]}) injects the training
+        U(-1/2,1/2) samples explicitly for bit-reproducible parity runs."""
+        y = self.g_a(x)
+        ref_features = self.extract_ref_features(ref_frames, y if self.match_refs else None)
+        z_lik, latent_scales, latent_means = self._hyper(y, noise)
+        y_hat, means, scales, y_lik = self._slice_loop(y, latent_means, latent_scales,
+                                                       ref_features if self.use_ref else None, noise)
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik},
+                "para": {"means": means, "scales": scales, "y": y}}
+
+    def symbols_and_indexes(self, x, ref_frames=None):
+        """Device-resident coder inputs of `compress` (CLC_run.py:629-716): per-slice int32 symbols
+        (:690) and scale-table indexes (:689), without the reference's `.tolist()` host copies."""
+        if self.gaussian_conditional.scale_table.numel() == 0:
+            self.update()
+        y = self.g_a(x)
+        ref_features = self.extract_ref_features(ref_frames, y if self.match_refs else None)
+        z = self.h_a(y)
+        _, _, z_hat = self.entropy_bottleneck(z, training=False, ste=True, want_outputs=False)
+        latent_scales, latent_means = self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        y_shape = y.shape[2:]
+        y_hat_slices, symbols, indexes = [], [], []
+        table = self.gaussian_conditional.scale_table.to(x.device)
+        for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
+            support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[:self.max_support_slices]
+            mean_support = self.atten_mean[i](torch.cat([latent_means] + support, dim=1))
+            scale_support = self.atten_scale[i](torch.cat([latent_scales] + support, dim=1))
+            if ref_features is not None:
+                mu = self.ref_cc_mean_transforms[i](torch.cat([mean_support, ref_features], dim=1))
+                scale = self.ref_cc_scale_transforms[i](torch.cat([scale_support, ref_features], dim=1))
+            else:
+                mu = self.cc_mean_transforms[i](mean_support)
+                scale = self.cc_scale_transforms[i](scale_support)
+            mu = mu[:, :, :y_shape[0], :y_shape[1]]
+            scale = scale[:, :, :y_shape[0], :y_shape[1]]
+            sym, idx = ops.gc_symbols_indexes(y_slice, scale, mu, table)
+            symbols.append(sym)
+            indexes.append(idx)
+            y_hat_i = sym.to(torch.float32) + mu
+            if ref_features is not None:
+                lrp = self.ref_lrp_transforms[i](torch.cat([mean_support, y_hat_i, ref_features], dim=1))
+            else:
+                lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_i], dim=1))
+            y_hat_slices.append(self._lrp_add(y_hat_i, lrp))
+        return {"symbols": torch.cat(symbols, 1), "indexes": torch.cat(indexes, 1),
+                "y_hat": torch.cat(y_hat_slices, 1)}
+
+    def load_state_dict(self, state_dict, strict=False):
+        """Non-strict, filtered load keeping compatibility with TCM / older checkpoints
+        (CLC_run.py:599-618)."""
+        own = self.state_dict()
+        filtered = {k: v for k, v in state_dict.items() if k in own}
+        _update_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
+                                   ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        return super().load_state_dict(filtered, strict=False)
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        N = state_dict["g_a.0.weight"].size(0)
+        M = state_dict["g_a.6.weight"].size(0)
+        net = cls(N=N // 2, M=M)
+        net.load_state_dict(state_dict)
+        return net

@@ -164,7 +164,8 @@ class _GaussianConditionalFn(torch.autograd.Function):
         lik = torch.empty(y.shape, dtype=torch.float32, device=y.device)
         y_hat = torch.empty_like(lik)
         outputs = torch.empty_like(lik) if want_outputs else None
-        gc_fwd_raw(y, scale, mean, noise, lik, y_hat, outputs, log2_acc, scale_bound, lik_bound)
+        if y.numel():
+            gc_fwd_raw(y, scale, mean, noise, lik, y_hat, outputs, log2_acc, scale_bound, lik_bound)
         ctx.save_for_backward(y, scale, mean, noise, lik)
         ctx.bounds = (scale_bound, lik_bound)
         ctx.train = noise is not None
@@ -181,7 +182,8 @@ class _GaussianConditionalFn(torch.autograd.Function):
         g_scale = torch.empty_like(g_y)
         g_mean = torch.empty_like(g_y) if mean is not None else None
         # g_lik None (likelihood unused downstream) -> NULL pointer + coef 0 = zero gradient.
-        gc_bwd_raw(y, scale, mean, noise, lik, g_lik, 0.0, g_y_hat, g_y, g_scale, g_mean, sb, lb)
+        if y.numel():
+            gc_bwd_raw(y, scale, mean, noise, lik, g_lik, 0.0, g_y_hat, g_y, g_scale, g_mean, sb, lb)
         if g_outputs is not None and g_outputs.numel():
             # `outputs` = y + noise (train: d/dy = 1) or round(y-mean)+mean (eval: d/dmean = 1)
             if ctx.train:

@@ -162,7 +162,7 @@ def test_lrp_add_and_symbols_indexes():
     lrp_c = lrp.to(d).requires_grad_(True)
     res_c = ops.lrp_add_(base_c * 1.0, lrp_c)
     (res_c * w.to(d)).sum().backward()
-    assert torch.allclose(res_c.detach().cpu(), res_o.detach(), rtol=0, atol=2e-7)
+    assert torch.allclose(res_c.detach().cpu(), res_o.detach(), rtol=2e-7, atol=2e-7)  # ~1 ulp (tanhf vs torch tanh)
     assert torch.allclose(lrp_c.grad.cpu(), lrp_o.grad, rtol=1e-5, atol=1e-7)
     assert torch.equal(base_c.grad.cpu(), base_o.grad)
     # symbols / indexes: bit-exact integers
@@ -256,8 +256,8 @@ def test_full_size_properties_cfg4():
     _, lik, y_hat = gc(yc, scc, muc, ste=True, want_outputs=False, log2_acc=acc)
     _, lik2, y_hat2 = gc(y_hat, scc, muc, ste=True, want_outputs=False)
     assert torch.equal(y_hat2, y_hat) and torch.equal(lik2, lik)          # idempotent
-    _, lik3, _ = gc(2 * muc - y_hat, scc, muc, ste=True, want_outputs=False)
-    assert torch.allclose(lik3, lik, rtol=1e-5, atol=0)                     # even in (y - mu)
+    _, lik3, y_hat3 = gc(-yc, scc, -muc, ste=True, want_outputs=False)
+    assert torch.equal(lik3, lik) and torch.equal(y_hat3, -y_hat)           # exact mirror symmetry
     assert lik.min().item() >= 1e-9 and lik.max().item() <= 1.0
     s2 = clc_b200.ops.log2_sum(lik)
     assert abs(acc.item() - s2.item()) < 1e-6 * abs(s2.item())
