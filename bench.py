@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- Mpix/s of the CLC latent path (match + CLM + entropy stage, fwd+bwd) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a kernels
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the
+                                                             # reference path on the host cores
+Under torchrun (N>1) every rank runs the same per-GPU batch (weak scaling, images sharded
+data-parallel); rank 0 prints ONE JSON line.
+
+A "step" = one pass of clc_b200.latent_path.LatentPath over one batch of synthetic inputs:
+  value : inputs resident in HBM, CUDA-event timed per step with an L2 flush between steps.
+  e2e   : the same operator sequence through the public autograd API (clc_b200 modules) with the
+          step's inputs copied from pinned host memory and the loss read back, every step.
+  roofline : the dominant C-ABI call of the step, algorithmic bytes / its mean
+          CUDA-event duration inside the same run, vs MEASURED_PEAKS.json.
+  cpu_baseline : the oracle port (oracle/latent_path_oracle.py) timed on this box's host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (per-GPU batch, H, W, n_refs, train)      BASELINE.json configs[...]
+    "cfg1": dict(B=1, H=256, W=256, R=3, train=False, desc="configs[0]: 1x3x256x256, 3 refs, forward"),
+    "cfg2": dict(B=8, H=256, W=256, R=3, train=True, desc="configs[1]: training step, batch 8 of 256x256, n_refs=3"),
+    "cfg3": dict(B=3, H=512, W=768, R=3, train=False, desc="configs[2]: Kodak-shaped 768x512 inference, 3 images per GPU"),
+    "cfg4": dict(B=1, H=1280, W=2048, R=3, train=False, desc="configs[3]: CLIC-shaped 2048x1280 inference, 3-ref matching"),
+    "cfg5": dict(B=8, H=256, W=256, R=3, train=True, desc="configs[4]: data-parallel training, 8 images per GPU"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf=float(d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_time(cfg, budget_s, steps=None, warmup=1, seed=1):
+    """Time the oracle port of the path on the host cores.  Returns dict(value Mpix/s, ...)."""
+    from oracle import latent_path_oracle as LO
+    from oracle import clc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, H, W, R, train = cfg["B"], cfg["H"], cfg["W"], cfg["R"], cfg["train"]
+    # bounded sample: shrink the batch (images are independent units) until one step is cheap
+    est = 0.06 * (H * W / 65536.0) ** 1.6 * R / 3.0      # rough s / image on ~8-32 cores
+    Bs = max(1, min(B, int(max(1.0, budget_s / 6.0 / max(est, 1e-3)))))
+    g = torch.Generator().manual_seed(seed)
+    h, w = H // 16, W // 16
+    y = 3 * torch.randn(Bs, 320, h, w, generator=g)
+    inp = dict(y=y, z=2 * torch.randn(Bs, 192, H // 64, W // 64, generator=g),
+               refs=torch.randn(Bs, R, 320, h, w, generator=g) + (y / 6).unsqueeze(1),
+               mu=torch.randn(Bs, 320, h, w, generator=g),
+               scale=torch.exp(torch.empty(Bs, 320, h, w).uniform_(math.log(0.05), math.log(300.0), generator=g)),
+               lrp=torch.randn(Bs, 320, h, w, generator=g), att=torch.randn(Bs, R, 1, h, w, generator=g),
+               noise_y=torch.rand(Bs, 320, h, w, generator=g) - 0.5,
+               noise_z=torch.rand(Bs, 192, H // 64, W // 64, generator=g) - 0.5,
+               g_y_hat=1e-3 * torch.randn(Bs, 320, h, w, generator=g),
+               g_fused=1e-3 * torch.randn(Bs, 320, h, w, generator=g))
+    eb = O.EntropyBottleneck(192)
+    for _ in range(warmup):
+        LO.step(inp, eb, train=train)
+        eb.zero_grad()
+    times = []
+    t_all = time.perf_counter()
+    n = 0
+    while True:
+        t0 = time.perf_counter()
+        LO.step(inp, eb, train=train)
+        eb.zero_grad()
+        times.append(time.perf_counter() - t0)
+        n += 1
+        if steps is not None and n >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_all > budget_s or n >= 50) and n >= 2:
+            break
+    t = sum(times) / len(times)
+    return dict(value=Bs * H * W / t / 1e6, unit="Mpix/s", cores=cores, kind="port",
+                sample=f"{Bs} of {B} images/step ({H}x{W}, {R} refs, {'fwd+bwd' if train else 'fwd'}), "
+                       f"{n} timed steps, oracle port on torch CPU ({cores} threads)",
+                ms_per_step=t * 1e3, steps=n, images=Bs)
+
+
+class PublicPath:
+    """The same operator sequence through the PUBLIC autograd API (what a user of the drop-in
+    modules calls), used for the end-to-end number."""
+
+    def __init__(self, cfg, device, match_mode):
+        import clc_b200
+        self.c = clc_b200
+        self.cfg, self.dev, self.mode = cfg, device, match_mode
+        self.gc = clc_b200.GaussianConditional(None).to(device).train(cfg["train"])
+        self.eb = clc_b200.EntropyBottleneck(192).to(device).train(cfg["train"])
+        self.npix = cfg["B"] * cfg["H"] * cfg["W"]
+
+    def step(self, d):
+        from clc_b200 import ops
+        c, train = self.c, self.cfg["train"]
+        B, R = d["refs"].shape[0], d["refs"].shape[1]
+        grad = ("y", "z", "refs", "mu", "scale", "lrp", "att")
+        t = {k: (v.requires_grad_(True) if (train and k in grad) else v) for k, v in d.items()}
+        aligned = c.match_and_gather(t["y"], t["refs"], 4, 4, 4, 15.0, True, False, self.mode)   # [B,R,C,h,w]
+        fused = c.clm_fuse(aligned.transpose(0, 1), t["att"].transpose(0, 1), t["y"])
+        _, lik_z, z_hat = self.eb(t["z"], noise=t["noise_z"] if train else None, ste=True, want_outputs=False)
+        liks, yh = [], []
+        for i in range(5):
+            sl = slice(64 * i, 64 * (i + 1))
+            _, lik, y_hat = self.gc(t["y"][:, sl], t["scale"][:, sl], t["mu"][:, sl],
+                                    noise=t["noise_y"][:, sl] if train else None, ste=True, want_outputs=False)
+            yh.append(ops.lrp_add_(y_hat, t["lrp"][:, sl]))
+            liks.append(lik)
+        bpp = -(ops.log2_sum(torch.cat(liks, 1)) + ops.log2_sum(lik_z)) / self.npix
+        if train:
+            loss = bpp.float() + (torch.cat(yh, 1) * t["g_y_hat"]).sum() + (fused * t["g_fused"]).sum()
+            loss.backward()
+            return loss
+        return bpp
+
+
+def run_ours(args):
+    from clc_b200 import _lib
+    from clc_b200 import dist as cdist
+    from clc_b200.latent_path import LatentPath
+    rank, world, local = cdist.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = WORKLOADS[args.workload]
+    K, Wm = args.steps, max(args.warmup, 3)
+    lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=args.match_mode,
+                    fused_slices=args.fused_slices, device=dev)
+    lp.randomize(seed=1 + rank)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    use_graph = not args.no_graph
+    launches_per_step = lp.step()  # also first-touch
+    torch.cuda.synchronize()
+    if use_graph:
+        lp.capture()
+    run = lp.replay if use_graph else lp.step
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    def exchange():
+        # the only collectives the path owns: EB parameter gradients (training)
+        # and the 2-double bpp statistic, one NCCL all-reduce each per step.
+        if world > 1:
+            if cfg["train"]:
+                torch.distributed.all_reduce(lp._acc[4:4 + 192 * 58])
+            torch.distributed.all_reduce(lp.log2)
+
+    for _ in range(Wm):
+        flush.zero_()
+        run()
+        exchange()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    l0 = _lib.launches()
+    barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()          # L2 flush between timed iterations (not inside the event bracket)
+        a.record()
+        run()
+        exchange()
+        b.record()
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    gpu_launches = (_lib.launches() - l0) if not use_graph else launches_per_step * K
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = total_ms.item()
+    pix_per_step = world * cfg["B"] * cfg["H"] * cfg["W"]
+    value = pix_per_step * K / (total_ms * 1e-3) / 1e6
+    bpp_dev = lp.bpp().item()
+
+    # ---- L2-warm variant (no flush), for context -------------------------------------------
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    warm_ms = a.elapsed_time(b) / K
+
+    # ---- end to end through the public API, host buffers, H2D + D2H inside the timed region --
+    pub = PublicPath(cfg, dev, args.match_mode)
+    host = {n: t.detach().cpu().pin_memory() for n, t in lp.inputs().items()}
+    names = [n for n in host if cfg["train"] or n not in ("noise_y", "noise_z", "g_y_hat", "g_fused")]
+    h2d = sum(host[n].numel() * 4 for n in names)
+    for _ in range(Wm):
+        d = {n: host[n].to(dev, non_blocking=True) for n in names}
+        pub.step(d).item()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ev = []
+    for _ in range(K):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        d = {n: host[n].to(dev, non_blocking=True) for n in names}
+        res = pub.step(d)
+        res_host = res.item()          # device -> host read of the step's result
+        b.record()
+        e2e_ev.append((a, b))
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = pix_per_step * K / (e2e_ms.item() * 1e-3) / 1e6
+    clocks = sampler.stop()
+
+    # ---- instrumented pass: CUDA events around every C-ABI call of the same step ------------
+    _lib.TRACE = []
+    for _ in range(K):
+        flush.zero_()
+        lp.step()
+    torch.cuda.synchronize()
+    per = {}
+    for name, e0, e1 in _lib.TRACE:
+        t = per.setdefault(name, [0.0, 0])
+        t[0] += e0.elapsed_time(e1)
+        t[1] += 1
+    _lib.TRACE = None
+    pk = peaks()
+    alg = lp.algorithmic_bytes()
+    breakdown = {n: {"ms_per_step": t[0] / K, "calls_per_step": t[1] / K, "us_per_call": 1e3 * t[0] / t[1]}
+                 for n, t in per.items()}
+    dom = max(per, key=lambda n: per[n][0])
+    us = 1e3 * per[dom][0] / per[dom][1]
+    key = dom.replace("clc_", "")
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}:{dom}")
+    if dom in ("clc_match_topk_tc", "clc_pearson_corr"):
+        flops = alg["match_flops"]
+        ach = flops / (us * 1e-6) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf"], "traffic": traffic, "us_per_launch": us, "peak_source": pk["src"],
+                "algorithmic_flop_per_launch": flops}
+    else:
+        nbytes = alg.get(key)
+        ach = (nbytes / (us * 1e-6) / 1e9) if nbytes else None
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": (ach / pk["hbm"]) if ach else None, "traffic": traffic, "us_per_launch": us,
+                "peak_source": pk["src"], "algorithmic_bytes_per_launch": nbytes}
+    # the bandwidth-bound entropy kernel, always reported next to the dominant one
+    g_us = breakdown.get("clc_gc_fwd", {}).get("us_per_call")
+    gc_roof = None
+    if g_us:
+        gbs = alg["gc_fwd"] / (g_us * 1e-6) / 1e9
+        gc_roof = {"kernel": "clc_gc_fwd", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                   "frac": gbs / pk["hbm"], "us_per_launch": g_us, "algorithmic_bytes_per_launch": alg["gc_fwd"]}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_time(cfg, budget_s=args.cpu_budget)
+    line = {
+        "metric": "Mpix/s of CLC latent path (match+CLM+entropy)", "value": value, "unit": "Mpix/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
+                   "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
+                   "slice_launches": "fused" if args.fused_slices else "per-slice", "cuda_graph": use_graph,
+                   "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                "api": "clc_b200 public autograd modules, pinned host inputs"},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "roofline_gc_fwd": gc_roof,
+        "cpu_baseline": cpu,
+        "l2_warm_ms_per_step": warm_ms,
+        "kernel_launches_per_step": launches_per_step,
+        "breakdown": breakdown,
+        "bpp": bpp_dev,
+        "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(line))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    r = cpu_port_time(cfg, budget_s=60.0, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "Mpix/s of CLC latent path (match+CLM+entropy)", "value": r["value"],
+            "unit": "Mpix/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"],
+                       "image": [cfg["H"], cfg["W"]], "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--match-mode", default="tc", choices=["tc", "fp32"])
+    ap.add_argument("--fused-slices", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

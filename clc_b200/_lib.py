@@ -31,6 +31,7 @@ PROTOTYPES = {
     "clc_version": (C.c_int, []),
     "clc_strerror": (C.c_char_p, [C.c_int]),
     "clc_last_cuda_error": (C.c_char_p, []),
+    "clc_kernel_launch_count": (C.c_uint64, []),
     "clc_gc_fwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p,
                              _i64, _i64, _f, _f, _p]),
     "clc_gc_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f, _p, _i64,
@@ -58,8 +59,8 @@ PROTOTYPES = {
                                        _i32, _i32, _p]),
     "clc_pearson_topk_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
                                        _i32, _i32, _i32, _i32, _p]),
-    "clc_clm_fuse_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
-    "clc_clm_fuse_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
+    "clc_clm_fuse_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i32, _i64, _i32, _i64, _p]),
+    "clc_clm_fuse_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
 }
 
 _lib = None
@@ -84,11 +85,22 @@ def lib():
     return _lib
 
 
+TRACE = None  # bench.py sets this to a list to collect (name, start_event, end_event) per call
+
+
 def call(name, *args):
     """Invoke a status-returning entry point; raise RuntimeError on a negative status."""
     global _launches
     h = lib()
-    rc = getattr(h, name)(*args)
+    if TRACE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(h, name)(*args)
+        e1.record()
+        TRACE.append((name, e0, e1))
+    else:
+        rc = getattr(h, name)(*args)
     _launches += 1
     if rc != 0:
         msg = h.clc_strerror(rc).decode()
@@ -98,7 +110,8 @@ def call(name, *args):
 
 
 def launches():
-    return _launches
+    """Kernels enqueued by libclc_b200.so in this process (counted inside the library)."""
+    return int(lib().clc_kernel_launch_count())
 
 
 def ptr(t):

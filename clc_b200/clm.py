@@ -20,7 +20,8 @@ class _ClmFuseFn(torch.autograd.Function):
         R, B, Cc = ref_t.shape[0], ref_t.shape[1], ref_t.shape[2]
         S = ref_t[0, 0, 0].numel()
         out = torch.empty_like(y)
-        call("clc_clm_fuse_fwd", ptr(ref_t), ptr(att), ptr(y), ptr(out), R, B, Cc, S, _stream())
+        call("clc_clm_fuse_fwd", ptr(ref_t), B * Cc * S, Cc * S, ptr(att), B * S, S, ptr(y), ptr(out), R, B, Cc, S,
+             _stream())
         ctx.save_for_backward(ref_t, att)
         return out
 
@@ -32,8 +33,8 @@ class _ClmFuseFn(torch.autograd.Function):
         g_out = g_out.contiguous()
         g_ref_t = torch.empty_like(ref_t)
         g_att = torch.empty_like(att)
-        call("clc_clm_fuse_bwd", ptr(ref_t), ptr(att), ptr(g_out), ptr(g_ref_t), ptr(g_att), R, B, Cc, S,
-             _stream())
+        call("clc_clm_fuse_bwd", ptr(ref_t), B * Cc * S, Cc * S, ptr(att), B * S, S, ptr(g_out), ptr(g_ref_t),
+             ptr(g_att), R, B, Cc, S, _stream())
         return g_ref_t, g_att, g_out
 
 

@@ -3,6 +3,7 @@
 
 namespace clc {
 thread_local char g_last_cuda_error[256] = {0};
+std::atomic<unsigned long long> g_kernel_launches{0};
 }
 
 extern "C" int clc_version(void) { return 1; }
@@ -20,3 +21,7 @@ extern "C" const char* clc_strerror(int status) {
 }
 
 extern "C" const char* clc_last_cuda_error(void) { return clc::g_last_cuda_error; }
+
+extern "C" uint64_t clc_kernel_launch_count(void) {
+  return clc::g_kernel_launches.load(std::memory_order_relaxed);
+}

@@ -29,7 +29,8 @@ __device__ __forceinline__ void clm_coef(const float* a, int R, float* coef, flo
 // grid = (ceil(S/VW/128), ceil(C/kChanGroup), B); thread = VW consecutive pixels.
 template <int VW>
 __global__ void __launch_bounds__(128)
-clm_fuse_fwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ att,
+clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref_sb,
+                    const float* __restrict__ att, int64_t att_sr, int64_t att_sb,
                     const float* __restrict__ y, float* __restrict__ out, int R, int64_t B, int C,
                     int64_t S) {
   const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VW;
@@ -39,7 +40,7 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
   {
     float a[VW][kMaxRefs];
     for (int r = 0; r < R; ++r) {
-      const float* ap = att + ((int64_t)r * B + b) * S + s0;
+      const float* ap = att + (int64_t)r * att_sr + b * att_sb + s0;
       if constexpr (VW == 4) {
         const float4 v = ld4(ap);
         a[0][r] = v.x; a[1][r] = v.y; a[2][r] = v.z; a[3][r] = v.w;
@@ -57,7 +58,7 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
     if constexpr (VW == 4) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < R; ++r) {
-        const float4 t = ld4_stream(ref_t + (((int64_t)r * B + b) * C + c) * S + s0);
+        const float4 t = ld4_stream(ref_t + (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0);
         // (aligned_stack * attention_weights).sum(dim=1): products summed left to right over r
         acc.x += t.x * coef[0][r]; acc.y += t.y * coef[1][r];
         acc.z += t.z * coef[2][r]; acc.w += t.w * coef[3][r];
@@ -66,7 +67,7 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
       st4_stream(out + o, make_float4(acc.x + yv.x, acc.y + yv.y, acc.z + yv.z, acc.w + yv.w));
     } else {
       float acc = 0.f;
-      for (int r = 0; r < R; ++r) acc += ref_t[(((int64_t)r * B + b) * C + c) * S + s0] * coef[0][r];
+      for (int r = 0; r < R; ++r) acc += ref_t[(int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0] * coef[0][r];
       out[o] = acc + y[o];
     }
   }
@@ -78,7 +79,8 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
 //   g_att[m]     = w_m s_m G_m - w_m * sum_r G_r s_r w_r + G_m w_m s_m (1 - s_m)
 template <int VW>
 __global__ void __launch_bounds__(256)
-clm_fuse_bwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ att,
+clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref_sb,
+                    const float* __restrict__ att, int64_t att_sr, int64_t att_sb,
                     const float* __restrict__ g_out, float* __restrict__ g_ref_t,
                     float* __restrict__ g_att, int R, int64_t B, int C, int64_t S) {
   __shared__ float Gs[8][kMaxRefs][32 * VW + 1];
@@ -94,7 +96,7 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
   if (live) {
     float a[VW][kMaxRefs];
     for (int r = 0; r < R; ++r) {
-      const float* ap = att + ((int64_t)r * B + b) * S + s0;
+      const float* ap = att + (int64_t)r * att_sr + b * att_sb + s0;
       if constexpr (VW == 4) {
         const float4 v = ld4(ap);
         a[0][r] = v.x; a[1][r] = v.y; a[2][r] = v.z; a[3][r] = v.w;
@@ -109,7 +111,7 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
       if constexpr (VW == 4) {
         const float4 g = ld4_stream(g_out + o);
         for (int r = 0; r < R; ++r) {
-          const int64_t ro = (((int64_t)r * B + b) * C + c) * S + s0;
+          const int64_t ro = (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0;
           const float4 t = ld4_stream(ref_t + ro);
           G[0][r] = fmaf(g.x, t.x, G[0][r]); G[1][r] = fmaf(g.y, t.y, G[1][r]);
           G[2][r] = fmaf(g.z, t.z, G[2][r]); G[3][r] = fmaf(g.w, t.w, G[3][r]);
@@ -118,7 +120,7 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
       } else {
         const float g = g_out[o];
         for (int r = 0; r < R; ++r) {
-          const int64_t ro = (((int64_t)r * B + b) * C + c) * S + s0;
+          const int64_t ro = (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0;
           G[0][r] = fmaf(g, ref_t[ro], G[0][r]);
           g_ref_t[ro] = g * coef[0][r];
         }
@@ -142,7 +144,7 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, const float* __restrict__ a
       }
       for (int m = 0; m < R; ++m) {
         const float ga = coef[v][m] * Gt[m] - w[v][m] * mix + Gt[m] * coef[v][m] * (1.f - sg[v][m]);
-        g_att[((int64_t)m * B + b) * S + s0 + v] = ga;
+        g_att[(int64_t)m * att_sr + b * att_sb + s0 + v] = ga;
       }
     }
   }
@@ -156,27 +158,30 @@ static bool clm_args_ok(int R, int64_t B, int C, int64_t S) {
   return R >= 1 && R <= kMaxRefs && B >= 0 && C >= 1 && S >= 1 && B <= 65535;
 }
 
-extern "C" int clc_clm_fuse_fwd(const float* ref_t, const float* att, const float* y, float* out,
+extern "C" int clc_clm_fuse_fwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb, const float* att,
+                                int64_t att_sr, int64_t att_sb, const float* y, float* out,
                                 int32_t R, int64_t B, int32_t C, int64_t S, void* stream) {
   if (!ref_t || !att || !y || !out) return CLC_ERR_INVALID_ARGUMENT;
   if (R > kMaxRefs || B > 65535) return CLC_ERR_UNSUPPORTED;
   if (!clm_args_ok(R, B, C, S)) return CLC_ERR_INVALID_ARGUMENT;
   if (B == 0) return CLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec = (S % 4 == 0) && aligned16(ref_t) && aligned16(att) && aligned16(y) && aligned16(out);
+  const bool vec = (S % 4 == 0) && aligned16(ref_t) && aligned16(att) && aligned16(y) && aligned16(out) &&
+                   !((ref_sr | ref_sb | att_sr | att_sb) & 3);
   const unsigned gy = (C + kChanGroup - 1) / kChanGroup;
   if (vec) {
     dim3 grid((unsigned)((S / 4 + 127) / 128), gy, (unsigned)B);
-    clm_fuse_fwd_kernel<4><<<grid, 128, 0, st>>>(ref_t, att, y, out, R, B, C, S);
+    clm_fuse_fwd_kernel<4><<<grid, 128, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, B, C, S);
   } else {
     dim3 grid((unsigned)((S + 127) / 128), gy, (unsigned)B);
-    clm_fuse_fwd_kernel<1><<<grid, 128, 0, st>>>(ref_t, att, y, out, R, B, C, S);
+    clm_fuse_fwd_kernel<1><<<grid, 128, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, B, C, S);
   }
   CLC_CHECK_LAUNCH("clc_clm_fuse_fwd");
   return CLC_OK;
 }
 
-extern "C" int clc_clm_fuse_bwd(const float* ref_t, const float* att, const float* g_out, float* g_ref_t,
+extern "C" int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb, const float* att,
+                                int64_t att_sr, int64_t att_sb, const float* g_out, float* g_ref_t,
                                 float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream) {
   if (!ref_t || !att || !g_out || !g_ref_t || !g_att) return CLC_ERR_INVALID_ARGUMENT;
   if (R > kMaxRefs || B > 65535) return CLC_ERR_UNSUPPORTED;
@@ -184,14 +189,14 @@ extern "C" int clc_clm_fuse_bwd(const float* ref_t, const float* att, const floa
   if (B == 0) return CLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (S % 4 == 0) && aligned16(ref_t) && aligned16(att) && aligned16(g_out) &&
-                   aligned16(g_ref_t);
+                   aligned16(g_ref_t) && aligned16(g_att) && !((ref_sr | ref_sb | att_sr | att_sb) & 3);
   dim3 block(32, 8);
   if (vec) {
     dim3 grid((unsigned)((S / 4 + 31) / 32), 1, (unsigned)B);
-    clm_fuse_bwd_kernel<4><<<grid, block, 0, st>>>(ref_t, att, g_out, g_ref_t, g_att, R, B, C, S);
+    clm_fuse_bwd_kernel<4><<<grid, block, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out, g_ref_t, g_att, R, B, C, S);
   } else {
     dim3 grid((unsigned)((S + 31) / 32), 1, (unsigned)B);
-    clm_fuse_bwd_kernel<1><<<grid, block, 0, st>>>(ref_t, att, g_out, g_ref_t, g_att, R, B, C, S);
+    clm_fuse_bwd_kernel<1><<<grid, block, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out, g_ref_t, g_att, R, B, C, S);
   }
   CLC_CHECK_LAUNCH("clc_clm_fuse_bwd");
   return CLC_OK;

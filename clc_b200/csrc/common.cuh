@@ -1,6 +1,7 @@
 // Shared helpers for libclc_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -19,10 +20,14 @@ inline int cuda_fail(cudaError_t e, const char* where) {
   return CLC_ERR_CUDA;
 }
 
+// Process-wide count of kernels enqueued by this library (statistics only; bench.py reports it).
+extern std::atomic<unsigned long long> g_kernel_launches;
+
 #define CLC_CHECK_LAUNCH(where)                                  \
   do {                                                           \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return ::clc::cuda_fail(e__, where); \
+    ::clc::g_kernel_launches.fetch_add(1, std::memory_order_relaxed); \
   } while (0)
 
 #define CLC_CUDA(call)                                           \

@@ -1,0 +1,108 @@
+"""Data-parallel plumbing for the CLC latent path: one process per GPU, images sharded across
+ranks, NCCL (NVLink 5 / NVSwitch) used only where the reference's training needs an exchange:
+the gradient all-reduce and one small statistics all-reduce per step.  The
+reference itself uses threaded nn.DataParallel (train_CLC.py:74-79,:472-473), replicating all
+weights every step; this replaces it.  Works with the `gloo` backend on CPU for tests."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun).
+    Returns (rank, world_size, local_rank).  Single-process runs return (0, 1, 0) untouched."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return 0, 1, 0
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [start, stop) of `n_items` independent units (images) for `rank`."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class GradAllReducer:
+    """Bucketed, overlapped gradient all-reduce (mean) for a replicated model.
+
+    Gradient hooks fire as autograd produces each parameter's gradient; parameters are packed
+    into flat buckets of ~`bucket_mb` in reverse registration order and each full bucket is
+    all-reduced asynchronously while the backward pass continues.  `finish()` flushes the last
+    bucket, waits, divides by world size and scatters the results back.  Parameters that receive
+    no gradient (the reference's unused `feature_alignment`, `multi_ref_fusion`, ... modules)
+    are simply absent from every rank's buckets, which keeps the ranks consistent because the
+    set is a property of the graph, not of the data."""
+
+    def __init__(self, module, bucket_mb=64.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket_elems = int(bucket_mb * 1024 * 1024 // 4)
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self._pending, self._pending_elems, self._inflight = [], 0, []
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    def _hook(self, p):
+        if self.world == 1 or p.grad is None:
+            return
+        self._pending.append(p)
+        self._pending_elems += p.grad.numel()
+        if self._pending_elems >= self.bucket_elems:
+            self._launch()
+
+    def _launch(self):
+        if not self._pending:
+            return
+        ps, self._pending, self._pending_elems = self._pending, [], 0
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight.append((work, flat, ps))
+
+    def finish(self):
+        """Call after backward(): completes all buckets; gradients become the cross-rank mean."""
+        if self.world == 1:
+            return
+        self._launch()
+        for work, flat, ps in self._inflight:
+            work.wait()
+            flat.div_(self.world)
+            off = 0
+            for p in ps:
+                n = p.grad.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+        self._inflight = []
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+
+
+def allreduce_stats(log2_lik_y, log2_lik_z, sq_err, n_pix, device=None, group=None):
+    """One 4-element float64 all-reduce(sum) of {sum log2 lik_y, sum log2 lik_z, sum sq err,
+    pixels}; returns global (bpp, mse) as python floats on every rank."""
+    vals = []
+    for v in (log2_lik_y, log2_lik_z, sq_err, n_pix):
+        vals.append(v.detach().to(torch.float64).reshape(1) if isinstance(v, torch.Tensor)
+                    else torch.tensor([float(v)], dtype=torch.float64))
+    dev = device if device is not None else next((v.device for v in vals if v.is_cuda), vals[0].device)
+    t = torch.cat([v.to(dev) for v in vals])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    s_y, s_z, s_e, n = t.tolist()
+    return -(s_y + s_z) / n, s_e / (3.0 * n)

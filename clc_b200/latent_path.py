@@ -1,0 +1,258 @@
+"""The CLC conditional-latent hot path as ONE object over preallocated HBM buffers, driven
+through the raw C ABI (no autograd, no allocation per step, CUDA-graph capturable):
+
+    match (Pearson correlation GEMM + top-k)  ->  gather/blend  ->  CLM fusion
+    -> EntropyBottleneck(z) -> 5 x [GaussianConditional + STE round, LRP add] -> bpp partial sums
+    and the backward of all of it.
+
+This is what bench.py times (`value`): the operator sequence of SURVEY.md 8a with the
+parameter networks' outputs (mu / scale / lrp, attention logits, upstream gradients) supplied
+as inputs, exactly as the reference's slice loop (CLC_run.py:535-590) sees them.  Training
+through real models uses the autograd wrappers (ops.py, matching.py, clm.py) instead.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import matching, ops
+from ._lib import call, lib, ptr
+
+
+class LatentPath:
+    """Buffers + launch sequence for a batch of B images of H x W pixels with n_refs references."""
+
+    INPUT_NAMES = ("y", "z", "refs", "mu", "scale", "lrp", "att", "noise_y", "noise_z", "g_y_hat", "g_fused")
+
+    def __init__(self, B, H, W, n_refs=3, M=320, num_slices=5, z_channels=192, train=True, patch=4, k=4,
+                 temperature=15.0, match_mode="tc", gaussian_mask=True, fused_slices=False,
+                 device="cuda", lmbda=0.013):
+        assert H % 64 == 0 and W % 64 == 0, "latent geometry: h = H/16, hz = H/64"
+        self.B, self.H, self.W, self.R, self.M = B, H, W, n_refs, M
+        self.h, self.w = H // 16, W // 16
+        self.hz, self.wz = H // 64, W // 64
+        self.num_slices, self.Cs = num_slices, M // num_slices
+        self.train, self.patch, self.k, self.T = train, patch, k, float(temperature)
+        self.match_mode, self.fused_slices = match_mode, fused_slices
+        self.P = (self.h // patch) * (self.w // patch)
+        self.corr_w = self.w - patch + 1
+        self.num_pixels = B * H * W
+        self.bpp_coef = 1.0 / (-math.log(2.0) * self.num_pixels)  # dL/dlik = bpp_coef / lik
+        dev = torch.device(device)
+        self.device = dev
+        f = dict(dtype=torch.float32, device=dev)
+        h, w, R = self.h, self.w, n_refs
+        # ---- inputs (resident in HBM when the timed region starts) ----
+        self.y = torch.empty(B, M, h, w, **f)
+        self.z = torch.empty(B, z_channels, self.hz, self.wz, **f)
+        self.refs = torch.empty(B, R, M, h, w, **f)          # reference latents, [B,R] problem order
+        self.mu = torch.empty(B, M, h, w, **f)
+        self.scale = torch.empty(B, M, h, w, **f)
+        self.lrp = torch.empty(B, M, h, w, **f)
+        self.att = torch.empty(B, R, 1, h, w, **f)           # CLM attention logits
+        self.noise_y = torch.empty(B, M, h, w, **f)
+        self.noise_z = torch.empty(B, z_channels, self.hz, self.wz, **f)
+        self.g_y_hat = torch.empty(B, M, h, w, **f)          # upstream dL/dy_hat (from g_s)
+        self.g_fused = torch.empty(B, M, h, w, **f)          # upstream dL/d(CLM output)
+        # ---- EntropyBottleneck parameters ----
+        from .entropy_models import EntropyBottleneck
+        eb = EntropyBottleneck(z_channels).to(dev)
+        self.eb_m = [getattr(eb, f"_matrix{i}").detach() for i in range(5)]
+        self.eb_b = [getattr(eb, f"_bias{i}").detach() for i in range(5)]
+        self.eb_f = [getattr(eb, f"_factor{i}").detach() for i in range(4)]
+        self.quantiles = eb.quantiles.detach()
+        # ---- outputs ----
+        self.val = torch.empty(B * R, self.P, k, **f)
+        self.idx = torch.empty(B * R, self.P, k, dtype=torch.int32, device=dev)
+        self.weights = torch.empty(B * R, self.P, k, **f)
+        self.aligned = torch.empty(B, R, M, h, w, **f)
+        self.fused = torch.empty(B, M, h, w, **f)
+        self.lik_z = torch.empty_like(self.z)
+        self.z_hat = torch.empty_like(self.z)
+        self.lik_y = torch.empty(B, M, h, w, **f)
+        self.y_hat = torch.empty(B, M, h, w, **f)
+        # backward outputs
+        self.g_y = torch.empty(B, M, h, w, **f)
+        self.g_mu = torch.empty(B, M, h, w, **f)
+        self.g_scale = torch.empty(B, M, h, w, **f)
+        self.g_lrp = torch.empty(B, M, h, w, **f)
+        self.g_z = torch.empty_like(self.z)
+        self.g_aligned = torch.empty(B, R, M, h, w, **f)
+        self.g_att = torch.empty(B, R, 1, h, w, **f)
+        self.g_val = torch.empty(B * R, self.P, k, **f)
+        # ---- accumulators: one flat buffer, one memset per step ----
+        n_eb = sum(t.numel() for t in self.eb_m + self.eb_b + self.eb_f)
+        n_acc = 4 + n_eb + B * R * M * h * w + B * M * h * w   # 2 doubles + EB grads + g_refs + g_q
+        self._acc = torch.zeros(n_acc, **f)
+        self.log2 = self._acc[:4].view(torch.float64)          # [sum log2 lik_y, sum log2 lik_z]
+        off = 4
+        self.g_eb = []
+        for t in self.eb_m + self.eb_b + self.eb_f:
+            self.g_eb.append(self._acc[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        self.g_refs = self._acc[off:off + B * R * M * h * w].view(B, R, M, h, w)
+        off += B * R * M * h * w
+        self.g_q = self._acc[off:off + B * M * h * w].view(B, M, h, w)
+        # ---- match workspace ----
+        self.mask = matching._cached_mask(h, w, patch, patch, dev) if gaussian_mask else None
+        self.gaussian_mask = gaussian_mask
+        if match_mode == "tc":
+            nb = lib().clc_match_topk_tc_workspace_bytes(B * R, R, M, h, w, patch, patch, k)
+            self.corr = None
+        elif match_mode == "fp32":
+            nb = lib().clc_pearson_corr_workspace_bytes(B * R, self.P, M, patch, patch, h, w)
+            self.corr = torch.empty(B * R, self.P, (h - patch + 1) * self.corr_w, **f)
+        else:
+            raise ValueError(f'Invalid match mode "{match_mode}"')
+        self.ws = torch.empty(max(int(nb), 16), dtype=torch.uint8, device=dev)
+        self._qview = matching._patch_view_from_image(self.y, patch, patch, R)
+        self._gqview = self._qview
+        self._graph = None
+
+    # -------------------------------------------------------------------------------------
+    def randomize(self, seed=1):
+        """Synthetic inputs of SURVEY.md 8d (operator-level distributions), generated on the
+        device: y~N(0,9), mu~N(0,1), scale log-uniform [0.05,300], ref = 0.5*latent + N(0,1)."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        rn = lambda t: t.normal_(generator=g)
+        rn(self.y).mul_(3.0)
+        rn(self.z).mul_(2.0)
+        rn(self.refs).add_((self.y / 6.0).unsqueeze(1))   # ref = 0.5 * (y / 3) + N(0,1)
+        rn(self.mu)
+        self.scale.uniform_(math.log(0.05), math.log(300.0), generator=g).exp_()
+        rn(self.lrp)
+        rn(self.att)
+        self.noise_y.uniform_(-0.5, 0.5, generator=g)
+        self.noise_z.uniform_(-0.5, 0.5, generator=g)
+        rn(self.g_y_hat).mul_(1e-3)
+        rn(self.g_fused).mul_(1e-3)
+
+    def inputs(self):
+        return {n: getattr(self, n) for n in self.INPUT_NAMES}
+
+    def load_inputs(self, host):
+        """Host (pinned) -> device copies of one step's inputs; returns bytes copied."""
+        n = 0
+        for name in self.INPUT_NAMES:
+            if not self.train and name in ("noise_y", "noise_z", "g_y_hat", "g_fused"):
+                continue
+            dst = getattr(self, name)
+            dst.copy_(host[name], non_blocking=True)
+            n += dst.numel() * 4
+        return n
+
+    # -------------------------------------------------------------------------------------
+    def _slices(self, t):
+        if self.fused_slices:
+            return [t]
+        return list(t.chunk(self.num_slices, 1))
+
+    def forward(self):
+        st = ops._stream()
+        B, R, M, h, w, p, k = self.B, self.R, self.M, self.h, self.w, self.patch, self.k
+        S = h * w
+        n = 0
+        self._acc.zero_()
+        # 1. match: masked Pearson correlation + top-k over all B*R (image, reference) problems
+        r = self.refs.view(B * R, M, h, w)
+        if self.match_mode == "tc":
+            call("clc_match_topk_tc", ptr(self.y), ptr(r), B * R, R, M, h, w, p, p, k,
+                 1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), None, ptr(self.ws),
+                 self.ws.numel(), st)
+            n += 4
+        else:
+            call("clc_pearson_corr", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.corr), B * R,
+                 self.P, M, p, p, h, w, ptr(self.ws), self.ws.numel(), st)
+            call("clc_topk_rows", ptr(self.corr), B * R * self.P, self.corr.shape[-1], k, ptr(self.val),
+                 ptr(self.idx), st)
+            n += 4
+        # 2. softmax weights + gather of the k matched patches + blend
+        call("clc_gather_blend_fwd", ptr(r), ptr(self.idx), ptr(self.val), self.T, ptr(self.aligned),
+             ptr(self.weights), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
+        # 3. CLM fusion over the aligned references ([B,R,C,S] layout, strided -- no transpose)
+        call("clc_clm_fuse_fwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S, ptr(self.y),
+             ptr(self.fused), R, B, M, S, st)
+        # 4. hyper-latent: factorised prior + STE round (+ bpp partial)
+        ops.eb_fwd_raw(self.z, self.noise_z if self.train else None, self.eb_m, self.eb_b, self.eb_f,
+                       self.quantiles, self.lik_z, self.z_hat, None, self.log2[1:2])
+        n += 3
+        # 5. slice loop: GaussianConditional + STE round (+ bpp partial), then LRP add
+        noise = self._slices(self.noise_y) if self.train else None
+        for i, (ys, ss, ms, ls, yh, lr) in enumerate(zip(*(self._slices(t) for t in (
+                self.y, self.scale, self.mu, self.lik_y, self.y_hat, self.lrp)))):
+            ops.gc_fwd_raw(ys, ss, ms, noise[i] if self.train else None, ls, yh, None, self.log2[0:1])
+            ops.lrp_add_fwd_raw(yh, lr)
+            n += 2
+        return n
+
+    def backward(self):
+        st = ops._stream()
+        B, R, M, h, w, p, k = self.B, self.R, self.M, self.h, self.w, self.patch, self.k
+        S = h * w
+        n = 0
+        noise = self._slices(self.noise_y)
+        for i, (ys, ss, ms, ls, lr, gyh, gy, gs, gm, gl) in enumerate(zip(*(self._slices(t) for t in (
+                self.y, self.scale, self.mu, self.lik_y, self.lrp, self.g_y_hat, self.g_y, self.g_scale,
+                self.g_mu, self.g_lrp)))):
+            ops.lrp_add_bwd_raw(gyh, lr, gl)
+            ops.gc_bwd_raw(ys, ss, ms, noise[i], ls, None, self.bpp_coef, gyh, gy, gs, gm)
+            n += 2
+        ops.eb_bwd_raw(self.z, self.noise_z, self.eb_m, self.eb_b, self.eb_f, self.quantiles, self.lik_z,
+                       None, self.bpp_coef, None, self.g_z, self.g_eb[0:5], self.g_eb[5:10], self.g_eb[10:14])
+        call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
+             ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
+        r = self.refs.view(B * R, M, h, w)
+        call("clc_gather_blend_bwd", ptr(r), ptr(self.idx), ptr(self.weights), self.T, ptr(self.g_aligned),
+             ptr(self.g_refs), ptr(self.g_val), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
+        call("clc_pearson_topk_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx),
+             ptr(self.g_val), ptr(self.g_refs), ptr(self.g_q), B * R, self.P, M, p, p, h, w, k, st)
+        n += 4
+        return n
+
+    def step(self):
+        """Enqueue one full pass (forward, and backward when training) on the current stream."""
+        n = self.forward()
+        if self.train:
+            n += self.backward()
+        return n
+
+    # -------------------------------------------------------------------------------------
+    def capture(self):
+        """Capture step() into a CUDA graph (launch-bound at the small configs)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step()
+        self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()
+
+    def bpp(self):
+        """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels."""
+        return -(self.log2[0] + self.log2[1]) / self.num_pixels
+
+    # ---- algorithmic bytes per launch ---------------------------------------
+    def algorithmic_bytes(self):
+        B, R, M, S, k, P = self.B, self.R, self.M, self.h * self.w, self.k, self.P
+        n_slice = B * (M if self.fused_slices else self.Cs) * S
+        nz = self.z.numel()
+        t = self.train
+        return {
+            "gc_fwd": n_slice * (20 + (4 if t else 0)),     # read y,mu,scale(+noise) write lik,y_hat
+            "lrp_add_fwd": n_slice * 12,
+            "gc_bwd": n_slice * (20 + 4 + 12),              # read y,mu,scale,noise,lik,g_yhat write 3 grads
+            "lrp_add_bwd": n_slice * 12,
+            "eb_fwd": nz * (12 + (4 if t else 0)),
+            "eb_bwd": nz * (16 + 4),
+            "gather_blend_fwd": B * R * (k * M * S * 4 + P * k * 8 + M * S * 4),
+            "clm_fuse_fwd": B * ((R * (M + 1) + M) * S * 4 + M * S * 4),
+            "match_flops": 2.0 * P * (self.h - self.patch + 1) * (self.w - self.patch + 1) * M * self.patch ** 2 * B * R,
+        }

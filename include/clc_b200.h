@@ -47,6 +47,8 @@ CLC_API int clc_version(void);                 /* ABI version, currently 1 */
 CLC_API const char* clc_strerror(int status);  /* static string */
 /* Text of the last CUDA error seen by the calling thread (empty if none). */
 CLC_API const char* clc_last_cuda_error(void);
+/* Number of CUDA kernels this library has enqueued in the calling process (statistics). */
+CLC_API uint64_t clc_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Entropy stage
@@ -231,13 +233,19 @@ CLC_API int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const
  * ---------------------------------------------------------------------------------- */
 
 /* Replaces: SimpleCLM.forward CLM.py:170-182 (sigmoid gate, softmax over refs, weighted sum, +y).
- *   ref_t [R, B, C, S], att [R, B, 1, S], y [B, C, S] -> out [B, C, S]
+ *   ref_t : R x B planes of [C, S]; plane (r, b) starts at ref_t + r*ref_sr + b*ref_sb
+ *   att   : R x B planes of [S];    plane (r, b) starts at att   + r*att_sr + b*att_sb
+ *   (strides in elements: [R,B,C,S] stacking has ref_sr = B*C*S, ref_sb = C*S; the [B,R,C,S]
+ *    layout produced by the match stage has ref_sr = C*S, ref_sb = R*C*S -- no transpose copy)
+ *   y [B, C, S] -> out [B, C, S]
  *   out = sum_r softmax_r(att) * ref_t[r] * sigmoid(att[r]) + y */
-CLC_API int clc_clm_fuse_fwd(const float* ref_t, const float* att, const float* y, float* out,
-                     int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
-/* g_ref_t [R,B,C,S], g_att [R,B,1,S]; g_y = g_out (no kernel). */
-CLC_API int clc_clm_fuse_bwd(const float* ref_t, const float* att, const float* g_out, float* g_ref_t,
-                     float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
+CLC_API int clc_clm_fuse_fwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb, const float* att,
+                             int64_t att_sr, int64_t att_sb, const float* y, float* out,
+                             int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
+/* g_ref_t / g_att are written with the same strides as ref_t / att; g_y = g_out (no kernel). */
+CLC_API int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb, const float* att,
+                             int64_t att_sr, int64_t att_sb, const float* g_out, float* g_ref_t,
+                             float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,73 @@
+"""GPU parity of the whole isolated latent path (the thing bench.py times) against the CPU
+oracle port: match indices and quantised symbols bit-exact, likelihoods 1e-4 rel, bpp 1e-3,
+gradients to fp32 round-off.  Both match modes, per-slice and fused-slice launches, CUDA graph."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(B, H, W, R, mode, train=True, fused=False, graph=False, k=4):
+    from clc_b200.latent_path import LatentPath
+    from oracle import latent_path_oracle as LO
+    lp = LatentPath(B, H, W, n_refs=R, train=train, match_mode=mode, fused_slices=fused, k=k, device="cuda:0")
+    lp.randomize(seed=3)
+    # make the EB parameters non-trivial
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    for t in lp.eb_f + lp.eb_b:
+        t.add_(0.1 * torch.randn(t.shape, generator=g, device="cuda:0"))
+    inp = {n: t.detach().cpu().clone() for n, t in lp.inputs().items()}
+    state = {f"_matrix{i}": lp.eb_m[i].cpu() for i in range(5)}
+    state.update({f"_bias{i}": lp.eb_b[i].cpu() for i in range(5)})
+    state.update({f"_factor{i}": lp.eb_f[i].cpu() for i in range(4)})
+    state["quantiles"] = lp.quantiles.cpu()
+    if graph:
+        lp.capture()
+        lp.replay()
+        lp.replay()  # accumulators are re-zeroed inside the graph -> replays are idempotent
+    else:
+        lp.step()
+    torch.cuda.synchronize()
+    ref = LO.step(inp, LO.make_eb(state), train=train, k=k)
+    return lp, ref
+
+
+def _relmax(a, b):
+    a, b = a.double().cpu(), b.double()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, H=256, W=256, R=3, mode="fp32"),
+    dict(B=2, H=256, W=256, R=3, mode="tc"),
+    dict(B=1, H=512, W=768, R=2, mode="tc"),
+    dict(B=2, H=256, W=256, R=1, mode="tc", fused=True),
+    dict(B=2, H=256, W=256, R=3, mode="tc", graph=True),
+    dict(B=1, H=256, W=320, R=5, mode="fp32", train=False),
+])
+def test_latent_path_vs_oracle(cfg):
+    lp, ref = _run(**cfg)
+    R = cfg["R"]
+    assert torch.equal(lp.idx.view(lp.B, R, lp.P, lp.k).cpu().long(), ref["idx"]), "match indices must be bit-exact"
+    assert torch.allclose(lp.val.view(lp.B, R, lp.P, lp.k).cpu(), ref["val"], atol=3e-6)
+    assert torch.allclose(lp.aligned.cpu(), ref["aligned"], atol=3e-5)
+    assert torch.allclose(lp.fused.cpu(), ref["fused"], atol=5e-5)
+    # symbols: y_hat before the LRP add is round(y-mu)+mu; after it both sides add 0.5*tanh(lrp)
+    assert torch.allclose(lp.y_hat.cpu(), ref["y_hat"], rtol=3e-7, atol=3e-7)
+    assert torch.equal(lp.z_hat.cpu(), ref["z_hat"])
+    for a, b in ((lp.lik_y, ref["lik_y"]), (lp.lik_z, ref["lik_z"])):
+        big = b > 1e-9
+        assert ((a.cpu().double() - b.double()).abs() / b.double())[big].max().item() < 1e-4
+    assert abs(lp.bpp().item() - ref["bpp"].item()) < 1e-3
+    if cfg.get("train", True):
+        total_g_y = lp.g_y + lp.g_q + lp.g_fused            # entropy + match-query + CLM residual paths
+        assert _relmax(total_g_y, ref["g_y"]) < 2e-3
+        assert _relmax(lp.g_mu, ref["g_mu"]) < 2e-4
+        assert _relmax(lp.g_scale, ref["g_scale"]) < 2e-4
+        assert _relmax(lp.g_lrp, ref["g_lrp"]) < 1e-5
+        assert _relmax(lp.g_z, ref["g_z"]) < 2e-4
+        assert _relmax(lp.g_refs, ref["g_refs"]) < 2e-3
+        assert _relmax(lp.g_att, ref["g_att"]) < 2e-4
+        names = [f"_matrix{i}" for i in range(5)] + [f"_bias{i}" for i in range(5)] + [f"_factor{i}" for i in range(4)]
+        for n, gt in zip(names, lp.g_eb):
+            assert _relmax(gt, ref["g_eb"][n]) < 5e-4, n
