@@ -1,13 +1,919 @@
-// tcgen05 screening path of the match stage (placeholder until the kernel lands).
+// Reference matching, tensor-core path: the correlation GEMM of L2_or_pearson_corr
+// (models/Patch_Matching.py:854-910, the F.conv2d at :869-870) on tcgen05 tensor cores fed by
+// TMA, with the Pearson normalisation (:880-905), the Gaussian mask (:182-183, :779-807) and a
+// per-patch candidate top-KC selection fused into the TMEM epilogue -- the P x L correlation
+// map is never written.  The KC candidates per patch are then re-scored in fp32 on CUDA cores
+// and the final top-k (torch.topk, :224) is taken from the exact values.
+//
+// GEMM formulation (no im2col):
+//   xy[patch, pos] = sum_{dy,dx} sum_c q[c, ph*py+dy, pw*px+dx] * r[c, pos + dy*W + dx]
+// with `pos` the LINEAR pixel index oy*W+ox of the window origin.  For every shift (dy,dx) this
+// is a plain [P x C] . [C x HW] product whose right operand is the channels-last reference
+// latent shifted by dy*W+dx ROWS, so all ph*pw shifts of one 64-channel chunk read the same
+// shared-memory buffer: the MMA's B descriptor simply starts dy*W+dx rows further down.  The
+// reference-side tile is therefore fetched once per chunk instead of once per shift
+// (16x less L2->smem traffic than an im2col formulation).  Window origins that wrap around the
+// image edge are computed and discarded in the epilogue.
+//
+//   M side (TMEM lanes)   : 128 query patches        A = packed patches  [shift][patch][C] bf16, K-major, SW128
+//   N side (TMEM columns) : TN x NACC linear positions B = channels-last ref [pos][C] bf16, K-major, SW128
+//   K                     : C per shift, 64-channel chunks (one 128 B swizzle row), UMMA K = 16
+//
+// Warp roles (192 threads, persistent over tiles):  warp 0 = TMA producer (+TMEM alloc),
+// warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (one TMEM lane quarter each).
 #include "match.cuh"
 
-extern "C" size_t clc_match_topk_tc_workspace_bytes(int64_t, int32_t, int32_t, int32_t, int32_t, int32_t,
-                                                    int32_t, int32_t) {
-  return 0;
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+namespace clc {
+namespace tc {
+
+constexpr int kChunk = 64;        // channels per K chunk = one 128-byte swizzle row of bf16
+constexpr int kTileM = 128;       // patches per tile (UMMA M)
+constexpr int kBoxRowsB = 32;     // rows per TMA box of the reference operand (4 KB)
+constexpr int kABytes = kTileM * kChunk * 2;   // 16 KB per A stage
+constexpr int kBoxBytesB = kBoxRowsB * kChunk * 2;
+constexpr int kThreads = 192;
+constexpr int kMaxKC = 16;
+constexpr int kSmemLimit = 227 * 1024;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 operands, fp32 accumulate, one CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 4 epilogue warps
+  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
-extern "C" int clc_match_topk_tc(const float*, const float*, int64_t, int32_t, int32_t, int32_t, int32_t,
-                                 int32_t, int32_t, int32_t, int32_t, float*, int32_t*, int32_t*, void*, size_t,
-                                 void*) {
-  return CLC_ERR_UNSUPPORTED;
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B:
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for one swizzle row of K) |
+//   [32,46) SBO >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel parameters
+// ------------------------------------------------------------------------------------------
+struct Params {
+  int NP, q_repeat, C, H, W, ph, pw, P, npx, S, HW;
+  int TN, NACC, n_tiles, m_tiles, total_tiles, chunks;
+  int nboxB, a_stages, b_bufs, acc_stages, tmem_cols;
+  int KC, gaussian;
+  const float *s1, *s2, *xs, *sxx;
+  float* cand_val;
+  int32_t* cand_idx;
+  float* dump;  // debug: raw xy accumulators [NP, P, HW] (NULL in production)
+};
+
+struct ColStat {  // per accumulator column (= window origin), shared by the 128 patch lanes
+  float ym;    // window mean                                   (Patch_Matching.py:872-874)
+  float rdY;   // 1/sqrt(denominator_y); NaN marks a wrapped / out-of-range origin
+  float wv;    // mask column coordinate                        (:799-803)
+  float hv;    // mask row coordinate
+};
+
+// ------------------------------------------------------------------------------------------
+// Sorted insertion into the per-thread candidate list (descending, ties keep the earlier position).
+// ------------------------------------------------------------------------------------------
+template <int KC>
+__device__ __forceinline__ void cand_insert(float (&cv)[KC], int (&ci)[KC], float s, int pos) {
+  cv[KC - 1] = s;
+  ci[KC - 1] = pos;
+#pragma unroll
+  for (int j = KC - 1; j > 0; --j) {
+    if (cv[j] > cv[j - 1]) {
+      const float tv = cv[j]; cv[j] = cv[j - 1]; cv[j - 1] = tv;
+      const int ti = ci[j]; ci[j] = ci[j - 1]; ci[j - 1] = ti;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The GEMM + fused Pearson / mask / candidate-selection kernel.
+// ------------------------------------------------------------------------------------------
+template <int KC, bool MASK>
+__global__ void __launch_bounds__(kThreads, 1)
+match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                  const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SW128 tiles need 1024-byte alignment
+  const uint32_t bBytes = (uint32_t)p.nboxB * kBoxBytesB;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + (uint32_t)p.a_stages * kABytes;
+  const uint32_t sCol = sB + (uint32_t)p.b_bufs * bBytes;
+  const int TNT = p.TN * p.NACC;
+  const uint32_t sBar = sCol + (uint32_t)TNT * (uint32_t)sizeof(ColStat);
+  // barrier map (8 bytes each): A_full[a_stages] A_empty[a_stages] B_full[2] B_empty[2] acc_full[2] acc_empty[2]
+  const uint32_t barAfull = sBar;
+  const uint32_t barAempty = barAfull + 8u * p.a_stages;
+  const uint32_t barBfull = barAempty + 8u * p.a_stages;
+  const uint32_t barBempty = barBfull + 16u;
+  const uint32_t barAccFull = barBempty + 16u;
+  const uint32_t barAccEmpty = barAccFull + 16u;
+  const uint32_t sTmemPtr = barAccEmpty + 16u;
+  ColStat* colstat = reinterpret_cast<ColStat*>(smem_raw + (sCol - raw));
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + (sTmemPtr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmapA);
+      tma_prefetch_desc(&tmapB);
+    }
+    tmem_alloc(sTmemPtr, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(barAfull + 8u * i, 1);
+      mbar_init(barAempty + 8u * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(barBfull + 8u * i, 1);
+      mbar_init(barBempty + 8u * i, 1);
+      mbar_init(barAccFull + 8u * i, 1);
+      mbar_init(barAccEmpty + 8u * i, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int acc_cols = TNT;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    uint32_t acount = 0, bcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int n = tile / (p.n_tiles * p.m_tiles);
+      const int nq = n / p.q_repeat;
+      const int row0 = n * p.HW + nt * TNT;
+      for (int c = 0; c < p.chunks; ++c) {
+        const uint32_t bb = bcount % (uint32_t)p.b_bufs;
+        const uint32_t bph = (bcount / (uint32_t)p.b_bufs) & 1u;
+        mbar_wait(barBempty + 8u * bb, bph ^ 1u);
+        if (lane == 0) {
+          mbar_expect_tx(barBfull + 8u * bb, bBytes);
+          for (int i = 0; i < p.nboxB; ++i)
+            tma_load_2d(sB + bb * bBytes + (uint32_t)i * kBoxBytesB, &tmapB, barBfull + 8u * bb, c * kChunk,
+                        row0 + i * kBoxRowsB);
+        }
+        ++bcount;
+        for (int s = 0; s < p.S; ++s) {
+          const uint32_t st = acount % (uint32_t)p.a_stages;
+          const uint32_t aph = (acount / (uint32_t)p.a_stages) & 1u;
+          mbar_wait(barAempty + 8u * st, aph ^ 1u);
+          if (lane == 0) {
+            mbar_expect_tx(barAfull + 8u * st, kABytes);
+            tma_load_3d(sA + st * kABytes, &tmapA, barAfull + 8u * st, c * kChunk, mt * kTileM, nq * p.S + s);
+          }
+          ++acount;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    const uint32_t idesc = make_idesc(kTileM, p.TN);
+    uint32_t acount = 0, bcount = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t as = tcount % (uint32_t)p.acc_stages;
+      const uint32_t accph = (tcount / (uint32_t)p.acc_stages) & 1u;
+      mbar_wait(barAccEmpty + 8u * as, accph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + as * (uint32_t)acc_cols;
+      for (int c = 0; c < p.chunks; ++c) {
+        const uint32_t bb = bcount % (uint32_t)p.b_bufs;
+        const uint32_t bph = (bcount / (uint32_t)p.b_bufs) & 1u;
+        mbar_wait(barBfull + 8u * bb, bph);
+        ++bcount;
+        const uint64_t bdesc0 = make_desc_sw128(sB + bb * bBytes);
+        for (int s = 0; s < p.S; ++s) {
+          const uint32_t st = acount % (uint32_t)p.a_stages;
+          const uint32_t aph = (acount / (uint32_t)p.a_stages) & 1u;
+          mbar_wait(barAfull + 8u * st, aph);
+          ++acount;
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t adesc0 = make_desc_sw128(sA + st * kABytes);
+            const int dy = s / p.pw, dx = s - dy * p.pw;
+            const int shift_rows = dy * p.W + dx;  // the window shift is a ROW offset into the B buffer
+            for (int j = 0; j < p.NACC; ++j) {
+              const uint64_t bdesc = bdesc0 + (uint64_t)((j * p.TN + shift_rows) * 8);  // 128 B/row = 8 x 16 B
+#pragma unroll
+              for (int k = 0; k < kChunk / 16; ++k) {
+                umma_bf16(d_base + (uint32_t)(j * p.TN), adesc0 + 2u * k, bdesc + 2u * k, idesc,
+                          (c | s | k) ? 1u : 0u);
+              }
+            }
+            umma_commit(barAempty + 8u * st);  // frees the A stage once these MMAs have read it
+          }
+          __syncwarp();
+        }
+        if (lane == 0) umma_commit(barBempty + 8u * bb);
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(barAccFull + 8u * as);
+      __syncwarp();
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;               // accumulator row = patch within the tile
+    const int et = threadIdx.x - 64;             // 0..127 among the epilogue threads
+    const int cw = p.W - p.pw + 1;
+    const int K = p.C * p.S;
+    const float Kf = (float)K, inv_k = 1.0f / Kf;
+    const float kh = -4.0f / (0.25f * (float)p.H * (float)p.H);  // exp(-4ln2*x) = 2^(-4x), sigma = size/2
+    const float kw = -4.0f / (0.25f * (float)p.W * (float)p.W);
+    const int r0 = (p.ph + 1) / 2 - 1, c0 = (p.pw + 1) / 2 - 1;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int n = tile / (p.n_tiles * p.m_tiles);
+      const int nq = n / p.q_repeat;
+      const int pos0 = nt * TNT;
+      // ---- per-column statistics (while the MMAs of this tile run) ----
+      const float* s1n = p.s1 + (int64_t)n * p.HW;
+      const float* s2n = p.s2 + (int64_t)n * p.HW;
+      for (int col = et; col < TNT; col += 128) {
+        const int pos = pos0 + col;
+        const int oy = pos / p.W, ox = pos - oy * p.W;
+        ColStat cs;
+        cs.ym = 0.f;
+        cs.rdY = __int_as_float(0x7fc00000);
+        cs.wv = (float)(ox + c0 + 1) - 0.5f * (float)(p.pw & 1);
+        cs.hv = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
+        if (oy <= p.H - p.ph && ox <= p.W - p.pw) {
+          float b1 = 0.f, b2 = 0.f;
+          for (int dy = 0; dy < p.ph; ++dy)
+            for (int dx = 0; dx < p.pw; ++dx) {
+              b1 += s1n[(oy + dy) * p.W + ox + dx];
+              b2 += s2n[(oy + dy) * p.W + ox + dx];
+            }
+          const PosStat ps = pos_stat(b1, b2, inv_k, Kf);
+          cs.ym = ps.ym;
+          cs.rdY = rsqrtf(ps.dY);
+        }
+        colstat[col] = cs;
+      }
+      // ---- per-patch constants ----
+      const int patch = mt * kTileM + row;
+      const bool live = patch < p.P;
+      float xs = 0.f, rdX = 0.f, ch = 0.f, cwc = 0.f;
+      if (live) {
+        const int64_t qi = (int64_t)nq * p.P + patch;
+        xs = p.xs[qi];
+        const float sxx = p.sxx[qi];
+        const float xm = xs / Kf;
+        rdX = rsqrtf(sxx - xm * xs);
+        const int py = patch / p.npx, px = patch - py * p.npx;
+        ch = ((float)py + 0.5f) * (float)p.ph;
+        cwc = ((float)px + 0.5f) * (float)p.pw;
+      }
+      float cv[KC];
+      int ci[KC];
+#pragma unroll
+      for (int j = 0; j < KC; ++j) { cv[j] = -INFINITY; ci[j] = -1; }
+      epi_bar_sync();  // colstat visible to the 4 epilogue warps
+
+      const uint32_t as = tcount % (uint32_t)p.acc_stages;
+      const uint32_t accph = (tcount / (uint32_t)p.acc_stages) & 1u;
+      mbar_wait(barAccFull + 8u * as, accph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)acc_cols;
+      for (int col0 = 0; col0 < TNT; col0 += 32) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)col0, v);
+        tmem_ld_wait();
+        if (p.dump != nullptr) {
+          if (live) {
+            float* dst = p.dump + ((int64_t)n * p.P + patch) * p.HW + pos0 + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (pos0 + col0 + j < p.HW) dst[j] = v[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 cs = *reinterpret_cast<const float4*>(&colstat[col0 + j]);  // {ym, rdY, wv, hv}
+          float s = fmaf(-cs.x, xs, v[j]) * cs.y;  // (xy - y_mean*x_sum) / sqrt(denominator_y); NaN if wrapped
+          if (MASK) {
+            const float dw = cs.z - cwc, dh = cs.w - ch;
+            s *= exp2f(fmaf(dh * dh, kh, dw * dw * kw));
+          }
+          if (s > cv[KC - 1]) cand_insert<KC>(cv, ci, s, pos0 + col0 + j);
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barAccEmpty + 8u * as);
+      if (live) {
+        const int64_t o = (((int64_t)n * p.P + patch) * p.n_tiles + nt) * KC;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+          int id = -1;
+          if (ci[j] >= 0) {
+            const int oy = ci[j] / p.W, ox = ci[j] - oy * p.W;
+            id = oy * cw + ox;
+          }
+          p.cand_val[o + j] = cv[j] * rdX;
+          p.cand_idx[o + j] = id;
+        }
+      }
+      epi_bar_sync();  // colstat may be overwritten for the next tile
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pre-pass 1: reference latents [NP, C, HW] fp32 -> channels-last bf16 [NP*HW, C], plus the
+// per-pixel channel sums S1 = sum_c r, S2 = sum_c r^2 (fp32, fixed combination order).
+// grid = (ceil(HW/32), NP), block = 256 (8 warps x 32 pixels); smem tile [C][33] fp32.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, float* __restrict__ s1,
+                float* __restrict__ s2, int C, int HW) {
+  extern __shared__ float tile[];  // [C][33] then 2 x [8][32] partial sums
+  float* part = tile + (size_t)C * 33;
+  const int n = blockIdx.y, px0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int px = px0 + lane;
+  const float* rn = r + (int64_t)n * C * HW;
+  float a = 0.f, b = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    const float v = (px < HW) ? rn[(int64_t)c * HW + px] : 0.f;
+    tile[c * 33 + lane] = v;
+    a += v;
+    b = fmaf(v, v, b);
+  }
+  part[warp * 32 + lane] = a;
+  part[256 + warp * 32 + lane] = b;
+  __syncthreads();
+  if (warp == 0 && px < HW) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ta += part[w * 32 + lane]; tb += part[256 + w * 32 + lane]; }
+    s1[(int64_t)n * HW + px] = ta;
+    s2[(int64_t)n * HW + px] = tb;
+  }
+  // transposed write: item = (pixel, group of 8 channels) -> one 16-byte store
+  const int groups = C / 8;
+  for (int it = threadIdx.x; it < 32 * groups; it += 256) {
+    const int pl = it / groups, g = it - pl * groups;
+    if (px0 + pl >= HW) continue;
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[(g * 8 + i) * 33 + pl]);
+    *reinterpret_cast<uint4*>(rT + ((int64_t)n * HW + px0 + pl) * C + g * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pre-pass 2: query latents [NQ, C, H, W] fp32 -> packed patches bf16 [NQ, S, P_pad, C]
+// (shift-major, then patch, channels contiguous).  grid = (npy, C/64, NQ), block = 256.
+// Rows P..P_pad-1 are zero-filled by the blocks of the last patch row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_query_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ A, int C, int H, int W, int ph,
+                  int pw, int P, int P_pad) {
+  extern __shared__ float tile[];  // [64][ph][W + 1]
+  const int py = blockIdx.x, c0 = blockIdx.y * 64, nq = blockIdx.z;
+  const int npx = W / pw, S = ph * pw;
+  const int Wp = W + 1;
+  const float* qn = q + ((int64_t)nq * C + c0) * H * W + (int64_t)py * ph * W;
+  for (int it = threadIdx.x; it < 64 * ph * W; it += 256) {
+    const int x = it % W, dy = (it / W) % ph, c = it / (W * ph);
+    tile[(c * ph + dy) * Wp + x] = qn[(int64_t)c * H * W + dy * W + x];
+  }
+  __syncthreads();
+  __nv_bfloat16* An = A + (int64_t)nq * S * P_pad * C;
+  for (int it = threadIdx.x; it < S * npx * 8; it += 256) {
+    const int g = it & 7, px = (it >> 3) % npx, s = it / (8 * npx);
+    const int dy = s / pw, dx = s - dy * pw;
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[((g * 8 + i) * ph + dy) * Wp + px * pw + dx]);
+    *reinterpret_cast<uint4*>(An + ((int64_t)s * P_pad + py * npx + px) * C + c0 + g * 8) =
+        *reinterpret_cast<const uint4*>(o);
+  }
+  if (py == gridDim.x - 1) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int it = threadIdx.x; it < S * (P_pad - P) * 8; it += 256) {
+      const int g = it & 7, pr = (it >> 3) % (P_pad - P), s = it / (8 * (P_pad - P));
+      *reinterpret_cast<uint4*>(An + ((int64_t)s * P_pad + P + pr) * C + c0 + g * 8) = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Candidate merge + exact fp32 re-scoring + final top-k.  One CTA per (problem, patch),
+// KC warps: warp 0 merges the per-tile candidate lists (top-KC by screened score), then warp c
+// re-scores candidate c with fp32 FMAs over the C*ph*pw patch elements (lane-strided partial
+// sums, xor-tree combine), the masked Pearson value is formed exactly as in the fp32 path
+// (match.cuh) and warp 0 takes the top-k by (value desc, index asc).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ranks_before(float av, int ai, float bv, int bi) {
+  if (av != bv) return av > bv;
+  return ai < bi;
+}
+
+__global__ void __launch_bounds__(512)
+rescore_kernel(const float* __restrict__ q_img, const float* __restrict__ r, const float* __restrict__ s1,
+               const float* __restrict__ s2, const float* __restrict__ xs_a, const float* __restrict__ sxx_a,
+               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int n_tiles, int KC,
+               int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian,
+               float* __restrict__ val, int32_t* __restrict__ idx, int32_t* __restrict__ n_uncertified) {
+  extern __shared__ float sm[];  // cand values [M], cand idx [M]
+  __shared__ float sel_v[kMaxKC], ex_v[kMaxKC];
+  __shared__ int sel_i[kMaxKC];
+  const int M = n_tiles * KC;
+  float* cvs = sm;
+  int* cis = reinterpret_cast<int*>(sm + M);
+  const int n = blockIdx.x / P, patch = blockIdx.x - n * P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t co = ((int64_t)n * P + patch) * M;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    cvs[i] = cand_val[co + i];
+    cis[i] = cand_idx[co + i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // KC rounds of warp arg-max over the merged list
+    for (int t = 0; t < KC; ++t) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff, bslot = -1;
+      for (int i = lane; i < M; i += 32) {
+        const int id = cis[i];
+        if (id < 0) continue;
+        const float v = cvs[i];
+        if (bslot < 0 || ranks_before(v, id, bv, bi)) { bv = v; bi = id; bslot = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+        if (os >= 0 && (bslot < 0 || ranks_before(ov, oi, bv, bi))) { bv = ov; bi = oi; bslot = os; }
+      }
+      if (lane == 0) {
+        sel_v[t] = bslot >= 0 ? bv : -INFINITY;
+        sel_i[t] = bslot >= 0 ? bi : -1;
+        if (bslot >= 0) cis[bslot] = -1;  // taken
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- exact re-scoring: warp c <-> candidate c ----
+  const int cw = W - pw + 1, L = (H - ph + 1) * cw;
+  const int pp = ph * pw, K = C * pp;
+  const int64_t HW = (int64_t)H * W;
+  const int nq = n / q_repeat;
+  const int npx = W / pw;
+  const int py = patch / npx, px = patch - py * npx;
+  if (warp < KC) {
+    const int id = sel_i[warp];
+    float out = -INFINITY;
+    if (id >= 0) {
+      const int oy = id / cw, ox = id - oy * cw;
+      const float* qb = q_img + (int64_t)nq * C * HW + (int64_t)(py * ph) * W + px * pw;
+      const float* rb = r + (int64_t)n * C * HW + (int64_t)oy * W + ox;
+      float acc = 0.f;
+      for (int e = lane; e < K; e += 32) {
+        const int c = e / pp, rem = e - c * pp;
+        const int dy = rem / pw, dx = rem - dy * pw;
+        const int64_t o = (int64_t)c * HW + dy * W + dx;
+        acc = fmaf(qb[o], rb[o], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float Kf = (float)K;
+        const float* s1n = s1 + (int64_t)n * HW;
+        const float* s2n = s2 + (int64_t)n * HW;
+        float b1 = 0.f, b2 = 0.f;
+        for (int dy = 0; dy < ph; ++dy)
+          for (int dx = 0; dx < pw; ++dx) {
+            b1 += s1n[(oy + dy) * W + ox + dx];
+            b2 += s2n[(oy + dy) * W + ox + dx];
+          }
+        const PosStat ps = pos_stat(b1, b2, 1.0f / Kf, Kf);
+        const int64_t qi = (int64_t)nq * P + patch;
+        out = pearson(acc, ps, xs_a[qi], sxx_a[qi], Kf);
+        if (gaussian) {
+          // create_gaussian_masks (:779-807): float64, rounded to fp32
+          const double center_h = ((double)py + 0.5) * ph, center_w = ((double)px + 0.5) * pw;
+          const double hv = (double)(oy + (ph + 1) / 2) - (double)(ph % 2) / 2.0;
+          const double wv = (double)(ox + (pw + 1) / 2) - (double)(pw % 2) / 2.0;
+          const double sh = 0.5 * H, sw = 0.5 * W;
+          const double rg = ((hv - center_h) * (hv - center_h)) / (sh * sh);
+          const double cg = ((wv - center_w) * (wv - center_w)) / (sw * sw);
+          out *= (float)exp(-4.0 * 0.693147180559945309417232121458 * (rg + cg));
+        }
+      }
+    }
+    if (lane == 0) ex_v[warp] = out;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // final top-k among the KC exact values, (value desc, index asc); NaN ranks first like torch.topk
+    float myv = (lane < KC) ? ex_v[lane] : -INFINITY;
+    int myi = (lane < KC) ? sel_i[lane] : -1;
+    bool taken = myi < 0;
+    float vk = -INFINITY;
+    for (int t = 0; t < k; ++t) {
+      float bv = myv;
+      int bi = taken ? -1 : myi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        bool better = false;
+        if (oi >= 0) {
+          if (bi < 0) better = true;
+          else {
+            const bool on = ov != ov, bn = bv != bv;
+            if (on != bn) better = on;
+            else if (!on && ov != bv) better = ov > bv;
+            else better = oi < bi;
+          }
+        }
+        if (better) { bv = ov; bi = oi; }
+      }
+      if (!taken && bi == myi) taken = true;
+      if (lane == 0) {
+        val[((int64_t)n * P + patch) * k + t] = bv;
+        idx[((int64_t)n * P + patch) * k + t] = bi;
+      }
+      vk = bv;
+    }
+    if (lane == 0 && n_uncertified != nullptr && L > KC) {
+      // any window outside the candidate set has a screened score <= sel_v[KC-1]; the set provably
+      // holds the exact top-k unless a screening error exceeds the margin to the k-th exact value.
+      const float eps = 0.03125f * sqrtf(2.0f / (float)K);  // 16 x the bf16 screening error model
+      if (!(vk - sel_v[KC - 1] > eps)) atomicAdd(n_uncertified, 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct Plan {
+  int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks;
+  int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid;
+  size_t smem_bytes;
+  // workspace offsets (bytes)
+  size_t off_rT, off_A, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, total;
+  bool ok;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int pw, int k) {
+  Plan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.ok = false;
+  if (NP < 1 || q_repeat < 1 || NP % q_repeat) return pl;
+  if (C < kChunk || C % kChunk) return pl;
+  if (ph < 1 || pw < 1 || ph * pw > 64 || H < ph || W < pw || H % ph || W % pw) return pl;
+  if (k < 1 || k > 8) return pl;
+  pl.KC = (k <= 4) ? 8 : 16;
+  pl.S = ph * pw;
+  pl.HW = H * W;
+  pl.npx = W / pw;
+  pl.P = (H / ph) * (W / pw);
+  pl.P_pad = (pl.P + kTileM - 1) / kTileM * kTileM;
+  pl.m_tiles = pl.P_pad / kTileM;
+  pl.chunks = C / kChunk;
+  const int halo = (ph - 1) * W + pw - 1;
+  const int span = (H - ph + 1) * W;  // linear origins 0 .. span-1 cover every valid window
+  // tile shape: minimise waves x (tile width + fixed per-tile cost), prefer wider tiles on ties
+  static const int cand[5][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
+  double best = 1e300;
+  for (int i = 0; i < 5; ++i) {
+    const int TN = cand[i][0], NACC = cand[i][1], TNT = TN * NACC;
+    const int n_tiles = (span + TNT - 1) / TNT;
+    const int64_t tiles = NP * pl.m_tiles * (int64_t)n_tiles;
+    const int rowsB = TNT + halo;
+    const int nboxB = (rowsB + kBoxRowsB - 1) / kBoxRowsB;
+    const size_t bB = (size_t)nboxB * kBoxBytesB;
+    const size_t misc = (size_t)TNT * sizeof(ColStat) + 256 + 1024;
+    const size_t lim = (size_t)kSmemLimit;
+    int b_bufs = 2, a_stages = 0;
+    if (lim >= misc + 2 * bB) a_stages = (int)((lim - misc - 2 * bB) / kABytes);
+    if (a_stages < 3) {
+      b_bufs = 1;
+      if (lim < misc + bB) continue;
+      a_stages = (int)((lim - misc - bB) / kABytes);
+      if (a_stages < 2) continue;
+    }
+    if (a_stages > 8) a_stages = 8;
+    const int64_t waves = (tiles + kNumSMs - 1) / kNumSMs;
+    const double cost = (double)waves * (TNT + 48);
+    if (cost < best) {
+      best = cost;
+      pl.TN = TN; pl.NACC = NACC; pl.n_tiles = n_tiles; pl.total_tiles = (int)tiles;
+      pl.rowsB = rowsB; pl.nboxB = nboxB; pl.a_stages = a_stages; pl.b_bufs = b_bufs;
+      pl.acc_stages = (TNT <= 256) ? 2 : 1;
+      int cols = pl.acc_stages * TNT, t = 32;
+      while (t < cols) t <<= 1;
+      pl.tmem_cols = t;
+      pl.smem_bytes = (size_t)a_stages * kABytes + (size_t)b_bufs * bB + misc;
+      pl.ok = tiles <= 0x7fffffff;
+    }
+  }
+  if (!pl.ok) return pl;
+  pl.grid = pl.total_tiles < kNumSMs ? pl.total_tiles : kNumSMs;
+  const int64_t NQ = NP / q_repeat;
+  size_t o = 0;
+  pl.off_rT = o;  o = align_up(o + (size_t)NP * pl.HW * C * 2, 256);
+  pl.off_A = o;   o = align_up(o + (size_t)NQ * pl.S * pl.P_pad * C * 2, 256);
+  pl.off_s1 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
+  pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
+  pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * 4, 256);
+  pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * 4, 256);
+  pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_tiles * pl.KC * 4, 256);
+  pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_tiles * pl.KC * 4, 256);
+  pl.total = o + 256;  // slack for aligning the caller's pointer
+  return pl;
+}
+
+template <int KC, bool MASK>
+static int launch_gemm(const Plan& pl, const CUtensorMap& ta, const CUtensorMap& tb, const Params& prm,
+                       cudaStream_t st) {
+  auto kern = match_gemm_kernel<KC, MASK>;
+  CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  kern<<<pl.grid, kThreads, pl.smem_bytes, st>>>(ta, tb, prm);
+  CLC_CHECK_LAUNCH("clc_match_topk_tc(gemm)");
+  return CLC_OK;
+}
+
+static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int C, int H, int W, int ph,
+               int pw, int k, int gaussian, float* val, int32_t* idx, int32_t* n_uncertified, float* dump,
+               void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const Plan pl = make_plan(NP, q_repeat, C, H, W, ph, pw, k);
+  if (!pl.ok) return CLC_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < pl.total) return CLC_ERR_WORKSPACE;
+  int dev = 0, major = 0;
+  CLC_CUDA(cudaGetDevice(&dev));
+  CLC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return CLC_ERR_ARCH;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return cuda_fail(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point");
+
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  __nv_bfloat16* rT = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_rT);
+  __nv_bfloat16* Apk = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_A);
+  float* s1 = reinterpret_cast<float*>(ws + pl.off_s1);
+  float* s2 = reinterpret_cast<float*>(ws + pl.off_s2);
+  float* xs = reinterpret_cast<float*>(ws + pl.off_xs);
+  float* sxx = reinterpret_cast<float*>(ws + pl.off_sxx);
+  float* cand_val = reinterpret_cast<float*>(ws + pl.off_cv);
+  int32_t* cand_idx = reinterpret_cast<int32_t*>(ws + pl.off_ci);
+  const int64_t NQ = NP / q_repeat;
+
+  // ---- tensor maps (host-side encode, no device work) ----
+  CUtensorMap ta, tb;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)pl.P_pad, (cuuint64_t)(NQ * pl.S)};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)pl.P_pad * C * 2};
+    const cuuint32_t box[3] = {kChunk, kTileM, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult cr = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Apk, dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A)");
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(NP * pl.HW)};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {kChunk, kBoxRowsB};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult cr = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rT, dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(B)");
+  }
+
+  // ---- pre-passes ----
+  {
+    const size_t sm = ((size_t)C * 33 + 512) * sizeof(float);
+    if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
+    if (sm > 48 * 1024)
+      CLC_CUDA(cudaFuncSetAttribute(pack_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid((pl.HW + 31) / 32, (unsigned)NP);
+    pack_ref_kernel<<<grid, 256, sm, st>>>(r, rT, s1, s2, C, pl.HW);
+    CLC_CHECK_LAUNCH("clc_match_topk_tc(pack_ref)");
+  }
+  {
+    const size_t sm = (size_t)64 * ph * (W + 1) * sizeof(float);
+    if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
+    if (sm > 48 * 1024)
+      CLC_CUDA(cudaFuncSetAttribute(pack_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid(H / ph, C / 64, (unsigned)NQ);
+    pack_query_kernel<<<grid, 256, sm, st>>>(q_img, Apk, C, H, W, ph, pw, pl.P, pl.P_pad);
+    CLC_CHECK_LAUNCH("clc_match_topk_tc(pack_query)");
+  }
+  {
+    PatchAddr qa;
+    qa.q = q_img; qa.sn = (int64_t)C * H * W; qa.spy = (int64_t)ph * W; qa.spx = pw; qa.sc = (int64_t)H * W;
+    qa.sy = W; qa.npx = pl.npx; qa.repeat = q_repeat;
+    int rc = launch_patch_stats(qa, xs, sxx, NQ, pl.P, C, ph, pw, st);
+    if (rc) return rc;
+  }
+
+  // ---- GEMM + fused epilogue ----
+  Params prm;
+  prm.NP = (int)NP; prm.q_repeat = q_repeat; prm.C = C; prm.H = H; prm.W = W; prm.ph = ph; prm.pw = pw;
+  prm.P = pl.P; prm.npx = pl.npx; prm.S = pl.S; prm.HW = pl.HW;
+  prm.TN = pl.TN; prm.NACC = pl.NACC; prm.n_tiles = pl.n_tiles; prm.m_tiles = pl.m_tiles;
+  prm.total_tiles = pl.total_tiles; prm.chunks = pl.chunks;
+  prm.nboxB = pl.nboxB; prm.a_stages = pl.a_stages; prm.b_bufs = pl.b_bufs; prm.acc_stages = pl.acc_stages;
+  prm.tmem_cols = pl.tmem_cols; prm.KC = pl.KC; prm.gaussian = gaussian;
+  prm.s1 = s1; prm.s2 = s2; prm.xs = xs; prm.sxx = sxx; prm.cand_val = cand_val; prm.cand_idx = cand_idx;
+  prm.dump = dump;
+  int rc;
+  if (pl.KC == 8) rc = gaussian ? launch_gemm<8, true>(pl, ta, tb, prm, st) : launch_gemm<8, false>(pl, ta, tb, prm, st);
+  else rc = gaussian ? launch_gemm<16, true>(pl, ta, tb, prm, st) : launch_gemm<16, false>(pl, ta, tb, prm, st);
+  if (rc) return rc;
+
+  // ---- merge + exact re-score + top-k ----
+  {
+    const int64_t blocks = NP * pl.P;
+    if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
+    const size_t sm = (size_t)pl.n_tiles * pl.KC * 8;
+    if (sm > 48 * 1024) return CLC_ERR_UNSUPPORTED;
+    rescore_kernel<<<(unsigned)blocks, pl.KC * 32, sm, st>>>(q_img, r, s1, s2, xs, sxx, cand_val, cand_idx,
+                                                             pl.n_tiles, pl.KC, q_repeat, C, H, W, ph, pw, pl.P, k,
+                                                             gaussian, val, idx, n_uncertified);
+    CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
+  }
+  return CLC_OK;
+}
+
+}  // namespace tc
+}  // namespace clc
+
+using namespace clc;
+
+extern "C" size_t clc_match_topk_tc_workspace_bytes(int64_t NP, int32_t q_repeat, int32_t C, int32_t H,
+                                                    int32_t W, int32_t ph, int32_t pw, int32_t k) {
+  const tc::Plan pl = tc::make_plan(NP, q_repeat, C, H, W, ph, pw, k);
+  return pl.ok ? pl.total : 0;
+}
+
+extern "C" int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
+                                 int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                 int32_t gaussian_mask, float* val, int32_t* idx, int32_t* n_uncertified,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q_img || !r || !val || !idx || NP < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  if (k > (H - ph + 1) * (W - pw + 1)) return CLC_ERR_INVALID_ARGUMENT;
+  return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, n_uncertified,
+                 nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Bring-up / test hook (not part of the public header): additionally dumps the raw bf16-GEMM
+// accumulators xy[NP, P, H*W] (linear window origins, wrapped ones included).
+extern "C" CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
+                                             int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                             int32_t gaussian_mask, float* val, int32_t* idx, float* xy,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q_img || !r || !val || !idx || !xy || NP < 1) return CLC_ERR_INVALID_ARGUMENT;
+  return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, nullptr, xy,
+                 workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -67,8 +67,9 @@ class _OracleEB(nn.Module):
 def to_oracle_mode(model):
     """Deep-copies `model` and replaces its hot-path ops with the oracle's.  Returns the copy."""
     m = copy.deepcopy(model)
-    m.gaussian_conditional = _OracleGC(model.gaussian_conditional)
-    m.entropy_bottleneck = _OracleEB(model.entropy_bottleneck)
+    dev = next(model.parameters()).device
+    m.gaussian_conditional = _OracleGC(model.gaussian_conditional).to(dev)
+    m.entropy_bottleneck = _OracleEB(model.entropy_bottleneck).to(dev)
     m._lrp_add = lambda y_hat, lrp: O.lrp_add(y_hat, lrp)
     if getattr(m, "match_refs", False):
         raise NotImplementedError("oracle mode covers the shipped forward (match_refs=False)")

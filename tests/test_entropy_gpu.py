@@ -258,7 +258,7 @@ def test_full_size_properties_cfg4():
     assert torch.equal(y_hat2, y_hat) and torch.equal(lik2, lik)          # idempotent
     _, lik3, y_hat3 = gc(-yc, scc, -muc, ste=True, want_outputs=False)
     assert torch.equal(lik3, lik) and torch.equal(y_hat3, -y_hat)           # exact mirror symmetry
-    assert lik.min().item() >= 1e-9 and lik.max().item() <= 1.0
+    assert lik.min().item() >= float(torch.tensor(1e-9, dtype=torch.float32)) and lik.max().item() <= 1.0
     s2 = clc_b200.ops.log2_sum(lik)
     assert abs(acc.item() - s2.item()) < 1e-6 * abs(s2.item())
     assert abs(s2.item() - torch.log2(lik.double()).sum().item()) < 1e-5 * abs(s2.item())
