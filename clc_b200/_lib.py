@@ -59,6 +59,12 @@ PROTOTYPES = {
                                        _i32, _i32, _p]),
     "clc_pearson_topk_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
                                        _i32, _i32, _i32, _i32, _p]),
+    "clc_match_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32,
+                                _i32, _i32, _i32, _p]),
+    "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                        _p, _sz, _p]),
+    "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                            _p, _sz, _p]),
     "clc_clm_fuse_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i32, _i64, _i32, _i64, _p]),
     "clc_clm_fuse_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
 }

@@ -5,10 +5,11 @@
 // the per-pixel coefficients are formed once per thread and reused over a channel group.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace clc {
 
 constexpr int kMaxRefs = 8;
-constexpr int kChanGroup = 16;  // channels handled by one thread of the forward kernel
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -26,14 +27,18 @@ __device__ __forceinline__ void clm_coef(const float* a, int R, float* coef, flo
   }
 }
 
-// grid = (ceil(S/VW/128), ceil(C/kChanGroup), B); thread = VW consecutive pixels.
+// Forward.  block = 256 threads = 8 warps; a lane owns VW consecutive pixels, a warp owns the
+// channels c0 + warp + 8*i (i < CPW) of its CTA.  grid = (ceil(S/(32*VW)), ceil(C/(8*CPW)), B).
+// The per-pixel coefficients (R exps + R sigmoids) are formed once per thread and reused over
+// its CPW channels; CPW is chosen by the host so the grid fills the 148 SMs.
 template <int VW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref_sb,
                     const float* __restrict__ att, int64_t att_sr, int64_t att_sb,
-                    const float* __restrict__ y, float* __restrict__ out, int R, int64_t B, int C,
-                    int64_t S) {
-  const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VW;
+                    const float* __restrict__ y, float* __restrict__ out, int R, int C, int64_t S,
+                    int CPW) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s0 = ((int64_t)blockIdx.x * 32 + lane) * VW;
   if (s0 >= S) return;
   const int64_t b = blockIdx.z;
   float coef[VW][kMaxRefs];
@@ -51,9 +56,10 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
 #pragma unroll
     for (int v = 0; v < VW; ++v) clm_coef(a[v], R, coef[v], nullptr, nullptr);
   }
-  const int c0 = blockIdx.y * kChanGroup;
-  const int c1 = min(C, c0 + kChanGroup);
-  for (int c = c0; c < c1; ++c) {
+  const int cbase = blockIdx.y * 8 * CPW + warp;
+  for (int i = 0; i < CPW; ++i) {
+    const int c = cbase + 8 * i;
+    if (c >= C) break;
     const int64_t o = (b * C + c) * S + s0;
     if constexpr (VW == 4) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -73,8 +79,10 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
   }
 }
 
-// Backward.  block = (32 pixel-threads, 8 channel lanes); channel lanes split C and reduce
-// G_r = sum_c g_c * ref_t[r,c] through shared memory.
+// Backward.  block = (32 pixel lanes, 8 channel lanes); a thread-block CLUSTER of CS CTAs along
+// grid.y splits the C channels, every CTA reduces its partial G_r = sum_c g_c * ref_t[r,c] over
+// its channel lanes in shared memory, and cluster rank 0 combines the CS partials through
+// distributed shared memory in fixed rank order (deterministic, no atomics, no workspace).
 //   g_ref_t[r,c] = g_c * coef_r
 //   g_att[m]     = w_m s_m G_m - w_m * sum_r G_r s_r w_r + G_m w_m s_m (1 - s_m)
 template <int VW>
@@ -82,12 +90,16 @@ __global__ void __launch_bounds__(256)
 clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref_sb,
                     const float* __restrict__ att, int64_t att_sr, int64_t att_sb,
                     const float* __restrict__ g_out, float* __restrict__ g_ref_t,
-                    float* __restrict__ g_att, int R, int64_t B, int C, int64_t S) {
+                    float* __restrict__ g_att, int R, int C, int64_t S) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float Gs[8][kMaxRefs][32 * VW + 1];
+  __shared__ float Gp[kMaxRefs][32 * VW];  // this CTA's partial, read by rank 0 through DSMEM
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t s0 = ((int64_t)blockIdx.x * 32 + tx) * VW;
   const int64_t b = blockIdx.z;
   const bool live = s0 < S;
+  const unsigned CS = cluster.dim_blocks().y, rank = cluster.block_rank();
   float coef[VW][kMaxRefs], w[VW][kMaxRefs], sg[VW][kMaxRefs];
   float G[VW][kMaxRefs];
 #pragma unroll
@@ -106,7 +118,8 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
     }
 #pragma unroll
     for (int v = 0; v < VW; ++v) clm_coef(a[v], R, coef[v], w[v], sg[v]);
-    for (int c = ty; c < C; c += 8) {
+    // channels of this CTA: c = blockIdx.y + gridDim.y * m  (interleaved), channel lane ty takes every 8th
+    for (int c = blockIdx.y + gridDim.y * ty; c < C; c += gridDim.y * 8) {
       const int64_t o = (b * C + c) * S + s0;
       if constexpr (VW == 4) {
         const float4 g = ld4_stream(g_out + o);
@@ -131,14 +144,27 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
 #pragma unroll
     for (int v = 0; v < VW; ++v) Gs[ty][r][tx * VW + v] = G[v][r];
   __syncthreads();
-  if (ty == 0 && live) {
+  if (ty == 0) {
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int v = 0; v < VW; ++v) {
+        float t = 0.f;
+        for (int l = 0; l < 8; ++l) t += Gs[l][r][tx * VW + v];
+        Gp[r][tx * VW + v] = t;
+      }
+  }
+  cluster.sync();  // partials of every CTA of the cluster are in place
+  if (rank == 0 && ty == 0 && live) {
 #pragma unroll
     for (int v = 0; v < VW; ++v) {
       float Gt[kMaxRefs];
       float mix = 0.f;
       for (int r = 0; r < R; ++r) {
         float t = 0.f;
-        for (int l = 0; l < 8; ++l) t += Gs[l][r][tx * VW + v];
+        for (unsigned k = 0; k < CS; ++k) {
+          const float* remote = cluster.map_shared_rank(&Gp[0][0], k);
+          t += remote[r * (32 * VW) + tx * VW + v];
+        }
         Gt[r] = t;
         mix = fmaf(t, coef[v][r], mix);  // sum_r G_r s_r w_r
       }
@@ -148,6 +174,7 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
       }
     }
   }
+  cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 }  // namespace clc
@@ -168,14 +195,18 @@ extern "C" int clc_clm_fuse_fwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (S % 4 == 0) && aligned16(ref_t) && aligned16(att) && aligned16(y) && aligned16(out) &&
                    !((ref_sr | ref_sb | att_sr | att_sb) & 3);
-  const unsigned gy = (C + kChanGroup - 1) / kChanGroup;
-  if (vec) {
-    dim3 grid((unsigned)((S / 4 + 127) / 128), gy, (unsigned)B);
-    clm_fuse_fwd_kernel<4><<<grid, 128, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, B, C, S);
-  } else {
-    dim3 grid((unsigned)((S + 127) / 128), gy, (unsigned)B);
-    clm_fuse_fwd_kernel<1><<<grid, 128, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, B, C, S);
-  }
+  const int VW = vec ? 4 : 1;
+  const unsigned gx = (unsigned)((S + 32 * VW - 1) / (32 * VW));
+  // channels per warp: as many as keeps >= 2 CTAs per SM in flight (coefficients amortised over them)
+  int CPW = 16;
+  while (CPW > 1 && (int64_t)gx * B * ((C + 8 * CPW - 1) / (8 * CPW)) < 2 * kNumSMs) CPW >>= 1;
+  const unsigned gy = (unsigned)((C + 8 * CPW - 1) / (8 * CPW));
+  if (gy > 65535) return CLC_ERR_UNSUPPORTED;
+  dim3 grid(gx, gy, (unsigned)B);
+  if (vec)
+    clm_fuse_fwd_kernel<4><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+  else
+    clm_fuse_fwd_kernel<1><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
   CLC_CHECK_LAUNCH("clc_clm_fuse_fwd");
   return CLC_OK;
 }
@@ -190,14 +221,30 @@ extern "C" int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (S % 4 == 0) && aligned16(ref_t) && aligned16(att) && aligned16(g_out) &&
                    aligned16(g_ref_t) && aligned16(g_att) && !((ref_sr | ref_sb | att_sr | att_sb) & 3);
-  dim3 block(32, 8);
-  if (vec) {
-    dim3 grid((unsigned)((S / 4 + 31) / 32), 1, (unsigned)B);
-    clm_fuse_bwd_kernel<4><<<grid, block, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out, g_ref_t, g_att, R, B, C, S);
-  } else {
-    dim3 grid((unsigned)((S + 31) / 32), 1, (unsigned)B);
-    clm_fuse_bwd_kernel<1><<<grid, block, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out, g_ref_t, g_att, R, B, C, S);
-  }
+  // pixels per lane: float4 only when that still leaves enough CTAs; cluster size: up to 8 CTAs
+  // (portable limit) split the channels of one pixel tile.
+  const bool vec4 = vec && (int64_t)((S / 4 + 31) / 32) * B * 8 >= 2 * kNumSMs;
+  const unsigned gx = (unsigned)(vec4 ? (S / 4 + 31) / 32 : (S + 31) / 32);
+  unsigned CS = 8;
+  while (CS > 1 && (unsigned)C < 8 * CS) CS >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, CS, (unsigned)B);
+  cfg.blockDim = dim3(32, 8, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CS;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (vec4)
+    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<4>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
+                                g_ref_t, g_att, (int)R, (int)C, S));
+  else
+    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<1>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
+                                g_ref_t, g_att, (int)R, (int)C, S));
   CLC_CHECK_LAUNCH("clc_clm_fuse_bwd");
   return CLC_OK;
 }

@@ -35,28 +35,29 @@ channel_sums_kernel(const float* __restrict__ r, float* __restrict__ s1, float* 
 }
 
 // Per-patch query statistics: xs = sum q, sxx = sum q^2 over the C*ph*pw patch elements.
-// One warp per (problem-query, patch).
+// One CTA per (query image, patch): thread-strided partial sums over the C*ph patch rows,
+// fixed-order block reduction (deterministic).
 __global__ void __launch_bounds__(256)
-patch_stats_kernel(PatchAddr qa, float* __restrict__ xs, float* __restrict__ sxx, int64_t NQ, int P,
-                   int C, int ph, int pw) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= NQ * P) return;
-  const int64_t nq = w / P;
-  const int patch = (int)(w - nq * P);
-  const float* base = qa.q + nq * qa.sn + qa.patch_off(patch);
-  const int K = C * ph * pw, pp = ph * pw;
+patch_stats_kernel(PatchAddr qa, float* __restrict__ xs, float* __restrict__ sxx, int P, int C, int ph,
+                   int pw) {
+  __shared__ float red[32];
+  const int w = blockIdx.x;
+  const int nq = w / P, patch = w - nq * P;
+  const float* base = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+  const int rows = C * ph;
   float a = 0.f, b = 0.f;
-  for (int e = lane; e < K; e += 32) {
-    const int c = e / pp, rem = e - c * pp;
-    const int dy = rem / pw, dx = rem - dy * pw;
-    const float v = base[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
-    a += v;
-    b = fmaf(v, v, b);
+  for (int e = threadIdx.x; e < rows; e += blockDim.x) {
+    const int c = e / ph, dy = e - c * ph;
+    const float* p = base + (int64_t)c * qa.sc + (int64_t)dy * qa.sy;
+    for (int dx = 0; dx < pw; ++dx) {
+      const float v = p[dx];
+      a += v;
+      b = fmaf(v, v, b);
+    }
   }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if (lane == 0) { xs[w] = a; sxx[w] = b; }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) { xs[w] = a; sxx[w] = b; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -258,59 +259,80 @@ gaussian_mask_kernel(float* __restrict__ mask, int img_h, int img_w, int ph, int
 }
 
 // ------------------------------------------------------------------------------------------
-// Gather + blend (SI_Wraper :226-238).  One thread per output element (n, c, y, x); weights =
-// softmax(val * T) recomputed per thread (k exps) and written once per patch.
+// Gather + blend (SI_Wraper :226-238).  One CTA per (problem, patch row, channel chunk): the
+// softmax(val * T) weights and source offsets of the row's patches are formed once in shared
+// memory, then every thread produces output pixels (coalesced along x) from the k gathered windows.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxK = 32;
 
+template <bool STACK>
 __global__ void __launch_bounds__(256)
 gather_blend_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
                         const float* __restrict__ val, float temperature, float* __restrict__ out,
-                        float* __restrict__ weights, int64_t NP, int C, int fh, int fw, int gh, int gw,
-                        int corr_w, int k, int is_stack) {
+                        float* __restrict__ weights, int C, int fh, int fw, int gh, int gw, int corr_w,
+                        int k, int CH, int cch) {
+  extern __shared__ float gsm[];  // w_s[npx*k], off_s[npx*k]
   const int npx = fw / gw, P = (fh / gh) * npx;
-  const int64_t HW = (int64_t)fh * fw;
-  const int64_t total = NP * C * HW;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % fw);
-    const int y = (int)((i / fw) % fh);
-    const int c = (int)((i / HW) % C);
-    const int64_t n = i / (HW * C);
-    const int py = y / gh, px = x / gw, dy = y - py * gh, dx = x - px * gw;
+  float* w_s = gsm;
+  int* off_s = reinterpret_cast<int*>(gsm + npx * k);
+  const int n = blockIdx.y;
+  const int py = blockIdx.x / cch, c0 = (blockIdx.x - py * cch) * CH;
+  const int c1 = min(C, c0 + CH);
+  const int HW = fh * fw;
+  for (int px = threadIdx.x; px < npx; px += blockDim.x) {
     const int patch = py * npx + px;
-    const int32_t* ip = idx + (n * P + patch) * k;
-    const float* fp = feat + (n * C + c) * HW;
-    if (is_stack) {
-      for (int j = 0; j < k; ++j) {
-        const int id = ip[j];
-        const int sy = id / corr_w, sx = id - sy * corr_w;
-        out[((n * k + j) * C + c) * HW + (int64_t)y * fw + x] = fp[(sy + dy) * fw + sx + dx];
+    const int64_t o = ((int64_t)n * P + patch) * k;
+    float mx = -INFINITY, den = 0.f;
+    if (!STACK) {
+      for (int j = 0; j < k; ++j) mx = fmaxf(mx, val[o + j] * temperature);
+      for (int j = 0; j < k; ++j) den += expf(val[o + j] * temperature - mx);
+    }
+    for (int j = 0; j < k; ++j) {
+      const int id = idx[o + j];
+      const int sy = id / corr_w, sx = id - sy * corr_w;
+      off_s[px * k + j] = sy * fw + sx;
+      if (!STACK) {
+        const float wj = expf(val[o + j] * temperature - mx) / den;
+        w_s[px * k + j] = wj;
+        if (weights && c0 == 0) weights[o + j] = wj;
       }
+    }
+  }
+  __syncthreads();
+  const int items = (c1 - c0) * gh * fw;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int x = it % fw, rowi = it / fw;
+    const int cl = rowi / gh, dy = rowi - cl * gh;
+    const int c = c0 + cl;
+    const int px = x / gw, dx = x - px * gw;
+    const float* fp = feat + ((int64_t)n * C + c) * HW + dy * fw + dx;
+    const int oo = (py * gh + dy) * fw + x;
+    if (STACK) {
+      for (int j = 0; j < k; ++j) out[(((int64_t)n * k + j) * C + c) * HW + oo] = fp[off_s[px * k + j]];
     } else {
-      const float* vp = val + (n * P + patch) * k;
-      float mx = -INFINITY;
-      for (int j = 0; j < k; ++j) mx = fmaxf(mx, vp[j] * temperature);
-      float den = 0.f;
-      for (int j = 0; j < k; ++j) den += expf(vp[j] * temperature - mx);
       float acc = 0.f;
-      const bool writer = weights && c == 0 && dy == 0 && dx == 0;
-      for (int j = 0; j < k; ++j) {
-        const float wj = expf(vp[j] * temperature - mx) / den;
-        const int id = ip[j];
-        const int sy = id / corr_w, sx = id - sy * corr_w;
-        // torch.sum over the k axis: sequential left-to-right accumulation of y_patch * weight
-        acc += fp[(sy + dy) * fw + sx + dx] * wj;
-        if (writer) weights[(n * P + patch) * k + j] = wj;
-      }
-      out[i] = acc;
+      // torch.sum over the k axis: sequential left-to-right accumulation of y_patch * weight
+      for (int j = 0; j < k; ++j) acc += fp[off_s[px * k + j]] * w_s[px * k + j];
+      out[((int64_t)n * C + c) * HW + oo] = acc;
     }
   }
 }
 
+// Block-wide sums of three values at once; results valid in every thread.
+__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*red)[3]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  __syncthreads();
+  if (lane == 0) { red[wid][0] = a; red[wid][1] = b; red[wid][2] = c; }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  a = b = c = 0.f;
+  for (int w = 0; w < nw; ++w) { a += red[w][0]; b += red[w][1]; c += red[w][2]; }
+}
+
 // Backward: one CTA per (n, patch).  g_feat scatter-add (windows overlap -> atomics);
 // g_w[j] = sum g_out * patch_j reduced over the CTA; g_val through the softmax.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 gather_blend_bwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
                         const float* __restrict__ weights, float temperature,
                         const float* __restrict__ g_out, float* __restrict__ g_feat,
@@ -319,23 +341,25 @@ gather_blend_bwd_kernel(const float* __restrict__ feat, const int32_t* __restric
   __shared__ float red[32];
   __shared__ float gw_s[kMaxK];
   const int npx = fw / gw, P = (fh / gh) * npx;
-  const int64_t HW = (int64_t)fh * fw;
-  const int64_t n = blockIdx.x / P;
-  const int patch = blockIdx.x - (int)(n * P);
+  const int HW = fh * fw;
+  const int n = blockIdx.x / P;
+  const int patch = blockIdx.x - n * P;
   const int py = patch / npx, px = patch - py * npx;
-  const int pp = gh * gw, K = C * pp;
-  const int32_t* ip = idx + (n * P + patch) * k;
+  const int rows = C * gh, pp = gh * gw;
+  const int32_t* ip = idx + ((int64_t)n * P + patch) * k;
+  const int dst0 = py * gh * fw + px * gw;
   for (int j = 0; j < k; ++j) {
     const int id = ip[j];
     const int sy = id / corr_w, sx = id - sy * corr_w;
-    const float wj = is_stack ? 1.f : weights[(n * P + patch) * k + j];
+    const int src0 = sy * fw + sx;
+    const float wj = is_stack ? 1.f : weights[((int64_t)n * P + patch) * k + j];
+    const float* gbase = is_stack ? g_out + ((int64_t)n * k + j) * C * HW : g_out + (int64_t)n * C * HW;
     float part = 0.f;
-    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+    for (int e = threadIdx.x; e < rows * gw; e += blockDim.x) {  // flat (c, dy, dx), dx fastest
       const int c = e / pp, rem = e - c * pp;
       const int dy = rem / gw, dx = rem - dy * gw;
-      const int64_t o = (int64_t)(py * gh + dy) * fw + px * gw + dx;
-      const float g = is_stack ? g_out[((n * k + j) * C + c) * HW + o] : g_out[(n * C + c) * HW + o];
-      const int64_t f = (n * C + c) * HW + (int64_t)(sy + dy) * fw + sx + dx;
+      const float g = gbase[(int64_t)c * HW + dst0 + dy * fw + dx];
+      const int64_t f = ((int64_t)n * C + c) * HW + src0 + dy * fw + dx;
       if (!is_stack) part = fmaf(g, feat[f], part);
       atomicAdd(&g_feat[f], wj * g);
     }
@@ -346,12 +370,12 @@ gather_blend_bwd_kernel(const float* __restrict__ feat, const int32_t* __restric
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float* gv = g_val + (n * P + patch) * k;
+    float* gv = g_val + ((int64_t)n * P + patch) * k;
     if (is_stack) {
       for (int j = 0; j < k; ++j) gv[j] = 0.f;
     } else {
       // w = softmax(v*T): dL/dv_j = T * w_j * (g_w_j - sum_i w_i g_w_i)
-      const float* w = weights + (n * P + patch) * k;
+      const float* w = weights + ((int64_t)n * P + patch) * k;
       float dot = 0.f;
       for (int j = 0; j < k; ++j) dot = fmaf(w[j], gw_s[j], dot);
       for (int j = 0; j < k; ++j) gv[j] = temperature * w[j] * (gw_s[j] - dot);
@@ -365,70 +389,62 @@ gather_blend_bwd_kernel(const float* __restrict__ feat, const int32_t* __restric
 // xy's query operand is detached in the reference (conv2d weights = x.data), every other use
 // of x (xs, sxx, xm) is attached.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 pearson_topk_bwd_kernel(PatchAddr qa, const float* __restrict__ r, const float* __restrict__ mask,
                         const int32_t* __restrict__ idx, const float* __restrict__ g_val,
                         float* __restrict__ g_r, float* __restrict__ g_q, int P, int C, int ph, int pw,
                         int fh, int fw, int k) {
-  __shared__ float red[32];
-  __shared__ float bc[4];
+  __shared__ float red[8][3];
   const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
-  const int64_t HW = (int64_t)fh * fw;
-  const int64_t n = blockIdx.x / P;
-  const int patch = blockIdx.x - (int)(n * P);
-  const int64_t nq = n / qa.repeat;
-  const float* qb = qa.q + nq * qa.sn + qa.patch_off(patch);
-  const float* rb = r + n * C * HW;
-  const int pp = ph * pw, K = C * pp;
+  const int HW = fh * fw;
+  const int n = blockIdx.x / P;
+  const int patch = blockIdx.x - n * P;
+  const int nq = n / qa.repeat;
+  const float* qb = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+  const float* rb = r + (int64_t)n * C * HW;
+  const int rows = C * ph, K = rows * pw, pp = ph * pw;
   const float Kf = (float)K, inv_k = 1.0f / Kf;
 
   // patch statistics
-  float a = 0.f, b = 0.f;
-  for (int e = threadIdx.x; e < K; e += blockDim.x) {
-    const int c = e / pp, rem = e - c * pp;
-    const int dy = rem / pw, dx = rem - dy * pw;
-    const float v = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
-    a += v;
-    b = fmaf(v, v, b);
+  float a = 0.f, b = 0.f, z = 0.f;
+  for (int e = threadIdx.x; e < rows; e += blockDim.x) {
+    const int c = e / ph, dy = e - c * ph;
+    const float* qp = qb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy;
+    for (int dx = 0; dx < pw; ++dx) {
+      const float v = qp[dx];
+      a += v;
+      b = fmaf(v, v, b);
+    }
   }
-  a = block_sum(a, red);
-  if (threadIdx.x == 0) bc[0] = a;
-  b = block_sum(b, red);
-  if (threadIdx.x == 0) bc[1] = b;
-  __syncthreads();
-  const float xs = bc[0], sxx = bc[1];
+  block_sum3(a, b, z, red);
+  const float xs = a, sxx = b;
   const float xm = xs / Kf;
   const float dX = sxx - xm * xs;
 
   float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;  // accumulated over the k positions
   for (int j = 0; j < k; ++j) {
-    const int id = idx[(n * P + patch) * k + j];
+    const int id = idx[((int64_t)n * P + patch) * k + j];
     const int oy = id / cw, ox = id - oy * cw;
+    const int src0 = oy * fw + ox;
     float s1 = 0.f, s2 = 0.f, xy = 0.f;
-    for (int e = threadIdx.x; e < K; e += blockDim.x) {
-      const int c = e / pp, rem = e - c * pp;
-      const int dy = rem / pw, dx = rem - dy * pw;
-      const float qv = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
-      const float rv = rb[(int64_t)c * HW + (int64_t)(oy + dy) * fw + ox + dx];
-      s1 += rv;
-      s2 = fmaf(rv, rv, s2);
-      xy = fmaf(qv, rv, xy);
+    for (int e = threadIdx.x; e < rows; e += blockDim.x) {
+      const int c = e / ph, dy = e - c * ph;
+      const float* qp = qb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy;
+      const float* rp = rb + (int64_t)c * HW + src0 + dy * fw;
+      for (int dx = 0; dx < pw; ++dx) {
+        const float qv = qp[dx], rv = rp[dx];
+        s1 += rv;
+        s2 = fmaf(rv, rv, s2);
+        xy = fmaf(qv, rv, xy);
+      }
     }
-    s1 = block_sum(s1, red);
-    if (threadIdx.x == 0) bc[0] = s1;
-    s2 = block_sum(s2, red);
-    if (threadIdx.x == 0) bc[1] = s2;
-    xy = block_sum(xy, red);
-    if (threadIdx.x == 0) bc[2] = xy;
-    __syncthreads();
-    s1 = bc[0]; s2 = bc[1]; xy = bc[2];
-    __syncthreads();
+    block_sum3(s1, s2, xy, red);
     const float ym = s1 * inv_k;
     const float dY = s2 - ym * ym * Kf;
     const float D = dY * dX;
     const float num = xy - ym * xs;
     const float rs = rsqrtf(D);
-    float g = g_val[(n * P + patch) * k + j];
+    float g = g_val[((int64_t)n * P + patch) * k + j];
     if (mask) g *= mask[(int64_t)patch * L + id];
     const float g_num = g * rs;
     const float g_D = -0.5f * g * num * rs / D;
@@ -439,23 +455,158 @@ pearson_topk_bwd_kernel(PatchAddr qa, const float* __restrict__ r, const float* 
     t_gsxx += g_dX;
     t_gxm += -g_dX * xs;
     const float c_mean = g_ym * inv_k;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {  // flat (c, dy, dx), dx fastest
+      const int c = e / pp, rem = e - c * pp;
+      const int dy = rem / pw, dx = rem - dy * pw;
+      const float qv = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+      const int64_t ro = (int64_t)c * HW + src0 + dy * fw + dx;
+      atomicAdd(&g_r[(int64_t)n * C * HW + ro], fmaf(g_xy, qv, fmaf(2.f * g_dY, rb[ro], c_mean)));
+    }
+  }
+  if (g_q) {
+    float* gqb = g_q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+    const float cst = t_gxs + t_gxm * inv_k;
+    for (int e = threadIdx.x; e < rows; e += blockDim.x) {
+      const int c = e / ph, dy = e - c * ph;
+      const int64_t o = (int64_t)c * qa.sc + (int64_t)dy * qa.sy;
+      for (int dx = 0; dx < pw; ++dx) atomicAdd(&gqb[o + dx], fmaf(2.f * t_gsxx, qb[o + dx], cst));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused backward of match + gather/blend for the single-scale case in which the gathered
+// feature map IS the matched reference (feat == r, gather patch == match patch): the two
+// scatters hit the same k windows, so one pass forms every reduction (g_w, s1, s2, xy per
+// window), one thread turns them into the softmax / Pearson coefficients, and a single pass
+// issues ONE atomic per window element:
+//   g_r[win_j] += w_j * g_out[patch]  +  g_xy_j * q[patch] + 2 g_dY_j * r[win_j] + c_mean_j
+// Elements are indexed flat (c, dy, dx) with dx fastest so the 32 lanes of a warp-wide atomic
+// fall into 32-byte sectors pw at a time.  One CTA per (problem, patch).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& d, float (*red)[4]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  __syncthreads();
+  if (lane == 0) { red[wid][0] = a; red[wid][1] = b; red[wid][2] = c; red[wid][3] = d; }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  a = b = c = d = 0.f;
+  for (int w = 0; w < nw; ++w) { a += red[w][0]; b += red[w][1]; c += red[w][2]; d += red[w][3]; }
+}
+
+__global__ void __launch_bounds__(256)
+match_bwd_kernel(PatchAddr qa, const float* __restrict__ r, const float* __restrict__ mask,
+                 const int32_t* __restrict__ idx, const float* __restrict__ weights, float temperature,
+                 const float* __restrict__ g_out, float* __restrict__ g_r, float* __restrict__ g_q,
+                 float* __restrict__ g_val_out, int P, int C, int ph, int pw, int fh, int fw, int k) {
+  __shared__ float red[8][4];
+  __shared__ float sums[kMaxK][4];   // per window: g_w, s1, s2, xy
+  __shared__ float coef[kMaxK][4];   // per window: w_j, g_xy, 2*g_dY, c_mean
+  __shared__ int src_s[kMaxK];
+  __shared__ float qcoef[2];         // g_q[e] += qcoef[0] * q[e] + qcoef[1]
+  const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
+  const int HW = fh * fw;
+  const int n = blockIdx.x / P;
+  const int patch = blockIdx.x - n * P;
+  const int nq = n / qa.repeat;
+  const int npx = fw / pw;
+  const int py = patch / npx, px = patch - py * npx;
+  const float* qb = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+  const float* rb = r + (int64_t)n * C * HW;
+  const float* gb = g_out + (int64_t)n * C * HW + (py * ph) * fw + px * pw;
+  const int pp = ph * pw, K = C * pp;
+  const float Kf = (float)K, inv_k = 1.0f / Kf;
+  const int64_t po = ((int64_t)n * P + patch) * k;
+  if (threadIdx.x < k) {
+    const int id = idx[po + threadIdx.x];
+    const int oy = id / cw, ox = id - oy * cw;
+    src_s[threadIdx.x] = oy * fw + ox;
+  }
+  // patch statistics
+  float a = 0.f, b = 0.f, z0 = 0.f, z1 = 0.f;
+  for (int e = threadIdx.x; e < K; e += blockDim.x) {
+    const int c = e / pp, rem = e - c * pp;
+    const int dy = rem / pw, dx = rem - dy * pw;
+    const float v = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+    a += v;
+    b = fmaf(v, v, b);
+  }
+  block_sum4(a, b, z0, z1, red);  // (also orders the src_s writes before their use)
+  const float xs = a, sxx = b;
+  // per-window reductions
+  for (int j = 0; j < k; ++j) {
+    const int src0 = src_s[j];
+    float gw = 0.f, s1 = 0.f, s2 = 0.f, xy = 0.f;
     for (int e = threadIdx.x; e < K; e += blockDim.x) {
       const int c = e / pp, rem = e - c * pp;
       const int dy = rem / pw, dx = rem - dy * pw;
       const float qv = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
-      const int64_t ro = (int64_t)c * HW + (int64_t)(oy + dy) * fw + ox + dx;
+      const float g = gb[(int64_t)c * HW + dy * fw + dx];
+      const float rv = rb[(int64_t)c * HW + src0 + dy * fw + dx];
+      gw = fmaf(g, rv, gw);
+      s1 += rv;
+      s2 = fmaf(rv, rv, s2);
+      xy = fmaf(qv, rv, xy);
+    }
+    block_sum4(gw, s1, s2, xy, red);
+    if (threadIdx.x == 0) { sums[j][0] = gw; sums[j][1] = s1; sums[j][2] = s2; sums[j][3] = xy; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float xm = xs / Kf;
+    const float dX = sxx - xm * xs;
+    // w = softmax(v*T): dL/dv_j = T * w_j * (g_w_j - sum_i w_i g_w_i)
+    float dot = 0.f;
+    for (int j = 0; j < k; ++j) dot = fmaf(weights[po + j], sums[j][0], dot);
+    float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float wj = weights[po + j];
+      const float gv = temperature * wj * (sums[j][0] - dot);
+      if (g_val_out) g_val_out[po + j] = gv;
+      const float s1 = sums[j][1], s2 = sums[j][2], xy = sums[j][3];
+      const float ym = s1 * inv_k;
+      const float dY = s2 - ym * ym * Kf;
+      const float D = dY * dX;
+      const float num = xy - ym * xs;
+      const float rs = rsqrtf(D);
+      float g = gv;
+      if (mask) g *= mask[(int64_t)patch * L + idx[po + j]];
+      const float g_num = g * rs;
+      const float g_D = -0.5f * g * num * rs / D;
+      const float g_dY = g_D * dX, g_dX = g_D * dY;
+      const float g_ym = -g_num * xs - 2.f * g_dY * ym * Kf;
+      t_gxs += -g_num * ym - g_dX * xm;
+      t_gsxx += g_dX;
+      t_gxm += -g_dX * xs;
+      coef[j][0] = wj; coef[j][1] = g_num; coef[j][2] = 2.f * g_dY; coef[j][3] = g_ym * inv_k;
+    }
+    qcoef[0] = 2.f * t_gsxx;
+    qcoef[1] = t_gxs + t_gxm * inv_k;
+  }
+  __syncthreads();
+  float* grb = g_r + (int64_t)n * C * HW;
+  for (int j = 0; j < k; ++j) {
+    const int src0 = src_s[j];
+    const float cw_ = coef[j][0], cxy = coef[j][1], cdy = coef[j][2], cm = coef[j][3];
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+      const int c = e / pp, rem = e - c * pp;
+      const int dy = rem / pw, dx = rem - dy * pw;
+      const float qv = qb[(int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx];
+      const float g = gb[(int64_t)c * HW + dy * fw + dx];
+      const int64_t ro = (int64_t)c * HW + src0 + dy * fw + dx;
       const float rv = rb[ro];
-      atomicAdd(&g_r[n * C * HW + ro], fmaf(g_xy, qv, fmaf(2.f * g_dY, rv, c_mean)));
+      atomicAdd(&grb[ro], fmaf(cw_, g, fmaf(cxy, qv, fmaf(cdy, rv, cm))));
     }
   }
   if (g_q) {
-    float* gqb = g_q + nq * qa.sn + qa.patch_off(patch);
-    const float cst = t_gxs + t_gxm * inv_k;
+    float* gqb = g_q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+    const float c0 = qcoef[0], c1 = qcoef[1];
     for (int e = threadIdx.x; e < K; e += blockDim.x) {
       const int c = e / pp, rem = e - c * pp;
       const int dy = rem / pw, dx = rem - dy * pw;
       const int64_t o = (int64_t)c * qa.sc + (int64_t)dy * qa.sy + dx;
-      atomicAdd(&gqb[o], fmaf(2.f * t_gsxx, qb[o], cst));
+      atomicAdd(&gqb[o], fmaf(c0, qb[o], c1));
     }
   }
 }
@@ -470,8 +621,8 @@ int launch_channel_sums(const float* r, float* s1, float* s2, int64_t NP, int C,
 
 int launch_patch_stats(const PatchAddr& qa, float* xs, float* sxx, int64_t NQ, int P, int C, int ph,
                        int pw, cudaStream_t st) {
-  const int64_t warps = NQ * P;
-  patch_stats_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(qa, xs, sxx, NQ, P, C, ph, pw);
+  if (NQ * P > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
+  patch_stats_kernel<<<(unsigned)(NQ * P), 256, 0, st>>>(qa, xs, sxx, P, C, ph, pw);
   CLC_CHECK_LAUNCH("patch_stats");
   return CLC_OK;
 }
@@ -558,9 +709,21 @@ extern "C" int clc_gather_blend_fwd(const float* feat, const int32_t* idx, const
   if (!feat || !idx || !out || (!is_stack && !val)) return CLC_ERR_INVALID_ARGUMENT;
   if (!gather_args_ok(NP, C, fh, fw, gh, gw, corr_w, k)) return CLC_ERR_INVALID_ARGUMENT;
   if (NP == 0) return CLC_OK;
-  const int64_t total = NP * C * (int64_t)fh * fw;
-  gather_blend_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      feat, idx, val, temperature, out, weights, NP, C, fh, fw, gh, gw, corr_w, k, is_stack);
+  if (NP > 65535 || (int64_t)C * fh * fw > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
+  const int npy = fh / gh, npx = fw / gw;
+  // channel chunk per CTA: aim for >= 4 CTAs per SM, at least 8 channels per CTA
+  int CH = 64;
+  while (CH > 8 && (int64_t)NP * npy * ((C + CH - 1) / CH) < 4 * kNumSMs) CH >>= 1;
+  const int cch = (C + CH - 1) / CH;
+  dim3 grid((unsigned)(npy * cch), (unsigned)NP);
+  const size_t sm = (size_t)npx * k * 8;
+  if (sm > 48 * 1024) return CLC_ERR_UNSUPPORTED;
+  if (is_stack)
+    gather_blend_fwd_kernel<true><<<grid, 256, sm, (cudaStream_t)stream>>>(
+        feat, idx, val, temperature, out, weights, C, fh, fw, gh, gw, corr_w, k, CH, cch);
+  else
+    gather_blend_fwd_kernel<false><<<grid, 256, sm, (cudaStream_t)stream>>>(
+        feat, idx, val, temperature, out, weights, C, fh, fw, gh, gw, corr_w, k, CH, cch);
   CLC_CHECK_LAUNCH("clc_gather_blend_fwd");
   return CLC_OK;
 }
@@ -574,7 +737,8 @@ extern "C" int clc_gather_blend_bwd(const float* feat, const int32_t* idx, const
   if (NP == 0) return CLC_OK;
   const int64_t blocks = NP * (fh / gh) * (fw / gw);
   if (blocks > 2147483647LL) return CLC_ERR_UNSUPPORTED;
-  gather_blend_bwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+  if ((int64_t)C * fh * fw > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
+  gather_blend_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       feat, idx, weights, temperature, g_out, g_feat, g_val, C, fh, fw, gh, gw, corr_w, k, is_stack);
   CLC_CHECK_LAUNCH("clc_gather_blend_bwd");
   return CLC_OK;
@@ -588,8 +752,25 @@ extern "C" int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, co
   if (NP < 0 || P < 1 || C < 1 || ph < 1 || pw < 1 || fh < ph || fw < pw || k < 1) return CLC_ERR_INVALID_ARGUMENT;
   if (NP == 0) return CLC_OK;
   if (NP * P > 2147483647LL) return CLC_ERR_UNSUPPORTED;
-  pearson_topk_bwd_kernel<<<(unsigned)(NP * P), 128, 0, (cudaStream_t)stream>>>(
+  if ((int64_t)C * fh * fw > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
+  pearson_topk_bwd_kernel<<<(unsigned)(NP * P), 256, 0, (cudaStream_t)stream>>>(
       make_addr(qv), r, mask, idx, g_val, g_r, g_q, P, C, ph, pw, fh, fw, k);
   CLC_CHECK_LAUNCH("clc_pearson_topk_bwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* mask, const int32_t* idx,
+                             const float* weights, float temperature, const float* g_out, float* g_r,
+                             float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
+                             int32_t pw, int32_t fh, int32_t fw, int32_t k, void* stream) {
+  if (!view_ok(qv) || !r || !idx || !weights || !g_out || !g_r) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP < 0 || P < 1 || C < 1 || ph < 1 || pw < 1 || fh < ph || fw < pw || k < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (fh % ph || fw % pw || P != (fh / ph) * (fw / pw)) return CLC_ERR_INVALID_ARGUMENT;
+  if (k > kMaxK) return CLC_ERR_UNSUPPORTED;
+  if (NP == 0) return CLC_OK;
+  if (NP * P > 2147483647LL || (int64_t)C * fh * fw > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
+  match_bwd_kernel<<<(unsigned)(NP * P), 256, 0, (cudaStream_t)stream>>>(
+      make_addr(qv), r, mask, idx, weights, temperature, g_out, g_r, g_q, g_val, P, C, ph, pw, fh, fw, k);
+  CLC_CHECK_LAUNCH("clc_match_bwd");
   return CLC_OK;
 }

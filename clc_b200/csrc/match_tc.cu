@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace clc {
@@ -141,6 +143,8 @@ __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 4 epil
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+#define CLC_STAMP(i) do { if (p.timing && lane == 0) p.timing[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B:
 //   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for one swizzle row of K) |
 //   [32,46) SBO >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
@@ -163,12 +167,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 struct Params {
   int NP, q_repeat, C, H, W, ph, pw, P, npx, S, HW;
   int TN, NACC, n_tiles, m_tiles, total_tiles, chunks;
-  int nboxB, a_stages, b_bufs, acc_stages, tmem_cols;
+  int nboxB, a_stages, b_bufs, acc_stages, tmem_cols, a_rows, SB;
   int KC, gaussian;
   const float *s1, *s2, *xs, *sxx;
   float* cand_val;
   int32_t* cand_idx;
   float* dump;  // debug: raw xy accumulators [NP, P, HW] (NULL in production)
+  int dbg;            // debug experiment bits (0 in production)
+  long long* timing;  // debug: per-CTA clock64 stamps [grid][16] (NULL in production)
 };
 
 struct ColStat {  // per accumulator column (= window origin), shared by the 128 patch lanes
@@ -222,6 +228,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + (sTmemPtr - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) CLC_STAMP(0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -248,10 +255,13 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int acc_cols = TNT;
+  if (warp == 0) CLC_STAMP(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    uint32_t acount = 0, bcount = 0;
+    uint32_t ast = 0, aph = 0, bst = 0, bph = 0;  // ring positions + phase parities (no divisions in the loop)
+    const uint32_t a_tx = (uint32_t)(p.SB * p.a_rows) * (kChunk * 2);
+    bool first = true;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
@@ -259,71 +269,82 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const int nq = n / p.q_repeat;
       const int row0 = n * p.HW + nt * TNT;
       for (int c = 0; c < p.chunks; ++c) {
-        const uint32_t bb = bcount % (uint32_t)p.b_bufs;
-        const uint32_t bph = (bcount / (uint32_t)p.b_bufs) & 1u;
-        mbar_wait(barBempty + 8u * bb, bph ^ 1u);
+        mbar_wait(barBempty + 8u * bst, bph ^ 1u);
         if (lane == 0) {
-          mbar_expect_tx(barBfull + 8u * bb, bBytes);
+          mbar_expect_tx(barBfull + 8u * bst, bBytes);
           for (int i = 0; i < p.nboxB; ++i)
-            tma_load_2d(sB + bb * bBytes + (uint32_t)i * kBoxBytesB, &tmapB, barBfull + 8u * bb, c * kChunk,
+            tma_load_2d(sB + bst * bBytes + (uint32_t)i * kBoxBytesB, &tmapB, barBfull + 8u * bst, c * kChunk,
                         row0 + i * kBoxRowsB);
         }
-        ++bcount;
-        for (int s = 0; s < p.S; ++s) {
-          const uint32_t st = acount % (uint32_t)p.a_stages;
-          const uint32_t aph = (acount / (uint32_t)p.a_stages) & 1u;
-          mbar_wait(barAempty + 8u * st, aph ^ 1u);
+        if (++bst == (uint32_t)p.b_bufs) { bst = 0; bph ^= 1u; }
+        for (int s0 = 0; s0 < p.S; s0 += p.SB) {
+          mbar_wait(barAempty + 8u * ast, aph ^ 1u);
           if (lane == 0) {
-            mbar_expect_tx(barAfull + 8u * st, kABytes);
-            tma_load_3d(sA + st * kABytes, &tmapA, barAfull + 8u * st, c * kChunk, mt * kTileM, nq * p.S + s);
+            if (p.dbg & 4) {
+              mbar_arrive(barAfull + 8u * ast);
+            } else {
+              mbar_expect_tx(barAfull + 8u * ast, a_tx);
+              tma_load_3d(sA + ast * kABytes, &tmapA, barAfull + 8u * ast, c * kChunk, mt * kTileM, nq * p.S + s0);
+            }
           }
-          ++acount;
+          if (++ast == (uint32_t)p.a_stages) { ast = 0; aph ^= 1u; }
+          if (first) { CLC_STAMP(2); first = false; }
         }
       }
     }
+    CLC_STAMP(3);
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     const uint32_t idesc = make_idesc(kTileM, p.TN);
-    uint32_t acount = 0, bcount = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t as = tcount % (uint32_t)p.acc_stages;
-      const uint32_t accph = (tcount / (uint32_t)p.acc_stages) & 1u;
-      mbar_wait(barAccEmpty + 8u * as, accph ^ 1u);
+    const uint32_t a_sub = (uint32_t)p.a_rows * 8u;  // one shift's sub-tile, in 16-byte units
+    uint32_t ast = 0, aph = 0, bst = 0, bph = 0, accst = 0, accph = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(barAccEmpty + 8u * accst, accph ^ 1u);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + as * (uint32_t)acc_cols;
+      const uint32_t d_base = tmem_base + accst * (uint32_t)acc_cols;
+      uint32_t accumulate = 0;
       for (int c = 0; c < p.chunks; ++c) {
-        const uint32_t bb = bcount % (uint32_t)p.b_bufs;
-        const uint32_t bph = (bcount / (uint32_t)p.b_bufs) & 1u;
-        mbar_wait(barBfull + 8u * bb, bph);
-        ++bcount;
-        const uint64_t bdesc0 = make_desc_sw128(sB + bb * bBytes);
-        for (int s = 0; s < p.S; ++s) {
-          const uint32_t st = acount % (uint32_t)p.a_stages;
-          const uint32_t aph = (acount / (uint32_t)p.a_stages) & 1u;
-          mbar_wait(barAfull + 8u * st, aph);
-          ++acount;
+        mbar_wait(barBfull + 8u * bst, bph);
+        if (first) CLC_STAMP(4);
+        const uint64_t bdesc0 = make_desc_sw128(sB + bst * bBytes);
+        int dy = 0, dx = 0;
+        for (int s0 = 0; s0 < p.S; s0 += p.SB) {
+          mbar_wait(barAfull + 8u * ast, aph);
+          if (first) { CLC_STAMP(5); first = false; }
           tc_fence_after();
           if (lane == 0) {
-            const uint64_t adesc0 = make_desc_sw128(sA + st * kABytes);
-            const int dy = s / p.pw, dx = s - dy * p.pw;
-            const int shift_rows = dy * p.W + dx;  // the window shift is a ROW offset into the B buffer
-            for (int j = 0; j < p.NACC; ++j) {
-              const uint64_t bdesc = bdesc0 + (uint64_t)((j * p.TN + shift_rows) * 8);  // 128 B/row = 8 x 16 B
+            uint64_t adesc = make_desc_sw128(sA + ast * kABytes);
+            for (int si = 0; si < p.SB; ++si) {
+              int shift_rows = dy * p.W + dx;  // the window shift is a ROW offset into the B buffer
+              if (p.dbg & 1) shift_rows &= ~7;
+              for (int j = 0; j < ((p.dbg & 2) ? 0 : p.NACC); ++j) {
+                const uint64_t bdesc = bdesc0 + (uint64_t)((j * p.TN + shift_rows) * 8);  // 128 B/row = 8 x 16 B
 #pragma unroll
-              for (int k = 0; k < kChunk / 16; ++k) {
-                umma_bf16(d_base + (uint32_t)(j * p.TN), adesc0 + 2u * k, bdesc + 2u * k, idesc,
-                          (c | s | k) ? 1u : 0u);
+                for (int k = 0; k < kChunk / 16; ++k)
+                  umma_bf16(d_base + (uint32_t)(j * p.TN), adesc + 2u * k, bdesc + 2u * k, idesc,
+                            k ? 1u : accumulate);
               }
+              accumulate = 1;
+              adesc += a_sub;
+              if (++dx == p.pw) { dx = 0; ++dy; }
             }
-            umma_commit(barAempty + 8u * st);  // frees the A stage once these MMAs have read it
+            umma_commit(barAempty + 8u * ast);  // frees the A stage once these MMAs have read it
+          } else {
+            for (int si = 0; si < p.SB; ++si)
+              if (++dx == p.pw) { dx = 0; ++dy; }
           }
           __syncwarp();
+          if (++ast == (uint32_t)p.a_stages) { ast = 0; aph ^= 1u; }
         }
-        if (lane == 0) umma_commit(barBempty + 8u * bb);
+        if (lane == 0) umma_commit(barBempty + 8u * bst);
         __syncwarp();
+        if (++bst == (uint32_t)p.b_bufs) { bst = 0; bph ^= 1u; }
       }
-      if (lane == 0) umma_commit(barAccFull + 8u * as);
+      if (lane == 0) umma_commit(barAccFull + 8u * accst);
       __syncwarp();
+      if (++accst == (uint32_t)p.acc_stages) { accst = 0; accph ^= 1u; }
+      CLC_STAMP(6);
     }
   } else {
     // ===================================== epilogue =========================================
@@ -336,8 +357,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const float kh = -4.0f / (0.25f * (float)p.H * (float)p.H);  // exp(-4ln2*x) = 2^(-4x), sigma = size/2
     const float kw = -4.0f / (0.25f * (float)p.W * (float)p.W);
     const int r0 = (p.ph + 1) / 2 - 1, c0 = (p.pw + 1) / 2 - 1;
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t accst = 0, accph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
       const int n = tile / (p.n_tiles * p.m_tiles);
@@ -386,11 +407,12 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
       for (int j = 0; j < KC; ++j) { cv[j] = -INFINITY; ci[j] = -1; }
       epi_bar_sync();  // colstat visible to the 4 epilogue warps
+      if (warp == 2) CLC_STAMP(7);
 
-      const uint32_t as = tcount % (uint32_t)p.acc_stages;
-      const uint32_t accph = (tcount / (uint32_t)p.acc_stages) & 1u;
+      const uint32_t as = accst;
       mbar_wait(barAccFull + 8u * as, accph);
       tc_fence_after();
+      if (warp == 2) CLC_STAMP(8);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)acc_cols;
       for (int col0 = 0; col0 < TNT; col0 += 32) {
         float v[32];
@@ -433,6 +455,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
       }
       epi_bar_sync();  // colstat may be overwritten for the next tile
+      if (warp == 2) CLC_STAMP(9);
+      if (++accst == (uint32_t)p.acc_stages) { accst = 0; accph ^= 1u; }
     }
   }
 
@@ -443,13 +467,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// Pre-pass 1: reference latents [NP, C, HW] fp32 -> channels-last bf16 [NP*HW, C], plus the
+// Pre-pass 1: reference latents [NP, C, HW] fp32 -> channels-last bf16 [NP*HW, C] (GEMM operand) and
+// channels-last fp32 [NP*HW, C] (coalesced exact re-scoring), plus the
 // per-pixel channel sums S1 = sum_c r, S2 = sum_c r^2 (fp32, fixed combination order).
 // grid = (ceil(HW/32), NP), block = 256 (8 warps x 32 pixels); smem tile [C][33] fp32.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, float* __restrict__ s1,
-                float* __restrict__ s2, int C, int HW) {
+pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, float* __restrict__ rT32,
+                float* __restrict__ s1, float* __restrict__ s2, int C, int HW) {
   extern __shared__ float tile[];  // [C][33] then 2 x [8][32] partial sums
   float* part = tile + (size_t)C * 33;
   const int n = blockIdx.y, px0 = blockIdx.x * 32;
@@ -482,17 +507,22 @@ pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, flo
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[(g * 8 + i) * 33 + pl]);
     *reinterpret_cast<uint4*>(rT + ((int64_t)n * HW + px0 + pl) * C + g * 8) = *reinterpret_cast<const uint4*>(o);
+    float* d32 = rT32 + ((int64_t)n * HW + px0 + pl) * C + g * 8;
+    st4(d32, make_float4(tile[(g * 8 + 0) * 33 + pl], tile[(g * 8 + 1) * 33 + pl], tile[(g * 8 + 2) * 33 + pl],
+                         tile[(g * 8 + 3) * 33 + pl]));
+    st4(d32 + 4, make_float4(tile[(g * 8 + 4) * 33 + pl], tile[(g * 8 + 5) * 33 + pl], tile[(g * 8 + 6) * 33 + pl],
+                             tile[(g * 8 + 7) * 33 + pl]));
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Pre-pass 2: query latents [NQ, C, H, W] fp32 -> packed patches bf16 [NQ, S, P_pad, C]
-// (shift-major, then patch, channels contiguous).  grid = (npy, C/64, NQ), block = 256.
+// Pre-pass 2: query latents [NQ, C, H, W] fp32 -> packed patches [NQ, S, P_pad, C] in bf16 (GEMM
+// operand) and fp32 (exact re-scoring)  (shift-major, then patch, channels contiguous).  grid = (npy, C/64, NQ), block = 256.
 // Rows P..P_pad-1 are zero-filled by the blocks of the last patch row.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_query_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ A, int C, int H, int W, int ph,
-                  int pw, int P, int P_pad) {
+pack_query_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ A, float* __restrict__ A32, int C,
+                  int H, int W, int ph, int pw, int P, int P_pad) {
   extern __shared__ float tile[];  // [64][ph][W + 1]
   const int py = blockIdx.x, c0 = blockIdx.y * 64, nq = blockIdx.z;
   const int npx = W / pw, S = ph * pw;
@@ -504,14 +534,19 @@ pack_query_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ A, in
   }
   __syncthreads();
   __nv_bfloat16* An = A + (int64_t)nq * S * P_pad * C;
+  float* An32 = A32 + (int64_t)nq * S * P_pad * C;
   for (int it = threadIdx.x; it < S * npx * 8; it += 256) {
     const int g = it & 7, px = (it >> 3) % npx, s = it / (8 * npx);
     const int dy = s / pw, dx = s - dy * pw;
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[((g * 8 + i) * ph + dy) * Wp + px * pw + dx]);
-    *reinterpret_cast<uint4*>(An + ((int64_t)s * P_pad + py * npx + px) * C + c0 + g * 8) =
-        *reinterpret_cast<const uint4*>(o);
+    const int64_t oo = ((int64_t)s * P_pad + py * npx + px) * C + c0 + g * 8;
+    *reinterpret_cast<uint4*>(An + oo) = *reinterpret_cast<const uint4*>(o);
+    const float* t0 = &tile[((g * 8) * ph + dy) * Wp + px * pw + dx];
+    const int cs = ph * Wp;  // channel stride inside the tile
+    st4(An32 + oo, make_float4(t0[0], t0[cs], t0[2 * cs], t0[3 * cs]));
+    st4(An32 + oo + 4, make_float4(t0[4 * cs], t0[5 * cs], t0[6 * cs], t0[7 * cs]));
   }
   if (py == gridDim.x - 1) {
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -535,7 +570,8 @@ __device__ __forceinline__ bool ranks_before(float av, int ai, float bv, int bi)
 }
 
 __global__ void __launch_bounds__(512)
-rescore_kernel(const float* __restrict__ q_img, const float* __restrict__ r, const float* __restrict__ s1,
+rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, int P_pad,
+               const float* __restrict__ s1,
                const float* __restrict__ s2, const float* __restrict__ xs_a, const float* __restrict__ sxx_a,
                const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int n_tiles, int KC,
                int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian,
@@ -593,15 +629,23 @@ rescore_kernel(const float* __restrict__ q_img, const float* __restrict__ r, con
     float out = -INFINITY;
     if (id >= 0) {
       const int oy = id / cw, ox = id - oy * cw;
-      const float* qb = q_img + (int64_t)nq * C * HW + (int64_t)(py * ph) * W + px * pw;
-      const float* rb = r + (int64_t)n * C * HW + (int64_t)oy * W + ox;
-      float acc = 0.f;
-      for (int e = lane; e < K; e += 32) {
-        const int c = e / pp, rem = e - c * pp;
-        const int dy = rem / pw, dx = rem - dy * pw;
-        const int64_t o = (int64_t)c * HW + dy * W + dx;
-        acc = fmaf(qb[o], rb[o], acc);
+      // both operands channels-last fp32: every shift is one contiguous row of C floats per side
+      const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
+      const float* rb = rT32 + ((int64_t)n * HW + (int64_t)oy * W + ox) * C;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const int c4n = C >> 2;
+      for (int s = 0; s < pp; ++s) {
+        const int dy = s / pw, dx = s - dy * pw;
+        const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)s * P_pad * C);
+        const float4* rrow = reinterpret_cast<const float4*>(rb + (int64_t)(dy * W + dx) * C);
+#pragma unroll 3
+        for (int c4 = lane; c4 < c4n; c4 += 32) {
+          const float4 qv = __ldg(qrow + c4), rv = __ldg(rrow + c4);
+          a0 = fmaf(qv.x, rv.x, a0); a1 = fmaf(qv.y, rv.y, a1);
+          a2 = fmaf(qv.z, rv.z, a2); a3 = fmaf(qv.w, rv.w, a3);
+        }
       }
+      float acc = (a0 + a1) + (a2 + a3);
       acc = warp_sum(acc);
       if (lane == 0) {
         const float Kf = (float)K;
@@ -616,16 +660,6 @@ rescore_kernel(const float* __restrict__ q_img, const float* __restrict__ r, con
         const PosStat ps = pos_stat(b1, b2, 1.0f / Kf, Kf);
         const int64_t qi = (int64_t)nq * P + patch;
         out = pearson(acc, ps, xs_a[qi], sxx_a[qi], Kf);
-        if (gaussian) {
-          // create_gaussian_masks (:779-807): float64, rounded to fp32
-          const double center_h = ((double)py + 0.5) * ph, center_w = ((double)px + 0.5) * pw;
-          const double hv = (double)(oy + (ph + 1) / 2) - (double)(ph % 2) / 2.0;
-          const double wv = (double)(ox + (pw + 1) / 2) - (double)(pw % 2) / 2.0;
-          const double sh = 0.5 * H, sw = 0.5 * W;
-          const double rg = ((hv - center_h) * (hv - center_h)) / (sh * sh);
-          const double cg = ((wv - center_w) * (wv - center_w)) / (sw * sw);
-          out *= (float)exp(-4.0 * 0.693147180559945309417232121458 * (rg + cg));
-        }
       }
     }
     if (lane == 0) ex_v[warp] = out;
@@ -635,6 +669,18 @@ rescore_kernel(const float* __restrict__ q_img, const float* __restrict__ r, con
     // final top-k among the KC exact values, (value desc, index asc); NaN ranks first like torch.topk
     float myv = (lane < KC) ? ex_v[lane] : -INFINITY;
     int myi = (lane < KC) ? sel_i[lane] : -1;
+    if (gaussian && myi >= 0) {
+      // create_gaussian_masks (:779-807): float64, rounded to fp32.  One lane per candidate: the
+      // fp64 exp runs once per CTA as a warp-wide instruction stream, not once per warp on one lane.
+      const int oy = myi / cw, ox = myi - oy * cw;
+      const double center_h = ((double)py + 0.5) * ph, center_w = ((double)px + 0.5) * pw;
+      const double hv = (double)(oy + (ph + 1) / 2) - (double)(ph % 2) / 2.0;
+      const double wv = (double)(ox + (pw + 1) / 2) - (double)(pw % 2) / 2.0;
+      const double sh = 0.5 * H, sw = 0.5 * W;
+      const double rg = ((hv - center_h) * (hv - center_h)) / (sh * sh);
+      const double cg = ((wv - center_w) * (wv - center_w)) / (sw * sw);
+      myv *= (float)exp(-4.0 * 0.693147180559945309417232121458 * (rg + cg));
+    }
     bool taken = myi < 0;
     float vk = -INFINITY;
     for (int t = 0; t < k; ++t) {
@@ -694,10 +740,10 @@ static EncodeTiledFn encode_fn() {
 
 struct Plan {
   int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks;
-  int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid;
+  int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid, a_rows, SB;
   size_t smem_bytes;
   // workspace offsets (bytes)
-  size_t off_rT, off_A, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, total;
+  size_t off_rT, off_A, off_r32, off_A32, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, total;
   bool ok;
 };
 
@@ -718,6 +764,13 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   pl.P = (H / ph) * (W / pw);
   pl.P_pad = (pl.P + kTileM - 1) / kTileM * kTileM;
   pl.m_tiles = pl.P_pad / kTileM;
+  // rows fetched per A stage: a small patch grid does not pay for the 128-row UMMA tile (the MMA
+  // reads stale shared memory for the other rows; accumulator rows are independent and discarded)
+  pl.a_rows = pl.m_tiles == 1 ? (pl.P + 7) / 8 * 8 : kTileM;
+  // shifts per A stage: as many whole shift sub-tiles as fit the 16 KB stage (fewer, fatter stages)
+  pl.SB = 1;
+  for (int d = pl.S; d >= 1; --d)
+    if (pl.S % d == 0 && d * pl.a_rows * kChunk * 2 <= kABytes && d <= 256) { pl.SB = d; break; }
   pl.chunks = C / kChunk;
   const int halo = (ph - 1) * W + pw - 1;
   const int span = (H - ph + 1) * W;  // linear origins 0 .. span-1 cover every valid window
@@ -762,6 +815,8 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   size_t o = 0;
   pl.off_rT = o;  o = align_up(o + (size_t)NP * pl.HW * C * 2, 256);
   pl.off_A = o;   o = align_up(o + (size_t)NQ * pl.S * pl.P_pad * C * 2, 256);
+  pl.off_r32 = o; o = align_up(o + (size_t)NP * pl.HW * C * 4, 256);
+  pl.off_A32 = o; o = align_up(o + (size_t)NQ * pl.S * pl.P_pad * C * 4, 256);
   pl.off_s1 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * 4, 256);
@@ -784,7 +839,7 @@ static int launch_gemm(const Plan& pl, const CUtensorMap& ta, const CUtensorMap&
 
 static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int C, int H, int W, int ph,
                int pw, int k, int gaussian, float* val, int32_t* idx, int32_t* n_uncertified, float* dump,
-               void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               long long* timing, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const Plan pl = make_plan(NP, q_repeat, C, H, W, ph, pw, k);
   if (!pl.ok) return CLC_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < pl.total) return CLC_ERR_WORKSPACE;
@@ -798,6 +853,8 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
   __nv_bfloat16* rT = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_rT);
   __nv_bfloat16* Apk = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_A);
+  float* rT32 = reinterpret_cast<float*>(ws + pl.off_r32);
+  float* A32 = reinterpret_cast<float*>(ws + pl.off_A32);
   float* s1 = reinterpret_cast<float*>(ws + pl.off_s1);
   float* s2 = reinterpret_cast<float*>(ws + pl.off_s2);
   float* xs = reinterpret_cast<float*>(ws + pl.off_xs);
@@ -811,7 +868,7 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   {
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)pl.P_pad, (cuuint64_t)(NQ * pl.S)};
     const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)pl.P_pad * C * 2};
-    const cuuint32_t box[3] = {kChunk, kTileM, 1};
+    const cuuint32_t box[3] = {kChunk, (cuuint32_t)pl.a_rows, (cuuint32_t)pl.SB};
     const cuuint32_t es[3] = {1, 1, 1};
     CUresult cr = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Apk, dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -836,7 +893,7 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     if (sm > 48 * 1024)
       CLC_CUDA(cudaFuncSetAttribute(pack_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((pl.HW + 31) / 32, (unsigned)NP);
-    pack_ref_kernel<<<grid, 256, sm, st>>>(r, rT, s1, s2, C, pl.HW);
+    pack_ref_kernel<<<grid, 256, sm, st>>>(r, rT, rT32, s1, s2, C, pl.HW);
     CLC_CHECK_LAUNCH("clc_match_topk_tc(pack_ref)");
   }
   {
@@ -845,7 +902,7 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     if (sm > 48 * 1024)
       CLC_CUDA(cudaFuncSetAttribute(pack_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid(H / ph, C / 64, (unsigned)NQ);
-    pack_query_kernel<<<grid, 256, sm, st>>>(q_img, Apk, C, H, W, ph, pw, pl.P, pl.P_pad);
+    pack_query_kernel<<<grid, 256, sm, st>>>(q_img, Apk, A32, C, H, W, ph, pw, pl.P, pl.P_pad);
     CLC_CHECK_LAUNCH("clc_match_topk_tc(pack_query)");
   }
   {
@@ -863,9 +920,12 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   prm.TN = pl.TN; prm.NACC = pl.NACC; prm.n_tiles = pl.n_tiles; prm.m_tiles = pl.m_tiles;
   prm.total_tiles = pl.total_tiles; prm.chunks = pl.chunks;
   prm.nboxB = pl.nboxB; prm.a_stages = pl.a_stages; prm.b_bufs = pl.b_bufs; prm.acc_stages = pl.acc_stages;
-  prm.tmem_cols = pl.tmem_cols; prm.KC = pl.KC; prm.gaussian = gaussian;
+  prm.tmem_cols = pl.tmem_cols; prm.a_rows = pl.a_rows; prm.SB = pl.SB; prm.KC = pl.KC; prm.gaussian = gaussian;
   prm.s1 = s1; prm.s2 = s2; prm.xs = xs; prm.sxx = sxx; prm.cand_val = cand_val; prm.cand_idx = cand_idx;
   prm.dump = dump;
+  prm.timing = timing;
+  prm.dbg = 0;
+  if (timing) { const char* e = getenv("CLC_TC_DBG"); if (e) prm.dbg = atoi(e); }
   int rc;
   if (pl.KC == 8) rc = gaussian ? launch_gemm<8, true>(pl, ta, tb, prm, st) : launch_gemm<8, false>(pl, ta, tb, prm, st);
   else rc = gaussian ? launch_gemm<16, true>(pl, ta, tb, prm, st) : launch_gemm<16, false>(pl, ta, tb, prm, st);
@@ -877,7 +937,7 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
     const size_t sm = (size_t)pl.n_tiles * pl.KC * 8;
     if (sm > 48 * 1024) return CLC_ERR_UNSUPPORTED;
-    rescore_kernel<<<(unsigned)blocks, pl.KC * 32, sm, st>>>(q_img, r, s1, s2, xs, sxx, cand_val, cand_idx,
+    rescore_kernel<<<(unsigned)blocks, pl.KC * 32, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
                                                              pl.n_tiles, pl.KC, q_repeat, C, H, W, ph, pw, pl.P, k,
                                                              gaussian, val, idx, n_uncertified);
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
@@ -904,7 +964,7 @@ extern "C" int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP,
   if (NP == 0) return CLC_OK;
   if (k > (H - ph + 1) * (W - pw + 1)) return CLC_ERR_INVALID_ARGUMENT;
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, n_uncertified,
-                 nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+                 nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // Bring-up / test hook (not part of the public header): additionally dumps the raw bf16-GEMM
@@ -915,5 +975,15 @@ extern "C" CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r,
                                              void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_img || !r || !val || !idx || !xy || NP < 1) return CLC_ERR_INVALID_ARGUMENT;
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, nullptr, xy,
-                 workspace, workspace_bytes, (cudaStream_t)stream);
+                 nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Bring-up hook: per-CTA clock64 stamps of the GEMM kernel's pipeline stages ([148][16] int64).
+extern "C" CLC_API int clc_debug_match_tc_timing(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
+                                                 int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                                 int32_t gaussian_mask, float* val, int32_t* idx, long long* timing,
+                                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q_img || !r || !val || !idx || !timing || NP < 1) return CLC_ERR_INVALID_ARGUMENT;
+  return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, nullptr, nullptr,
+                 timing, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -202,11 +202,10 @@ class LatentPath:
         call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
              ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
         r = self.refs.view(B * R, M, h, w)
-        call("clc_gather_blend_bwd", ptr(r), ptr(self.idx), ptr(self.weights), self.T, ptr(self.g_aligned),
-             ptr(self.g_refs), ptr(self.g_val), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
-        call("clc_pearson_topk_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx),
-             ptr(self.g_val), ptr(self.g_refs), ptr(self.g_q), B * R, self.P, M, p, p, h, w, k, st)
-        n += 4
+        call("clc_match_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx), ptr(self.weights),
+             self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val), B * R, self.P, M,
+             p, p, h, w, k, st)
+        n += 3
         return n
 
     def step(self):

@@ -296,12 +296,54 @@ def _cached_mask(h, w, ph, pw, device):
     return m
 
 
+class _MatchGatherFn(torch.autograd.Function):
+    """(y, r) -> aligned references: masked Pearson top-k + softmax-weighted gather in the forward,
+    ONE fused backward kernel (clc_match_bwd) for both -- the single-scale wiring where the
+    gathered feature map is the matched reference itself."""
+
+    @staticmethod
+    def forward(ctx, q_img, r, mask, ph, pw, k, q_repeat, temperature, mode):
+        with torch.no_grad():
+            val, idx = _PearsonTopkFn.apply(q_img, r, mask, ph, pw, k, q_repeat, mode)
+        NP, Cc, fh, fw = r.shape
+        out = torch.empty_like(r)
+        weights = torch.empty(idx.shape, dtype=torch.float32, device=r.device)
+        call("clc_gather_blend_fwd", ptr(r), ptr(idx), ptr(val), float(temperature), ptr(out), ptr(weights), NP,
+             Cc, fh, fw, ph, pw, fw - pw + 1, k, 0, _stream())
+        ctx.save_for_backward(q_img, r, mask, idx, weights)
+        ctx.geom = (ph, pw, k, q_repeat, float(temperature))
+        ctx.mark_non_differentiable(idx)
+        return out, val, idx
+
+    @staticmethod
+    def backward(ctx, g_out, _g_val, _g_idx):
+        q_img, r, mask, idx, weights = ctx.saved_tensors
+        ph, pw, k, q_repeat, temperature = ctx.geom
+        NP, Cc, fh, fw = r.shape
+        P = idx.shape[1]
+        g_r = torch.zeros_like(r)
+        g_q = torch.zeros_like(q_img) if ctx.needs_input_grad[0] else None
+        view = _patch_view_from_image(q_img, ph, pw, q_repeat)
+        call("clc_match_bwd", C.byref(view), ptr(r), ptr(mask), ptr(idx), ptr(weights), temperature,
+             ptr(g_out.contiguous()), ptr(g_r), ptr(g_q), None, NP, P, Cc, ph, pw, fh, fw, k, _stream())
+        return g_q, g_r, None, None, None, None, None, None, None
+
+
 def match_and_gather(y, refs, patch_h=4, patch_w=4, k=4, temperature=15.0, gaussian_mask=True,
                      is_stack=False, mode="tc"):
     """match_topk + gather/blend: aligned references [B, R, C(*k), h, w]."""
-    val, idx, r = match_topk(y, refs, patch_h, patch_w, k, gaussian_mask, mode)
-    B, R, P, _ = val.shape
-    h, w = r.shape[2], r.shape[3]
-    out = _GatherBlendFn.apply(r, val.view(B * R, P, k), idx.view(B * R, P, k), patch_h, patch_w,
-                               w - patch_w + 1, temperature, is_stack)
-    return out.view(B, R, -1, h, w)
+    if is_stack:
+        val, idx, r = match_topk(y, refs, patch_h, patch_w, k, gaussian_mask, mode)
+        B, R, P, _ = val.shape
+        h, w = r.shape[2], r.shape[3]
+        out = _GatherBlendFn.apply(r, val.view(B * R, P, k), idx.view(B * R, P, k), patch_h, patch_w,
+                                   w - patch_w + 1, temperature, is_stack)
+        return out.view(B, R, -1, h, w)
+    _check(y, "y")
+    if isinstance(refs, (list, tuple)):
+        refs = torch.stack(list(refs), dim=1)
+    B, R, Cc, h, w = refs.shape
+    r = refs.reshape(B * R, Cc, h, w).contiguous()
+    mask = _cached_mask(h, w, patch_h, patch_w, y.device) if gaussian_mask else None
+    out, _, _ = _MatchGatherFn.apply(y.contiguous(), r, mask, patch_h, patch_w, int(k), R, float(temperature), mode)
+    return out.view(B, R, Cc, h, w)

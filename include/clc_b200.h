@@ -228,6 +228,18 @@ CLC_API int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const
                          int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
                          int32_t fh, int32_t fw, int32_t k, void* stream);
 
+/* Fused backward of clc_gather_blend_fwd (is_stack = 0) + the masked Pearson top-k values for the
+ * single-scale wiring in which the gathered feature map IS the matched reference (feat == r and
+ * the gather patch equals the match patch): equivalent to clc_gather_blend_bwd followed by
+ * clc_pearson_topk_bwd, with one pass of reductions and ONE scatter-add per window element.
+ *   g_out : [NP, C, fh, fw] dL/d(blended reference);  weights : [NP, P, k] from the forward
+ *   g_r ACCUMULATED [NP, C, fh, fw];  g_q ACCUMULATED through `qv` (may be NULL);
+ *   g_val : optional out [NP, P, k] = dL/d(masked corr value) (may be NULL) */
+CLC_API int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* mask, const int32_t* idx,
+                          const float* weights, float temperature, const float* g_out, float* g_r,
+                          float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
+                          int32_t fh, int32_t fw, int32_t k, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * CLM conditional fusion (elementwise part; the 1x1 / 3x3 convolutions stay nn.Conv2d)
  * ---------------------------------------------------------------------------------- */
@@ -246,6 +258,24 @@ CLC_API int clc_clm_fuse_fwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb,
 CLC_API int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb, const float* att,
                              int64_t att_sr, int64_t att_sb, const float* g_out, float* g_ref_t,
                              float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Bring-up / test hooks of the tcgen05 match kernel (no reference counterpart; used by
+ * tests/test_match_tc_gpu.py and scripts/tc_timing.py)
+ * ---------------------------------------------------------------------------------- */
+
+/* clc_match_topk_tc that additionally dumps the raw bf16-GEMM accumulators
+ * xy[NP, P, H*W] (linear window origins oy*W+ox, wrapped ones included). */
+CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat, int32_t C,
+                                  int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                  int32_t gaussian_mask, float* val, int32_t* idx, float* xy, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+/* clc_match_topk_tc that additionally records per-CTA clock64 stamps of the GEMM kernel's
+ * pipeline stages into timing[148][16] (int64). */
+CLC_API int clc_debug_match_tc_timing(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
+                                      int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                      int32_t gaussian_mask, float* val, int32_t* idx, long long* timing,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
