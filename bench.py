@@ -167,10 +167,34 @@ class PublicPath:
         return bpp
 
 
+def _make_path(cfg, args, dev, fused, rank):
+    from clc_b200.latent_path import LatentPath
+    lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=args.match_mode,
+                    fused_slices=fused, device=dev)
+    lp.randomize(seed=1 + rank)
+    return lp
+
+
+def _time_steps(run, exchange, flush, K, barrier):
+    """K steps, each bracketed by its own CUDA events (the L2 flush sits outside the bracket).
+    Returns the summed device time in ms."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        run()
+        exchange()
+        b.record()
+    torch.cuda.synchronize()
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in ev)
+
+
 def run_ours(args):
     from clc_b200 import _lib
     from clc_b200 import dist as cdist
-    from clc_b200.latent_path import LatentPath
     rank, world, local = cdist.init_from_env("nccl")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -178,13 +202,16 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     cfg = WORKLOADS[args.workload]
     K, Wm = args.steps, max(args.warmup, 3)
-    lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=args.match_mode,
-                    fused_slices=args.fused_slices, device=dev)
-    lp.randomize(seed=1 + rank)
+    fused = not args.per_slice
+    lp = _make_path(cfg, args, dev, fused, rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     use_graph = not args.no_graph
-    launches_per_step = lp.step()  # also first-touch
+    launches_per_step_calls = lp.step()  # C-ABI calls per step; also first-touch
     torch.cuda.synchronize()
+    l0 = _lib.launches()
+    lp.step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launches() - l0          # kernels per step, counted inside the library
     if use_graph:
         lp.capture()
     run = lp.replay if use_graph else lp.step
@@ -193,14 +220,17 @@ def run_ours(args):
         if world > 1:
             torch.distributed.barrier()
 
-    def exchange():
+    def make_exchange(path):
         # the only collectives the path owns: EB parameter gradients (training)
         # and the 2-double bpp statistic, one NCCL all-reduce each per step.
-        if world > 1:
-            if cfg["train"]:
-                torch.distributed.all_reduce(lp._acc[4:4 + 192 * 58])
-            torch.distributed.all_reduce(lp.log2)
+        def exchange():
+            if world > 1:
+                if cfg["train"]:
+                    torch.distributed.all_reduce(path._acc[4:4 + 192 * 58])
+                torch.distributed.all_reduce(path.log2)
+        return exchange
 
+    exchange = make_exchange(lp)
     for _ in range(Wm):
         flush.zero_()
         run()
@@ -209,26 +239,14 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    l0 = _lib.launches()
-    barrier()
-    torch.cuda.synchronize()
     t_wall = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()          # L2 flush between timed iterations (not inside the event bracket)
-        a.record()
-        run()
-        exchange()
-        b.record()
-    torch.cuda.synchronize()
-    barrier()
+    total_ms = _time_steps(run, exchange, flush, K, barrier)
     t_wall = time.perf_counter() - t_wall
-    gpu_launches = (_lib.launches() - l0) if not use_graph else launches_per_step * K
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    gpu_launches = launches_per_step * K
+    tms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
-    total_ms = total_ms.item()
+        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = tms.item()
     pix_per_step = world * cfg["B"] * cfg["H"] * cfg["W"]
     value = pix_per_step * K / (total_ms * 1e-3) / 1e6
     bpp_dev = lp.bpp().item()
@@ -241,6 +259,24 @@ def run_ours(args):
     b.record()
     torch.cuda.synchronize()
     warm_ms = a.elapsed_time(b) / K
+
+    # ---- the other slice-launch granularity, same timing rules, for context -----------------
+    lp2 = _make_path(cfg, args, dev, not fused, rank)
+    lp2.step()
+    torch.cuda.synchronize()
+    if use_graph:
+        lp2.capture()
+    run2 = lp2.replay if use_graph else lp2.step
+    ex2 = make_exchange(lp2)
+    for _ in range(Wm):
+        flush.zero_()
+        run2()
+        ex2()
+    t2 = torch.tensor([_time_steps(run2, ex2, flush, K, barrier)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    value_other = pix_per_step * K / (t2.item() * 1e-3) / 1e6
+    del lp2
 
     # ---- end to end through the public API, host buffers, H2D + D2H inside the timed region --
     pub = PublicPath(cfg, dev, args.match_mode)
@@ -269,72 +305,68 @@ def run_ours(args):
     e2e_value = pix_per_step * K / (e2e_ms.item() * 1e-3) / 1e6
     clocks = sampler.stop()
 
-    # ---- instrumented pass: CUDA events around every C-ABI call of the same step ------------
-    _lib.TRACE = []
+    # ---- per-kernel pass: the library records a CUDA event after EVERY kernel of the same step ---
+    per = {}
+    stream = torch.cuda.current_stream().cuda_stream
     for _ in range(K):
         flush.zero_()
-        lp.step()
-    torch.cuda.synchronize()
-    per = {}
-    for name, e0, e1 in _lib.TRACE:
-        t = per.setdefault(name, [0.0, 0])
-        t[0] += e0.elapsed_time(e1)
-        t[1] += 1
-    _lib.TRACE = None
+        torch.cuda.synchronize()
+        for name, ms in _lib.kernel_trace(lp.step, stream):
+            t = per.setdefault(name, [0.0, 0])
+            t[0] += ms
+            t[1] += 1
     pk = peaks()
-    alg = lp.algorithmic_bytes()
-    breakdown = {n: {"ms_per_step": t[0] / K, "calls_per_step": t[1] / K, "us_per_call": 1e3 * t[0] / t[1]}
+    work = lp.algorithmic_work()
+    breakdown = {n: {"us_per_step": 1e3 * t[0] / K, "launches_per_step": t[1] / K, "us_per_launch": 1e3 * t[0] / t[1]}
                  for n, t in per.items()}
-    dom = max(per, key=lambda n: per[n][0])
-    us = 1e3 * per[dom][0] / per[dom][1]
-    key = dom.replace("clc_", "")
-    traffic = None
+    traffic_db = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{args.workload}:{dom}")
-    if dom in ("clc_match_topk_tc", "clc_pearson_corr"):
-        flops = alg["match_flops"]
-        ach = flops / (us * 1e-6) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf"], "traffic": traffic, "us_per_launch": us, "peak_source": pk["src"],
-                "algorithmic_flop_per_launch": flops}
-    else:
-        nbytes = alg.get(key)
-        ach = (nbytes / (us * 1e-6) / 1e9) if nbytes else None
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+        traffic_db = json.load(open(tp))
+
+    def roof(name):
+        us = 1e3 * per[name][0] / per[name][1]
+        kind, amount = work.get(name, ("bytes", None))
+        traffic = traffic_db.get(f"{args.workload}:{name}")
+        if kind == "flops":
+            ach = amount / (us * 1e-6) / 1e12
+            return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf"], "traffic": traffic, "us_per_launch": us, "peak_source": pk["src"],
+                    "algorithmic_flop_per_launch": amount}
+        ach = (amount / (us * 1e-6) / 1e9) if amount else None
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": (ach / pk["hbm"]) if ach else None, "traffic": traffic, "us_per_launch": us,
-                "peak_source": pk["src"], "algorithmic_bytes_per_launch": nbytes}
-    # the bandwidth-bound entropy kernel, always reported next to the dominant one
-    g_us = breakdown.get("clc_gc_fwd", {}).get("us_per_call")
-    gc_roof = None
-    if g_us:
-        gbs = alg["gc_fwd"] / (g_us * 1e-6) / 1e9
-        gc_roof = {"kernel": "clc_gc_fwd", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                   "frac": gbs / pk["hbm"], "us_per_launch": g_us, "algorithmic_bytes_per_launch": alg["gc_fwd"]}
+                "peak_source": pk["src"], "algorithmic_bytes_per_launch": amount}
+
+    dom = max(per, key=lambda n: per[n][0])
+    rooflines = {n: roof(n) for n in per}
 
     if rank != 0:
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_time(cfg, budget_s=args.cpu_budget)
+    this_mode, other_mode = ("fused", "per-slice") if fused else ("per-slice", "fused")
     line = {
         "metric": "Mpix/s of CLC latent path (match+CLM+entropy)", "value": value, "unit": "Mpix/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
                    "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
-                   "slice_launches": "fused" if args.fused_slices else "per-slice", "cuda_graph": use_graph,
+                   "slice_launches": this_mode, "cuda_graph": use_graph,
                    "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                "api": "clc_b200 public autograd modules, pinned host inputs"},
+                "api": "clc_b200 public autograd modules (per-slice calls), pinned host inputs"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "roofline": roof,
-        "roofline_gc_fwd": gc_roof,
+        "roofline": rooflines[dom],
         "cpu_baseline": cpu,
+        f"value_{other_mode.replace('-', '_')}_launches": value_other,
         "l2_warm_ms_per_step": warm_ms,
         "kernel_launches_per_step": launches_per_step,
+        "abi_calls_per_step": launches_per_step_calls,
         "breakdown": breakdown,
+        "rooflines": rooflines,
         "bpp": bpp_dev,
         "wall_s_timed_region": t_wall,
     }
@@ -367,7 +399,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--match-mode", default="tc", choices=["tc", "fp32"])
-    ap.add_argument("--fused-slices", action="store_true")
+    ap.add_argument("--per-slice", action="store_true",
+                    help="launch the GaussianConditional / LRP kernels once per channel slice (the model's call "
+                         "pattern) instead of once over all slices (the isolated path's all-slices entry point)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -32,6 +32,10 @@ PROTOTYPES = {
     "clc_strerror": (C.c_char_p, [C.c_int]),
     "clc_last_cuda_error": (C.c_char_p, []),
     "clc_kernel_launch_count": (C.c_uint64, []),
+    "clc_trace_start": (C.c_int, [_p]),
+    "clc_trace_stop": (C.c_int, []),
+    "clc_trace_count": (C.c_int, []),
+    "clc_trace_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "clc_gc_fwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p,
                              _i64, _i64, _f, _f, _p]),
     "clc_gc_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f, _p, _i64,
@@ -60,7 +64,8 @@ PROTOTYPES = {
     "clc_pearson_topk_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
                                        _i32, _i32, _i32, _i32, _p]),
     "clc_match_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32,
-                                _i32, _i32, _i32, _p]),
+                                _i32, _i32, _i32, _p, _sz, _p]),
+    "clc_match_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                         _p, _sz, _p]),
     "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
@@ -113,6 +118,23 @@ def call(name, *args):
         cuda = h.clc_last_cuda_error().decode()
         raise RuntimeError(f"{name} failed: {msg}" + (f" [{cuda}]" if cuda and rc == -4 else ""))
     return rc
+
+
+def kernel_trace(fn, stream):
+    """Run fn() with per-kernel tracing on `stream`; returns [(label, ms), ...] in launch order."""
+    h = lib()
+    if h.clc_trace_start(stream) != 0:
+        raise RuntimeError("clc_trace_start failed")
+    try:
+        fn()
+    finally:
+        h.clc_trace_stop()
+    out = []
+    name, ms = C.c_char_p(), C.c_float()
+    for i in range(h.clc_trace_count()):
+        if h.clc_trace_get(i, C.byref(name), C.byref(ms)) == 0:
+            out.append((name.value.decode(), ms.value))
+    return out
 
 
 def launches():

@@ -23,11 +23,16 @@ inline int cuda_fail(cudaError_t e, const char* where) {
 // Process-wide count of kernels enqueued by this library (statistics only; bench.py reports it).
 extern std::atomic<unsigned long long> g_kernel_launches;
 
+// Per-kernel tracing (clc_trace_*): when on, one cudaEvent is recorded after every kernel launch.
+extern std::atomic<bool> g_trace_on;
+void trace_record(const char* name);
+
 #define CLC_CHECK_LAUNCH(where)                                  \
   do {                                                           \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return ::clc::cuda_fail(e__, where); \
     ::clc::g_kernel_launches.fetch_add(1, std::memory_order_relaxed); \
+    if (::clc::g_trace_on.load(std::memory_order_relaxed)) ::clc::trace_record(where); \
   } while (0)
 
 #define CLC_CUDA(call)                                           \

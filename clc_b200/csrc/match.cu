@@ -611,6 +611,188 @@ match_bwd_kernel(PatchAddr qa, const float* __restrict__ r, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Channels-last variant of the fused backward (the fast path).  With the reference latents
+// transposed to [pixel][C] every window row is one contiguous run of C floats, so all loads are
+// coalesced float4 and the scatter is a float4 vector atomic (red.global.add.v4.f32) into a
+// channels-last gradient scratch that a tiled transpose then adds into the NCHW output.
+// The query and upstream-gradient patches are staged once per CTA in shared memory as [shift][C].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ xT, int C, int HW) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + (int64_t)n * C * HW;
+  float* xTn = xT + (int64_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < C && p < HW) ? xn[(int64_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) xTn[(int64_t)p * C + c] = t[threadIdx.x][i];
+  }
+}
+
+// x[n][c][p] += xT[n][p][c]
+__global__ void __launch_bounds__(256)
+cl_to_nchw_add_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, int HW) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xTn = xT + (int64_t)n * C * HW;
+  float* xn = x + (int64_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < C && p < HW) ? xTn[(int64_t)p * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) xn[(int64_t)c * HW + p] += t[threadIdx.x][i];
+  }
+}
+
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// Requires C % 4 == 0 and pw == 4 with 16-byte aligned patch rows in q / g_out / g_q.
+__global__ void __launch_bounds__(256)
+match_bwd_cl_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __restrict__ mask,
+                    const int32_t* __restrict__ idx, const float* __restrict__ weights, float temperature,
+                    const float* __restrict__ g_out, float* __restrict__ g_rT, float* __restrict__ g_q,
+                    float* __restrict__ g_val_out, int P, int C, int ph, int pw, int fh, int fw, int k) {
+  extern __shared__ float4 sm4[];           // Q[S][C/4], G[S][C/4]
+  __shared__ float red[8][4];
+  __shared__ float sums[kMaxK][4];          // per window: g_w, s1, s2, xy
+  __shared__ float coef[kMaxK][4];          // per window: w_j, g_xy, 2*g_dY, c_mean
+  __shared__ int src_s[kMaxK];
+  __shared__ float qcoef[2];
+  const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
+  const int HW = fh * fw;
+  const int n = blockIdx.x / P;
+  const int patch = blockIdx.x - n * P;
+  const int nq = n / qa.repeat;
+  const int npx = fw / pw;
+  const int py = patch / npx, px = patch - py * npx;
+  const int S = ph * pw, c4n = C >> 2, K = C * S;
+  const int items = S * c4n;                // float4 items of one patch / window
+  float4* Q = sm4;
+  float4* G = sm4 + items;
+  float* Qf = reinterpret_cast<float*>(Q);
+  float* Gf = reinterpret_cast<float*>(G);
+  const float Kf = (float)K, inv_k = 1.0f / Kf;
+  const int64_t po = ((int64_t)n * P + patch) * k;
+  if (threadIdx.x < k) {
+    const int id = idx[po + threadIdx.x];
+    const int oy = id / cw, ox = id - oy * cw;
+    src_s[threadIdx.x] = oy * fw + ox;
+  }
+  // stage q and g patches: global rows (c, dy) of pw = 4 floats -> shared [s = dy*4+dx][c]
+  const float* qb = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+  const float* gb = g_out + (int64_t)n * C * HW + (py * ph) * fw + px * pw;
+  for (int e = threadIdx.x; e < C * ph; e += blockDim.x) {
+    const int dy = e / C, c = e - dy * C;   // c fastest: conflict-free shared stores
+    const float4 qv = ld4(qb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy);
+    const float4 gv = ld4(gb + (int64_t)c * HW + dy * fw);
+    const int s0 = dy * 4;
+    Qf[(s0 + 0) * C + c] = qv.x; Qf[(s0 + 1) * C + c] = qv.y; Qf[(s0 + 2) * C + c] = qv.z; Qf[(s0 + 3) * C + c] = qv.w;
+    Gf[(s0 + 0) * C + c] = gv.x; Gf[(s0 + 1) * C + c] = gv.y; Gf[(s0 + 2) * C + c] = gv.z; Gf[(s0 + 3) * C + c] = gv.w;
+  }
+  __syncthreads();
+  // patch statistics
+  float a = 0.f, b = 0.f, z0 = 0.f, z1 = 0.f;
+  for (int f = threadIdx.x; f < items; f += blockDim.x) {
+    const float4 v = Q[f];
+    a += (v.x + v.y) + (v.z + v.w);
+    b = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, b))));
+  }
+  block_sum4(a, b, z0, z1, red);
+  const float xs = a, sxx = b;
+  const float* rTn = rT + (int64_t)n * HW * C;
+  // per-window reductions
+  for (int j = 0; j < k; ++j) {
+    const int src0 = src_s[j];
+    float gw = 0.f, s1 = 0.f, s2 = 0.f, xy = 0.f;
+    for (int f = threadIdx.x; f < items; f += blockDim.x) {
+      const int s = f / c4n, c4 = f - s * c4n;
+      const int dy = s >> 2, dx = s & 3;
+      const float4 rv = ld4(rTn + (int64_t)(src0 + dy * fw + dx) * C + 4 * c4);
+      const float4 qv = Q[f], gv = G[f];
+      gw = fmaf(gv.x, rv.x, fmaf(gv.y, rv.y, fmaf(gv.z, rv.z, fmaf(gv.w, rv.w, gw))));
+      s1 += (rv.x + rv.y) + (rv.z + rv.w);
+      s2 = fmaf(rv.x, rv.x, fmaf(rv.y, rv.y, fmaf(rv.z, rv.z, fmaf(rv.w, rv.w, s2))));
+      xy = fmaf(qv.x, rv.x, fmaf(qv.y, rv.y, fmaf(qv.z, rv.z, fmaf(qv.w, rv.w, xy))));
+    }
+    block_sum4(gw, s1, s2, xy, red);
+    if (threadIdx.x == 0) { sums[j][0] = gw; sums[j][1] = s1; sums[j][2] = s2; sums[j][3] = xy; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float xm = xs / Kf;
+    const float dX = sxx - xm * xs;
+    float dot = 0.f;
+    for (int j = 0; j < k; ++j) dot = fmaf(weights[po + j], sums[j][0], dot);
+    float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float wj = weights[po + j];
+      const float gv = temperature * wj * (sums[j][0] - dot);
+      if (g_val_out) g_val_out[po + j] = gv;
+      const float s1 = sums[j][1], s2 = sums[j][2], xy = sums[j][3];
+      const float ym = s1 * inv_k;
+      const float dY = s2 - ym * ym * Kf;
+      const float D = dY * dX;
+      const float num = xy - ym * xs;
+      const float rs = rsqrtf(D);
+      float g = gv;
+      if (mask) g *= mask[(int64_t)patch * L + idx[po + j]];
+      const float g_num = g * rs;
+      const float g_D = -0.5f * g * num * rs / D;
+      const float g_dY = g_D * dX, g_dX = g_D * dY;
+      const float g_ym = -g_num * xs - 2.f * g_dY * ym * Kf;
+      t_gxs += -g_num * ym - g_dX * xm;
+      t_gsxx += g_dX;
+      t_gxm += -g_dX * xs;
+      coef[j][0] = wj; coef[j][1] = g_num; coef[j][2] = 2.f * g_dY; coef[j][3] = g_ym * inv_k;
+    }
+    qcoef[0] = 2.f * t_gsxx;
+    qcoef[1] = t_gxs + t_gxm * inv_k;
+  }
+  __syncthreads();
+  float* g_rTn = g_rT + (int64_t)n * HW * C;
+  for (int j = 0; j < k; ++j) {
+    const int src0 = src_s[j];
+    const float cw_ = coef[j][0], cxy = coef[j][1], cdy = coef[j][2], cm = coef[j][3];
+    for (int f = threadIdx.x; f < items; f += blockDim.x) {
+      const int s = f / c4n, c4 = f - s * c4n;
+      const int dy = s >> 2, dx = s & 3;
+      const int64_t o = (int64_t)(src0 + dy * fw + dx) * C + 4 * c4;
+      const float4 rv = ld4(rTn + o);
+      const float4 qv = Q[f], gv = G[f];
+      float4 v;
+      v.x = fmaf(cw_, gv.x, fmaf(cxy, qv.x, fmaf(cdy, rv.x, cm)));
+      v.y = fmaf(cw_, gv.y, fmaf(cxy, qv.y, fmaf(cdy, rv.y, cm)));
+      v.z = fmaf(cw_, gv.z, fmaf(cxy, qv.z, fmaf(cdy, rv.z, cm)));
+      v.w = fmaf(cw_, gv.w, fmaf(cxy, qv.w, fmaf(cdy, rv.w, cm)));
+      red_add4(g_rTn + o, v);
+    }
+  }
+  if (g_q) {
+    float* gqb = g_q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+    const float c0 = qcoef[0], c1 = qcoef[1];
+    for (int e = threadIdx.x; e < C * ph; e += blockDim.x) {
+      const int dy = e / C, c = e - dy * C;
+      const int s0 = dy * 4;
+      float4 v;
+      v.x = fmaf(c0, Qf[(s0 + 0) * C + c], c1); v.y = fmaf(c0, Qf[(s0 + 1) * C + c], c1);
+      v.z = fmaf(c0, Qf[(s0 + 2) * C + c], c1); v.w = fmaf(c0, Qf[(s0 + 3) * C + c], c1);
+      red_add4(gqb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy, v);
+    }
+  }
+}
+
 // Host helpers shared with match_tc.cu --------------------------------------------------------
 int launch_channel_sums(const float* r, float* s1, float* s2, int64_t NP, int C, int64_t HW,
                         cudaStream_t st) {
@@ -759,18 +941,49 @@ extern "C" int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, co
   return CLC_OK;
 }
 
+extern "C" size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw) {
+  if (NP < 0 || C < 1 || fh < 1 || fw < 1) return 0;
+  return 2 * sizeof(float) * (size_t)NP * C * fh * fw + 512;  // channels-last copy of r + gradient scratch
+}
+
 extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* mask, const int32_t* idx,
                              const float* weights, float temperature, const float* g_out, float* g_r,
                              float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
-                             int32_t pw, int32_t fh, int32_t fw, int32_t k, void* stream) {
+                             int32_t pw, int32_t fh, int32_t fw, int32_t k, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (!view_ok(qv) || !r || !idx || !weights || !g_out || !g_r) return CLC_ERR_INVALID_ARGUMENT;
   if (NP < 0 || P < 1 || C < 1 || ph < 1 || pw < 1 || fh < ph || fw < pw || k < 1) return CLC_ERR_INVALID_ARGUMENT;
   if (fh % ph || fw % pw || P != (fh / ph) * (fw / pw)) return CLC_ERR_INVALID_ARGUMENT;
   if (k > kMaxK) return CLC_ERR_UNSUPPORTED;
   if (NP == 0) return CLC_OK;
-  if (NP * P > 2147483647LL || (int64_t)C * fh * fw > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
-  match_bwd_kernel<<<(unsigned)(NP * P), 256, 0, (cudaStream_t)stream>>>(
-      make_addr(qv), r, mask, idx, weights, temperature, g_out, g_r, g_q, g_val, P, C, ph, pw, fh, fw, k);
-  CLC_CHECK_LAUNCH("clc_match_bwd");
+  if (NP * P > 2147483647LL || (int64_t)C * fh * fw > 0x7fffffffLL || NP > 65535) return CLC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const PatchAddr qa = make_addr(qv);
+  const size_t smem = (size_t)2 * ph * pw * C * sizeof(float);
+  // fast path: channels-last operands, float4 everywhere (needs a workspace and 16-byte aligned patch rows)
+  const bool cl_ok = workspace && pw == 4 && C % 4 == 0 && fw % 4 == 0 && smem <= 200 * 1024 && aligned16(qv->q) &&
+                     aligned16(g_out) && (!g_q || aligned16(g_q)) && qa.sy % 4 == 0 && qa.sc % 4 == 0 &&
+                     qa.spx % 4 == 0 && qa.spy % 4 == 0 && qa.sn % 4 == 0;
+  if (!cl_ok) {
+    match_bwd_kernel<<<(unsigned)(NP * P), 256, 0, st>>>(qa, r, mask, idx, weights, temperature, g_out, g_r, g_q,
+                                                        g_val, P, C, ph, pw, fh, fw, k);
+    CLC_CHECK_LAUNCH("clc_match_bwd");
+    return CLC_OK;
+  }
+  if (workspace_bytes < clc_match_bwd_workspace_bytes(NP, C, fh, fw)) return CLC_ERR_WORKSPACE;
+  const int HW = fh * fw;
+  float* rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float* g_rT = rT + (size_t)NP * C * HW;
+  dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
+  nchw_to_cl_kernel<<<tgrid, tblock, 0, st>>>(r, rT, C, HW);
+  CLC_CHECK_LAUNCH("clc_match_bwd(nchw_to_cl)");
+  CLC_CUDA(cudaMemsetAsync(g_rT, 0, sizeof(float) * (size_t)NP * C * HW, st));
+  if (smem > 48 * 1024)
+    CLC_CUDA(cudaFuncSetAttribute(match_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  match_bwd_cl_kernel<<<(unsigned)(NP * P), 256, smem, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT,
+                                                            g_q, g_val, P, C, ph, pw, fh, fw, k);
+  CLC_CHECK_LAUNCH("clc_match_bwd(main)");
+  cl_to_nchw_add_kernel<<<tgrid, tblock, 0, st>>>(g_rT, g_r, C, HW);
+  CLC_CHECK_LAUNCH("clc_match_bwd(cl_to_nchw)");
   return CLC_OK;
 }

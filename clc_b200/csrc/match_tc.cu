@@ -634,15 +634,32 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       const float* rb = rT32 + ((int64_t)n * HW + (int64_t)oy * W + ox) * C;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       const int c4n = C >> 2;
-      for (int s = 0; s < pp; ++s) {
-        const int dy = s / pw, dx = s - dy * pw;
-        const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)s * P_pad * C);
-        const float4* rrow = reinterpret_cast<const float4*>(rb + (int64_t)(dy * W + dx) * C);
-#pragma unroll 3
-        for (int c4 = lane; c4 < c4n; c4 += 32) {
-          const float4 qv = __ldg(qrow + c4), rv = __ldg(rrow + c4);
-          a0 = fmaf(qv.x, rv.x, a0); a1 = fmaf(qv.y, rv.y, a1);
-          a2 = fmaf(qv.z, rv.z, a2); a3 = fmaf(qv.w, rv.w, a3);
+      // loads of 4 shifts x 3 float4 columns are issued together (24 x 2 LDG.128 in flight per lane)
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int cb = 0; cb < c4n; cb += 96) {
+        for (int s0 = 0; s0 < pp; s0 += 4) {
+          float4 qv[4][3], rv[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u;
+            const int dy = s / pw, dx = s - dy * pw;
+            const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)s * P_pad * C);
+            const float4* rrow = reinterpret_cast<const float4*>(rb + (int64_t)(dy * W + dx) * C);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int c4 = cb + lane + 32 * i;
+              const bool ok = s < pp && c4 < c4n;
+              qv[u][i] = ok ? __ldg(qrow + c4) : zero4;
+              rv[u][i] = ok ? __ldg(rrow + c4) : zero4;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              a0 = fmaf(qv[u][i].x, rv[u][i].x, a0); a1 = fmaf(qv[u][i].y, rv[u][i].y, a1);
+              a2 = fmaf(qv[u][i].z, rv[u][i].z, a2); a3 = fmaf(qv[u][i].w, rv[u][i].w, a3);
+            }
         }
       }
       float acc = (a0 + a1) + (a2 + a3);

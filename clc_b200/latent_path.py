@@ -105,6 +105,8 @@ class LatentPath:
         else:
             raise ValueError(f'Invalid match mode "{match_mode}"')
         self.ws = torch.empty(max(int(nb), 16), dtype=torch.uint8, device=dev)
+        nbb = lib().clc_match_bwd_workspace_bytes(B * R, M, h, w) if train else 0
+        self.ws_bwd = torch.empty(max(int(nbb), 16), dtype=torch.uint8, device=dev)
         self._qview = matching._patch_view_from_image(self.y, patch, patch, R)
         self._gqview = self._qview
         self._graph = None
@@ -204,7 +206,7 @@ class LatentPath:
         r = self.refs.view(B * R, M, h, w)
         call("clc_match_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx), ptr(self.weights),
              self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val), B * R, self.P, M,
-             p, p, h, w, k, st)
+             p, p, h, w, k, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
         n += 3
         return n
 
@@ -238,20 +240,51 @@ class LatentPath:
         """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels."""
         return -(self.log2[0] + self.log2[1]) / self.num_pixels
 
-    # ---- algorithmic bytes per launch (SURVEY.md 8d) ---------------------------------------
-    def algorithmic_bytes(self):
+    # ---- algorithmic work per kernel launch (SURVEY.md 8d; stated in DESIGN.md) ------------------
+    def algorithmic_work(self):
+        """{trace label: ("bytes"|"flops", amount per launch)} for every kernel of one step.
+        Labels are the ones the library's per-kernel tracing reports (clc_trace_get)."""
         B, R, M, S, k, P = self.B, self.R, self.M, self.h * self.w, self.k, self.P
+        NP = B * R
+        K = M * self.patch ** 2
         n_slice = B * (M if self.fused_slices else self.Cs) * S
         nz = self.z.numel()
         t = self.train
-        return {
-            "gc_fwd": n_slice * (20 + (4 if t else 0)),     # read y,mu,scale(+noise) write lik,y_hat
-            "lrp_add_fwd": n_slice * 12,
-            "gc_bwd": n_slice * (20 + 4 + 12),              # read y,mu,scale,noise,lik,g_yhat write 3 grads
-            "lrp_add_bwd": n_slice * 12,
-            "eb_fwd": nz * (12 + (4 if t else 0)),
-            "eb_bwd": nz * (16 + 4),
-            "gather_blend_fwd": B * R * (k * M * S * 4 + P * k * 8 + M * S * 4),
-            "clm_fuse_fwd": B * ((R * (M + 1) + M) * S * 4 + M * S * 4),
-            "match_flops": 2.0 * P * (self.h - self.patch + 1) * (self.w - self.patch + 1) * M * self.patch ** 2 * B * R,
+        KC = 8 if k <= 4 else 16
+        L = (self.h - self.patch + 1) * (self.w - self.patch + 1)
+        w = {
+            "clc_gc_fwd": ("bytes", n_slice * (20 + (4 if t else 0))),     # y,mu,scale(+noise) -> lik,y_hat
+            "clc_lrp_add_fwd": ("bytes", n_slice * 12),
+            "clc_gc_bwd": ("bytes", n_slice * (20 + 4 + 12)),              # y,mu,scale,noise,lik,g_yhat -> 3 grads
+            "clc_lrp_add_bwd": ("bytes", n_slice * 12),
+            "clc_eb_fwd": ("bytes", nz * (12 + (4 if t else 0))),
+            "clc_eb_bwd": ("bytes", nz * (16 + 4)),
+            "clc_gather_blend_fwd": ("bytes", NP * (k * M * S * 4 + P * k * 8 + M * S * 4)),
+            "clc_clm_fuse_fwd": ("bytes", B * ((R * (M + 1) + M) * S * 4 + M * S * 4)),
+            "clc_clm_fuse_bwd": ("bytes", B * ((R * (M + 1) + M) * S * 4 + R * (M + 1) * S * 4)),
+            # tensor-core match: 2*P*L*C*ph*pw flop per (image, reference), counted once
+            "clc_match_topk_tc(gemm)": ("flops", 2.0 * P * L * K * NP),
+            "clc_match_topk_tc(pack_ref)": ("bytes", NP * M * S * (4 + 2 + 4) + NP * S * 8),
+            "clc_match_topk_tc(pack_query)": ("bytes", B * M * S * (4 + 2 + 4)),
+            "patch_stats": ("bytes", B * M * S * 4 + B * P * 8),
+            "clc_match_topk_tc(rescore)": ("bytes", NP * P * K * 4 * (KC + 1) + NP * P * k * 8),
+            "clc_pearson_corr": ("flops", 2.0 * P * L * K * NP),
+            "clc_topk_rows": ("bytes", NP * P * L * 4 + NP * P * k * 8),
+            "channel_sums": ("bytes", NP * M * S * 4 + NP * S * 8),
+            # fused match backward: patches of q and g once, k windows read for the reductions and
+            # again for the scatter, k window read-modify-writes into the gradient scratch
+            "clc_match_bwd(nchw_to_cl)": ("bytes", NP * M * S * 8),
+            "clc_match_bwd(main)": ("bytes", NP * P * K * 4 * (2 + 2 * k + 2 * k) + B * M * S * 8),
+            "clc_match_bwd(cl_to_nchw)": ("bytes", NP * M * S * 12),
+            "clc_match_bwd": ("bytes", NP * P * K * 4 * (2 + 2 * k + 2 * k) + B * M * S * 8),
         }
+        return w
+
+    def algorithmic_bytes(self):
+        """Back-compat view: {short name: bytes} + match_flops."""
+        out = {}
+        for name, (kind, v) in self.algorithmic_work().items():
+            if kind == "bytes":
+                out[name.replace("clc_", "")] = v
+        out["match_flops"] = self.algorithmic_work()["clc_match_topk_tc(gemm)"][1]
+        return out

@@ -324,8 +324,10 @@ class _MatchGatherFn(torch.autograd.Function):
         g_r = torch.zeros_like(r)
         g_q = torch.zeros_like(q_img) if ctx.needs_input_grad[0] else None
         view = _patch_view_from_image(q_img, ph, pw, q_repeat)
+        ws = _workspace(lib().clc_match_bwd_workspace_bytes(NP, Cc, fh, fw), r.device)
         call("clc_match_bwd", C.byref(view), ptr(r), ptr(mask), ptr(idx), ptr(weights), temperature,
-             ptr(g_out.contiguous()), ptr(g_r), ptr(g_q), None, NP, P, Cc, ph, pw, fh, fw, k, _stream())
+             ptr(g_out.contiguous()), ptr(g_r), ptr(g_q), None, NP, P, Cc, ph, pw, fh, fw, k, ptr(ws), ws.numel(),
+             _stream())
         return g_q, g_r, None, None, None, None, None, None, None
 
 

@@ -50,6 +50,16 @@ CLC_API const char* clc_last_cuda_error(void);
 /* Number of CUDA kernels this library has enqueued in the calling process (statistics). */
 CLC_API uint64_t clc_kernel_launch_count(void);
 
+/* Per-kernel tracing (the reference only has wall-clock timers, train_CLC.py:126-217).
+ * Between clc_trace_start(stream) and clc_trace_stop() the library records one CUDA event on
+ * `stream` after every kernel it enqueues (all calls must target that stream; not capturable
+ * into a CUDA graph).  clc_trace_get(i) returns kernel i's label and the device time in ms
+ * since the previous event, i.e. that kernel's duration when launches are back to back. */
+CLC_API int clc_trace_start(void* stream);
+CLC_API int clc_trace_stop(void);
+CLC_API int clc_trace_count(void);
+CLC_API int clc_trace_get(int i, const char** name, float* ms);
+
 /* ------------------------------------------------------------------------------------
  * Entropy stage
  * ---------------------------------------------------------------------------------- */
@@ -234,11 +244,15 @@ CLC_API int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const
  * clc_pearson_topk_bwd, with one pass of reductions and ONE scatter-add per window element.
  *   g_out : [NP, C, fh, fw] dL/d(blended reference);  weights : [NP, P, k] from the forward
  *   g_r ACCUMULATED [NP, C, fh, fw];  g_q ACCUMULATED through `qv` (may be NULL);
- *   g_val : optional out [NP, P, k] = dL/d(masked corr value) (may be NULL) */
+ *   g_val : optional out [NP, P, k] = dL/d(masked corr value) (may be NULL)
+ *   workspace : clc_match_bwd_workspace_bytes(...) bytes enable the channels-last fast path
+ *               (coalesced float4 loads, vector atomics); NULL selects the workspace-free kernel. */
 CLC_API int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* mask, const int32_t* idx,
                           const float* weights, float temperature, const float* g_out, float* g_r,
                           float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
-                          int32_t fh, int32_t fw, int32_t k, void* stream);
+                          int32_t fh, int32_t fw, int32_t k, void* workspace, size_t workspace_bytes,
+                          void* stream);
+CLC_API size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw);
 
 /* ------------------------------------------------------------------------------------
  * CLM conditional fusion (elementwise part; the 1x1 / 3x3 convolutions stay nn.Conv2d)

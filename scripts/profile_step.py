@@ -18,11 +18,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--match-mode", default="tc")
-ap.add_argument("--fused-slices", action="store_true")
+ap.add_argument("--per-slice", action="store_true")
 a = ap.parse_args()
 cfg = WORKLOADS[a.workload]
 lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=a.match_mode,
-                fused_slices=a.fused_slices, device="cuda:0")
+                fused_slices=not a.per_slice, device="cuda:0")
 lp.randomize(seed=1)
 for _ in range(a.steps):
     lp.step()
