@@ -213,7 +213,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = _lib.launches() - l0          # kernels per step, counted inside the library
     if use_graph:
-        lp.capture()
+        lp.capture(fork=not args.no_fork)
     run = lp.replay if use_graph else lp.step
 
     def barrier():
@@ -265,7 +265,7 @@ def run_ours(args):
     lp2.step()
     torch.cuda.synchronize()
     if use_graph:
-        lp2.capture()
+        lp2.capture(fork=not args.no_fork)
     run2 = lp2.replay if use_graph else lp2.step
     ex2 = make_exchange(lp2)
     for _ in range(Wm):
@@ -278,14 +278,17 @@ def run_ours(args):
     value_other = pix_per_step * K / (t2.item() * 1e-3) / 1e6
     del lp2
 
-    # ---- end to end through the public API, host buffers, H2D + D2H inside the timed region --
-    pub = PublicPath(cfg, dev, args.match_mode)
-    host = {n: t.detach().cpu().pin_memory() for n, t in lp.inputs().items()}
-    names = [n for n in host if cfg["train"] or n not in ("noise_y", "noise_z", "g_y_hat", "g_fused")]
-    h2d = sum(host[n].numel() * 4 for n in names)
+    # ---- end to end, host buffers: H2D of the step's inputs + D2H of its result inside the timed
+    # region.  Headline: LatentPath.step_host (pinned flat staging buffer, two graphs, upload of the
+    # entropy inputs overlapped with the match chain).  Context: the same operator sequence through
+    # the per-operator autograd modules (eager, per-slice calls, as a model makes them).
+    host_flat, host_views = lp.host_staging()
+    for n, v in host_views.items():
+        v.copy_(getattr(lp, n))
+    h2d = lp.h2d_bytes_per_step()
+    lp.capture_split()
     for _ in range(Wm):
-        d = {n: host[n].to(dev, non_blocking=True) for n in names}
-        pub.step(d).item()
+        lp.step_host(host_flat)
     torch.cuda.synchronize()
     barrier()
     e2e_ev = []
@@ -293,9 +296,7 @@ def run_ours(args):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        d = {n: host[n].to(dev, non_blocking=True) for n in names}
-        res = pub.step(d)
-        res_host = res.item()          # device -> host read of the step's result
+        bpp_host = lp.step_host(host_flat)          # uploads, runs, reads the result back (synchronises)
         b.record()
         e2e_ev.append((a, b))
     torch.cuda.synchronize()
@@ -303,6 +304,29 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
     e2e_value = pix_per_step * K / (e2e_ms.item() * 1e-3) / 1e6
+
+    pub = PublicPath(cfg, dev, args.match_mode)
+    names = lp.step_inputs
+    for _ in range(Wm):
+        d = {n: host_views[n].to(dev, non_blocking=True) for n in names}
+        pub.step(d).item()
+    torch.cuda.synchronize()
+    barrier()
+    mod_ev = []
+    for _ in range(K):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        d = {n: host_views[n].to(dev, non_blocking=True) for n in names}
+        res = pub.step(d)
+        res_host = res.item()          # device -> host read of the step's result
+        b.record()
+        mod_ev.append((a, b))
+    torch.cuda.synchronize()
+    mod_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in mod_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(mod_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_modules_value = pix_per_step * K / (mod_ms.item() * 1e-3) / 1e6
     clocks = sampler.stop()
 
     # ---- per-kernel pass: the library records a CUDA event after EVERY kernel of the same step ---
@@ -353,10 +377,14 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
                    "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
-                   "slice_launches": this_mode, "cuda_graph": use_graph,
+                   "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else "match | hyper | slices",
                    "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
-        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                "api": "clc_b200 public autograd modules (per-slice calls), pinned host inputs"},
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                "api": "clc_b200.LatentPath.step_host: pinned host staging buffer -> 2 uploads -> match graph || "
+                       "entropy graph -> bpp read back",
+                "ms_per_step": e2e_ms.item() / K, "bpp": bpp_host,
+                "autograd_modules": {"value": e2e_modules_value, "ms_per_step": mod_ms.item() / K,
+                                     "api": "clc_b200 per-operator autograd modules, eager, per-slice calls"}},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": rooflines[dom],
@@ -403,6 +431,7 @@ def main():
                     help="launch the GaussianConditional / LRP kernels once per channel slice (the model's call "
                          "pattern) instead of once over all slices (the isolated path's all-slices entry point)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fork", action="store_true", help="capture the step as one serial chain instead of three branches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

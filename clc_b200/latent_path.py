@@ -23,6 +23,9 @@ class LatentPath:
     """Buffers + launch sequence for a batch of B images of H x W pixels with n_refs references."""
 
     INPUT_NAMES = ("y", "z", "refs", "mu", "scale", "lrp", "att", "noise_y", "noise_z", "g_y_hat", "g_fused")
+    MATCH_INPUTS = ("y", "refs", "att", "g_fused")                       # what match -> gather -> CLM reads
+    ENTROPY_INPUTS = ("z", "mu", "scale", "lrp", "noise_y", "noise_z", "g_y_hat")
+    TRAIN_ONLY = ("noise_y", "noise_z", "g_y_hat", "g_fused")
 
     def __init__(self, B, H, W, n_refs=3, M=320, num_slices=5, z_channels=192, train=True, patch=4, k=4,
                  temperature=15.0, match_mode="tc", gaussian_mask=True, fused_slices=False,
@@ -42,21 +45,35 @@ class LatentPath:
         self.device = dev
         f = dict(dtype=torch.float32, device=dev)
         h, w, R = self.h, self.w, n_refs
-        # ---- inputs (resident in HBM when the timed region starts) ----
-        self.y = torch.empty(B, M, h, w, **f)
-        self.z = torch.empty(B, z_channels, self.hz, self.wz, **f)
-        self.refs = torch.empty(B, R, M, h, w, **f)          # reference latents, [B,R] problem order
-        self.mu = torch.empty(B, M, h, w, **f)
-        self.scale = torch.empty(B, M, h, w, **f)
-        self.lrp = torch.empty(B, M, h, w, **f)
-        self.att = torch.empty(B, R, 1, h, w, **f)           # CLM attention logits
-        self.noise_y = torch.empty(B, M, h, w, **f)
-        self.noise_z = torch.empty(B, z_channels, self.hz, self.wz, **f)
-        self.g_y_hat = torch.empty(B, M, h, w, **f)          # upstream dL/dy_hat (from g_s)
-        self.g_fused = torch.empty(B, M, h, w, **f)          # upstream dL/d(CLM output)
+        # ---- inputs: ONE flat device buffer (views per tensor), match-chain inputs first so the
+        # host->device upload of a step can be split into two contiguous copies (step_host) ----
+        shapes = {"y": (B, M, h, w), "refs": (B, R, M, h, w), "att": (B, R, 1, h, w), "g_fused": (B, M, h, w),
+                  "z": (B, z_channels, self.hz, self.wz), "mu": (B, M, h, w), "scale": (B, M, h, w),
+                  "lrp": (B, M, h, w), "noise_y": (B, M, h, w), "noise_z": (B, z_channels, self.hz, self.wz),
+                  "g_y_hat": (B, M, h, w)}
+        self.step_inputs = [n for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS
+                            if train or n not in self.TRAIN_ONLY]
+        offs, off = {}, 0
+        for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS:
+            if n == self.ENTROPY_INPUTS[0]:
+                self._n_match_in = off
+            offs[n] = off
+            off += (math.prod(shapes[n]) + 63) // 64 * 64       # 256-byte aligned segments
+            if not train and n in self.TRAIN_ONLY:
+                off = offs[n]                                   # eval: no noise / upstream gradients uploaded
+        self._in = torch.zeros(off, **f)
+        self._in_offsets, self._in_shapes = offs, shapes
+        for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS:
+            if n in self.step_inputs:
+                setattr(self, n, self._in[offs[n]:offs[n] + math.prod(shapes[n])].view(shapes[n]))
+            else:
+                setattr(self, n, torch.empty(shapes[n], **f))   # unused in eval; kept for API symmetry
         # ---- EntropyBottleneck parameters ----
         from .entropy_models import EntropyBottleneck
-        eb = EntropyBottleneck(z_channels).to(dev)
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(0)                              # EB biases are U(-.5,.5): keep runs comparable
+            eb = EntropyBottleneck(z_channels)
+        eb = eb.to(dev)
         self.eb_m = [getattr(eb, f"_matrix{i}").detach() for i in range(5)]
         self.eb_b = [getattr(eb, f"_bias{i}").detach() for i in range(5)]
         self.eb_f = [getattr(eb, f"_factor{i}").detach() for i in range(4)]
@@ -80,11 +97,14 @@ class LatentPath:
         self.g_aligned = torch.empty(B, R, M, h, w, **f)
         self.g_att = torch.empty(B, R, 1, h, w, **f)
         self.g_val = torch.empty(B * R, self.P, k, **f)
-        # ---- accumulators: one flat buffer, one memset per step ----
+        # ---- accumulators: one flat buffer; each chain zeroes its own segment with one memset ----
         n_eb = sum(t.numel() for t in self.eb_m + self.eb_b + self.eb_f)
         n_acc = 4 + n_eb + B * R * M * h * w + B * M * h * w   # 2 doubles + EB grads + g_refs + g_q
         self._acc = torch.zeros(n_acc, **f)
         self.log2 = self._acc[:4].view(torch.float64)          # [sum log2 lik_y, sum log2 lik_z]
+        self._acc_y = self._acc[0:2]                           # slice-loop chain
+        self._acc_eb = self._acc[2:4 + n_eb]                   # hyper-latent chain (log2[1] + EB grads)
+        self._acc_match = self._acc[4 + n_eb:]                 # match chain (g_refs, g_q)
         off = 4
         self.g_eb = []
         for t in self.eb_m + self.eb_b + self.eb_f:
@@ -109,7 +129,8 @@ class LatentPath:
         self.ws_bwd = torch.empty(max(int(nbb), 16), dtype=torch.uint8, device=dev)
         self._qview = matching._patch_view_from_image(self.y, patch, patch, R)
         self._gqview = self._qview
-        self._graph = None
+        self._graph = self._g_match = self._g_entropy = None
+        self._streams = None
 
     # -------------------------------------------------------------------------------------
     def randomize(self, seed=1):
@@ -132,16 +153,26 @@ class LatentPath:
     def inputs(self):
         return {n: getattr(self, n) for n in self.INPUT_NAMES}
 
+    # ---- host staging (end-to-end path) ------------------------------------------------------
+    def host_staging(self):
+        """(flat pinned fp32 buffer, {name: view}) laid out like the device input buffer, so a
+        whole step's inputs are uploaded with two contiguous copies (see step_host)."""
+        flat = torch.empty(self._in.numel(), dtype=torch.float32).pin_memory()
+        views = {n: flat[self._in_offsets[n]:self._in_offsets[n] + math.prod(self._in_shapes[n])]
+                 .view(self._in_shapes[n]) for n in self.step_inputs}
+        return flat, views
+
     def load_inputs(self, host):
-        """Host (pinned) -> device copies of one step's inputs; returns bytes copied."""
+        """Host (pinned) -> device copies of one step's inputs, one per tensor; returns bytes copied."""
         n = 0
-        for name in self.INPUT_NAMES:
-            if not self.train and name in ("noise_y", "noise_z", "g_y_hat", "g_fused"):
-                continue
+        for name in self.step_inputs:
             dst = getattr(self, name)
             dst.copy_(host[name], non_blocking=True)
             n += dst.numel() * 4
         return n
+
+    def h2d_bytes_per_step(self):
+        return sum(math.prod(self._in_shapes[n]) for n in self.step_inputs) * 4
 
     # -------------------------------------------------------------------------------------
     def _slices(self, t):
@@ -149,92 +180,171 @@ class LatentPath:
             return [t]
         return list(t.chunk(self.num_slices, 1))
 
-    def forward(self):
+    def match_chain(self):
+        """match -> gather/blend -> CLM fusion (and their backward when training), enqueued on the
+        current stream.  Reads MATCH_INPUTS only."""
         st = ops._stream()
         B, R, M, h, w, p, k = self.B, self.R, self.M, self.h, self.w, self.patch, self.k
         S = h * w
-        n = 0
-        self._acc.zero_()
+        if self.train:
+            self._acc_match.zero_()
         # 1. match: masked Pearson correlation + top-k over all B*R (image, reference) problems
         r = self.refs.view(B * R, M, h, w)
         if self.match_mode == "tc":
             call("clc_match_topk_tc", ptr(self.y), ptr(r), B * R, R, M, h, w, p, p, k,
                  1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), None, ptr(self.ws),
                  self.ws.numel(), st)
-            n += 4
         else:
             call("clc_pearson_corr", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.corr), B * R,
                  self.P, M, p, p, h, w, ptr(self.ws), self.ws.numel(), st)
             call("clc_topk_rows", ptr(self.corr), B * R * self.P, self.corr.shape[-1], k, ptr(self.val),
                  ptr(self.idx), st)
-            n += 4
         # 2. softmax weights + gather of the k matched patches + blend
         call("clc_gather_blend_fwd", ptr(r), ptr(self.idx), ptr(self.val), self.T, ptr(self.aligned),
              ptr(self.weights), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
         # 3. CLM fusion over the aligned references ([B,R,C,S] layout, strided -- no transpose)
         call("clc_clm_fuse_fwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S, ptr(self.y),
              ptr(self.fused), R, B, M, S, st)
-        # 4. hyper-latent: factorised prior + STE round (+ bpp partial)
+        n = 3 if self.match_mode == "tc" else 4
+        if self.train:
+            call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
+                 ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
+            call("clc_match_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx), ptr(self.weights),
+                 self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val), B * R, self.P, M,
+                 p, p, h, w, k, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
+            n += 2
+        return n
+
+    def hyper_chain(self):
+        """EntropyBottleneck on z (+ STE round, bpp partial) and its backward.  Reads z / noise_z."""
+        self._acc_eb.zero_()
         ops.eb_fwd_raw(self.z, self.noise_z if self.train else None, self.eb_m, self.eb_b, self.eb_f,
                        self.quantiles, self.lik_z, self.z_hat, None, self.log2[1:2])
-        n += 3
-        # 5. slice loop: GaussianConditional + STE round (+ bpp partial), then LRP add
+        if not self.train:
+            return 1
+        ops.eb_bwd_raw(self.z, self.noise_z, self.eb_m, self.eb_b, self.eb_f, self.quantiles, self.lik_z,
+                       None, self.bpp_coef, None, self.g_z, self.g_eb[0:5], self.g_eb[5:10], self.g_eb[10:14])
+        return 2
+
+    def slice_chain(self):
+        """Slice loop: GaussianConditional + STE round (+ bpp partial), LRP add, and their backward."""
+        n = 0
+        self._acc_y.zero_()
         noise = self._slices(self.noise_y) if self.train else None
         for i, (ys, ss, ms, ls, yh, lr) in enumerate(zip(*(self._slices(t) for t in (
                 self.y, self.scale, self.mu, self.lik_y, self.y_hat, self.lrp)))):
             ops.gc_fwd_raw(ys, ss, ms, noise[i] if self.train else None, ls, yh, None, self.log2[0:1])
             ops.lrp_add_fwd_raw(yh, lr)
             n += 2
-        return n
-
-    def backward(self):
-        st = ops._stream()
-        B, R, M, h, w, p, k = self.B, self.R, self.M, self.h, self.w, self.patch, self.k
-        S = h * w
-        n = 0
-        noise = self._slices(self.noise_y)
+        if not self.train:
+            return n
         for i, (ys, ss, ms, ls, lr, gyh, gy, gs, gm, gl) in enumerate(zip(*(self._slices(t) for t in (
                 self.y, self.scale, self.mu, self.lik_y, self.lrp, self.g_y_hat, self.g_y, self.g_scale,
                 self.g_mu, self.g_lrp)))):
             ops.lrp_add_bwd_raw(gyh, lr, gl)
             ops.gc_bwd_raw(ys, ss, ms, noise[i], ls, None, self.bpp_coef, gyh, gy, gs, gm)
             n += 2
-        ops.eb_bwd_raw(self.z, self.noise_z, self.eb_m, self.eb_b, self.eb_f, self.quantiles, self.lik_z,
-                       None, self.bpp_coef, None, self.g_z, self.g_eb[0:5], self.g_eb[5:10], self.g_eb[10:14])
-        call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
-             ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
-        r = self.refs.view(B * R, M, h, w)
-        call("clc_match_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx), ptr(self.weights),
-             self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val), B * R, self.P, M,
-             p, p, h, w, k, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
-        n += 3
         return n
 
-    def step(self):
-        """Enqueue one full pass (forward, and backward when training) on the current stream."""
-        n = self.forward()
-        if self.train:
-            n += self.backward()
+    def entropy_chain(self):
+        return self.hyper_chain() + self.slice_chain()
+
+    def forward(self):
+        """Back-compat: whole step on the current stream (forward AND backward when training)."""
+        return self.step()
+
+    def step(self, fork=False):
+        """Enqueue one full pass (forward, and backward when training).  The three chains
+        (match, hyper-latent, slice loop) are data-independent; with fork=True the two entropy
+        chains run on side streams next to the match chain (CUDA graph capture turns this into a
+        forked graph).  Returns the number of C-ABI calls."""
+        if not fork:
+            return self.match_chain() + self.hyper_chain() + self.slice_chain()
+        cur = torch.cuda.current_stream(self.device)
+        s1, s2 = self._side_streams()
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            n = self.slice_chain()
+        with torch.cuda.stream(s2):
+            n += self.hyper_chain()
+        n += self.match_chain()
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
         return n
+
+    def _side_streams(self):
+        if self._streams is None:
+            self._streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
+        return self._streams[0], self._streams[1]
 
     # -------------------------------------------------------------------------------------
-    def capture(self):
-        """Capture step() into a CUDA graph (launch-bound at the small configs)."""
+    def _capture(self, fn):
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(2):
-                self.step()
+                fn()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.step()
-        self._graph = g
+            fn()
         return g
+
+    def capture(self, fork=True):
+        """Capture step() into ONE CUDA graph (launch-bound at the small configs); fork=True keeps
+        the three independent chains on parallel branches of the graph."""
+        self._graph = self._capture(lambda: self.step(fork=fork))
+        return self._graph
 
     def replay(self):
         self._graph.replay()
+
+    def capture_split(self):
+        """Two graphs for the end-to-end path: match chain / entropy chains, so the second half of
+        the host->device upload overlaps the match chain (step_host)."""
+        self._g_match = self._capture(self.match_chain)
+        self._g_entropy = self._capture(lambda: self._entropy_forked())
+        self._host_out = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self._ev = [torch.cuda.Event() for _ in range(2)]
+        self._side_streams()
+
+    def _entropy_forked(self):
+        cur = torch.cuda.current_stream(self.device)
+        s1, _ = self._side_streams()
+        s1.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            n = self.hyper_chain()
+        n += self.slice_chain()
+        cur.wait_stream(s1)
+        return n
+
+    def step_host(self, host_flat):
+        """One end-to-end step from HOST buffers: upload this step's inputs from the pinned staging
+        buffer (host_staging) in two contiguous copies, run the match chain as soon as its inputs
+        have landed while the rest is still in flight, run the entropy chains, read the step's
+        result (bpp) back.  Returns bpp as a Python float (synchronises)."""
+        if self._g_match is None:
+            self.capture_split()
+        cur = torch.cuda.current_stream(self.device)
+        cp, se = self._streams[2], self._streams[1]
+        n1 = self._n_match_in
+        cp.wait_stream(cur)
+        with torch.cuda.stream(cp):
+            self._in[:n1].copy_(host_flat[:n1], non_blocking=True)
+            self._ev[0].record(cp)
+            self._in[n1:].copy_(host_flat[n1:], non_blocking=True)
+            self._ev[1].record(cp)
+        cur.wait_event(self._ev[0])
+        self._g_match.replay()
+        se.wait_event(self._ev[1])
+        with torch.cuda.stream(se):
+            self._g_entropy.replay()
+        cur.wait_stream(se)
+        self._host_out.copy_(self.log2, non_blocking=True)
+        cur.synchronize()
+        return -(self._host_out[0].item() + self._host_out[1].item()) / self.num_pixels
 
     def bpp(self):
         """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels."""

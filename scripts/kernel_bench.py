@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Per-call / per-kernel device times of one LatentPath workload with everything L2-warm:
+  (a) each C-ABI call repeated REP times inside its own CUDA graph (time per call incl. the
+      in-graph launch gap), and
+  (b) the library's per-kernel trace (one CUDA event after every kernel) over un-graphed steps.
+Used to find which kernel of the serial match chain to shorten next."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from bench import WORKLOADS  # noqa: E402
+from clc_b200 import _lib  # noqa: E402
+from clc_b200.latent_path import LatentPath  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="cfg2")
+ap.add_argument("--rep", type=int, default=20)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--match-mode", default="tc")
+a = ap.parse_args()
+cfg = WORKLOADS[a.workload]
+lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=a.match_mode,
+                fused_slices=True, device="cuda:0")
+lp.randomize(seed=1)
+lp.step()
+torch.cuda.synchronize()
+
+# (a) record the C-ABI calls of one step, then replay each one REP times in a graph
+calls = []
+orig = _lib.call
+
+
+def rec(name, *args):
+    calls.append((name, args))
+    return orig(name, *args)
+
+
+import clc_b200.latent_path as LPm  # noqa: E402
+import clc_b200.ops as OPSm  # noqa: E402
+LPm.call = rec
+OPSm.call = rec
+lp.step()
+LPm.call = orig
+OPSm.call = orig
+torch.cuda.synchronize()
+print(f"# {a.workload}: {len(calls)} C-ABI calls per step; per-call time, L2-warm, {a.rep} back-to-back in a graph")
+s = torch.cuda.Stream()
+tot = 0.0
+for name, args in calls:
+    with torch.cuda.stream(s):
+        st = s.cuda_stream
+        args2 = list(args)
+        args2[-1] = st                       # the stream is the last argument of every entry point
+        for _ in range(2):
+            orig(name, *args2)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        args2[-1] = torch.cuda.current_stream().cuda_stream
+        for _ in range(a.rep):
+            orig(name, *args2)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (a.iters * a.rep)
+    tot += us
+    print(f"{name:28s} {us:8.2f} us/call")
+print(f"{'sum':28s} {tot:8.2f} us")
+
+# (b) per-kernel trace, warm
+per = {}
+stream = torch.cuda.current_stream().cuda_stream
+for _ in range(a.iters):
+    for name, ms in _lib.kernel_trace(lp.step, stream):
+        t = per.setdefault(name, [0.0, 0])
+        t[0] += ms
+        t[1] += 1
+print("# per-kernel trace (event after every kernel, includes the eager launch gap), L2-warm")
+for n, t in per.items():
+    print(f"{n:36s} {1e3 * t[0] / t[1]:8.2f} us x{t[1] / a.iters:g}")
