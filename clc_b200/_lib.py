@@ -32,6 +32,7 @@ PROTOTYPES = {
     "clc_strerror": (C.c_char_p, [C.c_int]),
     "clc_last_cuda_error": (C.c_char_p, []),
     "clc_kernel_launch_count": (C.c_uint64, []),
+    "clc_debug_set_stage_mask": (None, [C.c_int]),
     "clc_trace_start": (C.c_int, [_p]),
     "clc_trace_stop": (C.c_int, []),
     "clc_trace_count": (C.c_int, []),
@@ -55,7 +56,8 @@ PROTOTYPES = {
     "clc_topk_rows": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p]),
     "clc_gaussian_mask": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
     "clc_match_topk_tc": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
-                                    _p, _sz, _p]),
+                                    _f, _p, _p, _p, _sz, _p]),
+    "clc_match_topk_tc_ref_cl": (_p, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "clc_match_topk_tc_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "clc_gather_blend_fwd": (C.c_int, [_p, _p, _p, _f, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                        _i32, _p]),
@@ -63,8 +65,8 @@ PROTOTYPES = {
                                        _i32, _i32, _p]),
     "clc_pearson_topk_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
                                        _i32, _i32, _i32, _i32, _p]),
-    "clc_match_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32,
-                                _i32, _i32, _i32, _p, _sz, _p]),
+    "clc_match_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
+                                _i32, _i32, _i32, _i32, _i32, _p, _sz, _p]),
     "clc_match_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                         _p, _sz, _p]),

@@ -7,6 +7,7 @@
 namespace clc {
 thread_local char g_last_cuda_error[256] = {0};
 std::atomic<unsigned long long> g_kernel_launches{0};
+std::atomic<int> g_stage_mask{0xff};
 
 // ---- per-kernel tracing: CUDA events on the traced stream, one after every launch ----
 std::atomic<bool> g_trace_on{false};
@@ -29,7 +30,7 @@ void trace_record(const char* name) {
 }
 }
 
-extern "C" int clc_version(void) { return 1; }
+extern "C" int clc_version(void) { return 2; }
 
 extern "C" const char* clc_strerror(int status) {
   switch (status) {
@@ -42,6 +43,8 @@ extern "C" const char* clc_strerror(int status) {
     default: return "unknown status";
   }
 }
+
+extern "C" CLC_API void clc_debug_set_stage_mask(int mask) { clc::g_stage_mask.store(mask); }
 
 extern "C" const char* clc_last_cuda_error(void) { return clc::g_last_cuda_error; }
 

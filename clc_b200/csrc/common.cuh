@@ -23,6 +23,10 @@ inline int cuda_fail(cudaError_t e, const char* where) {
 // Process-wide count of kernels enqueued by this library (statistics only; bench.py reports it).
 extern std::atomic<unsigned long long> g_kernel_launches;
 
+// Bring-up: bit mask of the kernels a multi-kernel entry point enqueues (clc_debug_set_stage_mask).
+extern std::atomic<int> g_stage_mask;
+inline bool stage_on(int bit) { return (g_stage_mask.load(std::memory_order_relaxed) >> bit) & 1; }
+
 // Per-kernel tracing (clc_trace_*): when on, one cudaEvent is recorded after every kernel launch.
 extern std::atomic<bool> g_trace_on;
 void trace_record(const char* name);

@@ -635,9 +635,10 @@ nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ xT, int C, in
   }
 }
 
-// x[n][c][p] += xT[n][p][c]
+// x[n][c][p] (+)= xT[n][p][c]
+template <bool ADD>
 __global__ void __launch_bounds__(256)
-cl_to_nchw_add_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, int HW) {
+cl_to_nchw_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, int HW) {
   __shared__ float t[32][33];
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* xTn = xT + (int64_t)n * C * HW;
@@ -649,7 +650,10 @@ cl_to_nchw_add_kernel(const float* __restrict__ xT, float* __restrict__ x, int C
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i, p = p0 + threadIdx.x;
-    if (c < C && p < HW) xn[(int64_t)c * HW + p] += t[threadIdx.x][i];
+    if (c < C && p < HW) {
+      if (ADD) xn[(int64_t)c * HW + p] += t[threadIdx.x][i];
+      else xn[(int64_t)c * HW + p] = t[threadIdx.x][i];
+    }
   }
 }
 
@@ -791,6 +795,206 @@ match_bwd_cl_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __r
       red_add4(gqb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy, v);
     }
   }
+}
+
+// Register-resident variant for k <= 4 (the wiring's k): the k windows are loaded ONCE, all k*ITEMS
+// float4 loads of a thread are in flight together, every reduction of the CTA (patch statistics +
+// 4 sums per window) goes through ONE block reduction, and the scatter is issued from registers.
+// Three dependent global-memory phases per CTA instead of 2k+2.  ITEMS = ceil(S*C/4 / 256).
+template <int ITEMS>
+__global__ void __launch_bounds__(256, 2)
+match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __restrict__ mask,
+                        const int32_t* __restrict__ idx, const float* __restrict__ weights, float temperature,
+                        const float* __restrict__ g_out, float* __restrict__ g_rT, float* __restrict__ g_q,
+                        float* __restrict__ g_val_out, int P, int C, int ph, int pw, int fh, int fw, int k, int dbg) {
+  constexpr int KK = 4, NV = 2 + 4 * KK;
+  extern __shared__ float4 sm4[];           // Q[S][C/4], G[S][C/4]
+  __shared__ float red[8][NV];
+  __shared__ float tot[NV];                 // xs, sxx, then per window: g_w, s1, s2, xy
+  __shared__ float coef[KK][4];             // per window: w_j, g_xy, 2*g_dY, c_mean
+  __shared__ float part[KK][3];             // per window: its terms of t_gxs, t_gsxx, t_gxm
+  __shared__ int src_s[KK];
+  __shared__ float w_s[KK], m_s[KK];        // softmax weight and mask value of each window
+  const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
+  const int HW = fh * fw;
+  const int n = blockIdx.x / P;
+  const int patch = blockIdx.x - n * P;
+  const int nq = n / qa.repeat;
+  const int npx = fw / pw;
+  const int py = patch / npx, px = patch - py * npx;
+  const int S = ph * pw, c4n = C >> 2, K = C * S;
+  const int items = S * c4n;
+  float4* Q = sm4;
+  float4* G = sm4 + items;
+  float* Qf = reinterpret_cast<float*>(Q);
+  float* Gf = reinterpret_cast<float*>(G);
+  const float Kf = (float)K, inv_k = 1.0f / Kf;
+  const int64_t po = ((int64_t)n * P + patch) * k;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < KK) {
+    int src = 0;
+    float wj = 0.f, mj = 1.f;
+    if (tid < k) {
+      const int id = idx[po + tid];
+      wj = weights[po + tid];
+      const int oy = id / cw, ox = id - oy * cw;
+      src = oy * fw + ox;
+      if (mask) mj = mask[(int64_t)patch * L + id];
+    }
+    src_s[tid] = src; w_s[tid] = wj; m_s[tid] = mj;
+  }
+  // stage q and g patches: global rows (c, dy) of pw = 4 floats -> shared [s = dy*4+dx][c]; all of a
+  // thread's loads are issued before the first shared store (items == C*ph when pw == 4)
+  const float* qb = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+  const float* gb = g_out + (int64_t)n * C * HW + (py * ph) * fw + px * pw;
+  {
+    float4 qv[ITEMS], gv[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int e = tid + i * 256;
+      const int dy = e / C, c = e - dy * C;   // c fastest: conflict-free shared stores
+      if (e < C * ph) {
+        qv[i] = ld4(qb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy);
+        gv[i] = ld4(gb + (int64_t)c * HW + dy * fw);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int e = tid + i * 256;
+      const int dy = e / C, c = e - dy * C;
+      if (e < C * ph) {
+        const int s0 = dy * 4;
+        Qf[(s0 + 0) * C + c] = qv[i].x; Qf[(s0 + 1) * C + c] = qv[i].y; Qf[(s0 + 2) * C + c] = qv[i].z; Qf[(s0 + 3) * C + c] = qv[i].w;
+        Gf[(s0 + 0) * C + c] = gv[i].x; Gf[(s0 + 1) * C + c] = gv[i].y; Gf[(s0 + 2) * C + c] = gv[i].z; Gf[(s0 + 3) * C + c] = gv[i].w;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- all window loads of this thread, issued together ----
+  const float* rTn = rT + (int64_t)n * HW * C;
+  int woff[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int f = tid + i * 256;
+    const int s = f / c4n, c4 = f - s * c4n;
+    woff[i] = (f < items) ? ((s >> 2) * fw + (s & 3)) * C + 4 * c4 : -1;
+  }
+  float4 rv[KK][ITEMS];
+#pragma unroll
+  for (int j = 0; j < KK; ++j)
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i)
+      rv[j][i] = (j < k && woff[i] >= 0) ? ld4(rTn + (int64_t)src_s[j] * C + woff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- one pass of partial sums ----
+  float v[NV];
+#pragma unroll
+  for (int t = 0; t < NV; ++t) v[t] = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int f = tid + i * 256;
+    if (f >= items) continue;
+    const float4 q4 = Q[f], g4 = G[f];
+    v[0] += (q4.x + q4.y) + (q4.z + q4.w);
+    v[1] = fmaf(q4.x, q4.x, fmaf(q4.y, q4.y, fmaf(q4.z, q4.z, fmaf(q4.w, q4.w, v[1]))));
+#pragma unroll
+    for (int j = 0; j < KK; ++j) {
+      const float4 r4 = rv[j][i];
+      v[2 + 4 * j] = fmaf(g4.x, r4.x, fmaf(g4.y, r4.y, fmaf(g4.z, r4.z, fmaf(g4.w, r4.w, v[2 + 4 * j]))));
+      v[3 + 4 * j] += (r4.x + r4.y) + (r4.z + r4.w);
+      v[4 + 4 * j] = fmaf(r4.x, r4.x, fmaf(r4.y, r4.y, fmaf(r4.z, r4.z, fmaf(r4.w, r4.w, v[4 + 4 * j]))));
+      v[5 + 4 * j] = fmaf(q4.x, r4.x, fmaf(q4.y, r4.y, fmaf(q4.z, r4.z, fmaf(q4.w, r4.w, v[5 + 4 * j]))));
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NV; ++t) {
+    v[t] = warp_sum(v[t]);
+    if (lane == 0) red[wid][t] = v[t];
+  }
+  __syncthreads();
+  if (tid < NV) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][tid];
+    tot[tid] = a;
+  }
+  __syncthreads();
+  // ---- per-window coefficients: thread j <-> window j ----
+  if (tid < k) {
+    const int j = tid;
+    const float xs = tot[0], sxx = tot[1];
+    const float xm = xs / Kf;
+    const float dX = sxx - xm * xs;
+    float dot = 0.f;   // w = softmax(v*T): dL/dv_j = T * w_j * (g_w_j - sum_i w_i g_w_i)
+    for (int i = 0; i < k; ++i) dot = fmaf(w_s[i], tot[2 + 4 * i], dot);
+    const float wj = w_s[j];
+    const float gv = temperature * wj * (tot[2 + 4 * j] - dot);
+    if (g_val_out) g_val_out[po + j] = gv;
+    const float s1 = tot[3 + 4 * j], s2 = tot[4 + 4 * j], xy = tot[5 + 4 * j];
+    const float ym = s1 * inv_k;
+    const float dY = s2 - ym * ym * Kf;
+    const float D = dY * dX;
+    const float num = xy - ym * xs;
+    const float rs = rsqrtf(D);
+    float g = gv;
+    if (mask) g *= m_s[j];
+    const float g_num = g * rs;
+    const float g_D = -0.5f * g * num * rs / D;
+    const float g_dY = g_D * dX, g_dX = g_D * dY;
+    const float g_ym = -g_num * xs - 2.f * g_dY * ym * Kf;
+    part[j][0] = -g_num * ym - g_dX * xm;
+    part[j][1] = g_dX;
+    part[j][2] = -g_dX * xs;
+    coef[j][0] = wj; coef[j][1] = g_num; coef[j][2] = 2.f * g_dY; coef[j][3] = g_ym * inv_k;
+  }
+  __syncthreads();
+  // ---- scatter from registers: ONE vector atomic per window element ----
+  float* g_rTn = g_rT + (int64_t)n * HW * C;
+#pragma unroll
+  for (int j = 0; j < KK; ++j) {
+    if (j >= k) break;
+    const float cw_ = coef[j][0], cxy = coef[j][1], cdy = coef[j][2], cm = coef[j][3];
+    float* dst = g_rTn + (int64_t)src_s[j] * C;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int f = tid + i * 256;
+      if (f >= items) continue;
+      const float4 q4 = Q[f], g4 = G[f], r4 = rv[j][i];
+      float4 o;
+      o.x = fmaf(cw_, g4.x, fmaf(cxy, q4.x, fmaf(cdy, r4.x, cm)));
+      o.y = fmaf(cw_, g4.y, fmaf(cxy, q4.y, fmaf(cdy, r4.y, cm)));
+      o.z = fmaf(cw_, g4.z, fmaf(cxy, q4.z, fmaf(cdy, r4.z, cm)));
+      o.w = fmaf(cw_, g4.w, fmaf(cxy, q4.w, fmaf(cdy, r4.w, cm)));
+      if (!(dbg & 1)) red_add4(dst + woff[i], o);
+      else if (o.x == 1.2345e33f) dst[woff[i]] = o.y + o.z + o.w;
+    }
+  }
+  if (g_q && !(dbg & 2)) {
+    float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;
+    for (int j = 0; j < k; ++j) { t_gxs += part[j][0]; t_gsxx += part[j][1]; t_gxm += part[j][2]; }
+    const float c0 = 2.f * t_gsxx, c1 = t_gxs + t_gxm * inv_k;
+    float* gqb = g_q + (int64_t)nq * qa.sn + qa.patch_off(patch);
+    for (int e = tid; e < C * ph; e += 256) {
+      const int dy = e / C, c = e - dy * C;
+      const int s0 = dy * 4;
+      float4 o;
+      o.x = fmaf(c0, Qf[(s0 + 0) * C + c], c1); o.y = fmaf(c0, Qf[(s0 + 1) * C + c], c1);
+      o.z = fmaf(c0, Qf[(s0 + 2) * C + c], c1); o.w = fmaf(c0, Qf[(s0 + 3) * C + c], c1);
+      red_add4(gqb + (int64_t)c * qa.sc + (int64_t)dy * qa.sy, o);
+    }
+  }
+}
+
+template <int ITEMS>
+static int launch_bwd_reg(unsigned blocks, size_t smem, cudaStream_t st, PatchAddr qa, const float* rT,
+                          const float* mask, const int32_t* idx, const float* weights, float temperature,
+                          const float* g_out, float* g_rT, float* g_q, float* g_val, int P, int C, int ph,
+                          int pw, int fh, int fw, int k) {
+  auto kern = match_bwd_cl_reg_kernel<ITEMS>;
+  if (smem > 48 * 1024) CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  kern<<<blocks, 256, smem, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q, g_val, P, C, ph, pw,
+                                  fh, fw, k, (g_stage_mask.load() >> 8) & 0xff);
+  CLC_CHECK_LAUNCH("clc_match_bwd(main)");
+  return CLC_OK;
 }
 
 // Host helpers shared with match_tc.cu --------------------------------------------------------
@@ -946,10 +1150,10 @@ extern "C" size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t f
   return 2 * sizeof(float) * (size_t)NP * C * fh * fw + 512;  // channels-last copy of r + gradient scratch
 }
 
-extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* mask, const int32_t* idx,
-                             const float* weights, float temperature, const float* g_out, float* g_r,
-                             float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
-                             int32_t pw, int32_t fh, int32_t fw, int32_t k, void* workspace,
+extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* r_cl, const float* mask,
+                             const int32_t* idx, const float* weights, float temperature, const float* g_out,
+                             float* g_r, float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
+                             int32_t pw, int32_t fh, int32_t fw, int32_t k, int32_t flags, void* workspace,
                              size_t workspace_bytes, void* stream) {
   if (!view_ok(qv) || !r || !idx || !weights || !g_out || !g_r) return CLC_ERR_INVALID_ARGUMENT;
   if (NP < 0 || P < 1 || C < 1 || ph < 1 || pw < 1 || fh < ph || fw < pw || k < 1) return CLC_ERR_INVALID_ARGUMENT;
@@ -959,31 +1163,55 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   if (NP * P > 2147483647LL || (int64_t)C * fh * fw > 0x7fffffffLL || NP > 65535) return CLC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const PatchAddr qa = make_addr(qv);
+  const bool overwrite = (flags & CLC_MATCH_BWD_OVERWRITE_G_R) != 0;
   const size_t smem = (size_t)2 * ph * pw * C * sizeof(float);
+  const int HW = fh * fw;
+  const size_t plane = sizeof(float) * (size_t)NP * C * HW;
   // fast path: channels-last operands, float4 everywhere (needs a workspace and 16-byte aligned patch rows)
   const bool cl_ok = workspace && pw == 4 && C % 4 == 0 && fw % 4 == 0 && smem <= 200 * 1024 && aligned16(qv->q) &&
                      aligned16(g_out) && (!g_q || aligned16(g_q)) && qa.sy % 4 == 0 && qa.sc % 4 == 0 &&
-                     qa.spx % 4 == 0 && qa.spy % 4 == 0 && qa.sn % 4 == 0;
+                     qa.spx % 4 == 0 && qa.spy % 4 == 0 && qa.sn % 4 == 0 && (!r_cl || aligned16(r_cl));
   if (!cl_ok) {
+    if (overwrite) CLC_CUDA(cudaMemsetAsync(g_r, 0, plane, st));
     match_bwd_kernel<<<(unsigned)(NP * P), 256, 0, st>>>(qa, r, mask, idx, weights, temperature, g_out, g_r, g_q,
                                                         g_val, P, C, ph, pw, fh, fw, k);
     CLC_CHECK_LAUNCH("clc_match_bwd");
     return CLC_OK;
   }
   if (workspace_bytes < clc_match_bwd_workspace_bytes(NP, C, fh, fw)) return CLC_ERR_WORKSPACE;
-  const int HW = fh * fw;
-  float* rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  float* g_rT = rT + (size_t)NP * C * HW;
+  float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float* rT_own = g_rT + (size_t)NP * C * HW;
   dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
-  nchw_to_cl_kernel<<<tgrid, tblock, 0, st>>>(r, rT, C, HW);
-  CLC_CHECK_LAUNCH("clc_match_bwd(nchw_to_cl)");
-  CLC_CUDA(cudaMemsetAsync(g_rT, 0, sizeof(float) * (size_t)NP * C * HW, st));
-  if (smem > 48 * 1024)
-    CLC_CUDA(cudaFuncSetAttribute(match_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  match_bwd_cl_kernel<<<(unsigned)(NP * P), 256, smem, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT,
-                                                            g_q, g_val, P, C, ph, pw, fh, fw, k);
-  CLC_CHECK_LAUNCH("clc_match_bwd(main)");
-  cl_to_nchw_add_kernel<<<tgrid, tblock, 0, st>>>(g_rT, g_r, C, HW);
+  CLC_CUDA(cudaMemsetAsync(g_rT, 0, plane, st));
+  const float* rT = r_cl;
+  if (!rT) {  // no channels-last copy supplied (e.g. from clc_match_topk_tc_ref_cl): make one
+    nchw_to_cl_kernel<<<tgrid, tblock, 0, st>>>(r, rT_own, C, HW);
+    CLC_CHECK_LAUNCH("clc_match_bwd(nchw_to_cl)");
+    rT = rT_own;
+  }
+  const int items = ph * pw * (C / 4), per = (items + 255) / 256;
+  const unsigned blocks = (unsigned)(NP * P);
+  int rc = CLC_OK;
+  if (!stage_on(0)) {
+  } else if (k <= 4 && per <= 8) {
+#define CLC_BWD_CASE(I) case I: rc = launch_bwd_reg<I>(blocks, smem, st, qa, rT, mask, idx, weights, temperature, \
+                                                        g_out, g_rT, g_q, g_val, P, C, ph, pw, fh, fw, k); break;
+    switch (per) {
+      CLC_BWD_CASE(1) CLC_BWD_CASE(2) CLC_BWD_CASE(3) CLC_BWD_CASE(4)
+      CLC_BWD_CASE(5) CLC_BWD_CASE(6) CLC_BWD_CASE(7) CLC_BWD_CASE(8)
+    }
+#undef CLC_BWD_CASE
+    if (rc) return rc;
+  } else {
+    if (smem > 48 * 1024)
+      CLC_CUDA(cudaFuncSetAttribute(match_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    match_bwd_cl_kernel<<<blocks, 256, smem, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q, g_val,
+                                                   P, C, ph, pw, fh, fw, k);
+    CLC_CHECK_LAUNCH("clc_match_bwd(main)");
+  }
+  if (!stage_on(1)) return CLC_OK;
+  if (overwrite) cl_to_nchw_kernel<false><<<tgrid, tblock, 0, st>>>(g_rT, g_r, C, HW);
+  else cl_to_nchw_kernel<true><<<tgrid, tblock, 0, st>>>(g_rT, g_r, C, HW);
   CLC_CHECK_LAUNCH("clc_match_bwd(cl_to_nchw)");
   return CLC_OK;
 }

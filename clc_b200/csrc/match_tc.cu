@@ -169,7 +169,8 @@ struct Params {
   int TN, NACC, n_tiles, m_tiles, total_tiles, chunks;
   int nboxB, a_stages, b_bufs, acc_stages, tmem_cols, a_rows, SB;
   int KC, gaussian;
-  const float *s1, *s2, *xs, *sxx;
+  int st_rows, st_shifts, st_mt, st_stages, st_groups;  // small-latent ("stacked") kernel only
+  const float *s1, *s2, *xs, *sxx;  // xs/sxx: per-patch partial sums [NQ*P][chunks], combined in fixed order
   float* cand_val;
   int32_t* cand_idx;
   float* dump;  // debug: raw xy accumulators [NP, P, HW] (NULL in production)
@@ -183,6 +184,14 @@ struct ColStat {  // per accumulator column (= window origin), shared by the 128
   float wv;    // mask column coordinate                        (:799-803)
   float hv;    // mask row coordinate
 };
+
+// Per-patch statistic = fixed-order sum of its per-chunk partials (written by the pre-pass).
+__device__ __forceinline__ float chunk_sum(const float* __restrict__ part, int64_t qi, int chunks) {
+  const float* p = part + qi * chunks;
+  float a = 0.f;
+  for (int c = 0; c < chunks; ++c) a += p[c];
+  return a;
+}
 
 // ------------------------------------------------------------------------------------------
 // Sorted insertion into the per-thread candidate list (descending, ties keep the earlier position).
@@ -394,8 +403,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       float xs = 0.f, rdX = 0.f, ch = 0.f, cwc = 0.f;
       if (live) {
         const int64_t qi = (int64_t)nq * p.P + patch;
-        xs = p.xs[qi];
-        const float sxx = p.sxx[qi];
+        xs = chunk_sum(p.xs, qi, p.chunks);
+        const float sxx = chunk_sum(p.sxx, qi, p.chunks);
         const float xm = xs / Kf;
         rdX = rsqrtf(sxx - xm * xs);
         const int py = patch / p.npx, px = patch - py * p.npx;
@@ -467,23 +476,307 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// Pre-pass 1: reference latents [NP, C, HW] fp32 -> channels-last bf16 [NP*HW, C] (GEMM operand) and
-// channels-last fp32 [NP*HW, C] (coalesced exact re-scoring), plus the
-// per-pixel channel sums S1 = sum_c r, S2 = sum_c r^2 (fp32, fixed combination order).
-// grid = (ceil(HW/32), NP), block = 256 (8 warps x 32 pixels); smem tile [C][33] fp32.
+// Small-latent variant ("stacked shifts"), for latents of at most 256 pixels (e.g. the 16 x 16
+// latent of a 256 x 256 training patch, P = 16 query patches).  The general kernel above puts the
+// patches on the 128 accumulator rows and accumulates the ph*pw window shifts in K, which leaves
+// 112 of 128 rows idle when P = 16.  Here the shifts are STACKED on the rows instead:
+//   D[(s, p), pos'] = sum_c q[c, patch p, shift s] * r[c, pos']          (one plain GEMM, K = C)
+//   xy[p, pos]      = sum_s D[(s, p), pos + off(s)],   off(s) = dy*W + dx
+// so one (problem, patch group) needs ceil(S / (128 / PG)) M-tiles x C/16 MMAs of N = HW columns
+// (8x-16x fewer tensor-core instructions), and the shift sum is done by the epilogue: each
+// accumulator tile is dumped TMEM -> shared memory (reusing the operand stages), and every warp
+// sums, for its patches, the S shifted rows with lanes running over window positions.  The masked
+// Pearson score is formed in registers and the per-patch candidate list is selected with warp
+// shuffles (KC rounds of arg-max).  Operand rows: A = PG patches x (128 / PG) shifts per tile
+// (the 3-D TMA box of the packed patches), B = the whole channels-last reference image.
+//   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue; persistent over tiles.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, float* __restrict__ rT32,
-                float* __restrict__ s1, float* __restrict__ s2, int C, int HW) {
-  extern __shared__ float tile[];  // [C][33] then 2 x [8][32] partial sums
+constexpr int kStPW = 4;   // patches per epilogue warp (PG <= 16)
+constexpr int kStMP = 8;   // positions per lane (span <= 256)
+
+template <int KC, bool MASK>
+__global__ void __launch_bounds__(kThreads, 1)
+match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                          const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int Npad = p.TN;
+  const uint32_t aBytes = (uint32_t)p.st_mt * kABytes;
+  const uint32_t bBytes = (uint32_t)Npad * 128u;
+  const uint32_t stageBytes = aBytes + bBytes;
+  const int DS = Npad + 4;                                   // dump row stride (floats)
+  const uint32_t dumpBytes = 128u * (uint32_t)DS * 4u;
+  const uint32_t opBytes = (uint32_t)p.st_stages * stageBytes;
+  const uint32_t sMisc = base + (opBytes > dumpBytes ? opBytes : dumpBytes);
+  // misc: s1s[HW] s2s[HW] offs[S] | barriers full[st] empty[st] accFull tileDone | tmem ptr
+  const uint32_t sS1 = sMisc, sS2 = sS1 + 4u * p.HW, sOff = sS2 + 4u * p.HW;
+  const uint32_t sBar = (sOff + 4u * p.S + 7u) & ~7u;
+  const uint32_t barFull = sBar, barEmpty = barFull + 8u * p.st_stages;
+  const uint32_t barAccFull = barEmpty + 8u * p.st_stages, barTileDone = barAccFull + 8u;
+  const uint32_t sTmemPtr = barTileDone + 8u;
+  float* D = reinterpret_cast<float*>(smem_raw + (base - raw));
+  float* s1s = reinterpret_cast<float*>(smem_raw + (sS1 - raw));
+  float* s2s = reinterpret_cast<float*>(smem_raw + (sS2 - raw));
+  int* offs = reinterpret_cast<int*>(smem_raw + (sOff - raw));
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + (sTmemPtr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmapA);
+      tma_prefetch_desc(&tmapB);
+    }
+    tmem_alloc(sTmemPtr, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.st_stages; ++i) {
+      mbar_init(barFull + 8u * i, 1);
+      mbar_init(barEmpty + 8u * i, 1);
+    }
+    mbar_init(barAccFull, 1);
+    mbar_init(barTileDone, 4);   // one arrive per epilogue warp
+    fence_barrier_init();
+  } else if (warp >= 2) {
+    for (int s = threadIdx.x - 64; s < p.S; s += 128) offs[s] = (s / p.pw) * p.W + (s % p.pw);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int total = p.NP * p.st_groups;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    uint32_t st = 0, php = 0, tpar = 0;
+    // bytes one stage receives: st_mt boxes of {64 ch, st_rows, min(st_shifts, S)} + the reference rows
+    const uint32_t sh_box = (uint32_t)(p.st_shifts < p.S ? p.st_shifts : p.S);
+    const uint32_t txBytes = (uint32_t)p.st_mt * sh_box * (uint32_t)p.st_rows * 128u + bBytes;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int n = tile / p.st_groups, g = tile - n * p.st_groups;
+      const int nq = n / p.q_repeat;
+      mbar_wait(barTileDone, tpar ^ 1u);   // operand stages double as the epilogue's dump buffer
+      tpar ^= 1u;
+      for (int c = 0; c < p.chunks; ++c) {
+        mbar_wait(barEmpty + 8u * st, php ^ 1u);
+        if (lane == 0) {
+          const uint32_t bar = barFull + 8u * st;
+          const uint32_t sa = base + st * stageBytes, sb = sa + aBytes;
+          mbar_expect_tx(bar, txBytes);
+          for (int t = 0; t < p.st_mt; ++t)
+            tma_load_3d(sa + (uint32_t)t * kABytes, &tmapA, bar, c * kChunk, g * p.st_rows, nq * p.S + t * p.st_shifts);
+          for (int i = 0; i < p.nboxB; ++i)
+            tma_load_2d(sb + (uint32_t)i * kBoxBytesB, &tmapB, bar, c * kChunk, n * p.HW + i * kBoxRowsB);
+        }
+        if (++st == (uint32_t)p.st_stages) { st = 0; php ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    const uint32_t idesc = make_idesc(kTileM, Npad);
+    uint32_t st = 0, php = 0, tpar = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      mbar_wait(barTileDone, tpar ^ 1u);   // accumulators of the previous tile drained
+      tpar ^= 1u;
+      tc_fence_after();
+      for (int c = 0; c < p.chunks; ++c) {
+        mbar_wait(barFull + 8u * st, php);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + st * stageBytes, sb = sa + aBytes;
+          const uint64_t bdesc = make_desc_sw128(sb);
+          for (int t = 0; t < p.st_mt; ++t) {
+            const uint64_t adesc = make_desc_sw128(sa + (uint32_t)t * kABytes);
+#pragma unroll
+            for (int k = 0; k < kChunk / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)(t * Npad), adesc + 2u * k, bdesc + 2u * k, idesc, (c | k) ? 1u : 0u);
+          }
+          umma_commit(barEmpty + 8u * st);
+          if (c == p.chunks - 1) umma_commit(barAccFull);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)p.st_stages) { st = 0; php ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                      // TMEM lane quarter of this warp; also its patch residue
+    const int et = threadIdx.x - 64;
+    const int cw = p.W - p.pw + 1;
+    const int span = (p.H - p.ph + 1) * p.W;     // linear origins 0 .. span-1 cover every valid window
+    const int K = p.C * p.S;
+    const float Kf = (float)K, inv_k = 1.0f / Kf;
+    const float kh = -4.0f / (0.25f * (float)p.H * (float)p.H);
+    const float kw = -4.0f / (0.25f * (float)p.W * (float)p.W);
+    const int r0 = (p.ph + 1) / 2 - 1, c0 = (p.pw + 1) / 2 - 1;
+    const int rows_pw = p.st_rows / 4;           // patches per warp (<= kStPW)
+    uint32_t apar = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int n = tile / p.st_groups, g = tile - n * p.st_groups;
+      const int nq = n / p.q_repeat;
+      // ---- window statistics of this lane's positions (while the MMAs run) ----
+      for (int i = et; i < p.HW; i += 128) {
+        s1s[i] = p.s1[(int64_t)n * p.HW + i];
+        s2s[i] = p.s2[(int64_t)n * p.HW + i];
+      }
+      epi_bar_sync();
+      float ym[kStMP], rdY[kStMP], mwv[kStMP], mhv[kStMP];
+#pragma unroll
+      for (int m = 0; m < kStMP; ++m) {
+        const int pos = lane + 32 * m;
+        const int oy = pos / p.W, ox = pos - oy * p.W;
+        ym[m] = 0.f;
+        rdY[m] = __int_as_float(0x7fc00000);     // NaN marks a wrapped / out-of-range origin
+        mwv[m] = (float)(ox + c0 + 1) - 0.5f * (float)(p.pw & 1);
+        mhv[m] = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
+        if (pos < span && ox <= p.W - p.pw) {
+          float b1 = 0.f, b2 = 0.f;
+          for (int dy = 0; dy < p.ph; ++dy)
+            for (int dx = 0; dx < p.pw; ++dx) {
+              b1 += s1s[(oy + dy) * p.W + ox + dx];
+              b2 += s2s[(oy + dy) * p.W + ox + dx];
+            }
+          const PosStat ps = pos_stat(b1, b2, inv_k, Kf);
+          ym[m] = ps.ym;
+          rdY[m] = rsqrtf(ps.dY);
+        }
+      }
+      float acc[kStPW][kStMP];
+#pragma unroll
+      for (int pi = 0; pi < kStPW; ++pi)
+#pragma unroll
+        for (int m = 0; m < kStMP; ++m) acc[pi][m] = 0.f;
+
+      mbar_wait(barAccFull, apar);
+      apar ^= 1u;
+      tc_fence_after();
+      for (int t = 0; t < p.st_mt; ++t) {
+        // ---- dump accumulator tile t: TMEM lane (s_l, patch) -> D[row][pos'] ----
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Npad);
+        float* drow = D + (size_t)(q * 32 + lane) * DS;
+        for (int col0 = 0; col0 < Npad; col0 += 32) {
+          float v[32];
+          tmem_ld32(t_row + (uint32_t)col0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) st4(drow + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+        epi_bar_sync();
+        // ---- shifted-row sum: lanes run over window positions, one patch at a time ----
+        const int s_lo = t * p.st_shifts;
+        const int s_n = (p.S - s_lo) < p.st_shifts ? (p.S - s_lo) : p.st_shifts;
+#pragma unroll
+        for (int pi = 0; pi < kStPW; ++pi) {
+          if (pi >= rows_pw) break;
+          const int pl = q + 4 * pi;             // patch row inside the group
+          for (int sl = 0; sl < s_n; ++sl) {
+            const float* src = D + (size_t)(sl * p.st_rows + pl) * DS + offs[s_lo + sl] + lane;
+#pragma unroll
+            for (int m = 0; m < kStMP; ++m)
+              if (lane + 32 * m < span) acc[pi][m] += src[32 * m];
+          }
+        }
+        epi_bar_sync();                           // D is overwritten by the next tile / the next TMA loads
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barTileDone);
+
+      // ---- masked Pearson score + per-patch candidate top-KC by warp shuffles ----
+#pragma unroll
+      for (int pi = 0; pi < kStPW; ++pi) {
+        if (pi >= rows_pw) break;
+        const int patch = g * p.st_rows + q + 4 * pi;
+        if (patch >= p.P) continue;               // warp-uniform
+        const int64_t qi = (int64_t)nq * p.P + patch;
+        const float xs = chunk_sum(p.xs, qi, p.chunks);
+        const float sxx = chunk_sum(p.sxx, qi, p.chunks);
+        const float xm = xs / Kf;
+        const float rdX = rsqrtf(sxx - xm * xs);
+        const int py = patch / p.npx, px = patch - py * p.npx;
+        const float ch = ((float)py + 0.5f) * (float)p.ph, cwc = ((float)px + 0.5f) * (float)p.pw;
+        float sc[kStMP];
+#pragma unroll
+        for (int m = 0; m < kStMP; ++m) {
+          float s = fmaf(-ym[m], xs, acc[pi][m]) * rdY[m];
+          if (MASK) {
+            const float dw = mwv[m] - cwc, dh = mhv[m] - ch;
+            s *= exp2f(fmaf(dh * dh, kh, dw * dw * kw));
+          }
+          sc[m] = (s == s) ? s : -INFINITY;       // wrapped origins (NaN) never win
+          if (p.dump != nullptr && lane + 32 * m < span && rdY[m] == rdY[m])
+            p.dump[((int64_t)n * p.P + patch) * p.HW + lane + 32 * m] = acc[pi][m];
+        }
+        const int64_t o = ((int64_t)n * p.P + patch) * KC;   // n_tiles == 1
+        for (int j = 0; j < KC; ++j) {
+          // lane-local best (value desc, position asc), then xor-tree arg-max over the warp
+          float bv = -INFINITY;
+          int bm = 0;
+#pragma unroll
+          for (int m = 0; m < kStMP; ++m)
+            if (sc[m] > bv) { bv = sc[m]; bm = m; }
+          int bpos = lane + 32 * bm;
+          float wv = bv;
+          int wpos = bpos;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, wv, d);
+            const int op = __shfl_xor_sync(0xffffffffu, wpos, d);
+            if (ov > wv || (ov == wv && op < wpos)) { wv = ov; wpos = op; }
+          }
+          if (wv > -INFINITY && wpos == bpos) {
+#pragma unroll
+            for (int m = 0; m < kStMP; ++m)
+              if (m == bm) sc[m] = -INFINITY;     // taken
+          }
+          if (lane == 0) {
+            int id = -1;
+            if (wv > -INFINITY) {
+              const int oy = wpos / p.W, ox = wpos - oy * p.W;
+              id = oy * cw + ox;
+            }
+            p.cand_val[o + j] = wv * rdX;
+            p.cand_idx[o + j] = id;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pre-pass (ONE launch, two block roles).
+// Role R, reference latents [NP, C, HW] fp32 -> channels-last bf16 [NP*HW, C] (GEMM operand) and
+// channels-last fp32 [NP*HW, C] (coalesced exact re-scoring / backward), plus the per-pixel channel
+// sums S1 = sum_c r, S2 = sum_c r^2 (fp32, fixed combination order).  One block = 32 pixels of one
+// problem (8 warps x 32 pixels); smem tile [C][33] fp32.
+// Role Q, query latents [NQ, C, H, W] fp32 -> packed patches [NQ, S, P_pad, C] in bf16 (GEMM operand)
+// and fp32 (exact re-scoring), shift-major, then patch, channels contiguous; plus the per-patch
+// partial sums over the block's 64 channels (xs_part / sxx_part [NQ*P][C/64]).  One block = one
+// patch row x 64 channels of one query image.  Rows P..P_pad-1 are zero-filled by the blocks of
+// the last patch row.
+// ------------------------------------------------------------------------------------------
+struct PrepassParams {
+  const float* r; __nv_bfloat16* rT; float* rT32; float* s1; float* s2;
+  const float* q; __nv_bfloat16* A; float* A32; float* xs_part; float* sxx_part;
+  int C, H, W, HW, ph, pw, P, P_pad, chunks;
+  int ref_tiles, n_ref_blocks, npy, dbg, zero_rows;
+};
+
+__device__ __forceinline__ void pack_ref_block(const PrepassParams& pp, float* tile, int n, int px0) {
+  const int C = pp.C, HW = pp.HW;
   float* part = tile + (size_t)C * 33;
-  const int n = blockIdx.y, px0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = px0 + lane;
-  const float* rn = r + (int64_t)n * C * HW;
+  const float* rn = pp.r + (int64_t)n * C * HW;
   float a = 0.f, b = 0.f;
+#pragma unroll 8
   for (int c = warp; c < C; c += 8) {
-    const float v = (px < HW) ? rn[(int64_t)c * HW + px] : 0.f;
+    const float v = (px < HW) ? __ldcs(rn + (int64_t)c * HW + px) : 0.f;
     tile[c * 33 + lane] = v;
     a += v;
     b = fmaf(v, v, b);
@@ -495,10 +788,10 @@ pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, flo
     float ta = 0.f, tb = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { ta += part[w * 32 + lane]; tb += part[256 + w * 32 + lane]; }
-    s1[(int64_t)n * HW + px] = ta;
-    s2[(int64_t)n * HW + px] = tb;
+    pp.s1[(int64_t)n * HW + px] = ta;
+    pp.s2[(int64_t)n * HW + px] = tb;
   }
-  // transposed write: item = (pixel, group of 8 channels) -> one 16-byte store
+  // transposed write: item = (pixel, group of 8 channels) -> one 16-byte bf16 store + two fp32 stores
   const int groups = C / 8;
   for (int it = threadIdx.x; it < 32 * groups; it += 256) {
     const int pl = it / groups, g = it - pl * groups;
@@ -506,8 +799,8 @@ pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, flo
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[(g * 8 + i) * 33 + pl]);
-    *reinterpret_cast<uint4*>(rT + ((int64_t)n * HW + px0 + pl) * C + g * 8) = *reinterpret_cast<const uint4*>(o);
-    float* d32 = rT32 + ((int64_t)n * HW + px0 + pl) * C + g * 8;
+    *reinterpret_cast<uint4*>(pp.rT + ((int64_t)n * HW + px0 + pl) * C + g * 8) = *reinterpret_cast<const uint4*>(o);
+    float* d32 = pp.rT32 + ((int64_t)n * HW + px0 + pl) * C + g * 8;
     st4(d32, make_float4(tile[(g * 8 + 0) * 33 + pl], tile[(g * 8 + 1) * 33 + pl], tile[(g * 8 + 2) * 33 + pl],
                          tile[(g * 8 + 3) * 33 + pl]));
     st4(d32 + 4, make_float4(tile[(g * 8 + 4) * 33 + pl], tile[(g * 8 + 5) * 33 + pl], tile[(g * 8 + 6) * 33 + pl],
@@ -515,26 +808,19 @@ pack_ref_kernel(const float* __restrict__ r, __nv_bfloat16* __restrict__ rT, flo
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Pre-pass 2: query latents [NQ, C, H, W] fp32 -> packed patches [NQ, S, P_pad, C] in bf16 (GEMM
-// operand) and fp32 (exact re-scoring)  (shift-major, then patch, channels contiguous).  grid = (npy, C/64, NQ), block = 256.
-// Rows P..P_pad-1 are zero-filled by the blocks of the last patch row.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-pack_query_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ A, float* __restrict__ A32, int C,
-                  int H, int W, int ph, int pw, int P, int P_pad) {
-  extern __shared__ float tile[];  // [64][ph][W + 1]
-  const int py = blockIdx.x, c0 = blockIdx.y * 64, nq = blockIdx.z;
+__device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float* tile, int py, int chunk, int nq) {
+  const int C = pp.C, H = pp.H, W = pp.W, ph = pp.ph, pw = pp.pw, P = pp.P, P_pad = pp.P_pad;
+  const int c0 = chunk * 64;
   const int npx = W / pw, S = ph * pw;
   const int Wp = W + 1;
-  const float* qn = q + ((int64_t)nq * C + c0) * H * W + (int64_t)py * ph * W;
+  const float* qn = pp.q + ((int64_t)nq * C + c0) * H * W + (int64_t)py * ph * W;
   for (int it = threadIdx.x; it < 64 * ph * W; it += 256) {
     const int x = it % W, dy = (it / W) % ph, c = it / (W * ph);
     tile[(c * ph + dy) * Wp + x] = qn[(int64_t)c * H * W + dy * W + x];
   }
   __syncthreads();
-  __nv_bfloat16* An = A + (int64_t)nq * S * P_pad * C;
-  float* An32 = A32 + (int64_t)nq * S * P_pad * C;
+  __nv_bfloat16* An = pp.A + (int64_t)nq * S * P_pad * C;
+  float* An32 = pp.A32 + (int64_t)nq * S * P_pad * C;
   for (int it = threadIdx.x; it < S * npx * 8; it += 256) {
     const int g = it & 7, px = (it >> 3) % npx, s = it / (8 * npx);
     const int dy = s / pw, dx = s - dy * pw;
@@ -548,12 +834,52 @@ pack_query_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ A, fl
     st4(An32 + oo, make_float4(t0[0], t0[cs], t0[2 * cs], t0[3 * cs]));
     st4(An32 + oo + 4, make_float4(t0[4 * cs], t0[5 * cs], t0[6 * cs], t0[7 * cs]));
   }
-  if (py == gridDim.x - 1) {
+  // per-patch partial statistics over this block's 64 channels: one warp per patch, lane-strided
+  // over the 64*ph*pw elements, xor-tree combine (fixed order -> deterministic)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_el = 64 * S;
+    for (int px = warp; px < npx; px += 8) {
+      float a = 0.f, b = 0.f;
+      for (int e = lane; e < n_el; e += 32) {
+        const int c = e / S, rem = e - c * S;
+        const int dy = rem / pw, dx = rem - dy * pw;
+        const float v = tile[(c * ph + dy) * Wp + px * pw + dx];
+        a += v;
+        b = fmaf(v, v, b);
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) {
+        const int64_t o = ((int64_t)nq * P + py * npx + px) * pp.chunks + chunk;
+        pp.xs_part[o] = a;
+        pp.sxx_part[o] = b;
+      }
+    }
+  }
+  // zero rows P .. zero_rows-1 of every shift (the rows a TMA box can reach beyond the last patch)
+  if (py == pp.npy - 1 && pp.zero_rows > P) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int it = threadIdx.x; it < S * (P_pad - P) * 8; it += 256) {
-      const int g = it & 7, pr = (it >> 3) % (P_pad - P), s = it / (8 * (P_pad - P));
+    const int nz = pp.zero_rows - P;
+    for (int it = threadIdx.x; it < S * nz * 8; it += 256) {
+      const int g = it & 7, pr = (it >> 3) % nz, s = it / (8 * nz);
       *reinterpret_cast<uint4*>(An + ((int64_t)s * P_pad + P + pr) * C + c0 + g * 8) = z;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+prepass_kernel(const PrepassParams pp) {
+  extern __shared__ float tile[];
+  int b = blockIdx.x;
+  if (b < pp.n_ref_blocks) {
+    if (pp.dbg & 1) return;
+    pack_ref_block(pp, tile, b / pp.ref_tiles, (b % pp.ref_tiles) * 32);
+  } else {
+    if (pp.dbg & 2) return;
+    b -= pp.n_ref_blocks;
+    const int py = b % pp.npy, chunk = (b / pp.npy) % pp.chunks, nq = b / (pp.npy * pp.chunks);
+    pack_query_block(pp, tile, py, chunk, nq);
   }
 }
 
@@ -574,11 +900,14 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
                const float* __restrict__ s1,
                const float* __restrict__ s2, const float* __restrict__ xs_a, const float* __restrict__ sxx_a,
                const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int n_tiles, int KC,
-               int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian,
-               float* __restrict__ val, int32_t* __restrict__ idx, int32_t* __restrict__ n_uncertified) {
-  extern __shared__ float sm[];  // cand values [M], cand idx [M]
+               int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian, int chunks,
+               float* __restrict__ val, int32_t* __restrict__ idx, int32_t* __restrict__ n_uncertified,
+               float temperature, float* __restrict__ aligned, float* __restrict__ weights_out, int dbg) {
+  extern __shared__ float sm[];  // cand values [M], cand idx [M]; then the blend tile [C][S + 4]
   __shared__ float sel_v[kMaxKC], ex_v[kMaxKC];
   __shared__ int sel_i[kMaxKC];
+  __shared__ float top_w[8];
+  __shared__ int top_src[8];
   const int M = n_tiles * KC;
   float* cvs = sm;
   int* cis = reinterpret_cast<int*>(sm + M);
@@ -627,7 +956,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   if (warp < KC) {
     const int id = sel_i[warp];
     float out = -INFINITY;
-    if (id >= 0) {
+    if (id >= 0 && !(dbg & 1)) {
       const int oy = id / cw, ox = id - oy * cw;
       // both operands channels-last fp32: every shift is one contiguous row of C floats per side
       const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
@@ -676,7 +1005,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
           }
         const PosStat ps = pos_stat(b1, b2, 1.0f / Kf, Kf);
         const int64_t qi = (int64_t)nq * P + patch;
-        out = pearson(acc, ps, xs_a[qi], sxx_a[qi], Kf);
+        out = pearson(acc, ps, chunk_sum(xs_a, qi, chunks), chunk_sum(sxx_a, qi, chunks), Kf);
       }
     }
     if (lane == 0) ex_v[warp] = out;
@@ -723,14 +1052,70 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       if (lane == 0) {
         val[((int64_t)n * P + patch) * k + t] = bv;
         idx[((int64_t)n * P + patch) * k + t] = bi;
+        top_w[t] = bv;
+        const int oy = bi / cw, ox = bi - oy * cw;
+        top_src[t] = oy * W + ox;
       }
       vk = bv;
+    }
+    if (aligned != nullptr) {
+      // softmax(value * T) over the k selected positions (SI_Wraper, Patch_Matching.py:225)
+      __syncwarp();
+      if (lane == 0) {
+        float mx = -INFINITY, den = 0.f;
+        for (int j = 0; j < k; ++j) mx = fmaxf(mx, top_w[j] * temperature);
+        for (int j = 0; j < k; ++j) den += expf(top_w[j] * temperature - mx);
+        for (int j = 0; j < k; ++j) {
+          const float wj = expf(top_w[j] * temperature - mx) / den;
+          top_w[j] = wj;
+          if (weights_out) weights_out[((int64_t)n * P + patch) * k + j] = wj;
+        }
+      }
     }
     if (lane == 0 && n_uncertified != nullptr && L > KC) {
       // any window outside the candidate set has a screened score <= sel_v[KC-1]; the set provably
       // holds the exact top-k unless a screening error exceeds the margin to the k-th exact value.
       const float eps = 0.03125f * sqrtf(2.0f / (float)K);  // 16 x the bf16 screening error model
       if (!(vk - sel_v[KC - 1] > eps)) atomicAdd(n_uncertified, 1);
+    }
+  }
+  if (aligned == nullptr || (dbg & 2)) return;
+  // ---- fused gather + blend (SI_Wraper :226-238, is_stack = False): the k selected windows are read
+  // from the channels-last fp32 copy (coalesced float4; they were just re-scored, so mostly L1/L2
+  // hits), blended, transposed through shared memory and written as 16-byte NCHW patch rows ----
+  __syncthreads();
+  {
+    const int c4n = C >> 2, items = pp * c4n, TS = pp + 4;   // tile row stride (floats), 16-byte aligned
+    float* tile = sm + 2 * M;
+    tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tile) + 15) & ~(uintptr_t)15);
+    const float* rn = rT32 + (int64_t)n * HW * C;
+    for (int f = threadIdx.x; f < items; f += blockDim.x) {
+      const int c4 = f / pp, s = f - c4 * pp;                // lanes run over the shifts of one channel group
+      const int dy = s / pw, dx = s - dy * pw;
+      const float* src = rn + (int64_t)(dy * W + dx) * C + 4 * c4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // torch.sum over the k axis: sequential left-to-right accumulation of y_patch * weight
+      for (int j = 0; j < k; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)top_src[j] * C));
+        const float wj = top_w[j];
+        acc.x += v.x * wj; acc.y += v.y * wj; acc.z += v.z * wj; acc.w += v.w * wj;
+      }
+      tile[(4 * c4 + 0) * TS + s] = acc.x; tile[(4 * c4 + 1) * TS + s] = acc.y;
+      tile[(4 * c4 + 2) * TS + s] = acc.z; tile[(4 * c4 + 3) * TS + s] = acc.w;
+    }
+    __syncthreads();
+    float* on = aligned + (int64_t)n * C * HW + (int64_t)(py * ph) * W + px * pw;
+    if (pw == 4) {
+      for (int e = threadIdx.x; e < C * ph; e += blockDim.x) {
+        const int c = e / ph, dy = e - c * ph;
+        st4(on + (int64_t)c * HW + dy * W, *reinterpret_cast<const float4*>(&tile[c * TS + dy * 4]));
+      }
+    } else {
+      for (int e = threadIdx.x; e < C * pp; e += blockDim.x) {
+        const int c = e / pp, s = e - c * pp;
+        const int dy = s / pw, dx = s - dy * pw;
+        on[(int64_t)c * HW + dy * W + dx] = tile[c * TS + s];
+      }
     }
   }
 }
@@ -758,6 +1143,7 @@ static EncodeTiledFn encode_fn() {
 struct Plan {
   int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks;
   int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid, a_rows, SB;
+  int stacked, st_rows, st_shifts, st_mt, st_stages, st_groups, zero_rows;
   size_t smem_bytes;
   // workspace offsets (bytes)
   size_t off_rT, off_A, off_r32, off_A32, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, total;
@@ -828,6 +1214,36 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   }
   if (!pl.ok) return pl;
   pl.grid = pl.total_tiles < kNumSMs ? pl.total_tiles : kNumSMs;
+  pl.zero_rows = pl.m_tiles == 1 ? pl.a_rows : pl.P_pad;   // rows of A the TMA boxes can reach
+  // ---- small latents (<= 256 pixels): the stacked-shift kernel (match_gemm_stacked_kernel) ----
+  if (pl.HW <= 256 && pw <= 6 && !getenv("CLC_TC_NO_STACKED")) {
+    const int Npad = (pl.HW + 31) / 32 * 32;
+    int rows = 16;
+    if (pl.P <= 8 || NP * ((pl.P + 7) / 8) <= kNumSMs) rows = 8;
+    const int shifts = 128 / rows;
+    const int mt = (pl.S + shifts - 1) / shifts;
+    const size_t stage = (size_t)mt * kABytes + (size_t)Npad * 128;
+    const size_t dump = (size_t)128 * (Npad + 4) * 4;
+    const size_t misc = (size_t)8 * pl.HW + 4 * pl.S + 8 * (2 * 8 + 2) + 64 + 1024;
+    int stages = (int)(((size_t)kSmemLimit - misc) / stage);
+    if (stages > pl.chunks) stages = pl.chunks;
+    if (stages > 8) stages = 8;
+    if (mt * Npad <= 512 && stages >= 1 && dump + misc <= (size_t)kSmemLimit) {
+      pl.stacked = 1;
+      pl.st_rows = rows; pl.st_shifts = shifts; pl.st_mt = mt; pl.st_stages = stages;
+      pl.st_groups = (pl.P + rows - 1) / rows;
+      pl.zero_rows = pl.st_groups * rows;
+      pl.TN = Npad; pl.NACC = 1; pl.n_tiles = 1;
+      pl.nboxB = Npad / kBoxRowsB;
+      pl.total_tiles = (int)(NP * pl.st_groups);
+      pl.grid = pl.total_tiles < kNumSMs ? pl.total_tiles : kNumSMs;
+      int cols = mt * Npad, t = 32;
+      while (t < cols) t <<= 1;
+      pl.tmem_cols = t;
+      const size_t ops = (size_t)stages * stage;
+      pl.smem_bytes = (ops > dump ? ops : dump) + misc;
+    }
+  }
   const int64_t NQ = NP / q_repeat;
   size_t o = 0;
   pl.off_rT = o;  o = align_up(o + (size_t)NP * pl.HW * C * 2, 256);
@@ -836,8 +1252,8 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   pl.off_A32 = o; o = align_up(o + (size_t)NQ * pl.S * pl.P_pad * C * 4, 256);
   pl.off_s1 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
-  pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * 4, 256);
-  pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * 4, 256);
+  pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * pl.chunks * 4, 256);
+  pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * pl.chunks * 4, 256);
   pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_tiles * pl.KC * 4, 256);
   pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_tiles * pl.KC * 4, 256);
   pl.total = o + 256;  // slack for aligning the caller's pointer
@@ -854,12 +1270,24 @@ static int launch_gemm(const Plan& pl, const CUtensorMap& ta, const CUtensorMap&
   return CLC_OK;
 }
 
+template <int KC, bool MASK>
+static int launch_gemm_stacked(const Plan& pl, const CUtensorMap& ta, const CUtensorMap& tb, const Params& prm,
+                               cudaStream_t st) {
+  auto kern = match_gemm_stacked_kernel<KC, MASK>;
+  CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  kern<<<pl.grid, kThreads, pl.smem_bytes, st>>>(ta, tb, prm);
+  CLC_CHECK_LAUNCH("clc_match_topk_tc(gemm)");
+  return CLC_OK;
+}
+
 static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int C, int H, int W, int ph,
                int pw, int k, int gaussian, float* val, int32_t* idx, int32_t* n_uncertified, float* dump,
-               long long* timing, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               long long* timing, float temperature, float* aligned, float* weights_out, void* workspace,
+               size_t workspace_bytes, cudaStream_t st) {
   const Plan pl = make_plan(NP, q_repeat, C, H, W, ph, pw, k);
   if (!pl.ok) return CLC_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < pl.total) return CLC_ERR_WORKSPACE;
+  if (aligned && !aligned16(aligned)) return CLC_ERR_INVALID_ARGUMENT;
   int dev = 0, major = 0;
   CLC_CUDA(cudaGetDevice(&dev));
   CLC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -885,7 +1313,8 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   {
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)pl.P_pad, (cuuint64_t)(NQ * pl.S)};
     const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)pl.P_pad * C * 2};
-    const cuuint32_t box[3] = {kChunk, (cuuint32_t)pl.a_rows, (cuuint32_t)pl.SB};
+    const cuuint32_t box[3] = {kChunk, (cuuint32_t)(pl.stacked ? pl.st_rows : pl.a_rows),
+                               (cuuint32_t)(pl.stacked ? (pl.st_shifts < pl.S ? pl.st_shifts : pl.S) : pl.SB)};
     const cuuint32_t es[3] = {1, 1, 1};
     CUresult cr = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Apk, dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -903,31 +1332,28 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(B)");
   }
 
-  // ---- pre-passes ----
-  {
-    const size_t sm = ((size_t)C * 33 + 512) * sizeof(float);
+  // ---- pre-pass: one launch, reference blocks first, then query blocks ----
+  if (stage_on(0)) {
+    PrepassParams pp;
+    pp.r = r; pp.rT = rT; pp.rT32 = rT32; pp.s1 = s1; pp.s2 = s2;
+    pp.q = q_img; pp.A = Apk; pp.A32 = A32; pp.xs_part = xs; pp.sxx_part = sxx;
+    pp.C = C; pp.H = H; pp.W = W; pp.HW = pl.HW; pp.ph = ph; pp.pw = pw; pp.P = pl.P; pp.P_pad = pl.P_pad;
+    pp.chunks = pl.chunks;
+    pp.ref_tiles = (pl.HW + 31) / 32;
+    pp.npy = H / ph;
+    pp.zero_rows = pl.zero_rows;   // rows the A-operand TMA boxes read
+    const int64_t n_ref = (int64_t)pp.ref_tiles * NP, n_q = (int64_t)pp.npy * pl.chunks * NQ;
+    if (n_ref + n_q > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
+    pp.n_ref_blocks = (int)n_ref;
+    pp.dbg = (g_stage_mask.load() >> 8) & 0xff;
+    const size_t sm_r = ((size_t)C * 33 + 512) * sizeof(float);
+    const size_t sm_q = (size_t)64 * ph * (W + 1) * sizeof(float);
+    const size_t sm = sm_r > sm_q ? sm_r : sm_q;
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
     if (sm > 48 * 1024)
-      CLC_CUDA(cudaFuncSetAttribute(pack_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    dim3 grid((pl.HW + 31) / 32, (unsigned)NP);
-    pack_ref_kernel<<<grid, 256, sm, st>>>(r, rT, rT32, s1, s2, C, pl.HW);
-    CLC_CHECK_LAUNCH("clc_match_topk_tc(pack_ref)");
-  }
-  {
-    const size_t sm = (size_t)64 * ph * (W + 1) * sizeof(float);
-    if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
-    if (sm > 48 * 1024)
-      CLC_CUDA(cudaFuncSetAttribute(pack_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    dim3 grid(H / ph, C / 64, (unsigned)NQ);
-    pack_query_kernel<<<grid, 256, sm, st>>>(q_img, Apk, A32, C, H, W, ph, pw, pl.P, pl.P_pad);
-    CLC_CHECK_LAUNCH("clc_match_topk_tc(pack_query)");
-  }
-  {
-    PatchAddr qa;
-    qa.q = q_img; qa.sn = (int64_t)C * H * W; qa.spy = (int64_t)ph * W; qa.spx = pw; qa.sc = (int64_t)H * W;
-    qa.sy = W; qa.npx = pl.npx; qa.repeat = q_repeat;
-    int rc = launch_patch_stats(qa, xs, sxx, NQ, pl.P, C, ph, pw, st);
-    if (rc) return rc;
+      CLC_CUDA(cudaFuncSetAttribute(prepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    prepass_kernel<<<(unsigned)(n_ref + n_q), 256, sm, st>>>(pp);
+    CLC_CHECK_LAUNCH("clc_match_topk_tc(prepass)");
   }
 
   // ---- GEMM + fused epilogue ----
@@ -940,23 +1366,34 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   prm.tmem_cols = pl.tmem_cols; prm.a_rows = pl.a_rows; prm.SB = pl.SB; prm.KC = pl.KC; prm.gaussian = gaussian;
   prm.s1 = s1; prm.s2 = s2; prm.xs = xs; prm.sxx = sxx; prm.cand_val = cand_val; prm.cand_idx = cand_idx;
   prm.dump = dump;
+  prm.st_rows = pl.st_rows; prm.st_shifts = pl.st_shifts; prm.st_mt = pl.st_mt; prm.st_stages = pl.st_stages;
+  prm.st_groups = pl.st_groups;
   prm.timing = timing;
   prm.dbg = 0;
   if (timing) { const char* e = getenv("CLC_TC_DBG"); if (e) prm.dbg = atoi(e); }
   int rc;
-  if (pl.KC == 8) rc = gaussian ? launch_gemm<8, true>(pl, ta, tb, prm, st) : launch_gemm<8, false>(pl, ta, tb, prm, st);
+  if (!stage_on(1)) rc = CLC_OK;
+  else if (pl.stacked) {
+    if (pl.KC == 8) rc = gaussian ? launch_gemm_stacked<8, true>(pl, ta, tb, prm, st) : launch_gemm_stacked<8, false>(pl, ta, tb, prm, st);
+    else rc = gaussian ? launch_gemm_stacked<16, true>(pl, ta, tb, prm, st) : launch_gemm_stacked<16, false>(pl, ta, tb, prm, st);
+  } else if (pl.KC == 8) rc = gaussian ? launch_gemm<8, true>(pl, ta, tb, prm, st) : launch_gemm<8, false>(pl, ta, tb, prm, st);
   else rc = gaussian ? launch_gemm<16, true>(pl, ta, tb, prm, st) : launch_gemm<16, false>(pl, ta, tb, prm, st);
   if (rc) return rc;
 
-  // ---- merge + exact re-score + top-k ----
-  {
+  // ---- merge + exact re-score + top-k (+ fused gather / blend) ----
+  if (stage_on(2)) {
     const int64_t blocks = NP * pl.P;
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
-    const size_t sm = (size_t)pl.n_tiles * pl.KC * 8;
-    if (sm > 48 * 1024) return CLC_ERR_UNSUPPORTED;
+    size_t sm = (size_t)pl.n_tiles * pl.KC * 8;
+    if (aligned) sm += 16 + (size_t)C * (pl.S + 4) * sizeof(float);
+    if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
+    if (sm > 48 * 1024)
+      CLC_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     rescore_kernel<<<(unsigned)blocks, pl.KC * 32, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
                                                              pl.n_tiles, pl.KC, q_repeat, C, H, W, ph, pw, pl.P, k,
-                                                             gaussian, val, idx, n_uncertified);
+                                                             gaussian, pl.chunks, val, idx, n_uncertified,
+                                                             temperature, aligned, weights_out,
+                                                             (g_stage_mask.load() >> 8) & 0xff);
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
   }
   return CLC_OK;
@@ -976,23 +1413,32 @@ extern "C" size_t clc_match_topk_tc_workspace_bytes(int64_t NP, int32_t q_repeat
 extern "C" int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
                                  int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
                                  int32_t gaussian_mask, float* val, int32_t* idx, int32_t* n_uncertified,
+                                 float temperature, float* aligned, float* weights,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_img || !r || !val || !idx || NP < 0) return CLC_ERR_INVALID_ARGUMENT;
   if (NP == 0) return CLC_OK;
   if (k > (H - ph + 1) * (W - pw + 1)) return CLC_ERR_INVALID_ARGUMENT;
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, n_uncertified,
-                 nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+                 nullptr, nullptr, temperature, aligned, weights, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-// Bring-up / test hook (not part of the public header): additionally dumps the raw bf16-GEMM
-// accumulators xy[NP, P, H*W] (linear window origins, wrapped ones included).
-extern "C" CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
-                                             int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+extern "C" const float* clc_match_topk_tc_ref_cl(void* workspace, int64_t NP, int32_t q_repeat, int32_t C,
+                                                 int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k) {
+  const tc::Plan pl = tc::make_plan(NP, q_repeat, C, H, W, ph, pw, k);
+  if (!pl.ok || !workspace) return nullptr;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(tc::align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  return reinterpret_cast<const float*>(ws + pl.off_r32);
+}
+
+// Bring-up / test hook: additionally dumps the raw bf16-GEMM accumulators
+// xy[NP, P, H*W] (linear window origins, wrapped ones included).
+extern "C" CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat, int32_t C,
+                                             int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
                                              int32_t gaussian_mask, float* val, int32_t* idx, float* xy,
                                              void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_img || !r || !val || !idx || !xy || NP < 1) return CLC_ERR_INVALID_ARGUMENT;
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, nullptr, xy,
-                 nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+                 nullptr, 0.f, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // Bring-up hook: per-CTA clock64 stamps of the GEMM kernel's pipeline stages ([148][16] int64).
@@ -1002,5 +1448,5 @@ extern "C" CLC_API int clc_debug_match_tc_timing(const float* q_img, const float
                                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!q_img || !r || !val || !idx || !timing || NP < 1) return CLC_ERR_INVALID_ARGUMENT;
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, nullptr, nullptr,
-                 timing, workspace, workspace_bytes, (cudaStream_t)stream);
+                 timing, 0.f, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -99,19 +99,18 @@ class LatentPath:
         self.g_val = torch.empty(B * R, self.P, k, **f)
         # ---- accumulators: one flat buffer; each chain zeroes its own segment with one memset ----
         n_eb = sum(t.numel() for t in self.eb_m + self.eb_b + self.eb_f)
-        n_acc = 4 + n_eb + B * R * M * h * w + B * M * h * w   # 2 doubles + EB grads + g_refs + g_q
+        n_acc = 4 + n_eb + B * M * h * w                       # 2 doubles + EB grads + g_q
         self._acc = torch.zeros(n_acc, **f)
         self.log2 = self._acc[:4].view(torch.float64)          # [sum log2 lik_y, sum log2 lik_z]
         self._acc_y = self._acc[0:2]                           # slice-loop chain
         self._acc_eb = self._acc[2:4 + n_eb]                   # hyper-latent chain (log2[1] + EB grads)
-        self._acc_match = self._acc[4 + n_eb:]                 # match chain (g_refs, g_q)
+        self._acc_match = self._acc[4 + n_eb:]                 # match chain (g_q; g_refs is overwritten)
         off = 4
         self.g_eb = []
         for t in self.eb_m + self.eb_b + self.eb_f:
             self.g_eb.append(self._acc[off:off + t.numel()].view_as(t))
             off += t.numel()
-        self.g_refs = self._acc[off:off + B * R * M * h * w].view(B, R, M, h, w)
-        off += B * R * M * h * w
+        self.g_refs = torch.empty(B, R, M, h, w, **f)
         self.g_q = self._acc[off:off + B * M * h * w].view(B, M, h, w)
         # ---- match workspace ----
         self.mask = matching._cached_mask(h, w, patch, patch, dev) if gaussian_mask else None
@@ -127,6 +126,9 @@ class LatentPath:
         self.ws = torch.empty(max(int(nb), 16), dtype=torch.uint8, device=dev)
         nbb = lib().clc_match_bwd_workspace_bytes(B * R, M, h, w) if train else 0
         self.ws_bwd = torch.empty(max(int(nbb), 16), dtype=torch.uint8, device=dev)
+        # channels-last fp32 copy of the references that the forward leaves in its workspace
+        self._r_cl = (lib().clc_match_topk_tc_ref_cl(ptr(self.ws), B * R, R, M, h, w, patch, patch, k)
+                      if match_mode == "tc" else None)
         self._qview = matching._patch_view_from_image(self.y, patch, patch, R)
         self._gqview = self._qview
         self._graph = self._g_match = self._g_entropy = None
@@ -191,27 +193,30 @@ class LatentPath:
         # 1. match: masked Pearson correlation + top-k over all B*R (image, reference) problems
         r = self.refs.view(B * R, M, h, w)
         if self.match_mode == "tc":
+            # screening GEMM -> exact re-scoring + top-k + softmax + gather/blend (3 kernels, one call)
             call("clc_match_topk_tc", ptr(self.y), ptr(r), B * R, R, M, h, w, p, p, k,
-                 1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), None, ptr(self.ws),
-                 self.ws.numel(), st)
+                 1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), None, self.T, ptr(self.aligned),
+                 ptr(self.weights), ptr(self.ws), self.ws.numel(), st)
+            n = 1
         else:
             call("clc_pearson_corr", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.corr), B * R,
                  self.P, M, p, p, h, w, ptr(self.ws), self.ws.numel(), st)
             call("clc_topk_rows", ptr(self.corr), B * R * self.P, self.corr.shape[-1], k, ptr(self.val),
                  ptr(self.idx), st)
-        # 2. softmax weights + gather of the k matched patches + blend
-        call("clc_gather_blend_fwd", ptr(r), ptr(self.idx), ptr(self.val), self.T, ptr(self.aligned),
-             ptr(self.weights), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
+            # 2. softmax weights + gather of the k matched patches + blend
+            call("clc_gather_blend_fwd", ptr(r), ptr(self.idx), ptr(self.val), self.T, ptr(self.aligned),
+                 ptr(self.weights), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
+            n = 3
         # 3. CLM fusion over the aligned references ([B,R,C,S] layout, strided -- no transpose)
         call("clc_clm_fuse_fwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S, ptr(self.y),
              ptr(self.fused), R, B, M, S, st)
-        n = 3 if self.match_mode == "tc" else 4
+        n += 1
         if self.train:
             call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
                  ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
-            call("clc_match_bwd", C.byref(self._qview), ptr(r), ptr(self.mask), ptr(self.idx), ptr(self.weights),
-                 self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val), B * R, self.P, M,
-                 p, p, h, w, k, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
+            call("clc_match_bwd", C.byref(self._qview), ptr(r), self._r_cl, ptr(self.mask), ptr(self.idx),
+                 ptr(self.weights), self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val),
+                 B * R, self.P, M, p, p, h, w, k, 1, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
             n += 2
         return n
 
@@ -374,19 +379,20 @@ class LatentPath:
             "clc_clm_fuse_bwd": ("bytes", B * ((R * (M + 1) + M) * S * 4 + R * (M + 1) * S * 4)),
             # tensor-core match: 2*P*L*C*ph*pw flop per (image, reference), counted once
             "clc_match_topk_tc(gemm)": ("flops", 2.0 * P * L * K * NP),
-            "clc_match_topk_tc(pack_ref)": ("bytes", NP * M * S * (4 + 2 + 4) + NP * S * 8),
-            "clc_match_topk_tc(pack_query)": ("bytes", B * M * S * (4 + 2 + 4)),
+            # pre-pass: read fp32 refs + queries once, write bf16 + fp32 channels-last copies, channel sums
+            "clc_match_topk_tc(prepass)": ("bytes", (NP + B) * M * S * (4 + 2 + 4) + NP * S * 8),
+            # re-score KC windows + the patch, write val/idx/weights and the blended reference
+            "clc_match_topk_tc(rescore)": ("bytes", NP * P * K * 4 * (KC + 1) + NP * P * k * 12 + NP * M * S * 4),
             "patch_stats": ("bytes", B * M * S * 4 + B * P * 8),
-            "clc_match_topk_tc(rescore)": ("bytes", NP * P * K * 4 * (KC + 1) + NP * P * k * 8),
             "clc_pearson_corr": ("flops", 2.0 * P * L * K * NP),
             "clc_topk_rows": ("bytes", NP * P * L * 4 + NP * P * k * 8),
             "channel_sums": ("bytes", NP * M * S * 4 + NP * S * 8),
-            # fused match backward: patches of q and g once, k windows read for the reductions and
-            # again for the scatter, k window read-modify-writes into the gradient scratch
+            # fused match backward: patches of q and g once, k windows read once (kept in registers),
+            # k window read-modify-writes into the gradient scratch
             "clc_match_bwd(nchw_to_cl)": ("bytes", NP * M * S * 8),
-            "clc_match_bwd(main)": ("bytes", NP * P * K * 4 * (2 + 2 * k + 2 * k) + B * M * S * 8),
-            "clc_match_bwd(cl_to_nchw)": ("bytes", NP * M * S * 12),
-            "clc_match_bwd": ("bytes", NP * P * K * 4 * (2 + 2 * k + 2 * k) + B * M * S * 8),
+            "clc_match_bwd(main)": ("bytes", NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8),
+            "clc_match_bwd(cl_to_nchw)": ("bytes", NP * M * S * 8),
+            "clc_match_bwd": ("bytes", NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8),
         }
         return w
 

@@ -110,7 +110,7 @@ class _PearsonTopkFn(torch.autograd.Function):
             nb = lib().clc_match_topk_tc_workspace_bytes(NP, q_repeat, Cc, H, W, ph, pw, k)
             ws = _workspace(nb, r.device)
             call("clc_match_topk_tc", ptr(q_img), ptr(r), NP, q_repeat, Cc, H, W, ph, pw, k, gauss,
-                 ptr(val), ptr(idx), None, ptr(ws), ws.numel(), _stream())
+                 ptr(val), ptr(idx), None, 0.0, None, None, ptr(ws), ws.numel(), _stream())
         else:
             raise ValueError(f'Invalid match mode "{mode}" (expected "fp32" or "tc")')
         ctx.save_for_backward(q_img, r, mask, idx)
@@ -303,15 +303,40 @@ class _MatchGatherFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q_img, r, mask, ph, pw, k, q_repeat, temperature, mode):
-        with torch.no_grad():
-            val, idx = _PearsonTopkFn.apply(q_img, r, mask, ph, pw, k, q_repeat, mode)
         NP, Cc, fh, fw = r.shape
-        out = torch.empty_like(r)
-        weights = torch.empty(idx.shape, dtype=torch.float32, device=r.device)
-        call("clc_gather_blend_fwd", ptr(r), ptr(idx), ptr(val), float(temperature), ptr(out), ptr(weights), NP,
-             Cc, fh, fw, ph, pw, fw - pw + 1, k, 0, _stream())
+        r_cl = ws = None
+        if mode == "tc":
+            # fused: screening GEMM -> exact re-scoring + top-k + softmax + gather/blend in one C call
+            NQ, _, H, W = q_img.shape
+            if (fh, fw) != (H, W):
+                raise ValueError("tc mode needs query and reference latents of the same spatial size")
+            gauss = 0
+            if mask is not None:
+                if not getattr(mask, "_clc_gaussian", False):
+                    raise ValueError("tc mode supports mask=None or the mask from create_gaussian_masks")
+                gauss = 1
+            P = (H // ph) * (W // pw)
+            val = torch.empty((NP, P, k), dtype=torch.float32, device=r.device)
+            idx = torch.empty((NP, P, k), dtype=torch.int32, device=r.device)
+            weights = torch.empty_like(val)
+            out = torch.empty_like(r)
+            nb = lib().clc_match_topk_tc_workspace_bytes(NP, q_repeat, Cc, H, W, ph, pw, k)
+            ws = _workspace(nb, r.device)
+            call("clc_match_topk_tc", ptr(q_img), ptr(r), NP, q_repeat, Cc, H, W, ph, pw, k, gauss, ptr(val), ptr(idx),
+                 None, float(temperature), ptr(out), ptr(weights), ptr(ws), ws.numel(), _stream())
+            if any(ctx.needs_input_grad[:2]):
+                # channels-last fp32 copy of r left in the workspace: the backward reuses it
+                r_cl = lib().clc_match_topk_tc_ref_cl(ptr(ws), NP, q_repeat, Cc, H, W, ph, pw, k)
+        else:
+            with torch.no_grad():
+                val, idx = _PearsonTopkFn.apply(q_img, r, mask, ph, pw, k, q_repeat, mode)
+            out = torch.empty_like(r)
+            weights = torch.empty(idx.shape, dtype=torch.float32, device=r.device)
+            call("clc_gather_blend_fwd", ptr(r), ptr(idx), ptr(val), float(temperature), ptr(out), ptr(weights), NP,
+                 Cc, fh, fw, ph, pw, fw - pw + 1, k, 0, _stream())
         ctx.save_for_backward(q_img, r, mask, idx, weights)
         ctx.geom = (ph, pw, k, q_repeat, float(temperature))
+        ctx.r_cl, ctx.fwd_ws = r_cl, (ws if r_cl else None)   # keeps the workspace alive for the backward
         ctx.mark_non_differentiable(idx)
         return out, val, idx
 
@@ -321,13 +346,14 @@ class _MatchGatherFn(torch.autograd.Function):
         ph, pw, k, q_repeat, temperature = ctx.geom
         NP, Cc, fh, fw = r.shape
         P = idx.shape[1]
-        g_r = torch.zeros_like(r)
+        g_r = torch.empty_like(r)                 # written, not accumulated (CLC_MATCH_BWD_OVERWRITE_G_R)
         g_q = torch.zeros_like(q_img) if ctx.needs_input_grad[0] else None
         view = _patch_view_from_image(q_img, ph, pw, q_repeat)
         ws = _workspace(lib().clc_match_bwd_workspace_bytes(NP, Cc, fh, fw), r.device)
-        call("clc_match_bwd", C.byref(view), ptr(r), ptr(mask), ptr(idx), ptr(weights), temperature,
-             ptr(g_out.contiguous()), ptr(g_r), ptr(g_q), None, NP, P, Cc, ph, pw, fh, fw, k, ptr(ws), ws.numel(),
+        call("clc_match_bwd", C.byref(view), ptr(r), ctx.r_cl, ptr(mask), ptr(idx), ptr(weights), temperature,
+             ptr(g_out.contiguous()), ptr(g_r), ptr(g_q), None, NP, P, Cc, ph, pw, fh, fw, k, 1, ptr(ws), ws.numel(),
              _stream())
+        ctx.fwd_ws = None
         return g_q, g_r, None, None, None, None, None, None, None
 
 

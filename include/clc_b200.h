@@ -43,7 +43,7 @@ typedef enum clc_status {
   CLC_ERR_ARCH = -5              /* device is not sm_100 (tcgen05 / TMA path unavailable)  */
 } clc_status;
 
-CLC_API int clc_version(void);                 /* ABI version, currently 1 */
+CLC_API int clc_version(void);                 /* ABI version, currently 2 */
 CLC_API const char* clc_strerror(int status);  /* static string */
 /* Text of the last CUDA error seen by the calling thread (empty if none). */
 CLC_API const char* clc_last_cuda_error(void);
@@ -203,9 +203,21 @@ CLC_API int clc_gaussian_mask(float* mask, int32_t img_h, int32_t img_w, int32_t
 CLC_API int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
                       int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
                       int32_t gaussian_mask, float* val, int32_t* idx, int32_t* n_uncertified,
+                      float temperature, float* aligned, float* weights,
                       void* workspace, size_t workspace_bytes, void* stream);
+/*   aligned : optional out [NP, C, H, W] (16-byte aligned).  When non-NULL the gather + blend of
+ *             SI_Wraper (Patch_Matching.py:225-238, is_stack = False, same-scale features: the
+ *             gathered feature map is `r` itself) is fused into the re-scoring kernel:
+ *             aligned = sum_j softmax_j(val * temperature) * window_j(r), reassembled in place of
+ *             the query patches -- identical to clc_gather_blend_fwd(r, idx, val, ...).
+ *   weights : optional out [NP, P, k], the softmax weights (needed by clc_match_bwd). */
 CLC_API size_t clc_match_topk_tc_workspace_bytes(int64_t NP, int32_t q_repeat, int32_t C, int32_t H,
                                          int32_t W, int32_t ph, int32_t pw, int32_t k);
+/* Channels-last fp32 copy of the reference latents [NP, H*W, C] that clc_match_topk_tc leaves in
+ * its workspace (valid until the workspace is reused); pass it to clc_match_bwd as `r_cl` to skip
+ * that call's own transpose.  Returns NULL for an unsupported shape. */
+CLC_API const float* clc_match_topk_tc_ref_cl(void* workspace, int64_t NP, int32_t q_repeat, int32_t C,
+                                              int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k);
 
 /* softmax(value*T) weights + gather of the k matched patches + weighted sum + tile
  * reassembly (or channel stacking).
@@ -245,13 +257,17 @@ CLC_API int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const
  *   g_out : [NP, C, fh, fw] dL/d(blended reference);  weights : [NP, P, k] from the forward
  *   g_r ACCUMULATED [NP, C, fh, fw];  g_q ACCUMULATED through `qv` (may be NULL);
  *   g_val : optional out [NP, P, k] = dL/d(masked corr value) (may be NULL)
+ *   r_cl  : optional channels-last fp32 copy of r, [NP, fh*fw, C] (e.g. clc_match_topk_tc_ref_cl);
+ *           NULL -> the call transposes r itself (one more kernel)
+ *   flags : CLC_MATCH_BWD_OVERWRITE_G_R -> g_r is WRITTEN (no zero-init needed, no read-modify-write)
  *   workspace : clc_match_bwd_workspace_bytes(...) bytes enable the channels-last fast path
  *               (coalesced float4 loads, vector atomics); NULL selects the workspace-free kernel. */
-CLC_API int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* mask, const int32_t* idx,
-                          const float* weights, float temperature, const float* g_out, float* g_r,
-                          float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph, int32_t pw,
-                          int32_t fh, int32_t fw, int32_t k, void* workspace, size_t workspace_bytes,
-                          void* stream);
+#define CLC_MATCH_BWD_OVERWRITE_G_R 1
+CLC_API int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* r_cl, const float* mask,
+                          const int32_t* idx, const float* weights, float temperature, const float* g_out,
+                          float* g_r, float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
+                          int32_t pw, int32_t fh, int32_t fw, int32_t k, int32_t flags, void* workspace,
+                          size_t workspace_bytes, void* stream);
 CLC_API size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw);
 
 /* ------------------------------------------------------------------------------------
@@ -277,6 +293,11 @@ CLC_API int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb,
  * Bring-up / test hooks of the tcgen05 match kernel (no reference counterpart; used by
  * tests/test_match_tc_gpu.py and scripts/tc_timing.py)
  * ---------------------------------------------------------------------------------- */
+
+/* Timing aid: bit i of `mask` enables the i-th kernel of the multi-kernel entry points
+ * (clc_match_topk_tc: prepass, gemm, rescore; clc_match_bwd: main, transpose).  Default 0xff = all; bits 8-15 are kernel-specific experiment switches (0 in production).
+ * Results are only meaningful with every stage on. */
+CLC_API void clc_debug_set_stage_mask(int mask);
 
 /* clc_match_topk_tc that additionally dumps the raw bf16-GEMM accumulators
  * xy[NP, P, H*W] (linear window origins oy*W+ox, wrapped ones included). */

@@ -49,7 +49,20 @@ torch.cuda.synchronize()
 print(f"# {a.workload}: {len(calls)} C-ABI calls per step; per-call time, L2-warm, {a.rep} back-to-back in a graph")
 s = torch.cuda.Stream()
 tot = 0.0
+STAGES = {"clc_match_topk_tc": ["prepass", "gemm", "rescore+blend"], "clc_match_bwd": ["memset+main", "cl_to_nchw"]}
+# debug variants: (stage bit, dbg bits << 8, label)
+VARIANTS = {"clc_match_topk_tc": [(1, 1, "prepass: query role only"), (1, 2, "prepass: ref role only"),
+                                  (4, 1, "rescore: no re-scoring loads"), (4, 2, "rescore: no blend")],
+            "clc_match_bwd": [(1, 1, "main: no window atomics"), (1, 2, "main: no g_q atomics"), (1, 3, "main: no atomics")]}
+expanded = []
 for name, args in calls:
+    expanded.append((name, args, 0xff, name))
+    for i, lab in enumerate(STAGES.get(name, [])):
+        expanded.append((name, args, 1 << i, f"  {name}[{lab}]"))
+    for st_, dbg, lab in VARIANTS.get(name, []):
+        expanded.append((name, args, st_ | (dbg << 8), f"    dbg {lab}"))
+for name, args, mask, label in expanded:
+    _lib.lib().clc_debug_set_stage_mask(mask)
     with torch.cuda.stream(s):
         st = s.cuda_stream
         args2 = list(args)
@@ -71,8 +84,10 @@ for name, args in calls:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (a.iters * a.rep)
-    tot += us
-    print(f"{name:28s} {us:8.2f} us/call")
+    if mask == 0xff:
+        tot += us
+    print(f"{label:40s} {us:8.2f} us/call")
+_lib.lib().clc_debug_set_stage_mask(0xff)
 print(f"{'sum':28s} {tot:8.2f} us")
 
 # (b) per-kernel trace, warm

@@ -34,7 +34,7 @@ def test_prototypes_match_header_and_load():
     from clc_b200 import _lib
     assert sorted(_lib.PROTOTYPES) == _header_symbols()
     h = _lib.lib()  # resolves every symbol, sets argtypes
-    assert h.clc_version() == 1
+    assert h.clc_version() == 2
     assert h.clc_strerror(0) == b"ok"
     assert b"invalid" in h.clc_strerror(-1)
 

@@ -102,7 +102,7 @@ def test_tc_topk_equals_fp32_mode_and_oracle(geom):
     nb = _lib.lib().clc_match_topk_tc_workspace_bytes(NQ * R, R, Cc, h, w, p, p, k)
     ws = torch.empty(nb, dtype=torch.uint8, device=d)
     _lib.call("clc_match_topk_tc", yq.data_ptr(), r.data_ptr(), NQ * R, R, Cc, h, w, p, p, k, int(gauss),
-              val.data_ptr(), idx.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+              val.data_ptr(), idx.data_ptr(), cnt.data_ptr(), 0.0, None, None, ws.data_ptr(), ws.numel(), _stream())
     v32, i32, _ = clc_b200.match_topk(yq, refs.to(d), p, p, k, gaussian_mask=gauss, mode="fp32")
     assert torch.equal(idx.view(NQ, R, P, k), i32), "tc-mode indices differ from fp32 mode"
     assert torch.allclose(val.view(NQ, R, P, k), v32, atol=2e-6, rtol=0)
@@ -127,4 +127,4 @@ def test_tc_unsupported_shapes_fail_loudly():
     o = torch.zeros(1, 4, 4, device=d)
     with pytest.raises(RuntimeError, match="unsupported"):
         _lib.call("clc_match_topk_tc", t.data_ptr(), t.data_ptr(), 1, 1, 100, 8, 8, 4, 4, 4, 0, o.data_ptr(),
-                  o.data_ptr(), None, o.data_ptr(), 16, None)
+                  o.data_ptr(), None, 0.0, None, None, o.data_ptr(), 16, None)
