@@ -68,6 +68,7 @@ PROTOTYPES = {
     "clc_match_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
                                 _i32, _i32, _i32, _i32, _i32, _p, _sz, _p]),
     "clc_match_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "clc_match_bwd_zero_workspace": (C.c_int, [_p, _sz, _i64, _i32, _i32, _i32, _p]),
     "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                         _p, _sz, _p]),
     "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,

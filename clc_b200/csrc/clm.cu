@@ -31,7 +31,7 @@ __device__ __forceinline__ void clm_coef(const float* a, int R, float* coef, flo
 // channels c0 + warp + 8*i (i < CPW) of its CTA.  grid = (ceil(S/(32*VW)), ceil(C/(8*CPW)), B).
 // The per-pixel coefficients (R exps + R sigmoids) are formed once per thread and reused over
 // its CPW channels; CPW is chosen by the host so the grid fills the 148 SMs.
-template <int VW>
+template <int VW, int RT>
 __global__ void __launch_bounds__(256)
 clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref_sb,
                     const float* __restrict__ att, int64_t att_sr, int64_t att_sb,
@@ -44,7 +44,9 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
   float coef[VW][kMaxRefs];
   {
     float a[VW][kMaxRefs];
-    for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      if (r >= R) break;
       const float* ap = att + (int64_t)r * att_sr + b * att_sb + s0;
       if constexpr (VW == 4) {
         const float4 v = ld4(ap);
@@ -57,21 +59,43 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
     for (int v = 0; v < VW; ++v) clm_coef(a[v], R, coef[v], nullptr, nullptr);
   }
   const int cbase = blockIdx.y * 8 * CPW + warp;
-  for (int i = 0; i < CPW; ++i) {
-    const int c = cbase + 8 * i;
-    if (c >= C) break;
-    const int64_t o = (b * C + c) * S + s0;
-    if constexpr (VW == 4) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < R; ++r) {
-        const float4 t = ld4_stream(ref_t + (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0);
-        // (aligned_stack * attention_weights).sum(dim=1): products summed left to right over r
-        acc.x += t.x * coef[0][r]; acc.y += t.y * coef[1][r];
-        acc.z += t.z * coef[2][r]; acc.w += t.w * coef[3][r];
+  if constexpr (VW == 4) {
+    // two channels per iteration, all 2 * (R + 1) loads issued before the first use
+    for (int i = 0; i < CPW; i += 2) {
+      float4 t[2][RT], yv[2];
+      bool ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = cbase + 8 * (i + u);
+        ok[u] = (i + u < CPW) && c < C;
+        if (ok[u]) {
+#pragma unroll
+          for (int r = 0; r < RT; ++r)
+            if (r < R) t[u][r] = ld4_stream(ref_t + (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0);
+          yv[u] = ld4_stream(y + (b * C + c) * S + s0);
+        }
       }
-      const float4 yv = ld4_stream(y + o);
-      st4_stream(out + o, make_float4(acc.x + yv.x, acc.y + yv.y, acc.z + yv.z, acc.w + yv.w));
-    } else {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        const int c = cbase + 8 * (i + u);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // (aligned_stack * attention_weights).sum(dim=1): products summed left to right over r
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (r < R) {
+            acc.x += t[u][r].x * coef[0][r]; acc.y += t[u][r].y * coef[1][r];
+            acc.z += t[u][r].z * coef[2][r]; acc.w += t[u][r].w * coef[3][r];
+          }
+        st4_stream(out + (b * C + c) * S + s0,
+                   make_float4(acc.x + yv[u].x, acc.y + yv[u].y, acc.z + yv[u].z, acc.w + yv[u].w));
+      }
+    }
+  } else {
+    for (int i = 0; i < CPW; ++i) {
+      const int c = cbase + 8 * i;
+      if (c >= C) break;
+      const int64_t o = (b * C + c) * S + s0;
       float acc = 0.f;
       for (int r = 0; r < R; ++r) acc += ref_t[(int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0] * coef[0][r];
       out[o] = acc + y[o];
@@ -85,7 +109,7 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
 // distributed shared memory in fixed rank order (deterministic, no atomics, no workspace).
 //   g_ref_t[r,c] = g_c * coef_r
 //   g_att[m]     = w_m s_m G_m - w_m * sum_r G_r s_r w_r + G_m w_m s_m (1 - s_m)
-template <int VW>
+template <int VW, int RT>
 __global__ void __launch_bounds__(256)
 clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref_sb,
                     const float* __restrict__ att, int64_t att_sr, int64_t att_sb,
@@ -119,17 +143,24 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
 #pragma unroll
     for (int v = 0; v < VW; ++v) clm_coef(a[v], R, coef[v], w[v], sg[v]);
     // channels of this CTA: c = blockIdx.y + gridDim.y * m  (interleaved), channel lane ty takes every 8th
+#pragma unroll 2
     for (int c = blockIdx.y + gridDim.y * ty; c < C; c += gridDim.y * 8) {
       const int64_t o = (b * C + c) * S + s0;
       if constexpr (VW == 4) {
+        // all R + 1 loads of the channel are issued before the first use
         const float4 g = ld4_stream(g_out + o);
-        for (int r = 0; r < R; ++r) {
-          const int64_t ro = (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0;
-          const float4 t = ld4_stream(ref_t + ro);
-          G[0][r] = fmaf(g.x, t.x, G[0][r]); G[1][r] = fmaf(g.y, t.y, G[1][r]);
-          G[2][r] = fmaf(g.z, t.z, G[2][r]); G[3][r] = fmaf(g.w, t.w, G[3][r]);
-          st4_stream(g_ref_t + ro, make_float4(g.x * coef[0][r], g.y * coef[1][r], g.z * coef[2][r], g.w * coef[3][r]));
-        }
+        float4 t[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (r < R) t[r] = ld4_stream(ref_t + (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0);
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (r < R) {
+            const int64_t ro = (int64_t)r * ref_sr + b * ref_sb + (int64_t)c * S + s0;
+            G[0][r] = fmaf(g.x, t[r].x, G[0][r]); G[1][r] = fmaf(g.y, t[r].y, G[1][r]);
+            G[2][r] = fmaf(g.z, t[r].z, G[2][r]); G[3][r] = fmaf(g.w, t[r].w, G[3][r]);
+            st4_stream(g_ref_t + ro, make_float4(g.x * coef[0][r], g.y * coef[1][r], g.z * coef[2][r], g.w * coef[3][r]));
+          }
       } else {
         const float g = g_out[o];
         for (int r = 0; r < R; ++r) {
@@ -203,10 +234,12 @@ extern "C" int clc_clm_fuse_fwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   const unsigned gy = (unsigned)((C + 8 * CPW - 1) / (8 * CPW));
   if (gy > 65535) return CLC_ERR_UNSUPPORTED;
   dim3 grid(gx, gy, (unsigned)B);
-  if (vec)
-    clm_fuse_fwd_kernel<4><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+  if (vec && R <= 4)
+    clm_fuse_fwd_kernel<4, 4><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+  else if (vec)
+    clm_fuse_fwd_kernel<4, 8><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
   else
-    clm_fuse_fwd_kernel<1><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+    clm_fuse_fwd_kernel<1, 8><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
   CLC_CHECK_LAUNCH("clc_clm_fuse_fwd");
   return CLC_OK;
 }
@@ -239,11 +272,14 @@ extern "C" int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (vec4)
-    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<4>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
+  if (vec4 && R <= 4)
+    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<4, 4>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
+                                g_ref_t, g_att, (int)R, (int)C, S));
+  else if (vec4)
+    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<4, 8>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
                                 g_ref_t, g_att, (int)R, (int)C, S));
   else
-    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<1>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
+    CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<1, 8>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
                                 g_ref_t, g_att, (int)R, (int)C, S));
   CLC_CHECK_LAUNCH("clc_clm_fuse_bwd");
   return CLC_OK;

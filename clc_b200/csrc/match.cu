@@ -624,10 +624,14 @@ nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ xT, int C, in
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* xn = x + (int64_t)n * C * HW;
   float* xTn = xT + (int64_t)n * C * HW;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, p = p0 + threadIdx.x;
-    t[i][threadIdx.x] = (c < C && p < HW) ? xn[(int64_t)c * HW + p] : 0.f;
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = c0 + threadIdx.y + 8 * u, p = p0 + threadIdx.x;
+    v[u] = (c < C && p < HW) ? xn[(int64_t)c * HW + p] : 0.f;
   }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) t[threadIdx.y + 8 * u][threadIdx.x] = v[u];
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + threadIdx.x;
@@ -643,17 +647,27 @@ cl_to_nchw_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, in
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* xTn = xT + (int64_t)n * C * HW;
   float* xn = x + (int64_t)n * C * HW;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int p = p0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (c < C && p < HW) ? xTn[(int64_t)p * C + c] : 0.f;
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int p = p0 + threadIdx.y + 8 * u, c = c0 + threadIdx.x;
+    v[u] = (c < C && p < HW) ? xTn[(int64_t)p * C + c] : 0.f;
   }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) t[threadIdx.y + 8 * u][threadIdx.x] = v[u];
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, p = p0 + threadIdx.x;
-    if (c < C && p < HW) {
-      if (ADD) xn[(int64_t)c * HW + p] += t[threadIdx.x][i];
-      else xn[(int64_t)c * HW + p] = t[threadIdx.x][i];
+  if (ADD) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + threadIdx.y + 8 * u, p = p0 + threadIdx.x;
+      v[u] = (c < C && p < HW) ? xn[(int64_t)c * HW + p] : 0.f;
     }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.y + 8 * u;
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) xn[(int64_t)c * HW + p] = ADD ? v[u] + t[threadIdx.x][i] : t[threadIdx.x][i];
   }
 }
 
@@ -801,8 +815,8 @@ match_bwd_cl_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __r
 // float4 loads of a thread are in flight together, every reduction of the CTA (patch statistics +
 // 4 sums per window) goes through ONE block reduction, and the scatter is issued from registers.
 // Three dependent global-memory phases per CTA instead of 2k+2.  ITEMS = ceil(S*C/4 / 256).
-template <int ITEMS>
-__global__ void __launch_bounds__(256, 2)
+template <int ITEMS, bool REREAD>
+__global__ void __launch_bounds__(256, REREAD ? 3 : 2)
 match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __restrict__ mask,
                         const int32_t* __restrict__ idx, const float* __restrict__ weights, float temperature,
                         const float* __restrict__ g_out, float* __restrict__ g_rT, float* __restrict__ g_q,
@@ -879,13 +893,11 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
     const int s = f / c4n, c4 = f - s * c4n;
     woff[i] = (f < items) ? ((s >> 2) * fw + (s & 3)) * C + 4 * c4 : -1;
   }
-  float4 rv[KK][ITEMS];
-#pragma unroll
-  for (int j = 0; j < KK; ++j)
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i)
-      rv[j][i] = (j < k && woff[i] >= 0) ? ld4(rTn + (int64_t)src_s[j] * C + woff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-  // ---- one pass of partial sums ----
+  // REREAD = false: all KK windows stay in registers between the reduction and the scatter (128
+  // registers, 2 CTAs / SM).  REREAD = true: windows are processed two at a time and read again for
+  // the scatter (L1 / L2 hits), 85 registers, 3 CTAs / SM -- chosen when it saves a wave of CTAs.
+  constexpr int WB = REREAD ? 2 : KK;        // windows in flight
+  float4 rv[WB][ITEMS];
   float v[NV];
 #pragma unroll
   for (int t = 0; t < NV; ++t) v[t] = 0.f;
@@ -893,16 +905,32 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
   for (int i = 0; i < ITEMS; ++i) {
     const int f = tid + i * 256;
     if (f >= items) continue;
-    const float4 q4 = Q[f], g4 = G[f];
+    const float4 q4 = Q[f];
     v[0] += (q4.x + q4.y) + (q4.z + q4.w);
     v[1] = fmaf(q4.x, q4.x, fmaf(q4.y, q4.y, fmaf(q4.z, q4.z, fmaf(q4.w, q4.w, v[1]))));
+  }
 #pragma unroll
-    for (int j = 0; j < KK; ++j) {
-      const float4 r4 = rv[j][i];
-      v[2 + 4 * j] = fmaf(g4.x, r4.x, fmaf(g4.y, r4.y, fmaf(g4.z, r4.z, fmaf(g4.w, r4.w, v[2 + 4 * j]))));
-      v[3 + 4 * j] += (r4.x + r4.y) + (r4.z + r4.w);
-      v[4 + 4 * j] = fmaf(r4.x, r4.x, fmaf(r4.y, r4.y, fmaf(r4.z, r4.z, fmaf(r4.w, r4.w, v[4 + 4 * j]))));
-      v[5 + 4 * j] = fmaf(q4.x, r4.x, fmaf(q4.y, r4.y, fmaf(q4.z, r4.z, fmaf(q4.w, r4.w, v[5 + 4 * j]))));
+  for (int j0 = 0; j0 < KK; j0 += WB) {
+#pragma unroll
+    for (int jj = 0; jj < WB; ++jj)
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i)
+        rv[jj][i] = (j0 + jj < k && woff[i] >= 0) ? ld4(rTn + (int64_t)src_s[j0 + jj] * C + woff[i])
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int f = tid + i * 256;
+      if (f >= items) continue;
+      const float4 q4 = Q[f], g4 = G[f];
+#pragma unroll
+      for (int jj = 0; jj < WB; ++jj) {
+        const int j = j0 + jj;
+        const float4 r4 = rv[jj][i];
+        v[2 + 4 * j] = fmaf(g4.x, r4.x, fmaf(g4.y, r4.y, fmaf(g4.z, r4.z, fmaf(g4.w, r4.w, v[2 + 4 * j]))));
+        v[3 + 4 * j] += (r4.x + r4.y) + (r4.z + r4.w);
+        v[4 + 4 * j] = fmaf(r4.x, r4.x, fmaf(r4.y, r4.y, fmaf(r4.z, r4.z, fmaf(r4.w, r4.w, v[4 + 4 * j]))));
+        v[5 + 4 * j] = fmaf(q4.x, r4.x, fmaf(q4.y, r4.y, fmaf(q4.z, r4.z, fmaf(q4.w, r4.w, v[5 + 4 * j]))));
+      }
     }
   }
 #pragma unroll
@@ -947,25 +975,38 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
     coef[j][0] = wj; coef[j][1] = g_num; coef[j][2] = 2.f * g_dY; coef[j][3] = g_ym * inv_k;
   }
   __syncthreads();
-  // ---- scatter from registers: ONE vector atomic per window element ----
+  // ---- scatter: ONE vector atomic per window element ----
   float* g_rTn = g_rT + (int64_t)n * HW * C;
 #pragma unroll
-  for (int j = 0; j < KK; ++j) {
-    if (j >= k) break;
-    const float cw_ = coef[j][0], cxy = coef[j][1], cdy = coef[j][2], cm = coef[j][3];
-    float* dst = g_rTn + (int64_t)src_s[j] * C;
+  for (int j0 = 0; j0 < KK; j0 += WB) {
+    if (j0 >= k) break;
+    if (REREAD) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int f = tid + i * 256;
-      if (f >= items) continue;
-      const float4 q4 = Q[f], g4 = G[f], r4 = rv[j][i];
-      float4 o;
-      o.x = fmaf(cw_, g4.x, fmaf(cxy, q4.x, fmaf(cdy, r4.x, cm)));
-      o.y = fmaf(cw_, g4.y, fmaf(cxy, q4.y, fmaf(cdy, r4.y, cm)));
-      o.z = fmaf(cw_, g4.z, fmaf(cxy, q4.z, fmaf(cdy, r4.z, cm)));
-      o.w = fmaf(cw_, g4.w, fmaf(cxy, q4.w, fmaf(cdy, r4.w, cm)));
-      if (!(dbg & 1)) red_add4(dst + woff[i], o);
-      else if (o.x == 1.2345e33f) dst[woff[i]] = o.y + o.z + o.w;
+      for (int jj = 0; jj < WB; ++jj)
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+          rv[jj][i] = (j0 + jj < k && woff[i] >= 0) ? ld4(rTn + (int64_t)src_s[j0 + jj] * C + woff[i])
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int jj = 0; jj < WB; ++jj) {
+      const int j = j0 + jj;
+      if (j >= k) break;
+      const float cw_ = coef[j][0], cxy = coef[j][1], cdy = coef[j][2], cm = coef[j][3];
+      float* dst = g_rTn + (int64_t)src_s[j] * C;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int f = tid + i * 256;
+        if (f >= items) continue;
+        const float4 q4 = Q[f], g4 = G[f], r4 = rv[jj][i];
+        float4 o;
+        o.x = fmaf(cw_, g4.x, fmaf(cxy, q4.x, fmaf(cdy, r4.x, cm)));
+        o.y = fmaf(cw_, g4.y, fmaf(cxy, q4.y, fmaf(cdy, r4.y, cm)));
+        o.z = fmaf(cw_, g4.z, fmaf(cxy, q4.z, fmaf(cdy, r4.z, cm)));
+        o.w = fmaf(cw_, g4.w, fmaf(cxy, q4.w, fmaf(cdy, r4.w, cm)));
+        if (!(dbg & 1)) red_add4(dst + woff[i], o);
+        else if (o.x == 1.2345e33f) dst[woff[i]] = o.y + o.z + o.w;
+      }
     }
   }
   if (g_q && !(dbg & 2)) {
@@ -984,17 +1025,218 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
   }
 }
 
-template <int ITEMS>
-static int launch_bwd_reg(unsigned blocks, size_t smem, cudaStream_t st, PatchAddr qa, const float* rT,
-                          const float* mask, const int32_t* idx, const float* weights, float temperature,
-                          const float* g_out, float* g_rT, float* g_q, float* g_val, int P, int C, int ph,
-                          int pw, int fh, int fw, int k) {
-  auto kern = match_bwd_cl_reg_kernel<ITEMS>;
+// "Thread owns its items" variant (pw == 4, k <= 4, blockDim = ph * C/4 a multiple of 32): thread
+// (dy, c4) owns the 4 x 4 block {dx = 0..3} x {channels 4*c4 .. 4*c4+3} of the patch.  Its q / g values
+// come straight from the NCHW tensors as four float4 rows (one per channel) -- the [shift][channel]
+// transposition happens in register naming, there is no shared-memory staging -- and every window
+// address is base + dx * C, so the kernel has no per-item index arithmetic.  Windows are processed
+// two at a time and read again for the scatter (L1 / L2 hits).
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __restrict__ mask,
+                     const int32_t* __restrict__ idx, const float* __restrict__ weights, float temperature,
+                     const float* __restrict__ g_out, float* __restrict__ g_rT, float* __restrict__ g_q,
+                     float* __restrict__ g_val_out, int P, int C, int ph, int fh, int fw, int k, int dbg) {
+  constexpr int KK = 4, NV = 2 + 4 * KK, NW = NT / 32, pw = 4;
+  __shared__ float red[NW][NV];
+  __shared__ float tot[NV];                 // xs, sxx, then per window: g_w, s1, s2, xy
+  __shared__ float coef[KK][4];             // per window: w_j, g_xy, 2*g_dY, c_mean
+  __shared__ float part[KK][3];             // per window: its terms of t_gxs, t_gsxx, t_gxm
+  __shared__ int src_s[KK];
+  __shared__ float w_s[KK], m_s[KK];
+  const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
+  const int HW = fh * fw;
+  const int n = blockIdx.x / P;
+  const int patch = blockIdx.x - n * P;
+  const int nq = n / qa.repeat;
+  const int npx = fw / pw;
+  const int py = patch / npx, px = patch - py * npx;
+  const int c4n = C >> 2, K = C * ph * pw;
+  const float Kf = (float)K, inv_k = 1.0f / Kf;
+  const int64_t po = ((int64_t)n * P + patch) * k;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int dy = tid / c4n, c4 = tid - dy * c4n;
+  if (tid < KK) {
+    int src = 0;
+    float wj = 0.f, mj = 1.f;
+    if (tid < k) {
+      const int id = idx[po + tid];
+      wj = weights[po + tid];
+      const int oy = id / cw, ox = id - oy * cw;
+      src = oy * fw + ox;
+      if (mask) mj = mask[(int64_t)patch * L + id];
+    }
+    src_s[tid] = src; w_s[tid] = wj; m_s[tid] = mj;
+  }
+  // q / g: 4 channel rows of 4 floats each; q[dx][i] = channel 4*c4+i at (dy, dx)
+  const float* qp = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch) + (int64_t)(4 * c4) * qa.sc + (int64_t)dy * qa.sy;
+  const float* gp = g_out + ((int64_t)n * C + 4 * c4) * HW + (py * ph + dy) * fw + px * pw;
+  float4 qc[4], gc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    qc[i] = ld4(qp + (int64_t)i * qa.sc);
+    gc[i] = ld4(gp + (int64_t)i * HW);
+  }
+  float4 q[4], g[4];   // [dx] -> float4 over the 4 channels
+  q[0] = make_float4(qc[0].x, qc[1].x, qc[2].x, qc[3].x); q[1] = make_float4(qc[0].y, qc[1].y, qc[2].y, qc[3].y);
+  q[2] = make_float4(qc[0].z, qc[1].z, qc[2].z, qc[3].z); q[3] = make_float4(qc[0].w, qc[1].w, qc[2].w, qc[3].w);
+  g[0] = make_float4(gc[0].x, gc[1].x, gc[2].x, gc[3].x); g[1] = make_float4(gc[0].y, gc[1].y, gc[2].y, gc[3].y);
+  g[2] = make_float4(gc[0].z, gc[1].z, gc[2].z, gc[3].z); g[3] = make_float4(gc[0].w, gc[1].w, gc[2].w, gc[3].w);
+  __syncthreads();    // src_s visible
+  const float* rbase = rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;    // + (src + dx) * C
+  float* gbase = g_rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;
+  float v[NV];
+#pragma unroll
+  for (int t = 0; t < NV; ++t) v[t] = 0.f;
+#pragma unroll
+  for (int dx = 0; dx < 4; ++dx) {
+    v[0] += (q[dx].x + q[dx].y) + (q[dx].z + q[dx].w);
+    v[1] = fmaf(q[dx].x, q[dx].x, fmaf(q[dx].y, q[dx].y, fmaf(q[dx].z, q[dx].z, fmaf(q[dx].w, q[dx].w, v[1]))));
+  }
+  float4 rv[2][4];
+#pragma unroll
+  for (int j0 = 0; j0 < KK; j0 += 2) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const float* wp = rbase + (int64_t)src_s[j0 + jj] * C;
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx)
+        rv[jj][dx] = (j0 + jj < k) ? ld4(wp + dx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = j0 + jj;
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const float4 r4 = rv[jj][dx], g4 = g[dx], q4 = q[dx];
+        v[2 + 4 * j] = fmaf(g4.x, r4.x, fmaf(g4.y, r4.y, fmaf(g4.z, r4.z, fmaf(g4.w, r4.w, v[2 + 4 * j]))));
+        v[3 + 4 * j] += (r4.x + r4.y) + (r4.z + r4.w);
+        v[4 + 4 * j] = fmaf(r4.x, r4.x, fmaf(r4.y, r4.y, fmaf(r4.z, r4.z, fmaf(r4.w, r4.w, v[4 + 4 * j]))));
+        v[5 + 4 * j] = fmaf(q4.x, r4.x, fmaf(q4.y, r4.y, fmaf(q4.z, r4.z, fmaf(q4.w, r4.w, v[5 + 4 * j]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NV; ++t) {
+    v[t] = warp_sum(v[t]);
+    if (lane == 0) red[wid][t] = v[t];
+  }
+  __syncthreads();
+  if (tid < NV) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) a += red[w][tid];
+    tot[tid] = a;
+  }
+  __syncthreads();
+  if (tid < k) {
+    const int j = tid;
+    const float xs = tot[0], sxx = tot[1];
+    const float xm = xs / Kf;
+    const float dX = sxx - xm * xs;
+    float dot = 0.f;   // w = softmax(v*T): dL/dv_j = T * w_j * (g_w_j - sum_i w_i g_w_i)
+    for (int i = 0; i < k; ++i) dot = fmaf(w_s[i], tot[2 + 4 * i], dot);
+    const float wj = w_s[j];
+    const float gv = temperature * wj * (tot[2 + 4 * j] - dot);
+    if (g_val_out) g_val_out[po + j] = gv;
+    const float s1 = tot[3 + 4 * j], s2 = tot[4 + 4 * j], xy = tot[5 + 4 * j];
+    const float ym = s1 * inv_k;
+    const float dY = s2 - ym * ym * Kf;
+    const float D = dY * dX;
+    const float num = xy - ym * xs;
+    const float rs = rsqrtf(D);
+    float gg = gv;
+    if (mask) gg *= m_s[j];
+    const float g_num = gg * rs;
+    const float g_D = -0.5f * gg * num * rs / D;
+    const float g_dY = g_D * dX, g_dX = g_D * dY;
+    const float g_ym = -g_num * xs - 2.f * g_dY * ym * Kf;
+    part[j][0] = -g_num * ym - g_dX * xm;
+    part[j][1] = g_dX;
+    part[j][2] = -g_dX * xs;
+    coef[j][0] = wj; coef[j][1] = g_num; coef[j][2] = 2.f * g_dY; coef[j][3] = g_ym * inv_k;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j0 = 0; j0 < KK; j0 += 2) {
+    if (j0 >= k) break;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const float* wp = rbase + (int64_t)src_s[j0 + jj] * C;
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx)
+        rv[jj][dx] = (j0 + jj < k) ? ld4(wp + dx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = j0 + jj;
+      if (j >= k) break;
+      const float cw_ = coef[j][0], cxy = coef[j][1], cdy = coef[j][2], cm = coef[j][3];
+      float* dst = gbase + (int64_t)src_s[j] * C;
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const float4 q4 = q[dx], g4 = g[dx], r4 = rv[jj][dx];
+        float4 o;
+        o.x = fmaf(cw_, g4.x, fmaf(cxy, q4.x, fmaf(cdy, r4.x, cm)));
+        o.y = fmaf(cw_, g4.y, fmaf(cxy, q4.y, fmaf(cdy, r4.y, cm)));
+        o.z = fmaf(cw_, g4.z, fmaf(cxy, q4.z, fmaf(cdy, r4.z, cm)));
+        o.w = fmaf(cw_, g4.w, fmaf(cxy, q4.w, fmaf(cdy, r4.w, cm)));
+        if (!(dbg & 1)) red_add4(dst + dx * C, o);
+        else if (o.x == 1.2345e33f) dst[dx * C] = o.y + o.z + o.w;
+      }
+    }
+  }
+  if (g_q && !(dbg & 2)) {
+    float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;
+    for (int j = 0; j < k; ++j) { t_gxs += part[j][0]; t_gsxx += part[j][1]; t_gxm += part[j][2]; }
+    const float c0 = 2.f * t_gsxx, c1 = t_gxs + t_gxm * inv_k;
+    float* gqp = g_q + (int64_t)nq * qa.sn + qa.patch_off(patch) + (int64_t)(4 * c4) * qa.sc + (int64_t)dy * qa.sy;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 o;
+      o.x = fmaf(c0, qc[i].x, c1); o.y = fmaf(c0, qc[i].y, c1); o.z = fmaf(c0, qc[i].z, c1); o.w = fmaf(c0, qc[i].w, c1);
+      red_add4(gqp + (int64_t)i * qa.sc, o);
+    }
+  }
+}
+
+template <int NT>
+static int launch_bwd_own(unsigned blocks, cudaStream_t st, PatchAddr qa, const float* rT, const float* mask,
+                          const int32_t* idx, const float* weights, float temperature, const float* g_out,
+                          float* g_rT, float* g_q, float* g_val, int P, int C, int ph, int fh, int fw, int k) {
+  match_bwd_own_kernel<NT><<<blocks, NT, 0, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q, g_val,
+                                                  P, C, ph, fh, fw, k, (g_stage_mask.load() >> 8) & 0xff);
+  CLC_CHECK_LAUNCH("clc_match_bwd(main)");
+  return CLC_OK;
+}
+
+template <int ITEMS, bool REREAD>
+static int launch_bwd_reg2(unsigned blocks, size_t smem, cudaStream_t st, PatchAddr qa, const float* rT,
+                           const float* mask, const int32_t* idx, const float* weights, float temperature,
+                           const float* g_out, float* g_rT, float* g_q, float* g_val, int P, int C, int ph,
+                           int pw, int fh, int fw, int k) {
+  auto kern = match_bwd_cl_reg_kernel<ITEMS, REREAD>;
   if (smem > 48 * 1024) CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   kern<<<blocks, 256, smem, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q, g_val, P, C, ph, pw,
                                   fh, fw, k, (g_stage_mask.load() >> 8) & 0xff);
   CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   return CLC_OK;
+}
+
+template <int ITEMS>
+static int launch_bwd_reg(unsigned blocks, size_t smem, cudaStream_t st, PatchAddr qa, const float* rT,
+                          const float* mask, const int32_t* idx, const float* weights, float temperature,
+                          const float* g_out, float* g_rT, float* g_q, float* g_val, int P, int C, int ph,
+                          int pw, int fh, int fw, int k) {
+  // CTAs resident per SM: 2 with the windows kept in registers, 3 when they are re-read; re-read
+  // when that saves a wave (and shared memory allows 3 CTAs)
+  const unsigned w2 = (blocks + 2 * kNumSMs - 1) / (2 * kNumSMs), w3 = (blocks + 3 * kNumSMs - 1) / (3 * kNumSMs);
+  const bool reread = (w3 < w2 && 3 * (smem + 1024) <= 220 * 1024) || ((g_stage_mask.load() >> 8) & 4);
+  if (reread)
+    return launch_bwd_reg2<ITEMS, true>(blocks, smem, st, qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q,
+                                        g_val, P, C, ph, pw, fh, fw, k);
+  return launch_bwd_reg2<ITEMS, false>(blocks, smem, st, qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q,
+                                       g_val, P, C, ph, pw, fh, fw, k);
 }
 
 // Host helpers shared with match_tc.cu --------------------------------------------------------
@@ -1150,6 +1392,15 @@ extern "C" size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t f
   return 2 * sizeof(float) * (size_t)NP * C * fh * fw + 512;  // channels-last copy of r + gradient scratch
 }
 
+extern "C" int clc_match_bwd_zero_workspace(void* workspace, size_t workspace_bytes, int64_t NP, int32_t C,
+                                           int32_t fh, int32_t fw, void* stream) {
+  if (!workspace || NP < 0 || C < 1 || fh < 1 || fw < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < clc_match_bwd_workspace_bytes(NP, C, fh, fw)) return CLC_ERR_WORKSPACE;
+  float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  CLC_CUDA(cudaMemsetAsync(g_rT, 0, sizeof(float) * (size_t)NP * C * fh * fw, (cudaStream_t)stream));
+  return CLC_OK;
+}
+
 extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* r_cl, const float* mask,
                              const int32_t* idx, const float* weights, float temperature, const float* g_out,
                              float* g_r, float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
@@ -1182,7 +1433,7 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   float* rT_own = g_rT + (size_t)NP * C * HW;
   dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
-  CLC_CUDA(cudaMemsetAsync(g_rT, 0, plane, st));
+  if (!(flags & CLC_MATCH_BWD_WS_ZEROED)) CLC_CUDA(cudaMemsetAsync(g_rT, 0, plane, st));
   const float* rT = r_cl;
   if (!rT) {  // no channels-last copy supplied (e.g. from clc_match_topk_tc_ref_cl): make one
     nchw_to_cl_kernel<<<tgrid, tblock, 0, st>>>(r, rT_own, C, HW);
@@ -1192,7 +1443,16 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   const int items = ph * pw * (C / 4), per = (items + 255) / 256;
   const unsigned blocks = (unsigned)(NP * P);
   int rc = CLC_OK;
+  const int nt_own = ph * (C / 4);
+  const bool own_ok = k <= 4 && !((g_stage_mask.load() >> 8) & 8) &&
+                      (nt_own == 128 || nt_own == 192 || nt_own == 256 || nt_own == 320 || nt_own == 384);
   if (!stage_on(0)) {
+  } else if (own_ok) {
+#define CLC_OWN_CASE(N) case N: rc = launch_bwd_own<N>(blocks, st, qa, rT, mask, idx, weights, temperature, g_out, \
+                                                        g_rT, g_q, g_val, P, C, ph, fh, fw, k); break;
+    switch (nt_own) { CLC_OWN_CASE(128) CLC_OWN_CASE(192) CLC_OWN_CASE(256) CLC_OWN_CASE(320) CLC_OWN_CASE(384) }
+#undef CLC_OWN_CASE
+    if (rc) return rc;
   } else if (k <= 4 && per <= 8) {
 #define CLC_BWD_CASE(I) case I: rc = launch_bwd_reg<I>(blocks, smem, st, qa, rT, mask, idx, weights, temperature, \
                                                         g_out, g_rT, g_q, g_val, P, C, ph, pw, fh, fw, k); break;

@@ -142,6 +142,9 @@ __device__ __forceinline__ void tmem_ld_wait() {
 __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 4 epilogue warps
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
+__device__ __forceinline__ void epi_bar_sync8() {  // named barrier 1: the 8 epilogue warps of the stacked kernel
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
 
 #define CLC_STAMP(i) do { if (p.timing && lane == 0) p.timing[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
@@ -386,10 +389,13 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         cs.hv = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
         if (oy <= p.H - p.ph && ox <= p.W - p.pw) {
           float b1 = 0.f, b2 = 0.f;
+          // (partially unrolled so that several loads are in flight; the adds keep their order)
+#pragma unroll 4
           for (int dy = 0; dy < p.ph; ++dy)
+#pragma unroll 4
             for (int dx = 0; dx < p.pw; ++dx) {
-              b1 += s1n[(oy + dy) * p.W + ox + dx];
-              b2 += s2n[(oy + dy) * p.W + ox + dx];
+              b1 += __ldg(s1n + (oy + dy) * p.W + ox + dx);
+              b2 += __ldg(s2n + (oy + dy) * p.W + ox + dx);
             }
           const PosStat ps = pos_stat(b1, b2, inv_k, Kf);
           cs.ym = ps.ym;
@@ -491,11 +497,12 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 // (the 3-D TMA box of the packed patches), B = the whole channels-last reference image.
 //   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue; persistent over tiles.
 // ------------------------------------------------------------------------------------------
-constexpr int kStPW = 4;   // patches per epilogue warp (PG <= 16)
+constexpr int kStPW = 2;   // patches per epilogue warp (PG <= 16, 8 epilogue warps)
+constexpr int kStThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kStMP = 8;   // positions per lane (span <= 256)
 
 template <int KC, bool MASK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kStThreads, 1)
 match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                           const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -510,7 +517,8 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
   const uint32_t opBytes = (uint32_t)p.st_stages * stageBytes;
   const uint32_t sMisc = base + (opBytes > dumpBytes ? opBytes : dumpBytes);
   // misc: s1s[HW] s2s[HW] offs[S] | barriers full[st] empty[st] accFull tileDone | tmem ptr
-  const uint32_t sS1 = sMisc, sS2 = sS1 + 4u * p.HW, sOff = sS2 + 4u * p.HW;
+  const uint32_t sS1 = sMisc, sS2 = sS1 + 4u * Npad, sR1 = sS2 + 4u * Npad, sR2 = sR1 + 4u * Npad;
+  const uint32_t sYm = sR2 + 4u * Npad, sRd = sYm + 4u * Npad, sOff = sRd + 4u * Npad;
   const uint32_t sBar = (sOff + 4u * p.S + 7u) & ~7u;
   const uint32_t barFull = sBar, barEmpty = barFull + 8u * p.st_stages;
   const uint32_t barAccFull = barEmpty + 8u * p.st_stages, barTileDone = barAccFull + 8u;
@@ -518,10 +526,15 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
   float* D = reinterpret_cast<float*>(smem_raw + (base - raw));
   float* s1s = reinterpret_cast<float*>(smem_raw + (sS1 - raw));
   float* s2s = reinterpret_cast<float*>(smem_raw + (sS2 - raw));
+  float* rs1 = reinterpret_cast<float*>(smem_raw + (sR1 - raw));
+  float* rs2 = reinterpret_cast<float*>(smem_raw + (sR2 - raw));
+  float* ymS = reinterpret_cast<float*>(smem_raw + (sYm - raw));
+  float* rdS = reinterpret_cast<float*>(smem_raw + (sRd - raw));
   int* offs = reinterpret_cast<int*>(smem_raw + (sOff - raw));
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_raw + (sTmemPtr - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) CLC_STAMP(0);
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmapA);
@@ -535,16 +548,17 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
       mbar_init(barEmpty + 8u * i, 1);
     }
     mbar_init(barAccFull, 1);
-    mbar_init(barTileDone, 4);   // one arrive per epilogue warp
+    mbar_init(barTileDone, 8);   // one arrive per epilogue warp
     fence_barrier_init();
   } else if (warp >= 2) {
-    for (int s = threadIdx.x - 64; s < p.S; s += 128) offs[s] = (s / p.pw) * p.W + (s % p.pw);
+    for (int s = threadIdx.x - 64; s < p.S; s += 256) offs[s] = (s / p.pw) * p.W + (s % p.pw);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int total = p.NP * p.st_groups;
+  if (warp == 0) CLC_STAMP(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -569,8 +583,10 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
             tma_load_2d(sb + (uint32_t)i * kBoxBytesB, &tmapB, bar, c * kChunk, n * p.HW + i * kBoxRowsB);
         }
         if (++st == (uint32_t)p.st_stages) { st = 0; php ^= 1u; }
+        if (c == 0) CLC_STAMP(2);
       }
     }
+    CLC_STAMP(3);
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     const uint32_t idesc = make_idesc(kTileM, Npad);
@@ -581,6 +597,8 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
       tc_fence_after();
       for (int c = 0; c < p.chunks; ++c) {
         mbar_wait(barFull + 8u * st, php);
+        if (c == 0) CLC_STAMP(4);
+        if (c == p.chunks - 1) CLC_STAMP(5);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = base + st * stageBytes, sb = sa + aBytes;
@@ -600,7 +618,9 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
     }
   } else {
     // ===================================== epilogue =========================================
-    const int q = warp & 3;                      // TMEM lane quarter of this warp; also its patch residue
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                     // 0..7 among the epilogue warps; patches ew, ew + 8 of the group
+    const int half = ew >> 2;                    // which half of the columns this warp dumps
     const int et = threadIdx.x - 64;
     const int cw = p.W - p.pw + 1;
     const int span = (p.H - p.ph + 1) * p.W;     // linear origins 0 .. span-1 cover every valid window
@@ -609,66 +629,99 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
     const float kh = -4.0f / (0.25f * (float)p.H * (float)p.H);
     const float kw = -4.0f / (0.25f * (float)p.W * (float)p.W);
     const int r0 = (p.ph + 1) / 2 - 1, c0 = (p.pw + 1) / 2 - 1;
-    const int rows_pw = p.st_rows / 4;           // patches per warp (<= kStPW)
+    const int rows_pw = p.st_rows / 8;           // patches per warp (<= kStPW)
     uint32_t apar = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int n = tile / p.st_groups, g = tile - n * p.st_groups;
       const int nq = n / p.q_repeat;
-      // ---- window statistics of this lane's positions (while the MMAs run) ----
-      for (int i = et; i < p.HW; i += 128) {
-        s1s[i] = p.s1[(int64_t)n * p.HW + i];
-        s2s[i] = p.s2[(int64_t)n * p.HW + i];
+      // ---- window statistics of every position, computed cooperatively while the MMAs run:
+      // stage s1/s2, row sums over dx, box sums over dy -> ymS / rdS (NaN = wrapped origin) ----
+      for (int i = et; i < Npad; i += 256) {
+        const bool in = i < p.HW;
+        s1s[i] = in ? p.s1[(int64_t)n * p.HW + i] : 0.f;
+        s2s[i] = in ? p.s2[(int64_t)n * p.HW + i] : 0.f;
       }
-      epi_bar_sync();
-      float ym[kStMP], rdY[kStMP], mwv[kStMP], mhv[kStMP];
+      // per-patch constants of this warp's patches (global loads overlap the MMA phase too)
+      float pxs[kStPW], prdX[kStPW], pch[kStPW], pcw[kStPW];
 #pragma unroll
-      for (int m = 0; m < kStMP; ++m) {
-        const int pos = lane + 32 * m;
-        const int oy = pos / p.W, ox = pos - oy * p.W;
-        ym[m] = 0.f;
-        rdY[m] = __int_as_float(0x7fc00000);     // NaN marks a wrapped / out-of-range origin
-        mwv[m] = (float)(ox + c0 + 1) - 0.5f * (float)(p.pw & 1);
-        mhv[m] = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
-        if (pos < span && ox <= p.W - p.pw) {
-          float b1 = 0.f, b2 = 0.f;
-          for (int dy = 0; dy < p.ph; ++dy)
-            for (int dx = 0; dx < p.pw; ++dx) {
-              b1 += s1s[(oy + dy) * p.W + ox + dx];
-              b2 += s2s[(oy + dy) * p.W + ox + dx];
-            }
-          const PosStat ps = pos_stat(b1, b2, inv_k, Kf);
-          ym[m] = ps.ym;
-          rdY[m] = rsqrtf(ps.dY);
+      for (int pi = 0; pi < kStPW; ++pi) {
+        const int patch = g * p.st_rows + ew + 8 * pi;
+        pxs[pi] = 0.f; prdX[pi] = 0.f; pch[pi] = 0.f; pcw[pi] = 0.f;
+        if (pi < rows_pw && patch < p.P) {
+          const int64_t qi = (int64_t)nq * p.P + patch;
+          const float xs = chunk_sum(p.xs, qi, p.chunks);
+          const float sxx = chunk_sum(p.sxx, qi, p.chunks);
+          const float xm = xs / Kf;
+          pxs[pi] = xs;
+          prdX[pi] = rsqrtf(sxx - xm * xs);
+          const int py = patch / p.npx, px = patch - py * p.npx;
+          pch[pi] = ((float)py + 0.5f) * (float)p.ph;
+          pcw[pi] = ((float)px + 0.5f) * (float)p.pw;
         }
       }
+      epi_bar_sync8();
+      for (int i = et; i < Npad; i += 256) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+        for (int dx = 0; dx < p.pw; ++dx) {
+          const int j = i + dx < Npad ? i + dx : Npad - 1;
+          a1 += s1s[j];
+          a2 += s2s[j];
+        }
+        rs1[i] = a1;
+        rs2[i] = a2;
+      }
+      epi_bar_sync8();
+      for (int i = et; i < Npad; i += 256) {
+        const int oy = i / p.W, ox = i - oy * p.W;
+        float ymv = 0.f, rdv = __int_as_float(0x7fc00000);   // NaN marks a wrapped / out-of-range origin
+        if (i < span && ox <= p.W - p.pw) {
+          float b1 = 0.f, b2 = 0.f;
+#pragma unroll 4
+          for (int dy = 0; dy < p.ph; ++dy) {
+            b1 += rs1[i + dy * p.W];
+            b2 += rs2[i + dy * p.W];
+          }
+          const PosStat ps = pos_stat(b1, b2, inv_k, Kf);
+          ymv = ps.ym;
+          rdv = rsqrtf(ps.dY);
+        }
+        ymS[i] = ymv;
+        rdS[i] = rdv;
+      }
+      epi_bar_sync8();
       float acc[kStPW][kStMP];
 #pragma unroll
       for (int pi = 0; pi < kStPW; ++pi)
 #pragma unroll
         for (int m = 0; m < kStMP; ++m) acc[pi][m] = 0.f;
 
+      if (warp == 2) CLC_STAMP(7);
       mbar_wait(barAccFull, apar);
+      if (warp == 2) CLC_STAMP(8);
       apar ^= 1u;
       tc_fence_after();
       for (int t = 0; t < p.st_mt; ++t) {
         // ---- dump accumulator tile t: TMEM lane (s_l, patch) -> D[row][pos'] ----
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Npad);
         float* drow = D + (size_t)(q * 32 + lane) * DS;
-        for (int col0 = 0; col0 < Npad; col0 += 32) {
+        const int ncol = (Npad / 64) * 32;        // columns per half (Npad is a multiple of 32)
+        const int cbeg = half ? ncol : 0, cend = half ? Npad : ncol;
+        for (int col0 = cbeg; col0 < cend; col0 += 32) {
           float v[32];
           tmem_ld32(t_row + (uint32_t)col0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) st4(drow + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         }
-        epi_bar_sync();
+        epi_bar_sync8();
         // ---- shifted-row sum: lanes run over window positions, one patch at a time ----
         const int s_lo = t * p.st_shifts;
         const int s_n = (p.S - s_lo) < p.st_shifts ? (p.S - s_lo) : p.st_shifts;
 #pragma unroll
         for (int pi = 0; pi < kStPW; ++pi) {
           if (pi >= rows_pw) break;
-          const int pl = q + 4 * pi;             // patch row inside the group
+          const int pl = ew + 8 * pi;            // patch row inside the group
           for (int sl = 0; sl < s_n; ++sl) {
             const float* src = D + (size_t)(sl * p.st_rows + pl) * DS + offs[s_lo + sl] + lane;
 #pragma unroll
@@ -676,79 +729,78 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
               if (lane + 32 * m < span) acc[pi][m] += src[32 * m];
           }
         }
-        epi_bar_sync();                           // D is overwritten by the next tile / the next TMA loads
+        epi_bar_sync8();                           // D is overwritten by the next tile / the next TMA loads
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(barTileDone);
+      if (warp == 2) CLC_STAMP(10);
 
-      // ---- masked Pearson score + per-patch candidate top-KC by warp shuffles ----
+      // ---- masked Pearson score (in place of the accumulators) ----
+      int cid[kStMP];                             // correlation-map index of each of this lane's positions
 #pragma unroll
-      for (int pi = 0; pi < kStPW; ++pi) {
-        if (pi >= rows_pw) break;
-        const int patch = g * p.st_rows + q + 4 * pi;
-        if (patch >= p.P) continue;               // warp-uniform
-        const int64_t qi = (int64_t)nq * p.P + patch;
-        const float xs = chunk_sum(p.xs, qi, p.chunks);
-        const float sxx = chunk_sum(p.sxx, qi, p.chunks);
-        const float xm = xs / Kf;
-        const float rdX = rsqrtf(sxx - xm * xs);
-        const int py = patch / p.npx, px = patch - py * p.npx;
-        const float ch = ((float)py + 0.5f) * (float)p.ph, cwc = ((float)px + 0.5f) * (float)p.pw;
-        float sc[kStMP];
+      for (int m = 0; m < kStMP; ++m) {
+        const int pos = lane + 32 * m;
+        const float ymv = pos < Npad ? ymS[pos] : 0.f;
+        const float rdv = pos < Npad ? rdS[pos] : __int_as_float(0x7fc00000);
+        const int oy = pos / p.W, ox = pos - oy * p.W;
+        cid[m] = oy * cw + ox;
+        const float wv = (float)(ox + c0 + 1) - 0.5f * (float)(p.pw & 1);
+        const float hv = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
 #pragma unroll
-        for (int m = 0; m < kStMP; ++m) {
-          float s = fmaf(-ym[m], xs, acc[pi][m]) * rdY[m];
+        for (int pi = 0; pi < kStPW; ++pi) {
+          if (pi >= rows_pw) break;
+          const int patch = g * p.st_rows + ew + 8 * pi;
+          if (p.dump != nullptr && patch < p.P && pos < span && rdv == rdv)
+            p.dump[((int64_t)n * p.P + patch) * p.HW + pos] = acc[pi][m];
+          float sv = fmaf(-ymv, pxs[pi], acc[pi][m]) * rdv;
           if (MASK) {
-            const float dw = mwv[m] - cwc, dh = mhv[m] - ch;
-            s *= exp2f(fmaf(dh * dh, kh, dw * dw * kw));
+            const float dw = wv - pcw[pi], dh = hv - pch[pi];
+            sv *= exp2f(fmaf(dh * dh, kh, dw * dw * kw));
           }
-          sc[m] = (s == s) ? s : -INFINITY;       // wrapped origins (NaN) never win
-          if (p.dump != nullptr && lane + 32 * m < span && rdY[m] == rdY[m])
-            p.dump[((int64_t)n * p.P + patch) * p.HW + lane + 32 * m] = acc[pi][m];
+          acc[pi][m] = (sv == sv) ? sv : -INFINITY;   // wrapped origins (NaN) never win
         }
-        const int64_t o = ((int64_t)n * p.P + patch) * KC;   // n_tiles == 1
-        for (int j = 0; j < KC; ++j) {
-          // lane-local best (value desc, position asc), then xor-tree arg-max over the warp
+      }
+      // ---- per-patch candidate top-KC: KC rounds of a warp arg-max (redux.sync on order-preserving
+      // integer keys; ties -> lowest position); the winning lane writes the candidate ----
+      constexpr unsigned kNegInfKey = 0x007fffffu;           // key of -inf
+      for (int j = 0; j < KC; ++j) {
+#pragma unroll
+        for (int pi = 0; pi < kStPW; ++pi) {
+          if (pi >= rows_pw) break;
+          const int patch = g * p.st_rows + ew + 8 * pi;
+          if (patch >= p.P) continue;                        // warp-uniform
           float bv = -INFINITY;
-          int bm = 0;
+          int bm = 0, bid = -1;
 #pragma unroll
           for (int m = 0; m < kStMP; ++m)
-            if (sc[m] > bv) { bv = sc[m]; bm = m; }
-          int bpos = lane + 32 * bm;
-          float wv = bv;
-          int wpos = bpos;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, wv, d);
-            const int op = __shfl_xor_sync(0xffffffffu, wpos, d);
-            if (ov > wv || (ov == wv && op < wpos)) { wv = ov; wpos = op; }
-          }
-          if (wv > -INFINITY && wpos == bpos) {
+            if (acc[pi][m] > bv) { bv = acc[pi][m]; bm = m; bid = cid[m]; }
+          const unsigned u = __float_as_uint(bv);
+          const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+          const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+          const unsigned cand = (key == kmax) ? (unsigned)(lane + 32 * bm) : 0x7fffffffu;
+          const unsigned wpos = __reduce_min_sync(0xffffffffu, cand);
+          const int64_t o = ((int64_t)n * p.P + patch) * KC + j;   // n_tiles == 1
+          if (kmax == kNegInfKey) {                          // fewer than KC valid windows
+            if (lane == 0) { p.cand_val[o] = -INFINITY; p.cand_idx[o] = -1; }
+          } else if ((int)(wpos & 31u) == lane) {
+            p.cand_val[o] = bv * prdX[pi];
+            p.cand_idx[o] = bid;
 #pragma unroll
             for (int m = 0; m < kStMP; ++m)
-              if (m == bm) sc[m] = -INFINITY;     // taken
-          }
-          if (lane == 0) {
-            int id = -1;
-            if (wv > -INFINITY) {
-              const int oy = wpos / p.W, ox = wpos - oy * p.W;
-              id = oy * cw + ox;
-            }
-            p.cand_val[o + j] = wv * rdX;
-            p.cand_idx[o + j] = id;
+              if (m == bm) acc[pi][m] = -INFINITY;           // taken
           }
         }
       }
     }
   }
 
+  if (warp == 2) CLC_STAMP(9);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// ------------------------------------------------------------------------------------------
 // Pre-pass (ONE launch, two block roles).
 // Role R, reference latents [NP, C, HW] fp32 -> channels-last bf16 [NP*HW, C] (GEMM operand) and
 // channels-last fp32 [NP*HW, C] (coalesced exact re-scoring / backward), plus the per-pixel channel
@@ -814,9 +866,24 @@ __device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float*
   const int npx = W / pw, S = ph * pw;
   const int Wp = W + 1;
   const float* qn = pp.q + ((int64_t)nq * C + c0) * H * W + (int64_t)py * ph * W;
-  for (int it = threadIdx.x; it < 64 * ph * W; it += 256) {
-    const int x = it % W, dy = (it / W) % ph, c = it / (W * ph);
-    tile[(c * ph + dy) * Wp + x] = qn[(int64_t)c * H * W + dy * W + x];
+  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.q) & 15) == 0) {
+    // items = (row (c, dy), float4 column): consecutive threads read consecutive 16-byte pieces
+    const int w4 = W >> 2;
+    for (int r0 = 0; r0 < 64 * ph; r0 += 256 / w4 > 0 ? 256 / w4 : 1) {
+      // (w4 <= 256 always holds for the shapes the plan accepts; rows advance by whole groups of threads)
+      const int r = r0 + threadIdx.x / w4, x4 = threadIdx.x % w4;
+      if (threadIdx.x < (256 / w4) * w4 && r < 64 * ph) {
+        const int c = r / ph, dy = r - c * ph;
+        const float4 v = ld4(qn + (int64_t)c * H * W + dy * W + 4 * x4);
+        float* t = &tile[r * Wp + 4 * x4];
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+      }
+    }
+  } else {
+    for (int it = threadIdx.x; it < 64 * ph * W; it += 256) {
+      const int x = it % W, dy = (it / W) % ph, c = it / (W * ph);
+      tile[(c * ph + dy) * Wp + x] = qn[(int64_t)c * H * W + dy * W + x];
+    }
   }
   __syncthreads();
   __nv_bfloat16* An = pp.A + (int64_t)nq * S * P_pad * C;
@@ -895,118 +962,215 @@ __device__ __forceinline__ bool ranks_before(float av, int ai, float bv, int bi)
   return ai < bi;
 }
 
-__global__ void __launch_bounds__(512)
+// Blend of the k selected windows into the [S][C] shared tile: warp-strided shifts, lane-strided
+// float4 channel groups, KB x CB loads in flight per lane; torch.sum order (left to right over k).
+template <int KB, int CB, int KC>
+__device__ __forceinline__ void blend_rows(float4* T4, const float* __restrict__ rn, const int* top_src,
+                                           const float* top_w, int k, int pp, int pw, int W, int C, int warp,
+                                           int lane) {
+  const int c4n = C >> 2;
+  for (int sft = warp; sft < pp; sft += KC) {
+    const int dy = sft / pw, dx = sft - dy * pw;
+    const float4* srow = reinterpret_cast<const float4*>(rn + (int64_t)(dy * W + dx) * C);
+    for (int cb = 0; cb < c4n; cb += 32 * CB) {
+      float4 v[CB][KB];
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        const int c4 = cb + lane + 32 * i;
+#pragma unroll
+        for (int j = 0; j < KB; ++j)
+          if (j < k && c4 < c4n) v[i][j] = __ldg(srow + (int64_t)top_src[j] * c4n + c4);
+      }
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        const int c4 = cb + lane + 32 * i;
+        if (c4 >= c4n) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < KB; ++j)
+          if (j < k) {
+            const float wj = top_w[j];
+            acc.x += v[i][j].x * wj; acc.y += v[i][j].y * wj; acc.z += v[i][j].z * wj; acc.w += v[i][j].w * wj;
+          }
+        T4[sft * c4n + c4] = acc;
+      }
+    }
+  }
+}
+
+template <int KC>
+__global__ void __launch_bounds__(KC * 32, 768 / (KC * 32))
 rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, int P_pad,
                const float* __restrict__ s1,
                const float* __restrict__ s2, const float* __restrict__ xs_a, const float* __restrict__ sxx_a,
-               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int n_tiles, int KC,
+               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int n_tiles,
                int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian, int chunks,
                float* __restrict__ val, int32_t* __restrict__ idx, int32_t* __restrict__ n_uncertified,
                float temperature, float* __restrict__ aligned, float* __restrict__ weights_out, int dbg) {
-  extern __shared__ float sm[];  // cand values [M], cand idx [M]; then the blend tile [C][S + 4]
+  // dynamic shared memory: query patch Q[S][C] fp32 (also reused as the blend tile [S][C]) | cand values [M] |
+  // cand idx [M]
+  extern __shared__ float4 sm4[];
   __shared__ float sel_v[kMaxKC], ex_v[kMaxKC];
   __shared__ int sel_i[kMaxKC];
   __shared__ float top_w[8];
   __shared__ int top_src[8];
+  constexpr int NT = KC * 32;
   const int M = n_tiles * KC;
-  float* cvs = sm;
-  int* cis = reinterpret_cast<int*>(sm + M);
+  const int pp = ph * pw, K = C * pp, c4n = C >> 2, items = pp * c4n;
+  float4* Q = sm4;
+  float* cvs = reinterpret_cast<float*>(sm4 + items);
+  int* cis = reinterpret_cast<int*>(cvs + M);
   const int n = blockIdx.x / P, patch = blockIdx.x - n * P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = n / q_repeat;
   const int64_t co = ((int64_t)n * P + patch) * M;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    cvs[i] = cand_val[co + i];
-    cis[i] = cand_idx[co + i];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // KC rounds of warp arg-max over the merged list
-    for (int t = 0; t < KC; ++t) {
-      float bv = -INFINITY;
-      int bi = 0x7fffffff, bslot = -1;
-      for (int i = lane; i < M; i += 32) {
-        const int id = cis[i];
-        if (id < 0) continue;
-        const float v = cvs[i];
-        if (bslot < 0 || ranks_before(v, id, bv, bi)) { bv = v; bi = id; bslot = i; }
-      }
+  // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate lists ----
+  {
+    const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
+    // two shifts x three float4 columns per warp-iteration: 6 loads in flight before the first store
+    for (int s0 = warp; s0 < pp; s0 += 2 * KC)
+      for (int cb = 0; cb < c4n; cb += 96) {
+        float4 t[2][3];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
-        if (os >= 0 && (bslot < 0 || ranks_before(ov, oi, bv, bi))) { bv = ov; bi = oi; bslot = os; }
+        for (int u = 0; u < 2; ++u) {
+          const int sft = s0 + u * KC;
+          const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)sft * P_pad * C);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int c4 = cb + lane + 32 * i;
+            if (sft < pp && c4 < c4n) t[u][i] = __ldg(qrow + c4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int sft = s0 + u * KC;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int c4 = cb + lane + 32 * i;
+            if (sft < pp && c4 < c4n) Q[sft * c4n + c4] = t[u][i];
+          }
+        }
       }
-      if (lane == 0) {
-        sel_v[t] = bslot >= 0 ? bv : -INFINITY;
-        sel_i[t] = bslot >= 0 ? bi : -1;
-        if (bslot >= 0) cis[bslot] = -1;  // taken
+  }
+  if (n_tiles == 1) {
+    // a single candidate list (stacked kernel): already the screened top-KC in order
+    if (threadIdx.x < KC) {
+      sel_v[threadIdx.x] = cand_val[co + threadIdx.x];
+      sel_i[threadIdx.x] = cand_idx[co + threadIdx.x];
+    }
+  } else {
+    for (int i = threadIdx.x; i < M; i += NT) {
+      cvs[i] = cand_val[co + i];
+      cis[i] = cand_idx[co + i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // KC rounds of warp arg-max over the merged list
+      for (int t = 0; t < KC; ++t) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff, bslot = -1;
+        for (int i = lane; i < M; i += 32) {
+          const int id = cis[i];
+          if (id < 0) continue;
+          const float v = cvs[i];
+          if (bslot < 0 || ranks_before(v, id, bv, bi)) { bv = v; bi = id; bslot = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+          if (os >= 0 && (bslot < 0 || ranks_before(ov, oi, bv, bi))) { bv = ov; bi = oi; bslot = os; }
+        }
+        if (lane == 0) {
+          sel_v[t] = bslot >= 0 ? bv : -INFINITY;
+          sel_i[t] = bslot >= 0 ? bi : -1;
+          if (bslot >= 0) cis[bslot] = -1;  // taken
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __syncthreads();
   // ---- exact re-scoring: warp c <-> candidate c ----
   const int cw = W - pw + 1, L = (H - ph + 1) * cw;
-  const int pp = ph * pw, K = C * pp;
   const int64_t HW = (int64_t)H * W;
-  const int nq = n / q_repeat;
   const int npx = W / pw;
   const int py = patch / npx, px = patch - py * npx;
-  if (warp < KC) {
+  {
     const int id = sel_i[warp];
     float out = -INFINITY;
     if (id >= 0 && !(dbg & 1)) {
       const int oy = id / cw, ox = id - oy * cw;
-      // both operands channels-last fp32: every shift is one contiguous row of C floats per side
-      const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
+      // window rows are contiguous runs of C floats in the channels-last copy; the patch comes from
+      // shared memory.  8 float4 window loads are in flight per lane.
       const float* rb = rT32 + ((int64_t)n * HW + (int64_t)oy * W + ox) * C;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const int c4n = C >> 2;
-      // loads of 4 shifts x 3 float4 columns are issued together (24 x 2 LDG.128 in flight per lane)
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      // loads of 4 shifts x 3 float4 columns are issued together (12 LDG.128 in flight per lane);
+      // no per-item integer division: shifts advance by counters, channels by lane strides
       for (int cb = 0; cb < c4n; cb += 96) {
+        int dy = 0, dx = 0;
         for (int s0 = 0; s0 < pp; s0 += 4) {
-          float4 qv[4][3], rv[4][3];
+          float4 rv[4][3];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int s = s0 + u;
-            const int dy = s / pw, dx = s - dy * pw;
-            const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)s * P_pad * C);
             const float4* rrow = reinterpret_cast<const float4*>(rb + (int64_t)(dy * W + dx) * C);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               const int c4 = cb + lane + 32 * i;
-              const bool ok = s < pp && c4 < c4n;
-              qv[u][i] = ok ? __ldg(qrow + c4) : zero4;
-              rv[u][i] = ok ? __ldg(rrow + c4) : zero4;
+              rv[u][i] = (s0 + u < pp && c4 < c4n) ? __ldg(rrow + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (++dx == pw) { dx = 0; ++dy; }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-              a0 = fmaf(qv[u][i].x, rv[u][i].x, a0); a1 = fmaf(qv[u][i].y, rv[u][i].y, a1);
-              a2 = fmaf(qv[u][i].z, rv[u][i].z, a2); a3 = fmaf(qv[u][i].w, rv[u][i].w, a3);
+              const int c4 = cb + lane + 32 * i;
+              if (s0 + u < pp && c4 < c4n) {
+                const float4 qv = Q[(s0 + u) * c4n + c4];
+                a0 = fmaf(qv.x, rv[u][i].x, a0); a1 = fmaf(qv.y, rv[u][i].y, a1);
+                a2 = fmaf(qv.z, rv[u][i].z, a2); a3 = fmaf(qv.w, rv[u][i].w, a3);
+              }
             }
         }
       }
       float acc = (a0 + a1) + (a2 + a3);
       acc = warp_sum(acc);
-      if (lane == 0) {
-        const float Kf = (float)K;
-        const float* s1n = s1 + (int64_t)n * HW;
-        const float* s2n = s2 + (int64_t)n * HW;
-        float b1 = 0.f, b2 = 0.f;
-        for (int dy = 0; dy < ph; ++dy)
-          for (int dx = 0; dx < pw; ++dx) {
-            b1 += s1n[(oy + dy) * W + ox + dx];
-            b2 += s2n[(oy + dy) * W + ox + dx];
-          }
-        const PosStat ps = pos_stat(b1, b2, 1.0f / Kf, Kf);
-        const int64_t qi = (int64_t)nq * P + patch;
-        out = pearson(acc, ps, chunk_sum(xs_a, qi, chunks), chunk_sum(sxx_a, qi, chunks), Kf);
+      // window / patch statistics: the lanes fetch the terms in parallel, the sums are then formed in
+      // the reference's sequential order (same bits as the fp32 path) with warp shuffles
+      const float Kf = (float)K;
+      const float* s1n = s1 + (int64_t)n * HW;
+      const float* s2n = s2 + (int64_t)n * HW;
+      float b1 = 0.f, b2 = 0.f;
+      for (int e0 = 0; e0 < pp; e0 += 32) {
+        const int e = e0 + lane;
+        float x1 = 0.f, x2 = 0.f;
+        if (e < pp) {
+          const int dy = e / pw, dx = e - dy * pw;
+          x1 = __ldg(s1n + (oy + dy) * W + ox + dx);
+          x2 = __ldg(s2n + (oy + dy) * W + ox + dx);
+        }
+        const int cnt = pp - e0 < 32 ? pp - e0 : 32;
+        for (int j = 0; j < cnt; ++j) {
+          b1 += __shfl_sync(0xffffffffu, x1, j);
+          b2 += __shfl_sync(0xffffffffu, x2, j);
+        }
       }
+      const int64_t qi = (int64_t)nq * P + patch;
+      float xsum = 0.f, sxxsum = 0.f;
+      for (int c0 = 0; c0 < chunks; c0 += 32) {
+        const int c = c0 + lane;
+        const float x1 = c < chunks ? __ldg(xs_a + qi * chunks + c) : 0.f;
+        const float x2 = c < chunks ? __ldg(sxx_a + qi * chunks + c) : 0.f;
+        const int cnt = chunks - c0 < 32 ? chunks - c0 : 32;
+        for (int j = 0; j < cnt; ++j) {
+          xsum += __shfl_sync(0xffffffffu, x1, j);
+          sxxsum += __shfl_sync(0xffffffffu, x2, j);
+        }
+      }
+      const PosStat ps = pos_stat(b1, b2, 1.0f / Kf, Kf);
+      out = pearson(acc, ps, xsum, sxxsum, Kf);
     }
     if (lane == 0) ex_v[warp] = out;
   }
@@ -1016,8 +1180,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     float myv = (lane < KC) ? ex_v[lane] : -INFINITY;
     int myi = (lane < KC) ? sel_i[lane] : -1;
     if (gaussian && myi >= 0) {
-      // create_gaussian_masks (:779-807): float64, rounded to fp32.  One lane per candidate: the
-      // fp64 exp runs once per CTA as a warp-wide instruction stream, not once per warp on one lane.
+      // create_gaussian_masks (:779-807): float64, rounded to fp32.  One lane per candidate.
       const int oy = myi / cw, ox = myi - oy * cw;
       const double center_h = ((double)py + 0.5) * ph, center_w = ((double)px + 0.5) * pw;
       const double hv = (double)(oy + (ph + 1) / 2) - (double)(ph % 2) / 2.0;
@@ -1065,10 +1228,15 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         float mx = -INFINITY, den = 0.f;
         for (int j = 0; j < k; ++j) mx = fmaxf(mx, top_w[j] * temperature);
         for (int j = 0; j < k; ++j) den += expf(top_w[j] * temperature - mx);
-        for (int j = 0; j < k; ++j) {
-          const float wj = expf(top_w[j] * temperature - mx) / den;
+        for (int j = 0; j < 8; ++j) {
+          float wj = 0.f;
+          if (j < k) {
+            wj = expf(top_w[j] * temperature - mx) / den;
+            if (weights_out) weights_out[((int64_t)n * P + patch) * k + j] = wj;
+          } else {
+            top_src[j] = top_src[0];
+          }
           top_w[j] = wj;
-          if (weights_out) weights_out[((int64_t)n * P + patch) * k + j] = wj;
         }
       }
     }
@@ -1081,40 +1249,29 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   }
   if (aligned == nullptr || (dbg & 2)) return;
   // ---- fused gather + blend (SI_Wraper :226-238, is_stack = False): the k selected windows are read
-  // from the channels-last fp32 copy (coalesced float4; they were just re-scored, so mostly L1/L2
-  // hits), blended, transposed through shared memory and written as 16-byte NCHW patch rows ----
+  // again from the channels-last fp32 copy (coalesced float4, all k loads of an item in flight
+  // together; they were just re-scored, so mostly L1/L2 hits), blended into a [S][C] shared tile and
+  // written as 16-byte NCHW patch rows ----
   __syncthreads();
   {
-    const int c4n = C >> 2, items = pp * c4n, TS = pp + 4;   // tile row stride (floats), 16-byte aligned
-    float* tile = sm + 2 * M;
-    tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tile) + 15) & ~(uintptr_t)15);
+    float4* T4 = Q;                                          // the query patch is no longer needed
     const float* rn = rT32 + (int64_t)n * HW * C;
-    for (int f = threadIdx.x; f < items; f += blockDim.x) {
-      const int c4 = f / pp, s = f - c4 * pp;                // lanes run over the shifts of one channel group
-      const int dy = s / pw, dx = s - dy * pw;
-      const float* src = rn + (int64_t)(dy * W + dx) * C + 4 * c4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      // torch.sum over the k axis: sequential left-to-right accumulation of y_patch * weight
-      for (int j = 0; j < k; ++j) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)top_src[j] * C));
-        const float wj = top_w[j];
-        acc.x += v.x * wj; acc.y += v.y * wj; acc.z += v.z * wj; acc.w += v.w * wj;
-      }
-      tile[(4 * c4 + 0) * TS + s] = acc.x; tile[(4 * c4 + 1) * TS + s] = acc.y;
-      tile[(4 * c4 + 2) * TS + s] = acc.z; tile[(4 * c4 + 3) * TS + s] = acc.w;
-    }
+    if (k <= 4) blend_rows<4, 3, KC>(T4, rn, top_src, top_w, k, pp, pw, W, C, warp, lane);
+    else blend_rows<8, 1, KC>(T4, rn, top_src, top_w, k, pp, pw, W, C, warp, lane);
     __syncthreads();
+    const float* Tf = reinterpret_cast<const float*>(T4);
     float* on = aligned + (int64_t)n * C * HW + (int64_t)(py * ph) * W + px * pw;
     if (pw == 4) {
-      for (int e = threadIdx.x; e < C * ph; e += blockDim.x) {
-        const int c = e / ph, dy = e - c * ph;
-        st4(on + (int64_t)c * HW + dy * W, *reinterpret_cast<const float4*>(&tile[c * TS + dy * 4]));
-      }
+      for (int dy = 0; dy < ph; ++dy)
+        for (int c = threadIdx.x; c < C; c += NT) {          // c fastest: conflict-free shared loads
+          const float* t0 = Tf + (dy * 4) * C + c;
+          st4(on + (int64_t)c * HW + dy * W, make_float4(t0[0], t0[C], t0[2 * C], t0[3 * C]));
+        }
     } else {
-      for (int e = threadIdx.x; e < C * pp; e += blockDim.x) {
-        const int c = e / pp, s = e - c * pp;
-        const int dy = s / pw, dx = s - dy * pw;
-        on[(int64_t)c * HW + dy * W + dx] = tile[c * TS + s];
+      for (int e = threadIdx.x; e < C * pp; e += NT) {
+        const int sft = e / C, c = e - sft * C;
+        const int dy = sft / pw, dx = sft - dy * pw;
+        on[(int64_t)c * HW + dy * W + dx] = Tf[sft * C + c];
       }
     }
   }
@@ -1224,7 +1381,7 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
     const int mt = (pl.S + shifts - 1) / shifts;
     const size_t stage = (size_t)mt * kABytes + (size_t)Npad * 128;
     const size_t dump = (size_t)128 * (Npad + 4) * 4;
-    const size_t misc = (size_t)8 * pl.HW + 4 * pl.S + 8 * (2 * 8 + 2) + 64 + 1024;
+    const size_t misc = (size_t)24 * Npad + 4 * pl.S + 8 * (2 * 8 + 2) + 64 + 1024;
     int stages = (int)(((size_t)kSmemLimit - misc) / stage);
     if (stages > pl.chunks) stages = pl.chunks;
     if (stages > 8) stages = 8;
@@ -1275,7 +1432,7 @@ static int launch_gemm_stacked(const Plan& pl, const CUtensorMap& ta, const CUte
                                cudaStream_t st) {
   auto kern = match_gemm_stacked_kernel<KC, MASK>;
   CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  kern<<<pl.grid, kThreads, pl.smem_bytes, st>>>(ta, tb, prm);
+  kern<<<pl.grid, kStThreads, pl.smem_bytes, st>>>(ta, tb, prm);
   CLC_CHECK_LAUNCH("clc_match_topk_tc(gemm)");
   return CLC_OK;
 }
@@ -1384,16 +1541,24 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   if (stage_on(2)) {
     const int64_t blocks = NP * pl.P;
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
-    size_t sm = (size_t)pl.n_tiles * pl.KC * 8;
-    if (aligned) sm += 16 + (size_t)C * (pl.S + 4) * sizeof(float);
+    const size_t sm = (size_t)pl.S * C * sizeof(float) + (size_t)pl.n_tiles * pl.KC * 8;
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
-    if (sm > 48 * 1024)
-      CLC_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    rescore_kernel<<<(unsigned)blocks, pl.KC * 32, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
-                                                             pl.n_tiles, pl.KC, q_repeat, C, H, W, ph, pw, pl.P, k,
-                                                             gaussian, pl.chunks, val, idx, n_uncertified,
-                                                             temperature, aligned, weights_out,
-                                                             (g_stage_mask.load() >> 8) & 0xff);
+    const int dbg = (g_stage_mask.load() >> 8) & 0xff;
+    if (pl.KC == 8) {
+      if (sm > 48 * 1024)
+        CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      rescore_kernel<8><<<(unsigned)blocks, 256, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
+                                                          pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian,
+                                                          pl.chunks, val, idx, n_uncertified, temperature, aligned,
+                                                          weights_out, dbg);
+    } else {
+      if (sm > 48 * 1024)
+        CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      rescore_kernel<16><<<(unsigned)blocks, 512, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
+                                                           pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian,
+                                                           pl.chunks, val, idx, n_uncertified, temperature, aligned,
+                                                           weights_out, dbg);
+    }
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
   }
   return CLC_OK;

@@ -133,6 +133,7 @@ class LatentPath:
         self._gqview = self._qview
         self._graph = self._g_match = self._g_entropy = None
         self._streams = None
+        self._zs = None
 
     # -------------------------------------------------------------------------------------
     def randomize(self, seed=1):
@@ -189,7 +190,15 @@ class LatentPath:
         B, R, M, h, w, p, k = self.B, self.R, self.M, self.h, self.w, self.patch, self.k
         S = h * w
         if self.train:
-            self._acc_match.zero_()
+            # zero-fills needed only by the backward (g_q accumulator, gradient scratch) go on a side
+            # stream / graph branch: they run under the forward kernels instead of ahead of them
+            cur = torch.cuda.current_stream(self.device)
+            zs = self._zero_stream()
+            zs.wait_stream(cur)
+            with torch.cuda.stream(zs):
+                self._acc_match.zero_()
+                call("clc_match_bwd_zero_workspace", ptr(self.ws_bwd), self.ws_bwd.numel(), B * R, M, h, w,
+                     ops._stream())
         # 1. match: masked Pearson correlation + top-k over all B*R (image, reference) problems
         r = self.refs.view(B * R, M, h, w)
         if self.match_mode == "tc":
@@ -214,9 +223,10 @@ class LatentPath:
         if self.train:
             call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
                  ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
+            cur.wait_stream(zs)
             call("clc_match_bwd", C.byref(self._qview), ptr(r), self._r_cl, ptr(self.mask), ptr(self.idx),
                  ptr(self.weights), self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val),
-                 B * R, self.P, M, p, p, h, w, k, 1, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
+                 B * R, self.P, M, p, p, h, w, k, 3, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
             n += 2
         return n
 
@@ -277,6 +287,11 @@ class LatentPath:
         cur.wait_stream(s1)
         cur.wait_stream(s2)
         return n
+
+    def _zero_stream(self):
+        if self._zs is None:
+            self._zs = torch.cuda.Stream(device=self.device)
+        return self._zs
 
     def _side_streams(self):
         if self._streams is None:

@@ -263,12 +263,18 @@ CLC_API int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, const
  *   workspace : clc_match_bwd_workspace_bytes(...) bytes enable the channels-last fast path
  *               (coalesced float4 loads, vector atomics); NULL selects the workspace-free kernel. */
 #define CLC_MATCH_BWD_OVERWRITE_G_R 1
+#define CLC_MATCH_BWD_WS_ZEROED 2 /* the caller already ran clc_match_bwd_zero_workspace on `workspace` */
 CLC_API int clc_match_bwd(const clc_patch_view* qv, const float* r, const float* r_cl, const float* mask,
                           const int32_t* idx, const float* weights, float temperature, const float* g_out,
                           float* g_r, float* g_q, float* g_val, int64_t NP, int32_t P, int32_t C, int32_t ph,
                           int32_t pw, int32_t fh, int32_t fw, int32_t k, int32_t flags, void* workspace,
                           size_t workspace_bytes, void* stream);
 CLC_API size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw);
+/* Zeroes the gradient scratch inside `workspace` (one memset).  Lets the caller take the memset off
+ * the critical path (e.g. on a parallel stream / CUDA-graph branch during the forward pass) and then
+ * pass CLC_MATCH_BWD_WS_ZEROED. */
+CLC_API int clc_match_bwd_zero_workspace(void* workspace, size_t workspace_bytes, int64_t NP, int32_t C,
+                                         int32_t fh, int32_t fw, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * CLM conditional fusion (elementwise part; the 1x1 / 3x3 convolutions stay nn.Conv2d)

@@ -20,8 +20,11 @@ ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--rep", type=int, default=20)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--match-mode", default="tc")
+ap.add_argument("--batch", type=int, default=0)
 a = ap.parse_args()
-cfg = WORKLOADS[a.workload]
+cfg = dict(WORKLOADS[a.workload])
+if a.batch:
+    cfg["B"] = a.batch
 lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=a.match_mode,
                 fused_slices=True, device="cuda:0")
 lp.randomize(seed=1)

@@ -37,7 +37,7 @@ t = tm.cpu()
 live = t[:, 0] != 0
 t = t[live]
 names = ["start", "setup_done", "first_A_issued", "producer_done", "mma_first_B", "mma_first_A", "mma_all_issued",
-         "epi_colstat", "epi_acc_full", "epi_done", "mma_17th_A"]
+         "epi_colstat", "epi_acc_full", "epi_done", "epi_sum_done"]
 rel = t - t[:, :1]
 print("CTAs:", t.shape[0])
 for i, nme in enumerate(names):
