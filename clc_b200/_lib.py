@@ -34,6 +34,7 @@ PROTOTYPES = {
     "clc_kernel_launch_count": (C.c_uint64, []),
     "clc_debug_set_stage_mask": (None, [C.c_int]),
     "clc_trace_start": (C.c_int, [_p]),
+    "clc_trace_mark": (C.c_int, []),
     "clc_trace_stop": (C.c_int, []),
     "clc_trace_count": (C.c_int, []),
     "clc_trace_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
@@ -135,7 +136,7 @@ def kernel_trace(fn, stream):
     out = []
     name, ms = C.c_char_p(), C.c_float()
     for i in range(h.clc_trace_count()):
-        if h.clc_trace_get(i, C.byref(name), C.byref(ms)) == 0:
+        if h.clc_trace_get(i, C.byref(name), C.byref(ms)) == 0 and name.value != b"(mark)":
             out.append((name.value.decode(), ms.value))
     return out
 

@@ -64,6 +64,12 @@ extern "C" int clc_trace_start(void* stream) {
   return CLC_OK;
 }
 
+extern "C" int clc_trace_mark(void) {
+  if (!clc::g_trace_on.load()) return CLC_ERR_INVALID_ARGUMENT;
+  clc::trace_record("(mark)");
+  return CLC_OK;
+}
+
 extern "C" int clc_trace_stop(void) {
   clc::g_trace_on.store(false);
   std::lock_guard<std::mutex> lk(clc::g_trace_mu);

@@ -905,16 +905,17 @@ __device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float*
   // over the 64*ph*pw elements, xor-tree combine (fixed order -> deterministic)
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_el = 64 * S;
     for (int px = warp; px < npx; px += 8) {
       float a = 0.f, b = 0.f;
-      for (int e = lane; e < n_el; e += 32) {
-        const int c = e / S, rem = e - c * S;
-        const int dy = rem / pw, dx = rem - dy * pw;
-        const float v = tile[(c * ph + dy) * Wp + px * pw + dx];
-        a += v;
-        b = fmaf(v, v, b);
-      }
+      for (int c = lane; c < 64; c += 32)          // (no per-element index division)
+        for (int dy = 0; dy < ph; ++dy) {
+          const float* trow = &tile[(c * ph + dy) * Wp + px * pw];
+          for (int dx = 0; dx < pw; ++dx) {
+            const float v = trow[dx];
+            a += v;
+            b = fmaf(v, v, b);
+          }
+        }
       a = warp_sum(a);
       b = warp_sum(b);
       if (lane == 0) {

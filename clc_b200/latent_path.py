@@ -29,7 +29,7 @@ class LatentPath:
 
     def __init__(self, B, H, W, n_refs=3, M=320, num_slices=5, z_channels=192, train=True, patch=4, k=4,
                  temperature=15.0, match_mode="tc", gaussian_mask=True, fused_slices=False,
-                 device="cuda", lmbda=0.013):
+                 device="cuda", lmbda=0.013, data_parallel=False):
         assert H % 64 == 0 and W % 64 == 0, "latent geometry: h = H/16, hz = H/64"
         self.B, self.H, self.W, self.R, self.M = B, H, W, n_refs, M
         self.h, self.w = H // 16, W // 16
@@ -134,6 +134,13 @@ class LatentPath:
         self._graph = self._g_match = self._g_entropy = None
         self._streams = None
         self._zs = None
+        # data-parallel training: the only collectives the path owns are one NCCL all-reduce of
+        # the EntropyBottleneck parameter gradients and one of the 2-double bpp statistic per step.  They
+        # are enqueued on the entropy branches, i.e. they overlap the (longer) match chain.
+        self.data_parallel = bool(data_parallel) and torch.distributed.is_available() and \
+            torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        self._eb_grads_flat = self._acc[4:4 + n_eb]
+        self._world = torch.distributed.get_world_size() if self.data_parallel else 1
 
     # -------------------------------------------------------------------------------------
     def randomize(self, seed=1):
@@ -239,6 +246,8 @@ class LatentPath:
             return 1
         ops.eb_bwd_raw(self.z, self.noise_z, self.eb_m, self.eb_b, self.eb_f, self.quantiles, self.lik_z,
                        None, self.bpp_coef, None, self.g_z, self.g_eb[0:5], self.g_eb[5:10], self.g_eb[10:14])
+        if self.data_parallel:
+            torch.distributed.all_reduce(self._eb_grads_flat)
         return 2
 
     def slice_chain(self):
@@ -274,19 +283,27 @@ class LatentPath:
         chains run on side streams next to the match chain (CUDA graph capture turns this into a
         forked graph).  Returns the number of C-ABI calls."""
         if not fork:
-            return self.match_chain() + self.hyper_chain() + self.slice_chain()
+            n = self.match_chain() + self.hyper_chain() + self.slice_chain()
+            self._exchange_stats()
+            return n
         cur = torch.cuda.current_stream(self.device)
         s1, s2 = self._side_streams()
         s1.wait_stream(cur)
         s2.wait_stream(cur)
-        with torch.cuda.stream(s1):
-            n = self.slice_chain()
         with torch.cuda.stream(s2):
-            n += self.hyper_chain()
+            n = self.hyper_chain()
+        with torch.cuda.stream(s1):
+            n += self.slice_chain()
+            s1.wait_stream(s2)
+            self._exchange_stats()
         n += self.match_chain()
         cur.wait_stream(s1)
-        cur.wait_stream(s2)
         return n
+
+    def _exchange_stats(self):
+        """bpp statistic over all ranks (reporting only; gradients use the local normalisation)."""
+        if self.data_parallel:
+            torch.distributed.all_reduce(self.log2)
 
     def _zero_stream(self):
         if self._zs is None:
@@ -338,6 +355,7 @@ class LatentPath:
             n = self.hyper_chain()
         n += self.slice_chain()
         cur.wait_stream(s1)
+        self._exchange_stats()
         return n
 
     def step_host(self, host_flat):
@@ -364,11 +382,11 @@ class LatentPath:
         cur.wait_stream(se)
         self._host_out.copy_(self.log2, non_blocking=True)
         cur.synchronize()
-        return -(self._host_out[0].item() + self._host_out[1].item()) / self.num_pixels
+        return -(self._host_out[0].item() + self._host_out[1].item()) / (self.num_pixels * self._world)
 
     def bpp(self):
-        """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels."""
-        return -(self.log2[0] + self.log2[1]) / self.num_pixels
+        """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels (over all ranks when data-parallel)."""
+        return -(self.log2[0] + self.log2[1]) / (self.num_pixels * self._world)
 
     # ---- algorithmic work per kernel launch (SURVEY.md 8d; stated in DESIGN.md) ------------------
     def algorithmic_work(self):

@@ -56,6 +56,9 @@ CLC_API uint64_t clc_kernel_launch_count(void);
  * into a CUDA graph).  clc_trace_get(i) returns kernel i's label and the device time in ms
  * since the previous event, i.e. that kernel's duration when launches are back to back. */
 CLC_API int clc_trace_start(void* stream);
+/* Records an unlabeled event: the next kernel's time is measured from here (used after enqueueing
+ * foreign work, e.g. a spin kernel that lets the host run ahead of the device). */
+CLC_API int clc_trace_mark(void);
 CLC_API int clc_trace_stop(void);
 CLC_API int clc_trace_count(void);
 CLC_API int clc_trace_get(int i, const char** name, float* ms);

@@ -97,10 +97,38 @@ print(f"{'sum':28s} {tot:8.2f} us")
 per = {}
 stream = torch.cuda.current_stream().cuda_stream
 for _ in range(a.iters):
-    for name, ms in _lib.kernel_trace(lp.step, stream):
+    def traced():
+        torch.cuda._sleep(1_500_000)
+        _lib.lib().clc_trace_mark()
+        lp.step()
+    for name, ms in _lib.kernel_trace(traced, stream):
         t = per.setdefault(name, [0.0, 0])
         t[0] += ms
         t[1] += 1
-print("# per-kernel trace (event after every kernel, includes the eager launch gap), L2-warm")
+print("# per-kernel trace (event after every kernel, host running ahead of the device), L2-warm")
 for n, t in per.items():
     print(f"{n:36s} {1e3 * t[0] / t[1]:8.2f} us x{t[1] / a.iters:g}")
+
+# (c) the two graphs of the end-to-end path, each alone (L2-warm)
+lp.capture_split()
+for name, g in (("graph: match chain", lp._g_match), ("graph: entropy chains (forked)", lp._g_entropy)):
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name:40s} {e0.elapsed_time(e1) * 1e3 / a.iters:8.2f} us/replay")
+lp.capture(fork=True)
+for name in ("graph: full step (3 branches)",):
+    lp.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        lp.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name:40s} {e0.elapsed_time(e1) * 1e3 / a.iters:8.2f} us/replay")
