@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclc_b200.so")
+LIB_PATH = os.environ.get("CLC_B200_LIB") or os.path.join(_HERE, "libclc_b200.so")
 
 _p = C.c_void_p
 _i64 = C.c_int64

@@ -1,6 +1,8 @@
 // Version / error-string entry points of the C ABI.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -8,6 +10,7 @@ namespace clc {
 thread_local char g_last_cuda_error[256] = {0};
 std::atomic<unsigned long long> g_kernel_launches{0};
 std::atomic<int> g_stage_mask{0xff};
+std::atomic<int> g_pdl{getenv("CLC_NO_PDL") ? 0 : 1};
 
 // ---- per-kernel tracing: CUDA events on the traced stream, one after every launch ----
 std::atomic<bool> g_trace_on{false};

@@ -39,6 +39,8 @@ clm_fuse_fwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
                     int CPW) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s0 = ((int64_t)blockIdx.x * 32 + lane) * VW;
+  pdl_trigger();
+  pdl_wait();
   if (s0 >= S) return;
   const int64_t b = blockIdx.z;
   float coef[VW][kMaxRefs];
@@ -124,6 +126,8 @@ clm_fuse_bwd_kernel(const float* __restrict__ ref_t, int64_t ref_sr, int64_t ref
   const int64_t b = blockIdx.z;
   const bool live = s0 < S;
   const unsigned CS = cluster.dim_blocks().y, rank = cluster.block_rank();
+  pdl_trigger();
+  pdl_wait();
   float coef[VW][kMaxRefs], w[VW][kMaxRefs], sg[VW][kMaxRefs];
   float G[VW][kMaxRefs];
 #pragma unroll
@@ -235,11 +239,14 @@ extern "C" int clc_clm_fuse_fwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   if (gy > 65535) return CLC_ERR_UNSUPPORTED;
   dim3 grid(gx, gy, (unsigned)B);
   if (vec && R <= 4)
-    clm_fuse_fwd_kernel<4, 4><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+    CLC_CUDA(launch_pdl(clm_fuse_fwd_kernel<4, 4>, grid, dim3(256), 0, st, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out,
+                        R, C, S, CPW));
   else if (vec)
-    clm_fuse_fwd_kernel<4, 8><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+    CLC_CUDA(launch_pdl(clm_fuse_fwd_kernel<4, 8>, grid, dim3(256), 0, st, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out,
+                        R, C, S, CPW));
   else
-    clm_fuse_fwd_kernel<1, 8><<<grid, 256, 0, st>>>(ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out, R, C, S, CPW);
+    CLC_CUDA(launch_pdl(clm_fuse_fwd_kernel<1, 8>, grid, dim3(256), 0, st, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, y, out,
+                        R, C, S, CPW));
   CLC_CHECK_LAUNCH("clc_clm_fuse_fwd");
   return CLC_OK;
 }
@@ -265,13 +272,15 @@ extern "C" int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   cfg.blockDim = dim3(32, 8, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = CS;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl.load() ? 2 : 1;
   if (vec4 && R <= 4)
     CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<4, 4>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
                                 g_ref_t, g_att, (int)R, (int)C, S));

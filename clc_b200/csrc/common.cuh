@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
+
 #include "../../include/clc_b200.h"
 
 namespace clc {
@@ -44,6 +46,40 @@ void trace_record(const char* name);
     cudaError_t e__ = (call);                                    \
     if (e__ != cudaSuccess) return ::clc::cuda_fail(e__, #call); \
   } while (0)
+
+// ---- programmatic dependent launch (PDL): every kernel of the serial chains is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its launch + prologue overlap the tail of the
+// kernel before it (also inside captured CUDA graphs).  A kernel calls pdl_wait() before it touches
+// global memory (returns once the preceding grid has completed and its writes are visible); the
+// implicit trigger at CTA exit is used (pdl_trigger() compiles to nothing unless CLC_PDL_EARLY=1).
+// Both are no-ops without the attribute.
+extern std::atomic<int> g_pdl;   // 1 = on (default); CLC_NO_PDL=1 in the environment turns it off
+
+#ifndef CLC_PDL_EARLY
+#define CLC_PDL_EARLY 0   /* measured on B200: the explicit early trigger costs ~6% on the cfg2 chain */
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if CLC_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

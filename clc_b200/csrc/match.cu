@@ -621,6 +621,8 @@ match_bwd_kernel(PatchAddr qa, const float* __restrict__ r, const float* __restr
 __global__ void __launch_bounds__(256)
 nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ xT, int C, int HW) {
   __shared__ float t[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* xn = x + (int64_t)n * C * HW;
   float* xTn = xT + (int64_t)n * C * HW;
@@ -644,6 +646,8 @@ template <bool ADD>
 __global__ void __launch_bounds__(256)
 cl_to_nchw_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, int HW) {
   __shared__ float t[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* xTn = xT + (int64_t)n * C * HW;
   float* xn = x + (int64_t)n * C * HW;
@@ -1056,6 +1060,8 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
   const int64_t po = ((int64_t)n * P + patch) * k;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int dy = tid / c4n, c4 = tid - dy * c4n;
+  pdl_trigger();
+  pdl_wait();
   if (tid < KK) {
     int src = 0;
     float wj = 0.f, mj = 1.f;
@@ -1204,8 +1210,8 @@ template <int NT>
 static int launch_bwd_own(unsigned blocks, cudaStream_t st, PatchAddr qa, const float* rT, const float* mask,
                           const int32_t* idx, const float* weights, float temperature, const float* g_out,
                           float* g_rT, float* g_q, float* g_val, int P, int C, int ph, int fh, int fw, int k) {
-  match_bwd_own_kernel<NT><<<blocks, NT, 0, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q, g_val,
-                                                  P, C, ph, fh, fw, k, (g_stage_mask.load() >> 8) & 0xff);
+  CLC_CUDA(launch_pdl(match_bwd_own_kernel<NT>, dim3(blocks), dim3(NT), 0, st, qa, rT, mask, idx, weights, temperature,
+                      g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, (g_stage_mask.load() >> 8) & 0xff));
   CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   return CLC_OK;
 }
@@ -1436,7 +1442,7 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   if (!(flags & CLC_MATCH_BWD_WS_ZEROED)) CLC_CUDA(cudaMemsetAsync(g_rT, 0, plane, st));
   const float* rT = r_cl;
   if (!rT) {  // no channels-last copy supplied (e.g. from clc_match_topk_tc_ref_cl): make one
-    nchw_to_cl_kernel<<<tgrid, tblock, 0, st>>>(r, rT_own, C, HW);
+    CLC_CUDA(launch_pdl(nchw_to_cl_kernel, tgrid, tblock, 0, st, r, rT_own, C, HW));
     CLC_CHECK_LAUNCH("clc_match_bwd(nchw_to_cl)");
     rT = rT_own;
   }
@@ -1470,8 +1476,8 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
     CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   }
   if (!stage_on(1)) return CLC_OK;
-  if (overwrite) cl_to_nchw_kernel<false><<<tgrid, tblock, 0, st>>>(g_rT, g_r, C, HW);
-  else cl_to_nchw_kernel<true><<<tgrid, tblock, 0, st>>>(g_rT, g_r, C, HW);
+  if (overwrite) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
+  else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
   CLC_CHECK_LAUNCH("clc_match_bwd(cl_to_nchw)");
   return CLC_OK;
 }

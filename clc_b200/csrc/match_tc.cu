@@ -262,9 +262,11 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
     fence_barrier_init();
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above (TMEM allocation, barrier init, descriptor prefetch) overlaps the pre-pass
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int acc_cols = TNT;
   if (warp == 0) CLC_STAMP(1);
@@ -553,9 +555,11 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
   } else if (warp >= 2) {
     for (int s = threadIdx.x - 64; s < p.S; s += 256) offs[s] = (s / p.pw) * p.W + (s % p.pw);
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above (TMEM allocation, barrier init, descriptor prefetch) overlaps the pre-pass
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int total = p.NP * p.st_groups;
   if (warp == 0) CLC_STAMP(1);
@@ -939,6 +943,8 @@ __device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float*
 __global__ void __launch_bounds__(256)
 prepass_kernel(const PrepassParams pp) {
   extern __shared__ float tile[];
+  pdl_trigger();
+  pdl_wait();
   int b = blockIdx.x;
   if (b < pp.n_ref_blocks) {
     if (pp.dbg & 1) return;
@@ -1025,6 +1031,8 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = n / q_repeat;
   const int64_t co = ((int64_t)n * P + patch) * M;
+  pdl_trigger();
+  pdl_wait();
   // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate lists ----
   {
     const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
@@ -1423,7 +1431,7 @@ static int launch_gemm(const Plan& pl, const CUtensorMap& ta, const CUtensorMap&
                        cudaStream_t st) {
   auto kern = match_gemm_kernel<KC, MASK>;
   CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  kern<<<pl.grid, kThreads, pl.smem_bytes, st>>>(ta, tb, prm);
+  CLC_CUDA(launch_pdl(kern, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, st, ta, tb, prm));
   CLC_CHECK_LAUNCH("clc_match_topk_tc(gemm)");
   return CLC_OK;
 }
@@ -1433,7 +1441,7 @@ static int launch_gemm_stacked(const Plan& pl, const CUtensorMap& ta, const CUte
                                cudaStream_t st) {
   auto kern = match_gemm_stacked_kernel<KC, MASK>;
   CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  kern<<<pl.grid, kStThreads, pl.smem_bytes, st>>>(ta, tb, prm);
+  CLC_CUDA(launch_pdl(kern, dim3(pl.grid), dim3(kStThreads), pl.smem_bytes, st, ta, tb, prm));
   CLC_CHECK_LAUNCH("clc_match_topk_tc(gemm)");
   return CLC_OK;
 }
@@ -1510,7 +1518,7 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
     if (sm > 48 * 1024)
       CLC_CUDA(cudaFuncSetAttribute(prepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    prepass_kernel<<<(unsigned)(n_ref + n_q), 256, sm, st>>>(pp);
+    CLC_CUDA(launch_pdl(prepass_kernel, dim3((unsigned)(n_ref + n_q)), dim3(256), sm, st, pp));
     CLC_CHECK_LAUNCH("clc_match_topk_tc(prepass)");
   }
 
@@ -1548,17 +1556,15 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     if (pl.KC == 8) {
       if (sm > 48 * 1024)
         CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      rescore_kernel<8><<<(unsigned)blocks, 256, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
-                                                          pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian,
-                                                          pl.chunks, val, idx, n_uncertified, temperature, aligned,
-                                                          weights_out, dbg);
+      CLC_CUDA(launch_pdl(rescore_kernel<8>, dim3((unsigned)blocks), dim3(256), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
+                          sxx, cand_val, cand_idx, pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
+                          val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
     } else {
       if (sm > 48 * 1024)
         CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      rescore_kernel<16><<<(unsigned)blocks, 512, sm, st>>>(A32, rT32, pl.P_pad, s1, s2, xs, sxx, cand_val, cand_idx,
-                                                           pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian,
-                                                           pl.chunks, val, idx, n_uncertified, temperature, aligned,
-                                                           weights_out, dbg);
+      CLC_CUDA(launch_pdl(rescore_kernel<16>, dim3((unsigned)blocks), dim3(512), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
+                          sxx, cand_val, cand_idx, pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
+                          val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
     }
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
   }

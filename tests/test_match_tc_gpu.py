@@ -109,6 +109,7 @@ def test_tc_topk_equals_fp32_mode_and_oracle(geom):
     # public API + oracle
     vt, it, _ = clc_b200.match_topk(yq, refs.to(d), p, p, k, gaussian_mask=gauss, mode="tc")
     assert torch.equal(it, i32)
+    assert torch.equal(vt.reshape(val.shape), val), "public API and raw C call must agree bit for bit"
     mask = O.gaussian_masks(h, w, p, p) if gauss else None
     for rr in range(R):
         _, val_o, idx_o = O.si_finder(y, refs[:, rr], p, p, refs[:, rr], k, 15.0, mask=mask, return_index=True)
@@ -128,3 +129,113 @@ def test_tc_unsupported_shapes_fail_loudly():
     with pytest.raises(RuntimeError, match="unsupported"):
         _lib.call("clc_match_topk_tc", t.data_ptr(), t.data_ptr(), 1, 1, 100, 8, 8, 4, 4, 4, 0, o.data_ptr(),
                   o.data_ptr(), None, 0.0, None, None, o.data_ptr(), 16, None)
+
+
+def _tc_call(yq, r, R, p, k, gauss, want_aligned):
+    from clc_b200 import _lib
+    from clc_b200.ops import _stream
+    NP, Cc, h, w = r.shape
+    P = (h // p) * (w // p)
+    d = r.device
+    val = torch.empty(NP, P, k, device=d)
+    idx = torch.empty(NP, P, k, dtype=torch.int32, device=d)
+    aligned = torch.empty_like(r) if want_aligned else None
+    weights = torch.empty(NP, P, k, device=d) if want_aligned else None
+    nb = _lib.lib().clc_match_topk_tc_workspace_bytes(NP, R, Cc, h, w, p, p, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device=d)
+    _lib.call("clc_match_topk_tc", yq.data_ptr(), r.data_ptr(), NP, R, Cc, h, w, p, p, k, int(gauss), val.data_ptr(),
+              idx.data_ptr(), None, 15.0, _lib.ptr(aligned), _lib.ptr(weights), ws.data_ptr(), ws.numel(), _stream())
+    return val, idx, aligned, weights, ws
+
+
+@pytest.mark.parametrize("geom", [(2, 3, 320, 16, 16, 4, 4), (1, 2, 128, 32, 48, 4, 3), (2, 1, 64, 8, 12, 4, 2)])
+def test_tc_fused_gather_equals_gather_kernel(geom):
+    """The gather/blend fused into the re-scoring kernel == clc_gather_blend_fwd on the same (idx, val)."""
+    from clc_b200 import _lib
+    from clc_b200.ops import _stream
+    NQ, R, Cc, h, w, p, k = geom
+    y, refs = _inputs(NQ, R, Cc, h, w, seed=11 + sum(geom))
+    d = _dev()
+    yq = y.to(d)
+    r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
+    val, idx, aligned, weights, _ = _tc_call(yq, r, R, p, k, True, True)
+    val2, idx2, _, _, _ = _tc_call(yq, r, R, p, k, True, False)
+    assert torch.equal(idx, idx2) and torch.equal(val, val2)
+    out = torch.empty_like(r)
+    w2 = torch.empty_like(weights)
+    _lib.call("clc_gather_blend_fwd", r.data_ptr(), idx.data_ptr(), val.data_ptr(), 15.0, out.data_ptr(), w2.data_ptr(),
+              NQ * R, Cc, h, w, p, p, w - p + 1, k, 0, _stream())
+    assert torch.equal(weights, w2)
+    assert torch.allclose(aligned, out, atol=1e-6, rtol=0)
+
+
+def test_stacked_and_general_gemm_kernels_agree(monkeypatch):
+    """Small latents take the stacked-shift tcgen05 kernel; CLC_TC_NO_STACKED forces the general one."""
+    NQ, R, Cc, h, w, p, k = 3, 2, 320, 16, 16, 4, 4
+    y, refs = _inputs(NQ, R, Cc, h, w, seed=123)
+    d = _dev()
+    yq = y.to(d)
+    r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
+    v1, i1, a1, _, _ = _tc_call(yq, r, R, p, k, True, True)
+    monkeypatch.setenv("CLC_TC_NO_STACKED", "1")
+    v2, i2, a2, _, _ = _tc_call(yq, r, R, p, k, True, True)
+    monkeypatch.delenv("CLC_TC_NO_STACKED")
+    assert torch.equal(i1, i2), "stacked / general screening must select the same windows"
+    assert torch.equal(v1, v2) and torch.equal(a1, a2)      # final values come from the same fp32 re-scoring
+
+
+@pytest.mark.parametrize("geom", [(2, 3, 320, 16, 16, 4), (1, 2, 128, 8, 12, 3), (2, 2, 64, 16, 32, 4)])
+def test_match_bwd_variants_agree(geom):
+    """clc_match_bwd: thread-owns-items kernel (default) == register kernel == re-read kernel ==
+    workspace-free kernel; overwrite vs accumulate; supplied vs internally made channels-last copy;
+    pre-zeroed workspace."""
+    import ctypes as C
+    from clc_b200 import _lib
+    from clc_b200.matching import _patch_view_from_image
+    from clc_b200.ops import _stream
+    NQ, R, Cc, h, w, k = geom
+    p = 4
+    y, refs = _inputs(NQ, R, Cc, h, w, seed=31 + sum(geom))
+    d = _dev()
+    yq = y.to(d)
+    r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
+    val, idx, aligned, weights, ws_f = _tc_call(yq, r, R, p, k, False, True)
+    NP, P = r.shape[0], idx.shape[1]
+    g_out = torch.randn(r.shape, generator=torch.Generator().manual_seed(2)).to(d)
+    view = _patch_view_from_image(yq, p, p, R)
+    H = _lib.lib()
+    r_cl = H.clc_match_topk_tc_ref_cl(ws_f.data_ptr(), NP, R, Cc, h, w, p, p, k)
+    nb = H.clc_match_bwd_workspace_bytes(NP, Cc, h, w)
+
+    def run(flags, use_ws=True, use_cl=True, dbg=0, pre=None, zero_ws=False):
+        ws = torch.empty(nb, dtype=torch.uint8, device=d)
+        g_r = torch.zeros_like(r) if pre is None else pre.clone()
+        g_q = torch.zeros_like(yq)
+        g_val = torch.empty_like(val)
+        if zero_ws:
+            _lib.call("clc_match_bwd_zero_workspace", ws.data_ptr(), ws.numel(), NP, Cc, h, w, _stream())
+        H.clc_debug_set_stage_mask(0xff | (dbg << 8))
+        try:
+            _lib.call("clc_match_bwd", C.byref(view), r.data_ptr(), r_cl if use_cl else None, None, idx.data_ptr(),
+                      weights.data_ptr(), 15.0, g_out.data_ptr(), g_r.data_ptr(), g_q.data_ptr(), g_val.data_ptr(),
+                      NP, P, Cc, p, p, h, w, k, flags, ws.data_ptr() if use_ws else None, ws.numel() if use_ws else 0,
+                      _stream())
+        finally:
+            H.clc_debug_set_stage_mask(0xff)
+        torch.cuda.synchronize()
+        return g_r, g_q, g_val
+
+    base = run(1)
+    scale = base[0].abs().max().item()
+    for name, other in (("register kernel", run(1, dbg=8)), ("re-read kernel", run(1, dbg=8 | 4)),
+                        ("workspace-free kernel", run(1, use_ws=False)), ("own channels-last copy", run(1, use_cl=False)),
+                        ("pre-zeroed workspace", run(3, zero_ws=True))):
+        for a, b in zip(base, other):
+            # different summation orders (block reductions, atomics): fp32 round-off relative to each tensor's scale
+            assert (a - b).abs().max().item() <= 1e-4 * max(a.abs().max().item(), 1e-3), name
+    pre = torch.randn(r.shape, generator=torch.Generator().manual_seed(3)).to(d)
+    acc = run(0, pre=pre)
+    assert (acc[0] - (base[0] + pre)).abs().max().item() <= 2e-5 * max(scale, 1.0)
+    # overwrite mode ignores what g_r held before
+    ow = run(1, pre=pre)
+    assert (ow[0] - base[0]).abs().max().item() <= 2e-5 * max(scale, 1.0)
