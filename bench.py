@@ -380,7 +380,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
                    "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
-                   "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else "match | hyper | slices",
+                   "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else "match | hyper -> slices",
                    "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "api": "clc_b200.LatentPath.step_host: pinned host staging buffer -> 2 uploads -> match graph || "
@@ -434,7 +434,7 @@ def main():
                     help="launch the GaussianConditional / LRP kernels once per channel slice (the model's call "
                          "pattern) instead of once over all slices (the isolated path's all-slices entry point)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-fork", action="store_true", help="capture the step as one serial chain instead of three branches")
+    ap.add_argument("--no-fork", action="store_true", help="capture the step as one serial chain instead of two branches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

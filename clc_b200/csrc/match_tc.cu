@@ -821,11 +821,19 @@ struct PrepassParams {
   const float* q; __nv_bfloat16* A; float* A32; float* xs_part; float* sxx_part;
   int C, H, W, HW, ph, pw, P, P_pad, chunks;
   int ref_tiles, n_ref_blocks, npy, dbg, zero_rows;
+  int seg_w, n_seg;   // query blocks cover seg_w columns (a whole number of patches) of one patch row
 };
+
+// Shared tiles are skewed so that BOTH the pixel-major fills and the channel-group-major transposed
+// reads are bank-conflict free:
+//   reference tile: element (c, pl) at c*33 + (c>>5) + pl            (read: lanes = groups of 8 channels)
+//   query tile    : element (c, dy, x) at (c*ph+dy)*Wp + x + qskew(c)  (Wp odd)
+__device__ __forceinline__ int rskew(int c) { return c * 33 + (c >> 5); }
+__device__ __forceinline__ int qskew(int c) { const int g = c >> 3; return (g & 3) + ((g >> 2) << 4); }
 
 __device__ __forceinline__ void pack_ref_block(const PrepassParams& pp, float* tile, int n, int px0) {
   const int C = pp.C, HW = pp.HW;
-  float* part = tile + (size_t)C * 33;
+  float* part = tile + (size_t)C * 33 + (C >> 5) + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = px0 + lane;
   const float* rn = pp.r + (int64_t)n * C * HW;
@@ -833,7 +841,7 @@ __device__ __forceinline__ void pack_ref_block(const PrepassParams& pp, float* t
 #pragma unroll 8
   for (int c = warp; c < C; c += 8) {
     const float v = (px < HW) ? __ldcs(rn + (int64_t)c * HW + px) : 0.f;
-    tile[c * 33 + lane] = v;
+    tile[rskew(c) + lane] = v;
     a += v;
     b = fmaf(v, v, b);
   }
@@ -852,68 +860,89 @@ __device__ __forceinline__ void pack_ref_block(const PrepassParams& pp, float* t
   for (int it = threadIdx.x; it < 32 * groups; it += 256) {
     const int pl = it / groups, g = it - pl * groups;
     if (px0 + pl >= HW) continue;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tile[rskew(g * 8 + i) + pl];
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[(g * 8 + i) * 33 + pl]);
+    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(v[i]);
     *reinterpret_cast<uint4*>(pp.rT + ((int64_t)n * HW + px0 + pl) * C + g * 8) = *reinterpret_cast<const uint4*>(o);
     float* d32 = pp.rT32 + ((int64_t)n * HW + px0 + pl) * C + g * 8;
-    st4(d32, make_float4(tile[(g * 8 + 0) * 33 + pl], tile[(g * 8 + 1) * 33 + pl], tile[(g * 8 + 2) * 33 + pl],
-                         tile[(g * 8 + 3) * 33 + pl]));
-    st4(d32 + 4, make_float4(tile[(g * 8 + 4) * 33 + pl], tile[(g * 8 + 5) * 33 + pl], tile[(g * 8 + 6) * 33 + pl],
-                             tile[(g * 8 + 7) * 33 + pl]));
+    st4(d32, make_float4(v[0], v[1], v[2], v[3]));
+    st4(d32 + 4, make_float4(v[4], v[5], v[6], v[7]));
   }
 }
 
-__device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float* tile, int py, int chunk, int nq) {
+__device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float* tile, int py, int chunk, int nq,
+                                                 int seg) {
   const int C = pp.C, H = pp.H, W = pp.W, ph = pp.ph, pw = pp.pw, P = pp.P, P_pad = pp.P_pad;
   const int c0 = chunk * 64;
   const int npx = W / pw, S = ph * pw;
-  const int Wp = W + 1;
-  const float* qn = pp.q + ((int64_t)nq * C + c0) * H * W + (int64_t)py * ph * W;
-  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.q) & 15) == 0) {
-    // items = (row (c, dy), float4 column): consecutive threads read consecutive 16-byte pieces
-    const int w4 = W >> 2;
-    for (int r0 = 0; r0 < 64 * ph; r0 += 256 / w4 > 0 ? 256 / w4 : 1) {
-      // (w4 <= 256 always holds for the shapes the plan accepts; rows advance by whole groups of threads)
-      const int r = r0 + threadIdx.x / w4, x4 = threadIdx.x % w4;
-      if (threadIdx.x < (256 / w4) * w4 && r < 64 * ph) {
-        const int c = r / ph, dy = r - c * ph;
-        const float4 v = ld4(qn + (int64_t)c * H * W + dy * W + 4 * x4);
-        float* t = &tile[r * Wp + 4 * x4];
-        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  const int x0 = seg * pp.seg_w;                       // first column of this block
+  const int sw = (W - x0 < pp.seg_w) ? (W - x0) : pp.seg_w;   // columns of this block
+  const int px0 = x0 / pw, npx_s = sw / pw;            // patches of this block
+  const int Wp = pp.seg_w | 1;                         // odd row pitch
+  const int rows = 64 * ph;
+  const float* qn = pp.q + ((int64_t)nq * C + c0) * H * W + (int64_t)py * ph * W + x0;
+  if ((W & 3) == 0 && (pp.seg_w & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.q) & 15) == 0) {
+    // items = (row (c, dy), float4 column): consecutive threads read consecutive 16-byte pieces;
+    // four loads in flight per thread before the first shared store
+    const int w4 = sw >> 2, items = rows * w4;
+    for (int it0 = threadIdx.x; it0 < items; it0 += 4 * 256) {
+      float4 v[4];
+      int off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * 256;
+        if (it < items) {
+          const int r = it / w4, x4 = it - r * w4;
+          const int c = r / ph, dy = r - c * ph;
+          v[u] = ld4(qn + (int64_t)c * H * W + dy * W + 4 * x4);
+          off[u] = r * Wp + 4 * x4 + qskew(c);
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (it0 + u * 256 < items) {
+          float* t = &tile[off[u]];
+          t[0] = v[u].x; t[1] = v[u].y; t[2] = v[u].z; t[3] = v[u].w;
+        }
     }
   } else {
-    for (int it = threadIdx.x; it < 64 * ph * W; it += 256) {
-      const int x = it % W, dy = (it / W) % ph, c = it / (W * ph);
-      tile[(c * ph + dy) * Wp + x] = qn[(int64_t)c * H * W + dy * W + x];
+    for (int it = threadIdx.x; it < rows * sw; it += 256) {
+      const int x = it % sw, r = it / sw;
+      const int c = r / ph, dy = r - c * ph;
+      tile[r * Wp + x + qskew(c)] = qn[(int64_t)c * H * W + dy * W + x];
     }
   }
   __syncthreads();
   __nv_bfloat16* An = pp.A + (int64_t)nq * S * P_pad * C;
   float* An32 = pp.A32 + (int64_t)nq * S * P_pad * C;
-  for (int it = threadIdx.x; it < S * npx * 8; it += 256) {
-    const int g = it & 7, px = (it >> 3) % npx, s = it / (8 * npx);
+  const int cs = ph * Wp;  // channel stride inside the tile
+  for (int it = threadIdx.x; it < S * npx_s * 8; it += 256) {
+    const int g = it & 7, px = (it >> 3) % npx_s, s = it / (8 * npx_s);
     const int dy = s / pw, dx = s - dy * pw;
+    const float* t0 = &tile[((g * 8) * ph + dy) * Wp + px * pw + dx + qskew(g * 8)];
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t0[i * cs];
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(tile[((g * 8 + i) * ph + dy) * Wp + px * pw + dx]);
-    const int64_t oo = ((int64_t)s * P_pad + py * npx + px) * C + c0 + g * 8;
+    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(v[i]);
+    const int64_t oo = ((int64_t)s * P_pad + py * npx + px0 + px) * C + c0 + g * 8;
     *reinterpret_cast<uint4*>(An + oo) = *reinterpret_cast<const uint4*>(o);
-    const float* t0 = &tile[((g * 8) * ph + dy) * Wp + px * pw + dx];
-    const int cs = ph * Wp;  // channel stride inside the tile
-    st4(An32 + oo, make_float4(t0[0], t0[cs], t0[2 * cs], t0[3 * cs]));
-    st4(An32 + oo + 4, make_float4(t0[4 * cs], t0[5 * cs], t0[6 * cs], t0[7 * cs]));
+    st4(An32 + oo, make_float4(v[0], v[1], v[2], v[3]));
+    st4(An32 + oo + 4, make_float4(v[4], v[5], v[6], v[7]));
   }
   // per-patch partial statistics over this block's 64 channels: one warp per patch, lane-strided
   // over the 64*ph*pw elements, xor-tree combine (fixed order -> deterministic)
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int px = warp; px < npx; px += 8) {
+    for (int px = warp; px < npx_s; px += 8) {
       float a = 0.f, b = 0.f;
       for (int c = lane; c < 64; c += 32)          // (no per-element index division)
         for (int dy = 0; dy < ph; ++dy) {
-          const float* trow = &tile[(c * ph + dy) * Wp + px * pw];
+          const float* trow = &tile[(c * ph + dy) * Wp + px * pw + qskew(c)];
           for (int dx = 0; dx < pw; ++dx) {
             const float v = trow[dx];
             a += v;
@@ -923,14 +952,14 @@ __device__ __forceinline__ void pack_query_block(const PrepassParams& pp, float*
       a = warp_sum(a);
       b = warp_sum(b);
       if (lane == 0) {
-        const int64_t o = ((int64_t)nq * P + py * npx + px) * pp.chunks + chunk;
+        const int64_t o = ((int64_t)nq * P + py * npx + px0 + px) * pp.chunks + chunk;
         pp.xs_part[o] = a;
         pp.sxx_part[o] = b;
       }
     }
   }
   // zero rows P .. zero_rows-1 of every shift (the rows a TMA box can reach beyond the last patch)
-  if (py == pp.npy - 1 && pp.zero_rows > P) {
+  if (py == pp.npy - 1 && seg == pp.n_seg - 1 && pp.zero_rows > P) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     const int nz = pp.zero_rows - P;
     for (int it = threadIdx.x; it < S * nz * 8; it += 256) {
@@ -952,8 +981,10 @@ prepass_kernel(const PrepassParams pp) {
   } else {
     if (pp.dbg & 2) return;
     b -= pp.n_ref_blocks;
+    const int seg = b % pp.n_seg;
+    b /= pp.n_seg;
     const int py = b % pp.npy, chunk = (b / pp.npy) % pp.chunks, nq = b / (pp.npy * pp.chunks);
-    pack_query_block(pp, tile, py, chunk, nq);
+    pack_query_block(pp, tile, py, chunk, nq, seg);
   }
 }
 
@@ -1508,12 +1539,15 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     pp.ref_tiles = (pl.HW + 31) / 32;
     pp.npy = H / ph;
     pp.zero_rows = pl.zero_rows;   // rows the A-operand TMA boxes read
-    const int64_t n_ref = (int64_t)pp.ref_tiles * NP, n_q = (int64_t)pp.npy * pl.chunks * NQ;
+    // query blocks: one patch row x 64 channels x seg_w columns (about 32, a whole number of patches)
+    pp.seg_w = W <= 32 ? W : (32 / pw > 0 ? (32 / pw) * pw : pw);
+    pp.n_seg = (W + pp.seg_w - 1) / pp.seg_w;
+    const int64_t n_ref = (int64_t)pp.ref_tiles * NP, n_q = (int64_t)pp.npy * pl.chunks * NQ * pp.n_seg;
     if (n_ref + n_q > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
     pp.n_ref_blocks = (int)n_ref;
     pp.dbg = (g_stage_mask.load() >> 8) & 0xff;
-    const size_t sm_r = ((size_t)C * 33 + 512) * sizeof(float);
-    const size_t sm_q = (size_t)64 * ph * (W + 1) * sizeof(float);
+    const size_t sm_r = ((size_t)C * 33 + (C >> 5) + 32 + 512) * sizeof(float);
+    const size_t sm_q = ((size_t)64 * ph * (pp.seg_w | 1) + 32) * sizeof(float);
     const size_t sm = sm_r > sm_q ? sm_r : sm_q;
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
     if (sm > 48 * 1024)

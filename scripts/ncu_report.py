@@ -20,7 +20,9 @@ hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 
 # kernel function name -> the trace label bench.py uses
-LABELS = [("pack_ref", "clc_match_topk_tc(pack_ref)"), ("pack_query", "clc_match_topk_tc(pack_query)"),
+LABELS = [("prepass", "clc_match_topk_tc(prepass)"), ("match_bwd_own", "clc_match_bwd(main)"),
+          ("cl_to_nchw_kernel", "clc_match_bwd(cl_to_nchw)"),
+          ("pack_ref", "clc_match_topk_tc(pack_ref)"), ("pack_query", "clc_match_topk_tc(pack_query)"),
           ("patch_stats", "patch_stats"), ("match_gemm", "clc_match_topk_tc(gemm)"),
           ("rescore", "clc_match_topk_tc(rescore)"), ("gather_blend_fwd", "clc_gather_blend_fwd"),
           ("clm_fuse_fwd", "clc_clm_fuse_fwd"), ("clm_fuse_bwd", "clc_clm_fuse_bwd"), ("eb_fwd", "clc_eb_fwd"),

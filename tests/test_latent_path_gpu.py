@@ -111,3 +111,4 @@ def test_forked_step_eager_equals_serial():
     for n, t in a.items():
         assert torch.equal(getattr(lp, n), t), n
     assert abs(lp.bpp().item() - bpp) < 1e-9
+

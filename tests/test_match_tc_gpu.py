@@ -84,6 +84,8 @@ def test_tc_gemm_accumulators(geom):
     (1, 3, 64, 8, 12, 4, 2, True),
     (1, 1, 128, 12, 20, 2, 8, True),
     (3, 2, 192, 20, 16, 4, 3, False),
+    (1, 2, 64, 8, 80, 4, 4, True),       # wide rows: three column segments per query block row (32+32+16)
+    (1, 1, 64, 9, 36, 3, 2, True),       # 3x3 patches: 30-column segments (scalar staging path), 30 + 6
 ])
 def test_tc_topk_equals_fp32_mode_and_oracle(geom):
     import clc_b200
