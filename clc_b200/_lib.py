@@ -74,6 +74,10 @@ PROTOTYPES = {
                                         _p, _sz, _p]),
     "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                             _p, _sz, _p]),
+    "clc_pmf_to_quantized_cdf": (C.c_int, [_p, _i32, _i32, _p]),
+    "clc_rans_encode": (C.c_int, [_p, _p, _i64, _p, _i32, _i32, _p, _p, _p, _sz, C.POINTER(_sz)]),
+    "clc_rans_encode_capacity": (_sz, [_i64]),
+    "clc_rans_decode": (C.c_int, [_p, _sz, _p, _p, _i64, _p, _i32, _i32, _p, _p, _p]),
     "clc_clm_fuse_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i32, _i64, _i32, _i64, _p]),
     "clc_clm_fuse_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
 }

@@ -66,6 +66,76 @@ class EntropyModel(nn.Module):
             outputs = inputs.type(dtype)
         return outputs
 
+    # ---- range-coder side (EntropyModel._pmf_to_cdf / compress / decompress [upstream], reached from
+    # CLC_run.py:486-491, :643-644, :749).  Tables are built once per checkpoint on the host (they
+    # are saved in the state_dict and must be identical on the encoding and the decoding machine, so
+    # they do not depend on the device); the quantiser and the coder are C entry points. ----
+    def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
+        from .ans import pmf_to_quantized_cdf
+        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32)
+        for i, p in enumerate(pmf):
+            prob = torch.cat((p[: pmf_length[i]], tail_mass[i]), dim=0)
+            _cdf = torch.IntTensor(pmf_to_quantized_cdf(prob.tolist(), self.entropy_coder_precision))
+            cdf[i, : _cdf.size(0)] = _cdf
+        return cdf
+
+    def _check_tables(self):
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if len(self._quantized_cdf.size()) != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if len(self._offset.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._offset.size()}")
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if len(self._cdf_length.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+
+    def coder_tables(self):
+        """Host copy of (quantized_cdf, cdf_length, offset) in the coder's layout, cached until the
+        buffers change (the reference converts the whole table with `.tolist()` on every call)."""
+        from .ans import _Tables
+        self._check_tables()
+        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, tuple(self._quantized_cdf.shape))
+        if getattr(self, "_tables_key", None) != key:
+            self._tables = _Tables(self._quantized_cdf, self._cdf_length.reshape(-1), self._offset.reshape(-1))
+            self._tables_key = key
+        return self._tables
+
+    def compress(self, inputs, indexes, means=None):
+        """One rANS string per batch element (EntropyModel.compress [upstream])."""
+        from .ans import RansEncoder
+        if len(inputs.size()) < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        tables = self.coder_tables()
+        symbols = self.quantize(inputs, "symbols", means)
+        sym = symbols.reshape(symbols.size(0), -1).to(torch.int32).cpu()          # ONE device->host copy
+        idx = indexes.reshape(indexes.size(0), -1).to(torch.int32).cpu()
+        coder = RansEncoder()
+        return [coder.encode_with_indexes(sym[i], idx[i], tables, None, None) for i in range(sym.size(0))]
+
+    def decompress(self, strings, indexes, dtype=torch.float, means=None):
+        from .ans import RansDecoder
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if len(indexes.size()) < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        if means is not None and means.size()[:2] != indexes.size()[:2]:
+            raise ValueError("Invalid means or indexes parameters")
+        tables = self.coder_tables()
+        idx = indexes.reshape(indexes.size(0), -1).to(torch.int32).cpu()
+        coder = RansDecoder()
+        out = torch.stack([coder.decode_with_indexes(s, idx[i], tables, None, None, as_tensor=True)
+                           for i, s in enumerate(strings)])
+        outputs = out.reshape(indexes.size()).to(indexes.device)                  # ONE host->device copy
+        return self.dequantize(outputs, means, dtype)
+
 
 class _NoiseAddFn(torch.autograd.Function):
     """inputs + noise through the GC kernel's `outputs` path is overkill; the add is plumbing."""
@@ -125,7 +195,37 @@ class GaussianConditional(EntropyModel):
         if self._offset.numel() > 0 and not force:
             return False
         self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32).to(self.scale_table.device).clone()
+        self.update()
         return True
+
+    @staticmethod
+    def _standardized_cumulative(inputs: Tensor) -> Tensor:
+        return 0.5 * torch.erfc(float(-(2 ** -0.5)) * inputs)
+
+    @staticmethod
+    def _standardized_quantile(quantile: float) -> float:
+        # inverse normal CDF in float64 (upstream: scipy.stats.norm.ppf)
+        return float(torch.special.ndtri(torch.tensor(quantile, dtype=torch.float64)))
+
+    def update(self):
+        """Quantised CDF table per scale-table entry (GaussianConditional.update [upstream]): symmetric
+        integer support of half-width ceil(scale * |ppf(tail_mass / 2)|), bin masses from the same
+        erfc form as the likelihood."""
+        dev = self.scale_table.device
+        table = self.scale_table.detach().float().cpu()
+        multiplier = -self._standardized_quantile(self.tail_mass / 2)
+        pmf_center = torch.ceil(table * multiplier).int()
+        pmf_length = 2 * pmf_center + 1
+        max_length = int(torch.max(pmf_length).item())
+        samples = torch.abs(torch.arange(max_length).int() - pmf_center[:, None]).float()
+        samples_scale = table.unsqueeze(1)
+        upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
+        lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
+        pmf = upper - lower
+        tail_mass = 2 * lower[:, :1]
+        self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length).to(dev)
+        self._offset = (-pmf_center).to(dev)
+        self._cdf_length = (pmf_length + 2).to(dev)
 
     def forward(self, inputs, scales, means=None, training=None, *, noise=None, ste=False,
                 want_outputs=True, log2_acc=None):
@@ -191,15 +291,19 @@ class EntropyBottleneck(EntropyModel):
         fs = [getattr(self, f"_factor{i}") for i in range(4)]
         return ms, bs, fs
 
-    def loss(self) -> Tensor:
-        """Auxiliary quantile loss (3 values per channel; stays in torch, SURVEY a11)."""
-        logits = self.quantiles
+    def _logits_cumulative(self, inputs: Tensor) -> Tensor:
+        """Cumulative logits with detached parameters (torch; used by the aux loss and by update())."""
+        logits = inputs
         for i in range(5):
             logits = torch.matmul(torch.nn.functional.softplus(getattr(self, f"_matrix{i}").detach()), logits)
             logits = logits + getattr(self, f"_bias{i}").detach()
             if i < 4:
                 logits = logits + torch.tanh(getattr(self, f"_factor{i}").detach()) * torch.tanh(logits)
-        return torch.abs(logits - self.target).sum()
+        return logits
+
+    def loss(self) -> Tensor:
+        """Auxiliary quantile loss (3 values per channel; stays in torch, SURVEY a11)."""
+        return torch.abs(self._logits_cumulative(self.quantiles) - self.target).sum()
 
     def forward(self, x, training=None, *, noise=None, ste=False, want_outputs=True, log2_acc=None):
         if training is None:
@@ -217,4 +321,66 @@ class EntropyBottleneck(EntropyModel):
         return outputs, lik
 
     def update(self, force=False):
-        return False  # CDF tables belong to the rANS path (out of scope this round)
+        """Quantised CDF table per channel (EntropyBottleneck.update [upstream]): integer support from
+        the learned quantiles, bin masses from the factorised density (sign-stabilised form)."""
+        if self._offset.numel() > 0 and not force:
+            return False
+        dev = self.quantiles.device
+        with torch.no_grad():
+            host = {n: t.detach().float().cpu() for n, t in self.named_parameters()}
+            q = host["quantiles"]
+            medians = q[:, 0, 1]
+            minima = torch.clamp(torch.ceil(medians - q[:, 0, 0]).int(), min=0)
+            maxima = torch.clamp(torch.ceil(q[:, 0, 2] - medians).int(), min=0)
+            pmf_start = medians - minima
+            pmf_length = maxima + minima + 1
+            max_length = int(pmf_length.max().item())
+            samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
+
+            def logits(x):
+                for i in range(5):
+                    x = torch.matmul(torch.nn.functional.softplus(host[f"_matrix{i}"]), x) + host[f"_bias{i}"]
+                    if i < 4:
+                        x = x + torch.tanh(host[f"_factor{i}"]) * torch.tanh(x)
+                return x
+
+            lower, upper = logits(samples - 0.5), logits(samples + 0.5)
+            sign = -torch.sign(lower + upper)
+            pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+            tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+            self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length).to(dev)
+            self._offset = (-minima).to(dev)
+            self._cdf_length = (pmf_length + 2).to(dev)
+        return True
+
+    def _build_indexes(self, size):
+        N, C = size[0], size[1]
+        view = [1] * len(size)
+        view[1] = -1
+        return torch.arange(C, dtype=torch.int32).view(*view).repeat(N, 1, *size[2:])
+
+    def _medians_like(self, n, spatial_dims):
+        med = self._get_medians().detach().reshape(-1, *([1] * spatial_dims))
+        return med.expand(n, *([-1] * (spatial_dims + 1)))
+
+    def compress(self, x):
+        """One string per image (EntropyBottleneck.compress [upstream], CLC_run.py:643)."""
+        from .ans import RansEncoder
+        tables = self.coder_tables()
+        sym = torch.round(x - self._medians_like(x.size(0), x.dim() - 2)).to(torch.int32)
+        sym = sym.reshape(x.size(0), -1).cpu()                                      # one device->host copy
+        idx = self._build_indexes(x.size()).reshape(x.size(0), -1)
+        coder = RansEncoder()
+        return [coder.encode_with_indexes(sym[i], idx[i], tables, None, None) for i in range(sym.size(0))]
+
+    def decompress(self, strings, size):
+        """-> z_hat [len(strings), C, *size] on the module's device (CLC_run.py:644, :749)."""
+        from .ans import RansDecoder
+        tables = self.coder_tables()
+        out_size = (len(strings), self._quantized_cdf.size(0), *size)
+        idx = self._build_indexes(out_size).reshape(len(strings), -1)
+        coder = RansDecoder()
+        sym = torch.stack([coder.decode_with_indexes(s, idx[i], tables, None, None, as_tensor=True)
+                           for i, s in enumerate(strings)]).reshape(out_size)
+        med = self._medians_like(len(strings), len(size))
+        return self.dequantize(sym.to(med.device), med, med.dtype)

@@ -162,12 +162,72 @@ class _ChARMBase(CompressionModel):
     def _lrp_add(y_hat, lrp):
         return ops.lrp_add_(y_hat, lrp)
 
-    def compress(self, *a, **k):
-        raise NotImplementedError("rANS bitstream coding is the next scope row (SURVEY.md 8f-1); "
-                                  "use symbols_and_indexes() for the coder inputs")
+    # -- bitstreams (CLC_run.py:629-716, :738-814; tcm.py compress / decompress) ---------------------
+    def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, ref_features, y_shape):
+        support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[:self.max_support_slices]
+        mean_support = self.atten_mean[i](torch.cat([latent_means] + support, dim=1))
+        scale_support = self.atten_scale[i](torch.cat([latent_scales] + support, dim=1))
+        if ref_features is not None:
+            mu = self.ref_cc_mean_transforms[i](torch.cat([mean_support, ref_features], dim=1))
+            scale = self.ref_cc_scale_transforms[i](torch.cat([scale_support, ref_features], dim=1))
+        else:
+            mu = self.cc_mean_transforms[i](mean_support)
+            scale = self.cc_scale_transforms[i](scale_support)
+        return mean_support, mu[:, :, :y_shape[0], :y_shape[1]], scale[:, :, :y_shape[0], :y_shape[1]]
 
-    def decompress(self, *a, **k):
-        raise NotImplementedError("rANS bitstream decoding is the next scope row (SURVEY.md 8f-1)")
+    def _slice_refine(self, i, mean_support, y_hat_i, ref_features):
+        if ref_features is not None:
+            lrp = self.ref_lrp_transforms[i](torch.cat([mean_support, y_hat_i, ref_features], dim=1))
+        else:
+            lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_i], dim=1))
+        return self._lrp_add(y_hat_i, lrp)
+
+    def _compress(self, x, ref_features):
+        """Same stream layout as the reference: one string per image for z (EntropyBottleneck.compress),
+        ONE string for y holding, slice after slice, the symbols of the whole batch (CLC_run.py:693,:712).
+        Symbols and scale-table indexes are produced on the device by clc_gc_symbols_indexes and reach
+        the host coder in a single copy (the reference: two `.tolist()` per slice)."""
+        from .ans import BufferedRansEncoder
+        gc = self.gaussian_conditional
+        tables = gc.coder_tables()
+        y = self.g_a(x)
+        y_shape = y.shape[2:]
+        z = self.h_a(y)
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        latent_scales, latent_means = self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        table = gc.scale_table.to(x.device)
+        y_hat_slices, symbols, indexes = [], [], []
+        for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
+            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices,
+                                                         ref_features, y_shape)
+            sym, idx = ops.gc_symbols_indexes(y_slice, scale, mu, table)
+            symbols.append(sym.reshape(-1))
+            indexes.append(idx.reshape(-1))
+            y_hat_slices.append(self._slice_refine(i, mean_support, sym.to(torch.float32) + mu, ref_features))
+        encoder = BufferedRansEncoder()
+        encoder.encode_with_indexes(torch.cat(symbols), torch.cat(indexes), tables, None, None)
+        return {"strings": [[encoder.flush()], z_strings], "shape": z.size()[-2:]}
+
+    def _decompress(self, strings, shape, ref_features):
+        from .ans import RansDecoder
+        gc = self.gaussian_conditional
+        tables = gc.coder_tables()
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        latent_scales, latent_means = self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        y_shape = [z_hat.shape[2] * 4, z_hat.shape[3] * 4]
+        decoder = RansDecoder()
+        decoder.set_stream(strings[0][0])
+        y_hat_slices = []
+        for i in range(self.num_slices):
+            mean_support, mu, scale = self._slice_params(i, latent_means, latent_scales, y_hat_slices,
+                                                         ref_features, y_shape)
+            index = gc.build_indexes(scale)                                    # device kernel
+            rv = decoder.decode_stream(index.reshape(-1), tables, None, None, as_tensor=True)
+            y_hat_i = gc.dequantize(rv.reshape(mu.shape).to(mu.device), mu)
+            y_hat_slices.append(self._slice_refine(i, mean_support, y_hat_i, ref_features))
+        y_hat = torch.cat(y_hat_slices, dim=1)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
 
 
 class TCM(_ChARMBase):
@@ -194,6 +254,13 @@ class TCM(_ChARMBase):
         x_hat = self.g_s(y_hat)
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik},
                 "para": {"means": means, "scales": scales, "y": y}}
+
+    def compress(self, x):
+        """tcm.py compress: {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}."""
+        return self._compress(x, None)
+
+    def decompress(self, strings, shape):
+        return self._decompress(strings, shape, None)
 
     def load_state_dict(self, state_dict, strict=True):
         _update_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
@@ -267,6 +334,21 @@ class CLC(_ChARMBase):
         x_hat = self.g_s(y_hat)
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik},
                 "para": {"means": means, "scales": scales, "y": y}}
+
+    def _coder_ref_features(self, ref_frames):
+        if self.match_refs:
+            raise NotImplementedError("match_refs aligns the references to y, which a decoder does not have: "
+                                      "bitstreams are defined for the shipped wiring (match_refs=False)")
+        return self.extract_ref_features(ref_frames) if self.use_ref else None
+
+    def compress(self, x, ref_frames=None):
+        """CLC_run.py:629-716 -> {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}.
+        Call update() first (as with the reference) so the CDF tables exist."""
+        return self._compress(x, self._coder_ref_features(ref_frames))
+
+    def decompress(self, strings, shape, ref_frames=None):
+        """CLC_run.py:738-814 -> {"x_hat"} clamped to [0, 1]."""
+        return self._decompress(strings, shape, self._coder_ref_features(ref_frames))
 
     def symbols_and_indexes(self, x, ref_frames=None):
         """Device-resident coder inputs of `compress` (CLC_run.py:629-716): per-slice int32 symbols

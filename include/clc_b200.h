@@ -321,6 +321,34 @@ CLC_API int clc_debug_match_tc_timing(const float* q_img, const float* r, int64_
                                       int32_t gaussian_mask, float* val, int32_t* idx, long long* timing,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- range coder: compress() / decompress() (CLC_run.py:629-716, :738-814) ----
+ * HOST functions (no stream argument, plain host pointers): one rANS stream is a sequential
+ * recurrence, so the state machine runs on the host; its inputs (symbols, scale-table indexes) come
+ * from clc_gc_symbols_indexes on the device.  Wire format of compressai.ans (rans64: 64-bit state,
+ * 32-bit words, 16-bit probabilities, 4-bit bypass groups). */
+
+/* Replaces: compressai._CXX.pmf_to_quantized_cdf used by EntropyModel._pmf_to_cdf [upstream], reached
+ * from CLC.update() CLC_run.py:486-491.  pmf [n] -> cdf_out [n + 1], cdf_out[n] = 2^precision, every
+ * symbol keeps a non-zero frequency. */
+CLC_API int clc_pmf_to_quantized_cdf(const float* pmf, int32_t n, int32_t precision, int32_t* cdf_out);
+
+/* Replaces: BufferedRansEncoder.encode_with_indexes + flush (CLC_run.py:654, :712-713) and
+ * RansEncoder.encode_with_indexes (EntropyBottleneck.compress, CLC_run.py:643).
+ *   symbols, indexes [n]; cdfs [n_cdfs, cdf_stride]; cdf_sizes, offsets [n_cdfs]  (all host int32)
+ *   out : 4-byte aligned host buffer, out_capacity >= clc_rans_encode_capacity(n) bytes;
+ *   the stream is out[0 .. *out_bytes). */
+CLC_API int clc_rans_encode(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                            int32_t n_cdfs, int32_t cdf_stride, const int32_t* cdf_sizes,
+                            const int32_t* offsets, uint8_t* out, size_t out_capacity, size_t* out_bytes);
+CLC_API size_t clc_rans_encode_capacity(int64_t n);
+
+/* Replaces: RansDecoder.set_stream / decode_stream (CLC_run.py:758-760, :793) and decode_with_indexes
+ * (EntropyBottleneck.decompress, CLC_run.py:749).  state[2] = {rANS state, next word}; {0, 0} starts a
+ * stream, later calls continue it (one call per slice).  out [n] host int32 symbols. */
+CLC_API int clc_rans_decode(const uint8_t* stream, size_t stream_bytes, uint64_t* state, const int32_t* indexes,
+                            int64_t n, const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
+                            const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,6 +132,65 @@ def golden_model(CLC, TCM):
           bpp=bpp_t, n_params=sum(p.numel() for p in t.parameters()))
 
 
+def golden_coder(CLC, TCM):
+    """Bitstream path: the reference's own CLC.compress / decompress (CLC_run.py:629-716, :738-814)
+    and TCM.compress (tcm.py), run unmodified through the shim's range coder, cfg1 inputs and
+    detfill weights; plus the CDF tables its update() builds and a raw coder vector with bypass symbols."""
+    import random
+
+    from compressai import ans
+    x = detfill.det_image((1, 3, 256, 256), 11)
+    refs = [detfill.det_image((1, 3, 256, 256), 12 + i) for i in range(3)]
+    m = detfill.fill_(CLC(N=64).eval(), seed=0)
+    m.update()
+    captured = {}
+    enc_cls = ans.BufferedRansEncoder
+
+    class Spy(enc_cls):                      # records what the reference hands to the coder
+        def encode_with_indexes(self, symbols, indexes, *a):
+            captured["symbols"], captured["indexes"] = list(symbols), list(indexes)
+            return super().encode_with_indexes(symbols, indexes, *a)
+
+    import models.CLC_run as R
+    R.BufferedRansEncoder = Spy
+    try:
+        with torch.no_grad():
+            out = m.compress(x, refs)
+            rec = m.decompress(out["strings"], out["shape"], refs)
+    finally:
+        R.BufferedRansEncoder = enc_cls
+    gc, eb = m.gaussian_conditional, m.entropy_bottleneck
+    t = detfill.fill_(TCM(N=64).eval(), seed=0)
+    t.update()
+    with torch.no_grad():
+        out_t = t.compress(x)
+    # raw coder vector: random tables, out-of-range symbols on both sides (bypass coding)
+    rnd = random.Random(5)
+    cdfs, sizes, offsets = [], [], []
+    for _ in range(6):
+        n = rnd.randint(3, 30)
+        pmf = [rnd.random() ** 3 + 1e-6 for _ in range(n)]
+        tot = sum(pmf)
+        c = ans.pmf_to_quantized_cdf([p / tot for p in pmf] + [1e-9], 16)
+        cdfs.append(c + [0] * (34 - len(c)))
+        sizes.append(len(c))
+        offsets.append(-(n // 2))
+    idx = [rnd.randrange(6) for _ in range(3000)]
+    sym = [rnd.randint(offsets[i] - 9, offsets[i] + sizes[i] + (70000 if rnd.random() < 0.02 else 3)) for i in idx]
+    raw = ans.RansEncoder().encode_with_indexes(sym, idx, cdfs, sizes, offsets)
+    _save("coder.npz",
+          y_string=np.frombuffer(out["strings"][0][0], dtype=np.uint8), z_string=np.frombuffer(out["strings"][1][0], dtype=np.uint8),
+          shape=np.array(list(out["shape"])), symbols=np.array(captured["symbols"], dtype=np.int16),
+          indexes=np.array(captured["indexes"], dtype=np.int8), x_hat=rec["x_hat"].half(),
+          gc_cdf=gc.quantized_cdf.numpy().astype(np.int32), gc_cdf_length=gc.cdf_length.numpy().astype(np.int32),
+          gc_offset=gc.offset.numpy().astype(np.int32), eb_cdf=eb.quantized_cdf.numpy().astype(np.int32),
+          eb_cdf_length=eb.cdf_length.numpy().astype(np.int32), eb_offset=eb.offset.numpy().astype(np.int32),
+          tcm_y_bytes=np.array([len(out_t["strings"][0][0])]), tcm_z_bytes=np.array([len(out_t["strings"][1][0])]),
+          raw_cdfs=np.array(cdfs, dtype=np.int32), raw_sizes=np.array(sizes, dtype=np.int32),
+          raw_offsets=np.array(offsets, dtype=np.int32), raw_idx=np.array(idx, dtype=np.int32),
+          raw_sym=np.array(sym, dtype=np.int32), raw_string=np.frombuffer(raw, dtype=np.uint8))
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -142,6 +201,7 @@ def main():
     golden_clm()
     golden_rd_loss()
     golden_model(CLC, TCM)
+    golden_coder(CLC, TCM)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,5 @@
-"""compressai.entropy_models restatement (forward/likelihood/quantize side only; no rANS).
+"""compressai.entropy_models restatement: forward / likelihood / quantize, and the CDF-table
+(`update`) + `compress` / `decompress` side on top of the compressai.ans restatement.
 
 Restated from the published CompressAI algorithm [upstream, version un-pinned by the
 reference].  Choices where releases differ are stated inline.  The Gaussian likelihood is
@@ -55,6 +56,76 @@ class EntropyModel(nn.Module):
         else:
             outputs = inputs.type(dtype)
         return outputs
+
+    # ---- range-coder side [upstream entropy_models.py: _pmf_to_cdf, compress, decompress] ----
+    def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
+        from compressai.ans import pmf_to_quantized_cdf
+        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32, device=pmf.device)
+        for i, p in enumerate(pmf):
+            prob = torch.cat((p[: pmf_length[i]], tail_mass[i]), dim=0)
+            _cdf = torch.IntTensor(pmf_to_quantized_cdf(prob.tolist(), self.entropy_coder_precision))
+            cdf[i, : _cdf.size(0)] = _cdf
+        return cdf
+
+    def _check_cdf_size(self):
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if len(self._quantized_cdf.size()) != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+
+    def _check_offsets_size(self):
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if len(self._offset.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._offset.size()}")
+
+    def _check_cdf_length(self):
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if len(self._cdf_length.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+
+    def compress(self, inputs, indexes, means=None):
+        from compressai.ans import RansEncoder
+        symbols = self.quantize(inputs, "symbols", means)
+        if len(inputs.size()) < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        coder = RansEncoder()
+        strings = []
+        for i in range(symbols.size(0)):
+            strings.append(coder.encode_with_indexes(
+                symbols[i].reshape(-1).int().tolist(), indexes[i].reshape(-1).int().tolist(),
+                self._quantized_cdf.tolist(), self._cdf_length.reshape(-1).int().tolist(),
+                self._offset.reshape(-1).int().tolist()))
+        return strings
+
+    def decompress(self, strings, indexes, dtype=torch.float, means=None):
+        from compressai.ans import RansDecoder
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if len(indexes.size()) < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        if means is not None and means.size()[:2] != indexes.size()[:2]:
+            raise ValueError("Invalid means or indexes parameters")
+        cdf = self._quantized_cdf
+        outputs = cdf.new_empty(indexes.size())
+        coder = RansDecoder()
+        for i, s in enumerate(strings):
+            values = coder.decode_with_indexes(
+                s, indexes[i].reshape(-1).int().tolist(), cdf.tolist(),
+                self._cdf_length.reshape(-1).int().tolist(), self._offset.reshape(-1).int().tolist())
+            outputs[i] = torch.tensor(values, device=outputs.device, dtype=outputs.dtype).reshape(outputs[i].size())
+        return self.dequantize(outputs, means, dtype)
 
 
 class EntropyBottleneck(EntropyModel):
@@ -142,7 +213,59 @@ class EntropyBottleneck(EntropyModel):
         return outputs, likelihood
 
     def update(self, force=False):
-        return False  # CDF tables belong to the rANS path (out of scope)
+        # [upstream EntropyBottleneck.update]: integer support from the learned quantiles, pmf from
+        # the factorised density at the integer offsets around the median, quantised to 16-bit CDFs.
+        if self._offset.numel() > 0 and not force:
+            return False
+        medians = self.quantiles[:, 0, 1]
+        minima = torch.clamp(torch.ceil(medians - self.quantiles[:, 0, 0]).int(), min=0)
+        maxima = torch.clamp(torch.ceil(self.quantiles[:, 0, 2] - medians).int(), min=0)
+        self._offset = -minima
+        pmf_start = medians - minima
+        pmf_length = maxima + minima + 1
+        max_length = int(pmf_length.max().item())
+        device = pmf_start.device
+        samples = torch.arange(max_length, device=device)
+        samples = samples[None, :] + pmf_start[:, None, None]
+        half = float(0.5)
+        lower = self._logits_cumulative(samples - half, stop_gradient=True)
+        upper = self._logits_cumulative(samples + half, stop_gradient=True)
+        sign = -torch.sign(lower + upper)
+        pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+        pmf = pmf[:, 0, :]
+        tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+        quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._quantized_cdf = quantized_cdf
+        self._cdf_length = pmf_length + 2
+        return True
+
+    def _build_indexes(self, size):
+        dims = len(size)
+        N, C = size[0], size[1]
+        view_dims = np.ones((dims,), dtype=np.int64)
+        view_dims[1] = -1
+        indexes = torch.arange(C).view(*view_dims)
+        indexes = indexes.int()
+        return indexes.repeat(N, 1, *size[2:])
+
+    @staticmethod
+    def _extend_ndims(tensor, n):
+        return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
+
+    def compress(self, x):
+        indexes = self._build_indexes(x.size())
+        medians = self._get_medians().detach()
+        spatial_dims = len(x.size()) - 2
+        medians = self._extend_ndims(medians, spatial_dims)
+        medians = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+        return super().compress(x, indexes, medians)
+
+    def decompress(self, strings, size):
+        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+        indexes = self._build_indexes(output_size).to(self._quantized_cdf.device)
+        medians = self._extend_ndims(self._get_medians().detach(), len(size))
+        medians = medians.expand(len(strings), *([-1] * (len(size) + 1)))
+        return super().decompress(strings, indexes, medians.dtype, medians)
 
 
 class GaussianConditional(EntropyModel):
@@ -167,12 +290,39 @@ class GaussianConditional(EntropyModel):
         const = float(-(2 ** -0.5))
         return half * torch.erfc(const * inputs)
 
+    @staticmethod
+    def _standardized_quantile(quantile):
+        import scipy.stats
+        return scipy.stats.norm.ppf(quantile)
+
     def update_scale_table(self, scale_table, force=False):
         if self._offset.numel() > 0 and not force:
             return False
         self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32,
                                            device=self.scale_table.device).clone()
+        self.update()
         return True
+
+    def update(self):
+        # [upstream GaussianConditional.update]: per scale-table entry a symmetric integer support of
+        # half-width ceil(scale * |ppf(tail_mass / 2)|), pmf from the Gaussian bin masses.
+        multiplier = -self._standardized_quantile(self.tail_mass / 2)
+        pmf_center = torch.ceil(self.scale_table * multiplier).int()
+        pmf_length = 2 * pmf_center + 1
+        max_length = int(torch.max(pmf_length).item())
+        device = pmf_center.device
+        samples = torch.abs(torch.arange(max_length, device=device).int() - pmf_center[:, None])
+        samples_scale = self.scale_table.unsqueeze(1)
+        samples = samples.float()
+        samples_scale = samples_scale.float()
+        upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
+        lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
+        pmf = upper - lower
+        tail_mass = 2 * lower[:, :1]
+        quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._quantized_cdf = quantized_cdf
+        self._offset = -pmf_center
+        self._cdf_length = pmf_length + 2
 
     def _likelihood(self, inputs: Tensor, scales: Tensor, means=None) -> Tensor:
         half = float(0.5)

@@ -1,0 +1,147 @@
+"""CPU: the bitstream path.  The oracle restatement of the range coder and the
+product's C coder (host entry points of libclc_b200.so) against the committed fixtures produced by the
+reference's own compress()/decompress() run through the shim (tests/golden/coder.npz), bit for bit."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def _oracle_ans():
+    import oracle
+    oracle.enable_shim()
+    from compressai import ans
+    return ans
+
+
+def _raw(g):
+    return (g["raw_sym"].tolist(), g["raw_idx"].tolist(), g["raw_cdfs"].tolist(), g["raw_sizes"].tolist(),
+            g["raw_offsets"].tolist(), g["raw_string"].numpy().tobytes())
+
+
+def test_oracle_coder_vs_golden_and_round_trip():
+    O = _oracle_ans()
+    g = load_golden("coder.npz")
+    sym, idx, cdfs, sizes, offsets, want = _raw(g)
+    assert O.RansEncoder().encode_with_indexes(sym, idx, cdfs, sizes, offsets) == want
+    assert O.RansDecoder().decode_with_indexes(want, idx, cdfs, sizes, offsets) == sym
+    # the y stream of the reference's CLC.compress decodes to the symbols the reference handed to the coder
+    tab = (g["gc_cdf"].tolist(), g["gc_cdf_length"].tolist(), g["gc_offset"].tolist())
+    n = 4096                                              # prefix: the pure-Python coder is slow
+    dec = O.RansDecoder()
+    dec.set_stream(g["y_string"].numpy().tobytes())
+    assert dec.decode_stream(g["indexes"][:n].tolist(), *tab) == g["symbols"][:n].tolist()
+
+
+def test_c_coder_bit_exact_vs_golden():
+    from clc_b200 import ans as A
+    g = load_golden("coder.npz")
+    sym, idx, cdfs, sizes, offsets, want = _raw(g)
+    assert A.RansEncoder().encode_with_indexes(sym, idx, cdfs, sizes, offsets) == want
+    assert A.RansDecoder().decode_with_indexes(want, idx, cdfs, sizes, offsets) == sym
+    # tensors in, tensor out; streaming decode in pieces; buffered encoder fed in pieces
+    ts, ti = torch.tensor(sym, dtype=torch.int32), torch.tensor(idx, dtype=torch.int32)
+    assert A.RansEncoder().encode_with_indexes(ts, ti, g["raw_cdfs"], g["raw_sizes"], g["raw_offsets"]) == want
+    d = A.RansDecoder()
+    d.set_stream(want)
+    a = d.decode_stream(ti[:1000], cdfs, sizes, offsets, as_tensor=True)
+    b = d.decode_stream(ti[1000:], cdfs, sizes, offsets, as_tensor=True)
+    assert torch.equal(torch.cat([a, b]), ts)
+    e = A.BufferedRansEncoder()
+    e.encode_with_indexes(sym[:7], idx[:7], cdfs, sizes, offsets)
+    e.encode_with_indexes(sym[7:], idx[7:], cdfs, sizes, offsets)
+    assert e.flush() == want
+    # the whole y stream of the reference's CLC.compress (81 920 symbols, 64 scale-table CDFs)
+    tab = (g["gc_cdf"], g["gc_cdf_length"], g["gc_offset"])
+    y_string = g["y_string"].numpy().tobytes()
+    assert A.RansEncoder().encode_with_indexes(g["symbols"].int(), g["indexes"].int(), *tab) == y_string
+    out = A.RansDecoder().decode_with_indexes(y_string, g["indexes"].int(), *tab, as_tensor=True)
+    assert torch.equal(out, g["symbols"].int())
+
+
+def test_c_coder_edge_cases():
+    from clc_b200 import ans as A
+    cdfs, sizes, offsets = [[0, 40000, 65535, 65536]], [4], [-1]
+    assert A.RansDecoder().decode_with_indexes(A.RansEncoder().encode_with_indexes([], [], cdfs, sizes, offsets),
+                                               [], cdfs, sizes, offsets) == []
+    assert len(A.BufferedRansEncoder().flush()) == 8          # an empty stream is the 64-bit initial state
+    for sym in ([-1], [0], [1], [2], [-2], [2 ** 31 - 1], [-2 ** 31 + 1], [5, -7, 0, 123456, -1, -1]):
+        s = A.RansEncoder().encode_with_indexes(sym, [0] * len(sym), cdfs, sizes, offsets)
+        assert A.RansDecoder().decode_with_indexes(s, [0] * len(sym), cdfs, sizes, offsets) == sym
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        A.RansEncoder().encode_with_indexes([0], [3], cdfs, sizes, offsets)           # index out of range
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        A.RansDecoder().decode_with_indexes(b"\x00" * 8, [0] * 64, cdfs, sizes, offsets)   # truncated stream
+    with pytest.raises(ValueError):
+        A.RansDecoder().decode_stream([0], cdfs, sizes, offsets)                       # no stream set
+
+
+def test_pmf_to_quantized_cdf_vs_oracle():
+    O = _oracle_ans()
+    from clc_b200 import ans as A
+    rnd = random.Random(3)
+    for trial in range(200):
+        n = rnd.randint(1, 80)
+        pmf = [rnd.random() ** rnd.choice([1, 3, 8]) * rnd.choice([1, 1e-3, 1e-7]) for _ in range(n)]
+        tot = sum(pmf)
+        pmf = [p / tot for p in pmf]
+        got = A.pmf_to_quantized_cdf(pmf)
+        assert got == O.pmf_to_quantized_cdf(pmf), trial
+        assert got[0] == 0 and got[-1] == 65536 and all(b > a for a, b in zip(got, got[1:]))
+    with pytest.raises(RuntimeError):
+        A.pmf_to_quantized_cdf([0.5, float("nan")])
+    with pytest.raises(RuntimeError):
+        A.pmf_to_quantized_cdf([0.0, 0.0])
+
+
+def test_update_tables_equal_reference_tables():
+    """CLC.update() (CLC_run.py:486-491): the tables the drop-in modules build are the tables the
+    reference built (through the shim) for the same detfill weights."""
+    from clc_b200.models import CLC
+    from oracle import detfill
+    g = load_golden("coder.npz")
+    m = detfill.fill_(CLC(N=64), seed=0).eval()
+    assert m.update() is True
+    assert m.update() is False                      # already initialised, force=False
+    gc, eb = m.gaussian_conditional, m.entropy_bottleneck
+    for mod, pre in ((gc, "gc"), (eb, "eb")):
+        assert torch.equal(mod.quantized_cdf.cpu(), g[f"{pre}_cdf"].int())
+        assert torch.equal(mod.cdf_length.cpu(), g[f"{pre}_cdf_length"].int())
+        assert torch.equal(mod.offset.cpu(), g[f"{pre}_offset"].int())
+    # the z stream of the reference decodes with these tables; dequantised values are integers + medians
+    z_hat = eb.decompress([g["z_string"].numpy().tobytes()], tuple(int(v) for v in g["shape"]))
+    assert z_hat.shape == (1, 192, 4, 4)
+    med = eb._get_medians().reshape(1, -1, 1, 1)
+    assert torch.equal(torch.round(z_hat - med) + med, z_hat)
+    assert eb.compress(z_hat) == [g["z_string"].numpy().tobytes()]
+
+
+def test_uninitialised_tables_raise_like_the_reference():
+    import clc_b200
+    eb = clc_b200.EntropyBottleneck(4)
+    with pytest.raises(ValueError, match="Uninitialized CDFs"):
+        eb.compress(torch.zeros(1, 4, 2, 2))
+    gc = clc_b200.GaussianConditional(None)
+    with pytest.raises(ValueError, match="Uninitialized CDFs"):
+        gc.coder_tables()
+
+
+def test_reference_itself_reproduces_coder_golden():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import detfill
+    CLC, _ = ref_loader.import_models()
+    g = load_golden("coder.npz")
+    torch.set_num_threads(8)
+    m = detfill.fill_(CLC(N=64).eval(), seed=0)
+    m.update()
+    x = detfill.det_image((1, 3, 256, 256), 11)
+    refs = [detfill.det_image((1, 3, 256, 256), 12 + i) for i in range(3)]
+    with torch.no_grad():
+        out = m.compress(x, refs)
+    assert out["strings"][0][0] == g["y_string"].numpy().tobytes()
+    assert out["strings"][1][0] == g["z_string"].numpy().tobytes()
