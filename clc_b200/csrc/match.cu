@@ -284,15 +284,15 @@ gather_blend_fwd_kernel(const float* __restrict__ feat, const int32_t* __restric
     const int64_t o = ((int64_t)n * P + patch) * k;
     float mx = -INFINITY, den = 0.f;
     if (!STACK) {
-      for (int j = 0; j < k; ++j) mx = fmaxf(mx, val[o + j] * temperature);
-      for (int j = 0; j < k; ++j) den += expf(val[o + j] * temperature - mx);
+      for (int j = 0; j < k; ++j) mx = fmaxf(mx, __fmul_rn(val[o + j], temperature));
+      for (int j = 0; j < k; ++j) den += expf(__fsub_rn(__fmul_rn(val[o + j], temperature), mx));   // torch: exp(v*T - max), no FMA
     }
     for (int j = 0; j < k; ++j) {
       const int id = idx[o + j];
       const int sy = id / corr_w, sx = id - sy * corr_w;
       off_s[px * k + j] = sy * fw + sx;
       if (!STACK) {
-        const float wj = expf(val[o + j] * temperature - mx) / den;
+        const float wj = expf(__fsub_rn(__fmul_rn(val[o + j], temperature), mx)) / den;
         w_s[px * k + j] = wj;
         if (weights && c0 == 0) weights[o + j] = wj;
       }

@@ -1105,6 +1105,48 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     }
     __syncthreads();
     if (warp == 0) {
+      constexpr int TL = 4;       // per-tile lists owned by one lane
+      if (n_tiles <= 32 * TL) {
+        // every per-tile list is already sorted (screened value desc, position asc), so the global
+        // top-KC is a KC-step multiway merge over the list HEADS: lane <-> lists lane, lane+32, ...;
+        // one redux.max over order-preserving keys + one redux.min over the tied ids per step
+        int head[TL];
+#pragma unroll
+        for (int u = 0; u < TL; ++u) head[u] = 0;
+        for (int t = 0; t < KC; ++t) {
+          unsigned bkey = 0u;
+          int bid = 0x7fffffff, bl = -1;
+          float bvv = -INFINITY;
+#pragma unroll
+          for (int u = 0; u < TL; ++u) {
+            const int li = lane + 32 * u;
+            if (li < n_tiles && head[u] < KC) {
+              const int id = cis[li * KC + head[u]];
+              if (id >= 0) {
+                const float v = cvs[li * KC + head[u]];
+                const unsigned uu = __float_as_uint(v);
+                unsigned key = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);
+                key = key ? key : 1u;                         // 0 is the "nothing left" sentinel
+                if (key > bkey || (key == bkey && id < bid)) { bkey = key; bid = id; bl = u; bvv = v; }
+              }
+            }
+          }
+          const unsigned kmax = __reduce_max_sync(0xffffffffu, bkey);
+          if (kmax == 0u) {                                   // fewer than KC candidates in total
+            if (lane == 0)
+              for (int tt = t; tt < KC; ++tt) { sel_v[tt] = -INFINITY; sel_i[tt] = -1; }
+            break;
+          }
+          const unsigned imin = __reduce_min_sync(0xffffffffu, bkey == kmax ? (unsigned)bid : 0x7fffffffu);
+          if (bkey == kmax && (unsigned)bid == imin) {        // ids are unique: exactly one winner
+            sel_v[t] = bvv;
+            sel_i[t] = bid;
+#pragma unroll
+            for (int u = 0; u < TL; ++u)
+              if (u == bl) ++head[u];
+          }
+        }
+      } else {
       // KC rounds of warp arg-max over the merged list
       for (int t = 0; t < KC; ++t) {
         float bv = -INFINITY;
@@ -1128,6 +1170,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
           if (bslot >= 0) cis[bslot] = -1;  // taken
         }
         __syncwarp();
+      }
       }
     }
   }
@@ -1230,54 +1273,70 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       const double cg = ((wv - center_w) * (wv - center_w)) / (sw * sw);
       myv *= (float)exp(-4.0 * 0.693147180559945309417232121458 * (rg + cg));
     }
-    bool taken = myi < 0;
-    float vk = -INFINITY;
-    for (int t = 0; t < k; ++t) {
-      float bv = myv;
-      int bi = taken ? -1 : myi;
+    // final top-k by RANK: candidate j ranks before me iff it is valid and (I am not, or NaN first like
+    // torch.topk, or larger value, or equal value and smaller index).  KC independent shuffle pairs,
+    // no dependent reduction rounds; ids are distinct, so the valid ranks are a permutation.
+    int rank = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        bool better = false;
-        if (oi >= 0) {
-          if (bi < 0) better = true;
-          else {
-            const bool on = ov != ov, bn = bv != bv;
-            if (on != bn) better = on;
-            else if (!on && ov != bv) better = ov > bv;
-            else better = oi < bi;
-          }
+    for (int j = 0; j < KC; ++j) {
+      const float ov = __shfl_sync(0xffffffffu, myv, j);
+      const int oi = __shfl_sync(0xffffffffu, myi, j);
+      bool before = false;
+      if (oi >= 0 && j != lane) {
+        if (myi < 0) before = true;
+        else {
+          const bool on = ov != ov, bn = myv != myv;
+          if (on != bn) before = on;
+          else if (!on && ov != myv) before = ov > myv;
+          else before = oi < myi;
         }
-        if (better) { bv = ov; bi = oi; }
       }
-      if (!taken && bi == myi) taken = true;
-      if (lane == 0) {
-        val[((int64_t)n * P + patch) * k + t] = bv;
-        idx[((int64_t)n * P + patch) * k + t] = bi;
-        top_w[t] = bv;
-        const int oy = bi / cw, ox = bi - oy * cw;
-        top_src[t] = oy * W + ox;
-      }
-      vk = bv;
+      rank += before ? 1 : 0;
     }
+    const int64_t oo = ((int64_t)n * P + patch) * k;
+    const unsigned valid = __ballot_sync(0xffffffffu, myi >= 0);
+    const int nvalid = __popc(valid);
+    if (myi >= 0 && rank < k) {
+      val[oo + rank] = myv;
+      idx[oo + rank] = myi;
+      top_w[rank] = myv;
+      const int oy = myi / cw, ox = myi - oy * cw;
+      top_src[rank] = oy * W + ox;
+    }
+    if (lane >= nvalid && lane < k) {                        // fewer than k valid candidates (L < k)
+      val[oo + lane] = -INFINITY;
+      idx[oo + lane] = -1;
+      top_w[lane] = -INFINITY;
+      top_src[lane] = 0;
+    }
+    __syncwarp();
+    const float vk = top_w[k - 1];
     if (aligned != nullptr) {
-      // softmax(value * T) over the k selected positions (SI_Wraper, Patch_Matching.py:225)
+      // softmax(value * T) over the k selected positions (SI_Wraper, Patch_Matching.py:225): lanes
+      // 0..7 each form max and denominator in the reference's left-to-right order (identical bits in
+      // every lane) and their own weight
+      float tv[8];                                            // the k selected values
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tv[j] = (j < k) ? top_w[j] : -INFINITY;
+      const int src0 = top_src[0];
       __syncwarp();
-      if (lane == 0) {
-        float mx = -INFINITY, den = 0.f;
-        for (int j = 0; j < k; ++j) mx = fmaxf(mx, top_w[j] * temperature);
-        for (int j = 0; j < k; ++j) den += expf(top_w[j] * temperature - mx);
-        for (int j = 0; j < 8; ++j) {
-          float wj = 0.f;
-          if (j < k) {
-            wj = expf(top_w[j] * temperature - mx) / den;
-            if (weights_out) weights_out[((int64_t)n * P + patch) * k + j] = wj;
-          } else {
-            top_src[j] = top_src[0];
-          }
-          top_w[j] = wj;
+      float mx = -INFINITY, den = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < k) mx = fmaxf(mx, __fmul_rn(tv[j], temperature));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < k) den += expf(__fsub_rn(__fmul_rn(tv[j], temperature), mx));   // as torch: no FMA
+      if (lane < 8) {
+        float wj = 0.f;
+        if (lane < k) {
+          float mine = tv[0];
+#pragma unroll
+          for (int j = 1; j < 8; ++j) mine = (j == lane) ? tv[j] : mine;
+          wj = expf(__fsub_rn(__fmul_rn(mine, temperature), mx)) / den;
+          if (weights_out) weights_out[oo + lane] = wj;
+        } else {
+          top_src[lane] = src0;
         }
+        top_w[lane] = wj;
       }
     }
     if (lane == 0 && n_uncertified != nullptr && L > KC) {
