@@ -313,18 +313,25 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const uint32_t a_sub = (uint32_t)p.a_rows * 8u;  // one shift's sub-tile, in 16-byte units
     uint32_t ast = 0, aph = 0, bst = 0, bph = 0, accst = 0, accph = 0;
     bool first = true;
+    long long w_acc = 0, w_b = 0, w_a = 0, t0 = 0;      // bring-up: cycles spent waiting (timing runs only)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (p.timing) t0 = clock64();
       mbar_wait(barAccEmpty + 8u * accst, accph ^ 1u);
+      if (p.timing) w_acc += clock64() - t0;
       tc_fence_after();
       const uint32_t d_base = tmem_base + accst * (uint32_t)acc_cols;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.chunks; ++c) {
+        if (p.timing) t0 = clock64();
         mbar_wait(barBfull + 8u * bst, bph);
+        if (p.timing) w_b += clock64() - t0;
         if (first) CLC_STAMP(4);
         const uint64_t bdesc0 = make_desc_sw128(sB + bst * bBytes);
         int dy = 0, dx = 0;
         for (int s0 = 0; s0 < p.S; s0 += p.SB) {
+          if (p.timing) t0 = clock64();
           mbar_wait(barAfull + 8u * ast, aph);
+          if (p.timing) w_a += clock64() - t0;
           if (first) { CLC_STAMP(5); first = false; }
           tc_fence_after();
           if (lane == 0) {
@@ -359,6 +366,10 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       __syncwarp();
       if (++accst == (uint32_t)p.acc_stages) { accst = 0; accph ^= 1u; }
       CLC_STAMP(6);
+    }
+    if (p.timing && lane == 0) {
+      long long* tt = p.timing + (size_t)blockIdx.x * 16;
+      tt[11] = tt[0] + w_acc; tt[12] = tt[0] + w_b; tt[13] = tt[0] + w_a;   // reported relative to the start stamp
     }
   } else {
     // ===================================== epilogue =========================================
@@ -1064,16 +1075,25 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   const int64_t co = ((int64_t)n * P + patch) * M;
   pdl_trigger();
   pdl_wait();
-  // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate lists ----
-  {
+  // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate lists.
+  // With several per-tile lists, warp 0 merges them while warps 1..KC-1 stage the patch. ----
+  if (n_tiles > 1) {
+    for (int i = threadIdx.x; i < M; i += NT) {
+      cvs[i] = cand_val[co + i];
+      cis[i] = cand_idx[co + i];
+    }
+    __syncthreads();
+  }
+  const int sw = n_tiles > 1 ? warp - 1 : warp, snw = n_tiles > 1 ? KC - 1 : KC;   // staging warp id / count
+  if (sw >= 0) {
     const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
     // two shifts x three float4 columns per warp-iteration: 6 loads in flight before the first store
-    for (int s0 = warp; s0 < pp; s0 += 2 * KC)
+    for (int s0 = sw; s0 < pp; s0 += 2 * snw)
       for (int cb = 0; cb < c4n; cb += 96) {
         float4 t[2][3];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int sft = s0 + u * KC;
+          const int sft = s0 + u * snw;
           const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)sft * P_pad * C);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -1083,7 +1103,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int sft = s0 + u * KC;
+          const int sft = s0 + u * snw;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int c4 = cb + lane + 32 * i;
@@ -1099,13 +1119,8 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       sel_i[threadIdx.x] = cand_idx[co + threadIdx.x];
     }
   } else {
-    for (int i = threadIdx.x; i < M; i += NT) {
-      cvs[i] = cand_val[co + i];
-      cis[i] = cand_idx[co + i];
-    }
-    __syncthreads();
     if (warp == 0) {
-      constexpr int TL = 4;       // per-tile lists owned by one lane
+      constexpr int TL = 8;       // per-tile lists owned by one lane
       if (n_tiles <= 32 * TL) {
         // every per-tile list is already sorted (screened value desc, position asc), so the global
         // top-KC is a KC-step multiway merge over the list HEADS: lane <-> lists lane, lane+32, ...;
@@ -1399,7 +1414,7 @@ static EncodeTiledFn encode_fn() {
 struct Plan {
   int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks;
   int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid, a_rows, SB;
-  int stacked, st_rows, st_shifts, st_mt, st_stages, st_groups, zero_rows;
+  int stacked, st_rows, st_shifts, st_mt, st_stages, st_groups, zero_rows, n_lists;
   size_t smem_bytes;
   // workspace offsets (bytes)
   size_t off_rT, off_A, off_r32, off_A32, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, total;
@@ -1510,8 +1525,9 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * pl.chunks * 4, 256);
   pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * pl.chunks * 4, 256);
-  pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_tiles * pl.KC * 4, 256);
-  pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_tiles * pl.KC * 4, 256);
+  pl.n_lists = pl.n_tiles;                         // candidate lists per (problem, patch)
+  pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_lists * pl.KC * 4, 256);
+  pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_lists * pl.KC * 4, 256);
   pl.total = o + 256;  // slack for aligning the caller's pointer
   return pl;
 }
@@ -1643,20 +1659,20 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   if (stage_on(2)) {
     const int64_t blocks = NP * pl.P;
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
-    const size_t sm = (size_t)pl.S * C * sizeof(float) + (size_t)pl.n_tiles * pl.KC * 8;
+    const size_t sm = (size_t)pl.S * C * sizeof(float) + (size_t)pl.n_lists * pl.KC * 8;
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
     const int dbg = (g_stage_mask.load() >> 8) & 0xff;
     if (pl.KC == 8) {
       if (sm > 48 * 1024)
         CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CLC_CUDA(launch_pdl(rescore_kernel<8>, dim3((unsigned)blocks), dim3(256), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
-                          sxx, cand_val, cand_idx, pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
+                          sxx, cand_val, cand_idx, pl.n_lists, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
                           val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
     } else {
       if (sm > 48 * 1024)
         CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CLC_CUDA(launch_pdl(rescore_kernel<16>, dim3((unsigned)blocks), dim3(512), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
-                          sxx, cand_val, cand_idx, pl.n_tiles, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
+                          sxx, cand_val, cand_idx, pl.n_lists, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
                           val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
     }
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");

@@ -55,6 +55,8 @@ tot = 0.0
 STAGES = {"clc_match_topk_tc": ["prepass", "gemm", "rescore+blend"], "clc_match_bwd": ["memset+main", "cl_to_nchw"]}
 # debug variants: (stage bit, dbg bits << 8, label)
 VARIANTS = {"clc_match_topk_tc": [(1, 1, "prepass: query role only"), (1, 2, "prepass: ref role only"),
+                                  (2, 1, "gemm: shifts rounded to 8 rows (aligned descriptors)"),
+                                  (2, 2, "gemm: no MMAs (TMA + epilogue only)"), (2, 4, "gemm: no A loads"),
                                   (4, 1, "rescore: no re-scoring loads"), (4, 2, "rescore: no blend")],
             "clc_match_bwd": [(1, 1, "main: no window atomics"), (1, 2, "main: no g_q atomics"), (1, 3, "main: no atomics")]}
 expanded = []
@@ -122,7 +124,7 @@ for name, g in (("graph: match chain", lp._g_match), ("graph: entropy chains (fo
     torch.cuda.synchronize()
     print(f"{name:40s} {e0.elapsed_time(e1) * 1e3 / a.iters:8.2f} us/replay")
 lp.capture(fork=True)
-for name in ("graph: full step (3 branches)",):
+for name in ("graph: full step (forked)",):
     lp.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -37,9 +37,10 @@ t = tm.cpu()
 live = t[:, 0] != 0
 t = t[live]
 names = ["start", "setup_done", "first_A_issued", "producer_done", "mma_first_B", "mma_first_A", "mma_all_issued",
-         "epi_colstat", "epi_acc_full", "epi_done", "epi_sum_done"]
+         "epi_colstat", "epi_acc_full", "epi_done", "epi_sum_done", "mma_wait_acc_empty(sum)", "mma_wait_B_full(sum)",
+         "mma_wait_A_full(sum)"]
 rel = t - t[:, :1]
 print("CTAs:", t.shape[0])
 for i, nme in enumerate(names):
     col = rel[:, i].float()
-    print(f"{nme:>16}: median {col.median().item():9.0f}  min {col.min().item():9.0f}  max {col.max().item():9.0f} cycles")
+    print(f"{nme:>26}: median {col.median().item():9.0f}  min {col.min().item():9.0f}  max {col.max().item():9.0f} cycles")

@@ -64,6 +64,7 @@ def _xy_ref(y, refs, p):
     (2, 3, 320, 16, 16, 4),     # cfg2 latent: several narrow tiles per problem
     (1, 2, 320, 32, 48, 4),     # cfg3 latent
     (1, 1, 128, 12, 20, 2),     # 2x2 patches, P = 60
+    (1, 2, 64, 12, 128, 4),     # wide latent (CLIC-shaped rows): large halo, several tiles per problem
 ])
 def test_tc_gemm_accumulators(geom):
     NQ, R, Cc, h, w, p = geom
@@ -86,6 +87,7 @@ def test_tc_gemm_accumulators(geom):
     (3, 2, 192, 20, 16, 4, 3, False),
     (1, 2, 64, 8, 80, 4, 4, True),       # wide rows: three column segments per query block row (32+32+16)
     (1, 1, 64, 9, 36, 3, 2, True),       # 3x3 patches: 30-column segments (scalar staging path), 30 + 6
+    (1, 2, 64, 12, 128, 4, 4, True),     # wide latent: many candidate lists per patch (2 per tile)
 ])
 def test_tc_topk_equals_fp32_mode_and_oracle(geom):
     import clc_b200
