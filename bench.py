@@ -221,9 +221,9 @@ def run_ours(args):
             torch.distributed.barrier()
 
     def make_exchange(path):
-        # the only collectives the path owns -- EB parameter gradients (training) and the
-        # 2-double bpp statistic, one NCCL all-reduce each per step -- are enqueued by LatentPath itself on
-        # its entropy branches (captured into the graph), where they overlap the match chain.
+        # the only collective the path owns -- ONE NCCL all-reduce per step of the EB parameter
+        # gradients (training) + the 2-double bpp statistic -- is enqueued by LatentPath itself on its entropy
+        # branch (captured into the graph), where it overlaps the match chain.
         return lambda: None
 
     exchange = make_exchange(lp)
