@@ -9,8 +9,10 @@ data-parallel); rank 0 prints ONE JSON line.
 
 A "step" = one pass of clc_b200.latent_path.LatentPath over one batch of synthetic inputs:
   value : inputs resident in HBM, CUDA-event timed per step with an L2 flush between steps.
-  e2e   : the same operator sequence through the public autograd API (clc_b200 modules) with the
-          step's inputs copied from pinned host memory and the loss read back, every step.
+  e2e   : the same path from HOST buffers (clc_b200.latent_path.HostPipeline): every step uploads its inputs
+          from pinned host memory and reads its bpp back; double-buffered, so the upload of step i+1 overlaps
+          the kernels of step i.  The single-buffered step_host and the per-operator autograd modules are
+          reported next to it.
   roofline : the dominant C-ABI call of the step, algorithmic bytes / its mean
           CUDA-event duration inside the same run, vs MEASURED_PEAKS.json.
   cpu_baseline : the oracle port (oracle/latent_path_oracle.py) timed on this box's host cores.
@@ -275,7 +277,7 @@ def run_ours(args):
     del lp2
 
     # ---- end to end, host buffers: H2D of the step's inputs + D2H of its result inside the timed
-    # region.  Headline: LatentPath.step_host (pinned flat staging buffer, two graphs, upload of the
+    # region.  First the single-buffered LatentPath.step_host (pinned flat staging buffer, two graphs, upload of the
     # entropy inputs overlapped with the match chain).  Context: the same operator sequence through
     # the per-operator autograd modules (eager, per-slice calls, as a model makes them).
     host_flat, host_views = lp.host_staging()
@@ -296,10 +298,43 @@ def run_ours(args):
         b.record()
         e2e_ev.append((a, b))
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
+    e2e1_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e1_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_single_value = pix_per_step * K / (e2e1_ms.item() * 1e-3) / 1e6
+
+    # Headline: the double-buffered driver (HostPipeline): two LatentPath instances alternate, the upload of
+    # step i+1 overlaps the kernels + read-back of step i.  Every step uploads its inputs from pinned host
+    # memory and reads its bpp back; the L2 flush of each step is enqueued on the compute stream INSIDE the
+    # timed region; one event pair brackets the K steps.
+    from clc_b200.latent_path import HostPipeline
+    lpb = _make_path(cfg, args, dev, fused, rank)
+    lpb.step()
+    host_flat_b, views_b = lpb.host_staging()
+    for n, v in views_b.items():
+        v.copy_(getattr(lpb, n))
+    pipe = HostPipeline([lp, lpb])
+    flats = [host_flat, host_flat_b]
+    for i in range(Wm + (Wm & 1)):
+        pipe.submit(i, flats[i % 2], before_compute=flush.zero_)
+        pipe.result(i)
+    torch.cuda.synchronize()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(K):
+        pipe.submit(i, flats[i % 2], before_compute=flush.zero_)
+        if i:
+            bpp_host = pipe.result(i - 1)
+    bpp_host = pipe.result(K - 1)
+    b.record()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
     e2e_value = pix_per_step * K / (e2e_ms.item() * 1e-3) / 1e6
+    del lpb, pipe
 
     pub = PublicPath(cfg, dev, args.match_mode)
     names = lp.step_inputs
@@ -383,9 +418,12 @@ def run_ours(args):
                    "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else "match | hyper -> slices",
                    "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
-                "api": "clc_b200.LatentPath.step_host: pinned host staging buffer -> 2 uploads -> match graph || "
-                       "entropy graph -> bpp read back",
+                "api": "clc_b200.latent_path.HostPipeline (double-buffered): per step pinned host staging buffer -> 2 "
+                       "uploads -> L2 flush -> match graph || entropy graph -> bpp read back; upload of step i+1 "
+                       "overlaps the kernels of step i",
                 "ms_per_step": e2e_ms.item() / K, "bpp": bpp_host,
+                "single_buffered": {"value": e2e_single_value, "ms_per_step": e2e1_ms.item() / K,
+                                    "api": "clc_b200.LatentPath.step_host (no overlap between steps)"},
                 "autograd_modules": {"value": e2e_modules_value, "ms_per_step": mod_ms.item() / K,
                                      "api": "clc_b200 per-operator autograd modules, eager, per-slice calls"}},
         "gpu_launches": int(gpu_launches),

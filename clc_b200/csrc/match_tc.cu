@@ -1062,7 +1062,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   __shared__ float sel_v[kMaxKC], ex_v[kMaxKC];
   __shared__ int sel_i[kMaxKC];
   __shared__ float top_w[8];
-  __shared__ int top_src[8];
+  __shared__ int top_src[8], top_id[8];
   constexpr int NT = KC * 32;
   const int M = n_tiles * KC;
   const int pp = ph * pw, K = C * pp, c4n = C >> 2, items = pp * c4n;
@@ -1315,14 +1315,31 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       val[oo + rank] = myv;
       idx[oo + rank] = myi;
       top_w[rank] = myv;
+      top_id[rank] = myi;
       const int oy = myi / cw, ox = myi - oy * cw;
       top_src[rank] = oy * W + ox;
     }
-    if (lane >= nvalid && lane < k) {                        // fewer than k valid candidates (L < k)
-      val[oo + lane] = -INFINITY;
-      idx[oo + lane] = -1;
-      top_w[lane] = -INFINITY;
-      top_src[lane] = 0;
+    __syncwarp();
+    if (lane >= nvalid && lane < k) {
+      // fewer than k scored candidates: the patch or the windows have zero variance, their correlation is
+      // NaN and never enters a candidate list.  The reference's torch.topk ranks NaN first; mirror the
+      // all-NaN case (value NaN, lowest window indices not already selected) and, above all, keep every
+      // index a valid window so that the gather and the backward stay in bounds.
+      int c = 0, seen = 0;
+      const int want = lane - nvalid;
+      for (;; ++c) {
+        bool used = false;
+        for (int j = 0; j < nvalid && j < k; ++j) used |= (top_id[j] == c);
+        if (used) continue;
+        if (seen == want || c >= L - 1) break;
+        ++seen;
+      }
+      const float nanv = __int_as_float(0x7fc00000);
+      val[oo + lane] = nanv;
+      idx[oo + lane] = c;
+      top_w[lane] = nanv;
+      const int oy = c / cw, ox = c - oy * cw;
+      top_src[lane] = oy * W + ox;
     }
     __syncwarp();
     const float vk = top_w[k - 1];
@@ -1430,7 +1447,7 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   if (NP < 1 || q_repeat < 1 || NP % q_repeat) return pl;
   if (C < kChunk || C % kChunk) return pl;
   if (ph < 1 || pw < 1 || ph * pw > 64 || H < ph || W < pw || H % ph || W % pw) return pl;
-  if (k < 1 || k > 8) return pl;
+  if (k < 1 || k > 8 || k > (H - ph + 1) * (W - pw + 1)) return pl;   // torch.topk needs k <= L
   pl.KC = (k <= 4) ? 8 : 16;
   pl.S = ph * pw;
   pl.HW = H * W;

@@ -447,3 +447,64 @@ class LatentPath:
                 out[name.replace("clc_", "")] = v
         out["match_flops"] = self.algorithmic_work()["clc_match_topk_tc(gemm)"][1]
         return out
+
+
+class HostPipeline:
+    """Double-buffered end-to-end driver over HOST inputs: two LatentPath instances (own device buffers
+    and graphs) alternate, so the upload of step i+1 runs on the copy stream while the kernels and the
+    result read-back of step i run on the compute stream.  Every step still uploads its own inputs from
+    pinned host memory and reads its own result (bpp) back; at cfg2 the step is PCIe-bound, so this hides
+    the kernels and the read-back latency behind the next upload.
+
+        pipe = HostPipeline([LatentPath(...), LatentPath(...)])
+        for i, flat in enumerate(batches):            # flat: pinned buffer laid out by host_staging()
+            pipe.submit(i, flat)
+            if i: bpp = pipe.result(i - 1)            # synchronises on step i-1 only
+        bpp = pipe.result(len(batches) - 1)
+    """
+
+    def __init__(self, paths):
+        assert len(paths) == 2 and paths[0]._in.numel() == paths[1]._in.numel()
+        self.lp = list(paths)
+        for lp in self.lp:
+            if lp._g_match is None:
+                lp.capture_split()
+        self.copy_stream = torch.cuda.Stream(device=self.lp[0].device)
+        self.done = [None, None]
+
+    def submit(self, i, host_flat, before_compute=None):
+        """Enqueue step i (no host synchronisation).  `before_compute` (optional callable) is enqueued on
+        the compute stream ahead of the step's kernels (bench.py: the L2 flush)."""
+        lp = self.lp[i % 2]
+        cur = torch.cuda.current_stream(lp.device)
+        cp, se = self.copy_stream, lp._streams[1]
+        n1 = lp._n_match_in
+        if self.done[i % 2] is not None:
+            cp.wait_event(self.done[i % 2])          # this slot's previous step has consumed its inputs
+        else:
+            cp.wait_stream(cur)
+        with torch.cuda.stream(cp):
+            lp._in[:n1].copy_(host_flat[:n1], non_blocking=True)
+            ev0 = cp.record_event()
+            lp._in[n1:].copy_(host_flat[n1:], non_blocking=True)
+            ev1 = cp.record_event()
+        if before_compute is not None:
+            before_compute()
+        prev = self.done[(i - 1) % 2]
+        cur.wait_event(ev0)
+        lp._g_match.replay()                         # match chain on the compute stream ...
+        if prev is not None:
+            se.wait_event(prev)                      # (collectives of consecutive steps never overlap)
+        se.wait_event(ev1)
+        with torch.cuda.stream(se):
+            lp._g_entropy.replay()                   # ... entropy chains next to it, once their inputs landed
+        cur.wait_stream(se)
+        lp._host_out.copy_(lp.log2, non_blocking=True)
+        self.done[i % 2] = cur.record_event()
+
+    def result(self, i):
+        """bpp of step i as a Python float (waits for that step only)."""
+        lp = self.lp[i % 2]
+        self.done[i % 2].synchronize()
+        return -(lp._host_out[0].item() + lp._host_out[1].item()) / (lp.num_pixels * lp._world)
+

@@ -112,3 +112,32 @@ def test_forked_step_eager_equals_serial():
         assert torch.equal(getattr(lp, n), t), n
     assert abs(lp.bpp().item() - bpp) < 1e-9
 
+
+
+def test_host_pipeline_matches_step_host():
+    """HostPipeline (two LatentPath instances, upload of step i+1 under the kernels of step i) returns,
+    step by step, the bpp that the un-pipelined step_host returns for the same host inputs."""
+    from clc_b200.latent_path import HostPipeline, LatentPath
+    mk = lambda: LatentPath(2, 256, 256, n_refs=3, train=True, match_mode="tc", fused_slices=True, device="cuda:0")
+    a, b, ref = mk(), mk(), mk()
+    flats, want = [], []
+    for seed in (21, 22, 23, 24, 25):
+        ref.randomize(seed=seed)
+        flat, views = ref.host_staging()
+        for n, v in views.items():
+            v.copy_(getattr(ref, n))
+        flats.append(flat)
+        want.append(ref.step_host(flat))
+    pipe = HostPipeline([a, b])
+    got = []
+    for i, flat in enumerate(flats):
+        pipe.submit(i, flat)
+        if i:
+            got.append(pipe.result(i - 1))
+    got.append(pipe.result(len(flats) - 1))
+    assert all(abs(g - w) < 1e-9 for g, w in zip(got, want)), (got, want)   # double atomics: order-dependent last bits
+    # outputs of the last two steps are still resident in their slots
+    ref.randomize(seed=25)
+    ref.step()
+    torch.cuda.synchronize()
+    assert torch.equal(a.idx, ref.idx) and torch.equal(a.y_hat, ref.y_hat) and torch.equal(a.lik_y, ref.lik_y)

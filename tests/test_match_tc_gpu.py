@@ -243,3 +243,31 @@ def test_match_bwd_variants_agree(geom):
     # overwrite mode ignores what g_r held before
     ow = run(1, pre=pre)
     assert (ow[0] - base[0]).abs().max().item() <= 2e-5 * max(scale, 1.0)
+
+
+def test_degenerate_inputs_keep_indices_in_bounds():
+    """Zero-variance patches / windows have NaN correlation (0/0) in the reference; torch.topk then
+    returns NaN values at valid positions.  The tc path must do the same: NaN values, indices that are
+    valid windows (the gather and the backward index memory with them), no fault -- e.g. the warm-up
+    replay of a freshly allocated, zero-filled LatentPath."""
+    from clc_b200.latent_path import LatentPath
+    d = _dev()
+    lp = LatentPath(2, 256, 256, n_refs=2, train=True, match_mode="tc", device="cuda:0")    # inputs all zero
+    lp.step()
+    torch.cuda.synchronize()
+    L = (lp.h - 3) * (lp.w - 3)
+    assert int(lp.idx.min()) >= 0 and int(lp.idx.max()) < L
+    assert torch.isnan(lp.val).all()
+    # one constant query patch among normal ones: only that patch degenerates
+    NQ, R, Cc, h, w, p, k = 1, 2, 64, 16, 16, 4, 4
+    y, refs = _inputs(NQ, R, Cc, h, w, seed=77)
+    y[:, :, 4:8, 8:12] = 0.25                               # patch (1, 2) -> index 1 * 4 + 2 = 6
+    r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
+    val, idx, aligned, _, _ = _tc_call(y.to(d), r, R, p, k, True, True)
+    torch.cuda.synchronize()
+    Lw = (h - p + 1) * (w - p + 1)
+    assert int(idx.min()) >= 0 and int(idx.max()) < Lw
+    # the constant patch has (numerically) zero variance: its values are NaN / inf like the reference's 0/0 and
+    # x/0, every other patch is untouched
+    assert not torch.isfinite(val[:, 6]).any()
+    assert torch.isfinite(val[:, :6]).all() and torch.isfinite(val[:, 7:]).all()
