@@ -145,3 +145,37 @@ def test_reference_itself_reproduces_coder_golden():
         out = m.compress(x, refs)
     assert out["strings"][0][0] == g["y_string"].numpy().tobytes()
     assert out["strings"][1][0] == g["z_string"].numpy().tobytes()
+
+
+def test_full_size_round_trip_clic_stream():
+    """BASELINE cfg4 size: the y stream of one 2048x1280 image (3 276 800 symbols over the 64 scale-table
+    CDFs, heavy tails so that bypass coding occurs) -- encode -> decode is the identity, and a single
+    flipped payload word is detected as a different symbol sequence."""
+    import clc_b200
+    from clc_b200 import ans as A
+    from clc_b200.models import get_scale_table
+    gc = clc_b200.GaussianConditional(None)
+    gc.update_scale_table(get_scale_table())
+    tab = gc.coder_tables()
+    rng = np.random.default_rng(7)
+    n = 3_276_800
+    idx = rng.integers(0, 64, n).astype(np.int32)
+    scale = get_scale_table().numpy()[idx]
+    sym = np.rint(rng.standard_t(3, n) * scale).clip(-2 ** 20, 2 ** 20).astype(np.int32)
+    s = A.RansEncoder().encode_with_indexes(sym, idx, tab, None, None)
+    out = A.RansDecoder().decode_with_indexes(s, idx, tab, None, None, as_tensor=True).numpy()
+    assert (out == sym).all()
+    assert 0.5 * n < len(s) < 4 * n                       # ~1 byte per symbol for this mix
+    # decoding is resumable at any split point (the per-slice decode_stream of decompress())
+    d = A.RansDecoder()
+    d.set_stream(s)
+    parts = [d.decode_stream(idx[a:b], tab, None, None, as_tensor=True).numpy()
+             for a, b in ((0, 1), (1, 655_360), (655_360, n))]
+    assert (np.concatenate(parts) == sym).all()
+    bad = bytearray(s)
+    bad[len(bad) // 2] ^= 0x40
+    try:
+        out2 = A.RansDecoder().decode_with_indexes(bytes(bad), idx, tab, None, None, as_tensor=True).numpy()
+        assert (out2 != sym).any()
+    except RuntimeError:
+        pass                                              # a corrupted stream may also run out of words
