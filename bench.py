@@ -415,7 +415,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
                    "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
-                   "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else "match | hyper -> slices",
+                   "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else ("match | hyper -> slices" if world == 1 else "match | hyper | slices -> all-reduce"),
                    "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "api": "clc_b200.latent_path.HostPipeline (double-buffered): per step pinned host staging buffer -> 2 "

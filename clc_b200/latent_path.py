@@ -287,14 +287,24 @@ class LatentPath:
             self._exchange_stats()
             return n
         cur = torch.cuda.current_stream(self.device)
-        s1, _ = self._side_streams()
+        s1, s2 = self._side_streams()
         s1.wait_stream(cur)
-        with torch.cuda.stream(s1):
-            # both entropy chains on ONE side branch (measured on B200: two branches next to the match
-            # chain are 5% faster than three -- scripts/chain_timing.py)
-            n = self.hyper_chain()
-            n += self.slice_chain()
-            self._exchange_stats()
+        if self.data_parallel:
+            # multi-GPU: the step's all-reduce sits at the end of the entropy work and its latency (plus rank
+            # skew) must stay under the match chain, so the two entropy chains run on TWO branches
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s2):
+                n = self.hyper_chain()
+            with torch.cuda.stream(s1):
+                n += self.slice_chain()
+                s1.wait_stream(s2)
+                self._exchange_stats()
+        else:
+            with torch.cuda.stream(s1):
+                # single GPU: both entropy chains on ONE side branch (measured on B200: two branches next to
+                # the match chain are 5% faster than three -- scripts/chain_timing.py)
+                n = self.hyper_chain()
+                n += self.slice_chain()
         n += self.match_chain()
         cur.wait_stream(s1)
         return n
