@@ -1663,6 +1663,9 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   prm.timing = timing;
   prm.dbg = 0;
   if (timing) { const char* e = getenv("CLC_TC_DBG"); if (e) prm.dbg = atoi(e); }
+  // bring-up (scripts/kernel_bench.py): when the stage mask selects the GEMM alone, its upper byte carries
+  // the GEMM experiment bits (1 = shifts rounded to 8 rows, 2 = no MMAs, 4 = no A loads); 0 in production
+  if ((g_stage_mask.load() & 0xff) == 2) prm.dbg = (g_stage_mask.load() >> 8) & 0xff;
   int rc;
   if (!stage_on(1)) rc = CLC_OK;
   else if (pl.stacked) {

@@ -189,6 +189,27 @@ extern "C" int clc_rans_decode(const uint8_t* stream, size_t stream_bytes, uint6
   }
   const uint64_t mask = (1ull << kPrecision) - 1;
   bool truncated = false;
+  // Long streams: per-table bucket index over the top 8 bits of the cumulative frequency, lut[b] = the
+  // symbol whose interval contains b * 256, so the search for `cum` only scans lut[b] .. lut[b + 1]
+  // (a handful of entries) instead of bisecting the whole row.  Built per call (64 x ~3k entries).
+  constexpr int kBuckets = 1 << 8, kShift = kPrecision - 8;
+  std::vector<int32_t> lut;
+  const bool use_lut = n >= 4096;
+  if (use_lut) {
+    lut.resize((size_t)n_cdfs * (kBuckets + 1));
+    for (int c = 0; c < n_cdfs; ++c) {
+      const int32_t* cdf = cdfs + (int64_t)c * cdf_stride;
+      const int32_t size = cdf_sizes[c];
+      int32_t* l = lut.data() + (size_t)c * (kBuckets + 1);
+      int32_t sidx = 0;
+      for (int b = 0; b < kBuckets; ++b) {
+        const int32_t v = b << kShift;
+        while (sidx + 1 < size && cdf[sidx + 1] <= v) ++sidx;
+        l[b] = sidx;
+      }
+      l[kBuckets] = size - 2 > 0 ? size - 2 : 0;
+    }
+  }
   auto renorm = [&]() {
     if (x < kRansL) {
       if (pos >= nwords) { truncated = true; return; }
@@ -207,9 +228,17 @@ extern "C" int clc_rans_decode(const uint8_t* stream, size_t stream_bytes, uint6
     const int32_t* cdf = cdfs + (int64_t)ci * cdf_stride;
     const int32_t size = cdf_sizes[ci], max_value = size - 2;
     const uint32_t cum = (uint32_t)(x & mask);
-    // first entry > cum (the table is increasing): binary search instead of the upstream linear scan
-    const int32_t* it = std::upper_bound(cdf, cdf + size, (int32_t)cum);
-    const int32_t s = (int32_t)(it - cdf) - 1;
+    // first entry > cum (the table is increasing): bucketed / binary search instead of the upstream linear scan
+    int32_t s;
+    if (use_lut) {
+      const int32_t* l = lut.data() + (size_t)ci * (kBuckets + 1);
+      s = l[cum >> kShift];
+      const int32_t hi = l[(cum >> kShift) + 1];
+      while (s < hi && cdf[s + 1] <= (int32_t)cum) ++s;
+    } else {
+      const int32_t* it = std::upper_bound(cdf, cdf + size, (int32_t)cum);
+      s = (int32_t)(it - cdf) - 1;
+    }
     if (s < 0 || s > max_value) return CLC_ERR_INVALID_ARGUMENT;
     const uint32_t start = (uint32_t)cdf[s], freq = (uint32_t)(cdf[s + 1] - cdf[s]);
     x = (uint64_t)freq * (x >> kPrecision) + (x & mask) - start;
