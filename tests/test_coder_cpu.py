@@ -179,3 +179,46 @@ def test_full_size_round_trip_clic_stream():
         assert (out2 != sym).any()
     except RuntimeError:
         pass                                              # a corrupted stream may also run out of words
+
+
+def test_coder_property_random_tables_vs_oracle():
+    """Property test (hypothesis): for random quantised tables, offsets and symbol sequences -- including
+    values far outside the table support on both sides -- the C coder's stream equals the oracle's byte for
+    byte and decodes back to the input, whole or in two resumed pieces."""
+    from hypothesis import given, settings, strategies as st
+    O = _oracle_ans()
+    from clc_b200 import ans as A
+
+    @st.composite
+    def case(draw):
+        n_cdfs = draw(st.integers(1, 5))
+        cdfs, sizes, offsets = [], [], []
+        for _ in range(n_cdfs):
+            m = draw(st.integers(1, 24))
+            w = draw(st.lists(st.floats(1e-6, 1.0), min_size=m, max_size=m))
+            tot = sum(w)
+            c = O.pmf_to_quantized_cdf([x / tot for x in w] + [1e-9], 16)
+            cdfs.append(c + [0] * (26 - len(c)))
+            sizes.append(len(c))
+            offsets.append(draw(st.integers(-40, 10)))
+        n = draw(st.integers(0, 200))
+        idx = draw(st.lists(st.integers(0, n_cdfs - 1), min_size=n, max_size=n))
+        sym = [draw(st.one_of(st.integers(offsets[i] - 3, offsets[i] + sizes[i] + 1),
+                              st.integers(-2 ** 31 + 1, 2 ** 31 - 1))) for i in idx]
+        cut = draw(st.integers(0, n))
+        return cdfs, sizes, offsets, idx, sym, cut
+
+    @settings(max_examples=150, deadline=None)
+    @given(case())
+    def run(c):
+        cdfs, sizes, offsets, idx, sym, cut = c
+        want = O.RansEncoder().encode_with_indexes(sym, idx, cdfs, sizes, offsets)
+        got = A.RansEncoder().encode_with_indexes(sym, idx, cdfs, sizes, offsets)
+        assert got == want
+        assert A.RansDecoder().decode_with_indexes(got, idx, cdfs, sizes, offsets) == sym
+        d = A.RansDecoder()
+        d.set_stream(got)
+        assert d.decode_stream(idx[:cut], cdfs, sizes, offsets) + d.decode_stream(idx[cut:], cdfs, sizes, offsets) == sym
+        assert O.RansDecoder().decode_with_indexes(got, idx, cdfs, sizes, offsets) == sym
+
+    run()
