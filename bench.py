@@ -37,8 +37,33 @@ WORKLOADS = {
     "cfg2": dict(B=8, H=256, W=256, R=3, train=True, desc="configs[1]: training step, batch 8 of 256x256, n_refs=3"),
     "cfg3": dict(B=3, H=512, W=768, R=3, train=False, desc="configs[2]: Kodak-shaped 768x512 inference, 3 images per GPU"),
     "cfg4": dict(B=1, H=1280, W=2048, R=3, train=False, desc="configs[3]: CLIC-shaped 2048x1280 inference, 3-ref matching"),
-    "cfg5": dict(B=8, H=256, W=256, R=3, train=True, desc="configs[4]: data-parallel training, 8 images per GPU"),
+    # configs[4]: n_refs sweep 1/3/5, data-parallel training, GLOBAL batch 64 -> 64 / n_gpus images per GPU
+    # (strong scaling in the batch; --n-refs picks the sweep point)
+    "cfg5": dict(B=64, H=256, W=256, R=3, train=True, global_batch=64,
+                 desc="configs[4]: data-parallel training, global batch 64 of 256x256, n_refs sweep 1/3/5"),
 }
+
+
+def workload(args, world):
+    """The per-GPU problem of this run: BASELINE.json config + the --n-refs / world-size dependent parts."""
+    cfg = dict(WORKLOADS[args.workload])
+    if args.n_refs is not None:
+        cfg["R"] = args.n_refs
+    if "global_batch" in cfg:
+        cfg["B"] = max(1, cfg["global_batch"] // world)
+    return cfg
+
+
+def make_config(args, cfg, world):
+    """`config` of the JSON line -- the SAME dict for both arms (`--impl ours` / `--impl reference`)."""
+    fused = not args.per_slice
+    use_graph = not args.no_graph
+    return {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
+            "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
+            "slice_launches": "fused" if fused else "per-slice", "cuda_graph": use_graph,
+            "graph_branches": "serial" if args.no_fork else ("match | hyper -> slices" if world == 1
+                                                              else "match | hyper | slices -> all-reduce"),
+            "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4}
 
 
 def peaks():
@@ -202,7 +227,7 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    cfg = WORKLOADS[args.workload]
+    cfg = workload(args, world)
     K, Wm = args.steps, max(args.warmup, 3)
     fused = not args.per_slice
     lp = _make_path(cfg, args, dev, fused, rank)
@@ -248,6 +273,7 @@ def run_ours(args):
     pix_per_step = world * cfg["B"] * cfg["H"] * cfg["W"]
     value = pix_per_step * K / (total_ms * 1e-3) / 1e6
     bpp_dev = lp.bpp().item()
+    n_uncert = lp.n_uncertified() if args.match_mode == "tc" else None
 
     # ---- L2-warm variant (no flush), for context -------------------------------------------
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,6 +405,7 @@ def run_ours(args):
             t[1] += 1
     pk = peaks()
     work = lp.algorithmic_work()
+    gathered = lp.gathered_bytes()
     breakdown = {n: {"us_per_step": 1e3 * t[0] / K, "launches_per_step": t[1] / K, "us_per_launch": 1e3 * t[0] / t[1]}
                  for n, t in per.items()}
     traffic_db = {}
@@ -398,9 +425,13 @@ def run_ours(args):
         ach = (amount / (us * 1e-6) / 1e9) if amount else None
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": (ach / pk["hbm"]) if ach else None, "traffic": traffic, "us_per_launch": us,
-                "peak_source": pk["src"], "algorithmic_bytes_per_launch": amount}
+                "peak_source": pk["src"], "algorithmic_bytes_per_launch": amount,
+                "l2_bytes": gathered.get(name)}
 
-    dom = max(per, key=lambda n: per[n][0])
+    # dominant kernel = largest share of the step; kernels within 2 % of the largest are tied and the tie goes
+    # to name order, so the headline does not flip between runs
+    top = max(t[0] for t in per.values())
+    dom = sorted(n for n in per if per[n][0] >= 0.98 * top)[0]
     rooflines = {n: roof(n) for n in per}
 
     if rank != 0:
@@ -412,11 +443,9 @@ def run_ours(args):
     line = {
         "metric": "Mpix/s of CLC latent path (match+CLM+entropy)", "value": value, "unit": "Mpix/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"], "image": [cfg["H"], cfg["W"]],
-                   "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd", "match_mode": args.match_mode,
-                   "slice_launches": this_mode, "cuda_graph": use_graph, "graph_branches": "serial" if args.no_fork else ("match | hyper -> slices" if world == 1 else "match | hyper | slices -> all-reduce"),
-                   "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4},
+        "scaling": "strong" if "global_batch" in cfg else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": make_config(args, cfg, world),
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "api": "clc_b200.latent_path.HostPipeline (double-buffered): per step pinned host staging buffer -> 2 "
                        "uploads -> L2 flush -> match graph || entropy graph -> bpp read back; upload of step i+1 "
@@ -437,6 +466,7 @@ def run_ours(args):
         "breakdown": breakdown,
         "rooflines": rooflines,
         "bpp": bpp_dev,
+        "n_uncertified": n_uncert,
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line))
@@ -444,16 +474,17 @@ def run_ours(args):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    cfg = WORKLOADS[args.workload]
-    r = cpu_port_time(cfg, budget_s=60.0, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    cfg = workload(args, world)
+    r = cpu_port_time(cfg, budget_s=60.0, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "Mpix/s of CLC latent path (match+CLM+entropy)", "value": r["value"],
-            "unit": "Mpix/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)),
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "unit": "Mpix/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if "global_batch" in cfg else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {cfg['desc']}", "per_gpu_batch": cfg["B"],
-                       "image": [cfg["H"], cfg["W"]], "n_refs": cfg["R"], "pass": "fwd+bwd" if cfg["train"] else "fwd"},
+            "config": make_config(args, cfg, world),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -467,6 +498,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-refs", type=int, default=None, help="references per image (configs[4] sweeps 1/3/5)")
     ap.add_argument("--match-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--per-slice", action="store_true",
                     help="launch the GaussianConditional / LRP kernels once per channel slice (the model's call "

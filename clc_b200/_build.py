@@ -8,7 +8,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libclc_b200.so")
+# bring-up build: the same sources with -DCLC_DEBUG_ABI (clc_debug_* entry points, stage masks, in-kernel
+# stamps); loaded only by tests/ and scripts/ through _lib.debug_lib(), never by the product path
+LIB_DBG = os.path.join(HERE, "libclc_b200_dbg.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
+OBJ_DIR_DBG = os.path.join(HERE, "csrc", "_obj_dbg")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -33,19 +37,25 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ and link libclc_b200.so.  Returns the library path."""
+def build(force=False, verbose=False, debug_too=True):
+    """Compile every .cu under csrc/ and link libclc_b200.so (and the bring-up variant).  Returns the
+    production library path."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    os.makedirs(OBJ_DIR, exist_ok=True)
     hdrs = _headers()
-    jobs = []
-    objs = []
-    for src in _sources():
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        objs.append(obj)
-        if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-            jobs.append(cmd)
+    variants = [(LIB, OBJ_DIR, [])]
+    if debug_too:
+        variants.append((LIB_DBG, OBJ_DIR_DBG, ["-DCLC_DEBUG_ABI"]))
+    jobs, links = [], []
+    for lib, obj_dir, defs in variants:
+        os.makedirs(obj_dir, exist_ok=True)
+        objs, dirty = [], False
+        for src in _sources():
+            obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+            objs.append(obj)
+            if force or _stale(obj, [src] + hdrs):
+                jobs.append([nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+                dirty = True
+        links.append((lib, objs, dirty))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,8 +68,9 @@ def build(force=False, verbose=False):
     if verbose:
         for l in logs:
             sys.stderr.write(l)
-    if jobs or force or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    for lib, objs, dirty in links:
+        if dirty or force or _stale(lib, objs):
+            run([nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 
 

@@ -32,7 +32,6 @@ PROTOTYPES = {
     "clc_strerror": (C.c_char_p, [C.c_int]),
     "clc_last_cuda_error": (C.c_char_p, []),
     "clc_kernel_launch_count": (C.c_uint64, []),
-    "clc_debug_set_stage_mask": (None, [C.c_int]),
     "clc_trace_start": (C.c_int, [_p]),
     "clc_trace_mark": (C.c_int, []),
     "clc_trace_stop": (C.c_int, []),
@@ -70,10 +69,6 @@ PROTOTYPES = {
                                 _i32, _i32, _i32, _i32, _i32, _p, _sz, _p]),
     "clc_match_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "clc_match_bwd_zero_workspace": (C.c_int, [_p, _sz, _i64, _i32, _i32, _i32, _p]),
-    "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
-                                        _p, _sz, _p]),
-    "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
-                                            _p, _sz, _p]),
     "clc_pmf_to_quantized_cdf": (C.c_int, [_p, _i32, _i32, _p]),
     "clc_rans_encode": (C.c_int, [_p, _p, _i64, _p, _i32, _i32, _p, _p, _p, _sz, C.POINTER(_sz)]),
     "clc_rans_encode_capacity": (_sz, [_i64]),
@@ -82,7 +77,18 @@ PROTOTYPES = {
     "clc_clm_fuse_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
 }
 
+# Bring-up entry points: only in libclc_b200_dbg.so (the -DCLC_DEBUG_ABI build), see debug_lib().
+DEBUG_PROTOTYPES = {
+    "clc_debug_set_stage_mask": (None, [C.c_int]),
+    "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                        _p, _sz, _p]),
+    "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                            _p, _sz, _p]),
+}
+DEBUG_LIB_PATH = os.path.join(_HERE, "libclc_b200_dbg.so")
+
 _lib = None
+_dbg_lib = None
 _launches = 0  # number of C-ABI kernel-enqueueing calls made by this process (bench.py reads it)
 
 
@@ -102,6 +108,23 @@ def lib():
             fn.argtypes = args
         _lib = h
     return _lib
+
+
+def debug_lib():
+    """Bring-up build of the same sources (clc_debug_* hooks, stage masks, in-kernel stamps).  For tests/ and
+    scripts/ only -- nothing under clc_b200/ calls this."""
+    global _dbg_lib
+    if _dbg_lib is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise RuntimeError(f"clc_b200: {DEBUG_LIB_PATH} is missing -- run __graft_entry__.build()")
+        h = C.CDLL(DEBUG_LIB_PATH)
+        for table in (PROTOTYPES, DEBUG_PROTOTYPES):
+            for name, (res, args) in table.items():
+                fn = getattr(h, name)
+                fn.restype = res
+                fn.argtypes = args
+        _dbg_lib = h
+    return _dbg_lib
 
 
 TRACE = None  # bench.py sets this to a list to collect (name, start_event, end_event) per call

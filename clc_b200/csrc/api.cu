@@ -9,8 +9,10 @@
 namespace clc {
 thread_local char g_last_cuda_error[256] = {0};
 std::atomic<unsigned long long> g_kernel_launches{0};
+#ifdef CLC_DEBUG_ABI
 std::atomic<int> g_stage_mask{0xff};
 std::atomic<int> g_pdl{getenv("CLC_NO_PDL") ? 0 : 1};
+#endif
 
 // ---- per-kernel tracing: CUDA events on the traced stream, one after every launch ----
 std::atomic<bool> g_trace_on{false};
@@ -47,7 +49,9 @@ extern "C" const char* clc_strerror(int status) {
   }
 }
 
+#ifdef CLC_DEBUG_ABI
 extern "C" CLC_API void clc_debug_set_stage_mask(int mask) { clc::g_stage_mask.store(mask); }
+#endif
 
 extern "C" const char* clc_last_cuda_error(void) { return clc::g_last_cuda_error; }
 

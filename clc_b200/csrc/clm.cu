@@ -280,7 +280,7 @@ extern "C" int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl.load() ? 2 : 1;
+  cfg.numAttrs = pdl_on() ? 2 : 1;
   if (vec4 && R <= 4)
     CLC_CUDA(cudaLaunchKernelEx(&cfg, clm_fuse_bwd_kernel<4, 4>, ref_t, ref_sr, ref_sb, att, att_sr, att_sb, g_out,
                                 g_ref_t, g_att, (int)R, (int)C, S));

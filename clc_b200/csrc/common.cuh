@@ -25,9 +25,20 @@ inline int cuda_fail(cudaError_t e, const char* where) {
 // Process-wide count of kernels enqueued by this library (statistics only; bench.py reports it).
 extern std::atomic<unsigned long long> g_kernel_launches;
 
-// Bring-up: bit mask of the kernels a multi-kernel entry point enqueues (clc_debug_set_stage_mask).
+// Bring-up hooks exist only in the debug build of the library (libclc_b200_dbg.so, -DCLC_DEBUG_ABI): a bit
+// mask of the kernels a multi-kernel entry point enqueues (clc_debug_set_stage_mask), kernel-specific
+// experiment bits and a PDL switch.  The production library has no mutable global state on its call paths.
+#ifdef CLC_DEBUG_ABI
 extern std::atomic<int> g_stage_mask;
 inline bool stage_on(int bit) { return (g_stage_mask.load(std::memory_order_relaxed) >> bit) & 1; }
+inline int dbg_bits() { return (g_stage_mask.load(std::memory_order_relaxed) >> 8) & 0xff; }
+extern std::atomic<int> g_pdl;   // 1 = on (default); CLC_NO_PDL=1 in the environment turns it off
+inline bool pdl_on() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+#else
+inline constexpr bool stage_on(int) { return true; }
+inline constexpr int dbg_bits() { return 0; }
+inline constexpr bool pdl_on() { return true; }
+#endif
 
 // Per-kernel tracing (clc_trace_*): when on, one cudaEvent is recorded after every kernel launch.
 extern std::atomic<bool> g_trace_on;
@@ -53,8 +64,6 @@ void trace_record(const char* name);
 // global memory (returns once the preceding grid has completed and its writes are visible); the
 // implicit trigger at CTA exit is used (pdl_trigger() compiles to nothing unless CLC_PDL_EARLY=1).
 // Both are no-ops without the attribute.
-extern std::atomic<int> g_pdl;   // 1 = on (default); CLC_NO_PDL=1 in the environment turns it off
-
 #ifndef CLC_PDL_EARLY
 #define CLC_PDL_EARLY 0   /* measured on B200: the explicit early trigger costs ~6% on the cfg2 chain */
 #endif
@@ -77,7 +86,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  cfg.numAttrs = pdl_on() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 

@@ -1211,7 +1211,7 @@ static int launch_bwd_own(unsigned blocks, cudaStream_t st, PatchAddr qa, const 
                           const int32_t* idx, const float* weights, float temperature, const float* g_out,
                           float* g_rT, float* g_q, float* g_val, int P, int C, int ph, int fh, int fw, int k) {
   CLC_CUDA(launch_pdl(match_bwd_own_kernel<NT>, dim3(blocks), dim3(NT), 0, st, qa, rT, mask, idx, weights, temperature,
-                      g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, (g_stage_mask.load() >> 8) & 0xff));
+                      g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, dbg_bits()));
   CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   return CLC_OK;
 }
@@ -1224,7 +1224,7 @@ static int launch_bwd_reg2(unsigned blocks, size_t smem, cudaStream_t st, PatchA
   auto kern = match_bwd_cl_reg_kernel<ITEMS, REREAD>;
   if (smem > 48 * 1024) CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   kern<<<blocks, 256, smem, st>>>(qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q, g_val, P, C, ph, pw,
-                                  fh, fw, k, (g_stage_mask.load() >> 8) & 0xff);
+                                  fh, fw, k, dbg_bits());
   CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   return CLC_OK;
 }
@@ -1237,7 +1237,7 @@ static int launch_bwd_reg(unsigned blocks, size_t smem, cudaStream_t st, PatchAd
   // CTAs resident per SM: 2 with the windows kept in registers, 3 when they are re-read; re-read
   // when that saves a wave (and shared memory allows 3 CTAs)
   const unsigned w2 = (blocks + 2 * kNumSMs - 1) / (2 * kNumSMs), w3 = (blocks + 3 * kNumSMs - 1) / (3 * kNumSMs);
-  const bool reread = (w3 < w2 && 3 * (smem + 1024) <= 220 * 1024) || ((g_stage_mask.load() >> 8) & 4);
+  const bool reread = (w3 < w2 && 3 * (smem + 1024) <= 220 * 1024) || (dbg_bits() & 4);
   if (reread)
     return launch_bwd_reg2<ITEMS, true>(blocks, smem, st, qa, rT, mask, idx, weights, temperature, g_out, g_rT, g_q,
                                         g_val, P, C, ph, pw, fh, fw, k);
@@ -1450,7 +1450,7 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   const unsigned blocks = (unsigned)(NP * P);
   int rc = CLC_OK;
   const int nt_own = ph * (C / 4);
-  const bool own_ok = k <= 4 && !((g_stage_mask.load() >> 8) & 8) &&
+  const bool own_ok = k <= 4 && !(dbg_bits() & 8) &&
                       (nt_own == 128 || nt_own == 192 || nt_own == 256 || nt_own == 320 || nt_own == 384);
   if (!stage_on(0)) {
   } else if (own_ok) {

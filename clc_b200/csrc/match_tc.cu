@@ -25,6 +25,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <stdlib.h>
 
@@ -38,7 +39,8 @@ constexpr int kTileM = 128;       // patches per tile (UMMA M)
 constexpr int kBoxRowsB = 32;     // rows per TMA box of the reference operand (4 KB)
 constexpr int kABytes = kTileM * kChunk * 2;   // 16 KB per A stage
 constexpr int kBoxBytesB = kBoxRowsB * kChunk * 2;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;       // epilogue warps of the general kernel: 2 column halves x 4 TMEM lane quarters
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // + TMA producer warp + MMA warp
 constexpr int kMaxKC = 16;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -136,17 +138,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 16 consecutive fp32 columns of this thread's TMEM lane (into v[0..15]).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 4 epilogue warps
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 8 epilogue warps of the general kernel
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 __device__ __forceinline__ void epi_bar_sync8() {  // named barrier 1: the 8 epilogue warps of the stacked kernel
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
-
-#define CLC_STAMP(i) do { if (p.timing && lane == 0) p.timing[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B:
 //   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for one swizzle row of K) |
@@ -172,20 +183,43 @@ struct Params {
   int TN, NACC, n_tiles, m_tiles, total_tiles, chunks;
   int nboxB, a_stages, b_bufs, acc_stages, tmem_cols, a_rows, SB;
   int KC, gaussian;
+  int stat_chunks;        // per-patch statistic partials written by the pre-pass (one per 64 channels)
+  int units_per_group;    // general kernel: accumulator units (TN columns) per (problem, patch tile)
+  int total_units;        // general kernel: NP * m_tiles * units_per_group
+  int halo;               // (ph-1)*W + pw-1 extra reference rows a tile needs
+  int64_t map_pitch;      // general kernel: halves per row of the screened score map (= units_per_group * TN)
+  __half* smap;           // general kernel: screened scores [NP, P, map_pitch] fp16 (linear window origins)
   int st_rows, st_shifts, st_mt, st_stages, st_groups;  // small-latent ("stacked") kernel only
-  const float *s1, *s2, *xs, *sxx;  // xs/sxx: per-patch partial sums [NQ*P][chunks], combined in fixed order
+  const float *s1, *s2, *xs, *sxx;  // xs/sxx: per-patch partial sums [NQ*P][stat_chunks], combined in fixed order
   float* cand_val;
   int32_t* cand_idx;
-  float* dump;  // debug: raw xy accumulators [NP, P, HW] (NULL in production)
-  int dbg;            // debug experiment bits (0 in production)
-  long long* timing;  // debug: per-CTA clock64 stamps [grid][16] (NULL in production)
+#ifdef CLC_DEBUG_ABI
+  float* dump;  // debug: raw xy accumulators [NP, P, HW]
+  int dbg;            // debug experiment bits
+  long long* timing;  // debug: per-CTA clock64 stamps [grid][16]
+#endif
 };
+
+#ifdef CLC_DEBUG_ABI
+#define CLC_STAMP(i) do { if (p.timing && lane == 0) p.timing[(size_t)blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#define CLC_DBG(bit) (p.dbg & (bit))
+#else
+#define CLC_STAMP(i) do { } while (0)
+#define CLC_DBG(bit) 0
+#endif
+// bring-up: cycles the MMA warp spends waiting on each barrier class (timing runs of the debug build only)
+#ifdef CLC_DEBUG_ABI
+#define CLC_WAIT_T0() do { if (p.timing) t0_ = clock64(); } while (0)
+#define CLC_WAIT_ADD(v) do { if (p.timing) v += clock64() - t0_; } while (0)
+#else
+#define CLC_WAIT_T0() do { } while (0)
+#define CLC_WAIT_ADD(v) do { } while (0)
+#endif
 
 struct ColStat {  // per accumulator column (= window origin), shared by the 128 patch lanes
   float ym;    // window mean                                   (Patch_Matching.py:872-874)
-  float rdY;   // 1/sqrt(denominator_y); NaN marks a wrapped / out-of-range origin
-  float wv;    // mask column coordinate                        (:799-803)
-  float hv;    // mask row coordinate
+  float e;     // log2(1/sqrt(denominator_y)) + column part of the mask exponent; NaN = wrapped / out-of-range origin
+  float a, b;  // mask exponent coefficients of the patch centre (row, column):  -2*kh*hv, -2*kw*wv
 };
 
 // Per-patch statistic = fixed-order sum of its per-chunk partials (written by the pre-pass).
@@ -214,20 +248,116 @@ __device__ __forceinline__ void cand_insert(float (&cv)[KC], int (&ci)[KC], floa
 
 // ------------------------------------------------------------------------------------------
 // The GEMM + fused Pearson / mask / candidate-selection kernel.
+//
+// Work decomposition.  A UNIT is one accumulator of 128 patches x TN window origins (TN fp32 TMEM
+// columns); the TMEM holds two unit SLOTS.  A (problem, patch tile) GROUP has units_per_group units.
+// The flattened unit list is split into gridDim.x contiguous, balanced ranges -- one per persistent
+// CTA, so no wave quantisation -- and a CTA walks its range in TILES of up to NACC consecutive units
+// of one group.  All units of a tile share the patch operand: one A stage (a shift's 128 x CK patch
+// sub-tile) feeds NACC x CK/16 MMAs, which is what bounds the kernel -- every A stage comes from L2
+// and the L2 -> SM path (~27 B/cycle/SM with all SMs pulling) is slower than the tensor pipe at
+// NACC = 1 (measured, scripts/umma_bench.cu: the pipe itself accepts a 128x256x16 MMA every 128
+// cycles from shared memory, cta_group::1, row-shifted descriptors included).
+//   NACC = 1: consecutive tiles alternate between the two slots, the epilogue of tile i overlaps the
+//             MMAs of tile i+1.
+//   NACC = 2: a tile owns both slots (half the patch-operand traffic per flop); CK = 32 (64-byte
+//             swizzle rows) keeps the (2*TN + halo)-row reference buffer double-buffered.
 // ------------------------------------------------------------------------------------------
-template <int KC, bool MASK>
+template <int CK> struct OpLayout;
+template <> struct OpLayout<64> {   // 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart
+  static constexpr uint32_t kRowBytes = 128, kLayout = 2, kSBO = 1024;
+};
+template <> struct OpLayout<32> {   // 64-byte rows, SWIZZLE_64B, 8-row groups 512 B apart
+  static constexpr uint32_t kRowBytes = 64, kLayout = 4, kSBO = 512;
+};
+// Shared-memory matrix descriptor, K-major operand of one swizzle row of K:
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused) | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout
+template <int CK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(OpLayout<CK>::kSBO >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)OpLayout<CK>::kLayout << 61;
+  return d;
+}
+
+// One lane of the issuing warp is elected ONCE; every lane runs the (warp-uniform) issue loop and
+// the elected lane's predicate guards the tcgen05 instructions, so descriptors stay in uniform
+// registers (no per-instruction divergence handling around UTCHMMA).
+__device__ __forceinline__ uint32_t elect_one_pred() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(pred)
+      : "memory");
+}
+
+// This CTA's range of units and the walk over it in tiles (identical in the three warp roles).
+struct TileWalk {
+  int g, g_end, U, NACC;
+  int group, u0, nu;    // current tile: group, first unit inside the group, number of units
+  int slot0;            // TMEM slot of the tile's first unit (unit j uses slot (slot0 + j) & 1)
+  uint32_t uses0, uses1;  // completed uses per slot (-> mbarrier phase parities)
+  __device__ __forceinline__ TileWalk(const Params& p) {
+    const long long T = p.total_units;
+    g = (int)((long long)blockIdx.x * T / gridDim.x);
+    g_end = (int)((long long)(blockIdx.x + 1) * T / gridDim.x);
+    U = p.units_per_group;
+    NACC = p.NACC;
+    slot0 = 0;
+    uses0 = uses1 = 0;
+    nu = 0;
+  }
+  __device__ __forceinline__ uint32_t parity(int slot) const { return (slot ? uses1 : uses0) & 1u; }
+  __device__ __forceinline__ bool next() {
+    // retire the previous tile: unit j used slot (slot0 + j) & 1
+    if (nu == 2) { ++uses0; ++uses1; }
+    else if (nu == 1) { if (slot0) ++uses1; else ++uses0; }
+    slot0 = (slot0 + nu) & 1;
+    g += nu;
+    if (g >= g_end) return false;
+    group = g / U;
+    u0 = g - group * U;
+    nu = NACC;
+    if (nu > U - u0) nu = U - u0;
+    if (nu > g_end - g) nu = g_end - g;
+    return true;
+  }
+};
+
+template <int KC, bool MASK, int CK>
 __global__ void __launch_bounds__(kThreads, 1)
 match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const Params p) {
+  constexpr uint32_t kRowBytes = OpLayout<CK>::kRowBytes;
+  constexpr uint32_t kRow16 = kRowBytes / 16;              // descriptor units (16 B) per operand row
+  constexpr uint32_t kBoxBytes = kBoxRowsB * kRowBytes;    // one TMA box of the reference operand
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;  // SW128 tiles need 1024-byte alignment
-  const uint32_t bBytes = (uint32_t)p.nboxB * kBoxBytesB;
+  const uint32_t base = (raw + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
+  const uint32_t bBytes = (uint32_t)p.nboxB * kBoxBytes;
   const uint32_t sA = base;
   const uint32_t sB = sA + (uint32_t)p.a_stages * kABytes;
   const uint32_t sCol = sB + (uint32_t)p.b_bufs * bBytes;
-  const int TNT = p.TN * p.NACC;
-  const uint32_t sBar = sCol + (uint32_t)TNT * (uint32_t)sizeof(ColStat);
+  const int TN = p.TN;
+  const uint32_t sBar = sCol + (uint32_t)(p.NACC * TN) * (uint32_t)sizeof(ColStat);
   // barrier map (8 bytes each): A_full[a_stages] A_empty[a_stages] B_full[2] B_empty[2] acc_full[2] acc_empty[2]
   const uint32_t barAfull = sBar;
   const uint32_t barAempty = barAfull + 8u * p.a_stages;
@@ -258,7 +388,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       mbar_init(barBfull + 8u * i, 1);
       mbar_init(barBempty + 8u * i, 1);
       mbar_init(barAccFull + 8u * i, 1);
-      mbar_init(barAccEmpty + 8u * i, 4);  // one arrive per epilogue warp
+      mbar_init(barAccEmpty + 8u * i, kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -268,138 +398,166 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   tc_fence_after();
   pdl_wait();   // everything above (TMEM allocation, barrier init, descriptor prefetch) overlaps the pre-pass
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int acc_cols = TNT;
   if (warp == 0) CLC_STAMP(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     uint32_t ast = 0, aph = 0, bst = 0, bph = 0;  // ring positions + phase parities (no divisions in the loop)
-    const uint32_t a_tx = (uint32_t)(p.SB * p.a_rows) * (kChunk * 2);
-    bool first = true;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
-      const int n = tile / (p.n_tiles * p.m_tiles);
+    const uint32_t a_tx = (uint32_t)(p.SB * p.a_rows) * kRowBytes;
+    TileWalk tw(p);
+    while (tw.next()) {
+      const int n = tw.group / p.m_tiles, mt = tw.group - n * p.m_tiles;
       const int nq = n / p.q_repeat;
-      const int row0 = n * p.HW + nt * TNT;
+      const int row0 = n * p.HW + tw.u0 * TN;
+      const int nbox = (tw.nu * TN + p.halo + kBoxRowsB - 1) / kBoxRowsB;   // <= p.nboxB
       for (int c = 0; c < p.chunks; ++c) {
         mbar_wait(barBempty + 8u * bst, bph ^ 1u);
         if (lane == 0) {
-          mbar_expect_tx(barBfull + 8u * bst, bBytes);
-          for (int i = 0; i < p.nboxB; ++i)
-            tma_load_2d(sB + bst * bBytes + (uint32_t)i * kBoxBytesB, &tmapB, barBfull + 8u * bst, c * kChunk,
+          mbar_expect_tx(barBfull + 8u * bst, (uint32_t)nbox * kBoxBytes);
+          for (int i = 0; i < nbox; ++i)
+            tma_load_2d(sB + bst * bBytes + (uint32_t)i * kBoxBytes, &tmapB, barBfull + 8u * bst, c * CK,
                         row0 + i * kBoxRowsB);
         }
         if (++bst == (uint32_t)p.b_bufs) { bst = 0; bph ^= 1u; }
         for (int s0 = 0; s0 < p.S; s0 += p.SB) {
           mbar_wait(barAempty + 8u * ast, aph ^ 1u);
           if (lane == 0) {
-            if (p.dbg & 4) {
+            if (CLC_DBG(4)) {
               mbar_arrive(barAfull + 8u * ast);
             } else {
               mbar_expect_tx(barAfull + 8u * ast, a_tx);
-              tma_load_3d(sA + ast * kABytes, &tmapA, barAfull + 8u * ast, c * kChunk, mt * kTileM, nq * p.S + s0);
+              tma_load_3d(sA + ast * kABytes, &tmapA, barAfull + 8u * ast, c * CK, mt * kTileM, nq * p.S + s0);
             }
           }
           if (++ast == (uint32_t)p.a_stages) { ast = 0; aph ^= 1u; }
-          if (first) { CLC_STAMP(2); first = false; }
         }
       }
     }
     CLC_STAMP(3);
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    const uint32_t idesc = make_idesc(kTileM, p.TN);
-    const uint32_t a_sub = (uint32_t)p.a_rows * 8u;  // one shift's sub-tile, in 16-byte units
-    uint32_t ast = 0, aph = 0, bst = 0, bph = 0, accst = 0, accph = 0;
-    bool first = true;
-    long long w_acc = 0, w_b = 0, w_a = 0, t0 = 0;      // bring-up: cycles spent waiting (timing runs only)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      if (p.timing) t0 = clock64();
-      mbar_wait(barAccEmpty + 8u * accst, accph ^ 1u);
-      if (p.timing) w_acc += clock64() - t0;
+    const uint32_t pred = elect_one_pred();
+    const uint32_t idesc = make_idesc(kTileM, TN);
+    const uint32_t a_sub = (uint32_t)p.a_rows * kRow16;  // one shift's sub-tile, in 16-byte units
+    uint32_t ast = 0, aph = 0, bst = 0, bph = 0;
+#ifdef CLC_DEBUG_ABI
+    long long w_acc = 0, w_b = 0, w_a = 0, t0_ = 0;
+#endif
+    TileWalk tw(p);
+    while (tw.next()) {
+      CLC_WAIT_T0();
+      for (int j = 0; j < tw.nu; ++j) {
+        const int sl = (tw.slot0 + j) & 1;
+        mbar_wait(barAccEmpty + 8u * sl, tw.parity(sl) ^ 1u);
+      }
+      CLC_WAIT_ADD(w_acc);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + accst * (uint32_t)acc_cols;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.chunks; ++c) {
-        if (p.timing) t0 = clock64();
+        CLC_WAIT_T0();
         mbar_wait(barBfull + 8u * bst, bph);
-        if (p.timing) w_b += clock64() - t0;
-        if (first) CLC_STAMP(4);
-        const uint64_t bdesc0 = make_desc_sw128(sB + bst * bBytes);
+        CLC_WAIT_ADD(w_b);
+        const uint64_t bdesc0 = make_desc<CK>(sB + bst * bBytes);
         int dy = 0, dx = 0;
         for (int s0 = 0; s0 < p.S; s0 += p.SB) {
-          if (p.timing) t0 = clock64();
+          CLC_WAIT_T0();
           mbar_wait(barAfull + 8u * ast, aph);
-          if (p.timing) w_a += clock64() - t0;
-          if (first) { CLC_STAMP(5); first = false; }
+          CLC_WAIT_ADD(w_a);
           tc_fence_after();
-          if (lane == 0) {
-            uint64_t adesc = make_desc_sw128(sA + ast * kABytes);
-            for (int si = 0; si < p.SB; ++si) {
-              int shift_rows = dy * p.W + dx;  // the window shift is a ROW offset into the B buffer
-              if (p.dbg & 1) shift_rows &= ~7;
-              for (int j = 0; j < ((p.dbg & 2) ? 0 : p.NACC); ++j) {
-                const uint64_t bdesc = bdesc0 + (uint64_t)((j * p.TN + shift_rows) * 8);  // 128 B/row = 8 x 16 B
+          uint64_t adesc = make_desc<CK>(sA + ast * kABytes);
+          for (int si = 0; si < p.SB; ++si) {
+            int shift_rows = dy * p.W + dx;  // the window shift is a ROW offset into the B buffer
+            if (CLC_DBG(1)) shift_rows &= ~7;
+            if (!CLC_DBG(2)) {
+              for (int j = 0; j < tw.nu; ++j) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(((tw.slot0 + j) & 1) * TN);
+                const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(j * TN + shift_rows) * kRow16);
 #pragma unroll
-                for (int k = 0; k < kChunk / 16; ++k)
-                  umma_bf16(d_base + (uint32_t)(j * p.TN), adesc + 2u * k, bdesc + 2u * k, idesc,
-                            k ? 1u : accumulate);
+                for (int k = 0; k < CK / 16; ++k)
+                  umma_bf16_p(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, k ? 1u : accumulate, pred);
               }
-              accumulate = 1;
-              adesc += a_sub;
-              if (++dx == p.pw) { dx = 0; ++dy; }
             }
-            umma_commit(barAempty + 8u * ast);  // frees the A stage once these MMAs have read it
-          } else {
-            for (int si = 0; si < p.SB; ++si)
-              if (++dx == p.pw) { dx = 0; ++dy; }
+            accumulate = 1;
+            adesc += a_sub;
+            if (++dx == p.pw) { dx = 0; ++dy; }
           }
-          __syncwarp();
+          umma_commit_p(barAempty + 8u * ast, pred);  // frees the A stage once these MMAs have read it
           if (++ast == (uint32_t)p.a_stages) { ast = 0; aph ^= 1u; }
         }
-        if (lane == 0) umma_commit(barBempty + 8u * bst);
-        __syncwarp();
+        umma_commit_p(barBempty + 8u * bst, pred);
         if (++bst == (uint32_t)p.b_bufs) { bst = 0; bph ^= 1u; }
       }
-      if (lane == 0) umma_commit(barAccFull + 8u * accst);
-      __syncwarp();
-      if (++accst == (uint32_t)p.acc_stages) { accst = 0; accph ^= 1u; }
+      for (int j = 0; j < tw.nu; ++j) umma_commit_p(barAccFull + 8u * ((tw.slot0 + j) & 1), pred);
       CLC_STAMP(6);
     }
+#ifdef CLC_DEBUG_ABI
     if (p.timing && lane == 0) {
       long long* tt = p.timing + (size_t)blockIdx.x * 16;
       tt[11] = tt[0] + w_acc; tt[12] = tt[0] + w_b; tt[13] = tt[0] + w_a;   // reported relative to the start stamp
     }
+#endif
   } else {
     // ===================================== epilogue =========================================
+    // 8 warps: warp -> (TMEM lane quarter q = warp % 4, column half).  A thread owns one patch (accumulator
+    // row) and, of every unit, the TN/2 columns of its half: it turns each accumulator into the masked
+    // Pearson SCREENING score and streams it out as fp16 (64 contiguous bytes per 32 columns).  No
+    // data-dependent branches: the per-patch candidate selection happens in the re-scoring kernel, which
+    // scans the patch's score row with all lanes across window positions.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;            // column half 0..1
     const int row = q * 32 + lane;               // accumulator row = patch within the tile
-    const int et = threadIdx.x - 64;             // 0..127 among the epilogue threads
-    const int cw = p.W - p.pw + 1;
+    const int et = threadIdx.x - 64;             // 0..255 among the epilogue threads
     const int K = p.C * p.S;
     const float Kf = (float)K, inv_k = 1.0f / Kf;
     const float kh = -4.0f / (0.25f * (float)p.H * (float)p.H);  // exp(-4ln2*x) = 2^(-4x), sigma = size/2
     const float kw = -4.0f / (0.25f * (float)p.W * (float)p.W);
     const int r0 = (p.ph + 1) / 2 - 1, c0 = (p.pw + 1) / 2 - 1;
-    uint32_t accst = 0, accph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
-      const int n = tile / (p.n_tiles * p.m_tiles);
-      const int nq = n / p.q_repeat;
-      const int pos0 = nt * TNT;
+    const int HWc = TN >> 1;                     // columns per half (>= 32)
+    int cur_group = -1, n = 0, mt = 0, patch = 0;
+    bool live = false;
+    float xs = 0.f, lrs = 0.f, ch = 0.f, cwc = 0.f;
+    __half* mrow = nullptr;
+    TileWalk tw(p);
+    while (tw.next()) {
+      if (tw.group != cur_group) {
+        cur_group = tw.group;
+        n = tw.group / p.m_tiles;
+        mt = tw.group - n * p.m_tiles;
+        const int nq = n / p.q_repeat;
+        patch = mt * kTileM + row;
+        live = patch < p.P;
+        xs = 0.f; lrs = 0.f; ch = 0.f; cwc = 0.f;
+        if (live) {
+          const int64_t qi = (int64_t)nq * p.P + patch;
+          xs = chunk_sum(p.xs, qi, p.stat_chunks);
+          const float sxx = chunk_sum(p.sxx, qi, p.stat_chunks);
+          const float xm = xs / Kf;
+          const int py = patch / p.npx, px = patch - py * p.npx;
+          ch = ((float)py + 0.5f) * (float)p.ph;
+          cwc = ((float)px + 0.5f) * (float)p.pw;
+          // log2 of the per-patch factor: 1/sqrt(denominator_x) and the row part of the mask exponent
+          lrs = -0.5f * log2f(sxx - xm * xs);
+          if (MASK) lrs += fmaf(ch * ch, kh, cwc * cwc * kw);
+          mrow = p.smap + ((int64_t)n * p.P + patch) * p.map_pitch;
+        }
+      }
+      const int cols = tw.nu * TN;
+      const int tpos0 = tw.u0 * TN;
       // ---- per-column statistics (while the MMAs of this tile run) ----
+      //   score = (xy - ym*xs) * rdY * 2^(kh*(hv-ch)^2 + kw*(wv-cwc)^2) * rdX
+      //         = (xy - ym*xs) * 2^(E + a*ch + b*cwc + lrs)
+      //   with E = kh*hv^2 + kw*wv^2 + log2(rdY), a = -2*kh*hv, b = -2*kw*wv   (mask off: E = log2 rdY, a = b = 0)
+      //        lrs = log2(rdX) + kh*ch^2 + kw*cwc^2  (per patch)
       const float* s1n = p.s1 + (int64_t)n * p.HW;
       const float* s2n = p.s2 + (int64_t)n * p.HW;
-      for (int col = et; col < TNT; col += 128) {
-        const int pos = pos0 + col;
+      for (int col = et; col < cols; col += 32 * kEpiWarps) {
+        const int pos = tpos0 + col;
         const int oy = pos / p.W, ox = pos - oy * p.W;
         ColStat cs;
         cs.ym = 0.f;
-        cs.rdY = __int_as_float(0x7fc00000);
-        cs.wv = (float)(ox + c0 + 1) - 0.5f * (float)(p.pw & 1);
-        cs.hv = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
+        cs.e = __int_as_float(0x7fc00000);      // NaN marks a wrapped / out-of-range origin: its score is NaN
+        cs.a = 0.f;
+        cs.b = 0.f;
         if (oy <= p.H - p.ph && ox <= p.W - p.pw) {
           float b1 = 0.f, b2 = 0.f;
           // (partially unrolled so that several loads are in flight; the adds keep their order)
@@ -412,79 +570,69 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             }
           const PosStat ps = pos_stat(b1, b2, inv_k, Kf);
           cs.ym = ps.ym;
-          cs.rdY = rsqrtf(ps.dY);
+          cs.e = -0.5f * log2f(ps.dY);          // log2(1/sqrt(denominator_y))
+          if (MASK) {
+            const float wv = (float)(ox + c0 + 1) - 0.5f * (float)(p.pw & 1);   // mask coordinates (:799-803)
+            const float hv = (float)(oy + r0 + 1) - 0.5f * (float)(p.ph & 1);
+            cs.e += fmaf(hv * hv, kh, wv * wv * kw);
+            cs.a = -2.0f * kh * hv;
+            cs.b = -2.0f * kw * wv;
+          }
         }
         colstat[col] = cs;
       }
-      // ---- per-patch constants ----
-      const int patch = mt * kTileM + row;
-      const bool live = patch < p.P;
-      float xs = 0.f, rdX = 0.f, ch = 0.f, cwc = 0.f;
-      if (live) {
-        const int64_t qi = (int64_t)nq * p.P + patch;
-        xs = chunk_sum(p.xs, qi, p.chunks);
-        const float sxx = chunk_sum(p.sxx, qi, p.chunks);
-        const float xm = xs / Kf;
-        rdX = rsqrtf(sxx - xm * xs);
-        const int py = patch / p.npx, px = patch - py * p.npx;
-        ch = ((float)py + 0.5f) * (float)p.ph;
-        cwc = ((float)px + 0.5f) * (float)p.pw;
-      }
-      float cv[KC];
-      int ci[KC];
-#pragma unroll
-      for (int j = 0; j < KC; ++j) { cv[j] = -INFINITY; ci[j] = -1; }
-      epi_bar_sync();  // colstat visible to the 4 epilogue warps
+      epi_bar_sync();  // colstat visible to all epilogue warps
       if (warp == 2) CLC_STAMP(7);
 
-      const uint32_t as = accst;
-      mbar_wait(barAccFull + 8u * as, accph);
-      tc_fence_after();
-      if (warp == 2) CLC_STAMP(8);
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)acc_cols;
-      for (int col0 = 0; col0 < TNT; col0 += 32) {
-        float v[32];
-        tmem_ld32(t_row + (uint32_t)col0, v);
-        tmem_ld_wait();
-        if (p.dump != nullptr) {
+      for (int j = 0; j < tw.nu; ++j) {
+        const int sl = (tw.slot0 + j) & 1;
+        const int pos0 = tpos0 + j * TN + half * HWc;   // first window origin of this thread's columns
+        mbar_wait(barAccFull + 8u * sl, tw.parity(sl));
+        tc_fence_after();
+        if (warp == 2) CLC_STAMP(8);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * TN + half * HWc);
+        const ColStat* cst = colstat + j * TN + half * HWc;
+        for (int col0 = 0; col0 < HWc; col0 += 32) {
+          float v[32];
+          tmem_ld32(t_row + (uint32_t)col0, v);
+          tmem_ld_wait();
+#ifdef CLC_DEBUG_ABI
+          if (p.dump != nullptr) {
+            if (live) {
+              float* dst = p.dump + ((int64_t)n * p.P + patch) * p.HW + pos0 + col0;
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                if (pos0 + col0 + t < p.HW) dst[t] = v[t];
+            }
+          }
+#endif
+          uint32_t h2[16];
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            float sc[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 cs = *reinterpret_cast<const float4*>(&cst[col0 + t + u]);  // {ym, e, a, b}
+              const float num = fmaf(-cs.x, xs, v[t + u]);      // xy - y_mean * x_sum
+              const float ex = MASK ? fmaf(cs.z, ch, fmaf(cs.w, cwc, cs.y + lrs)) : cs.y + lrs;
+              sc[u] = num * exp2f(ex);
+            }
+            const __half2 hh = __floats2half2_rn(sc[0], sc[1]);
+            h2[t >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
           if (live) {
-            float* dst = p.dump + ((int64_t)n * p.P + patch) * p.HW + pos0 + col0;
+            uint4* dst = reinterpret_cast<uint4*>(mrow + pos0 + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (pos0 + col0 + j < p.HW) dst[j] = v[j];
+            for (int t = 0; t < 4; ++t) dst[t] = make_uint4(h2[4 * t], h2[4 * t + 1], h2[4 * t + 2], h2[4 * t + 3]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 cs = *reinterpret_cast<const float4*>(&colstat[col0 + j]);  // {ym, rdY, wv, hv}
-          float s = fmaf(-cs.x, xs, v[j]) * cs.y;  // (xy - y_mean*x_sum) / sqrt(denominator_y); NaN if wrapped
-          if (MASK) {
-            const float dw = cs.z - cwc, dh = cs.w - ch;
-            s *= exp2f(fmaf(dh * dh, kh, dw * dw * kw));
-          }
-          if (s > cv[KC - 1]) cand_insert<KC>(cv, ci, s, pos0 + col0 + j);
-        }
-      }
-      // accumulator drained: hand the TMEM stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(barAccEmpty + 8u * as);
-      if (live) {
-        const int64_t o = (((int64_t)n * p.P + patch) * p.n_tiles + nt) * KC;
-#pragma unroll
-        for (int j = 0; j < KC; ++j) {
-          int id = -1;
-          if (ci[j] >= 0) {
-            const int oy = ci[j] / p.W, ox = ci[j] - oy * p.W;
-            id = oy * cw + ox;
-          }
-          p.cand_val[o + j] = cv[j] * rdX;
-          p.cand_idx[o + j] = id;
-        }
+        // accumulator drained: hand the TMEM slot back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(barAccEmpty + 8u * sl);
       }
       epi_bar_sync();  // colstat may be overwritten for the next tile
       if (warp == 2) CLC_STAMP(9);
-      if (++accst == (uint32_t)p.acc_stages) { accst = 0; accph ^= 1u; }
     }
   }
 
@@ -766,8 +914,10 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
         for (int pi = 0; pi < kStPW; ++pi) {
           if (pi >= rows_pw) break;
           const int patch = g * p.st_rows + ew + 8 * pi;
+#ifdef CLC_DEBUG_ABI
           if (p.dump != nullptr && patch < p.P && pos < span && rdv == rdv)
             p.dump[((int64_t)n * p.P + patch) * p.HW + pos] = acc[pi][m];
+#endif
           float sv = fmaf(-ymv, pxs[pi], acc[pi][m]) * rdv;
           if (MASK) {
             const float dw = wv - pcw[pi], dh = hv - pch[pi];
@@ -833,6 +983,7 @@ struct PrepassParams {
   int C, H, W, HW, ph, pw, P, P_pad, chunks;
   int ref_tiles, n_ref_blocks, npy, dbg, zero_rows;
   int seg_w, n_seg;   // query blocks cover seg_w columns (a whole number of patches) of one patch row
+  int32_t* n_uncert;  // optional counter the re-scoring kernel adds to; reset here (first kernel of the call)
 };
 
 // Shared tiles are skewed so that BOTH the pixel-major fills and the channel-group-major transposed
@@ -986,6 +1137,7 @@ prepass_kernel(const PrepassParams pp) {
   pdl_trigger();
   pdl_wait();
   int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0 && pp.n_uncert != nullptr) *pp.n_uncert = 0;
   if (b < pp.n_ref_blocks) {
     if (pp.dbg & 1) return;
     pack_ref_block(pp, tile, b / pp.ref_tiles, (b % pp.ref_tiles) * 32);
@@ -1047,44 +1199,166 @@ __device__ __forceinline__ void blend_rows(float4* T4, const float* __restrict__
   }
 }
 
+constexpr int kListCap = 256;   // screened scores collected per patch by the threshold scan
+
+// Order-preserving integer key of a float (larger float <-> larger key; -0 < +0).
+__device__ __forceinline__ unsigned float_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 template <int KC>
 __global__ void __launch_bounds__(KC * 32, 768 / (KC * 32))
 rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, int P_pad,
                const float* __restrict__ s1,
                const float* __restrict__ s2, const float* __restrict__ xs_a, const float* __restrict__ sxx_a,
-               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int n_tiles,
+               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+               const __half* __restrict__ smap, long long map_pitch,
                int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian, int chunks,
                float* __restrict__ val, int32_t* __restrict__ idx, int32_t* __restrict__ n_uncertified,
                float temperature, float* __restrict__ aligned, float* __restrict__ weights_out, int dbg) {
-  // dynamic shared memory: query patch Q[S][C] fp32 (also reused as the blend tile [S][C]) | cand values [M] |
-  // cand idx [M]
+  // dynamic shared memory: query patch Q[S][C] fp32 (also reused as the blend tile [S][C]) | collected
+  // scores [kListCap] | their window ids [kListCap]
   extern __shared__ float4 sm4[];
   __shared__ float sel_v[kMaxKC], ex_v[kMaxKC];
   __shared__ int sel_i[kMaxKC];
   __shared__ float top_w[8];
   __shared__ int top_src[8], top_id[8];
+  __shared__ float wtop_v[kMaxKC * kMaxKC];   // per-warp top-KC of the thread maxima (threshold selection)
+  __shared__ float thr_s;
+  __shared__ int cnt_s;
   constexpr int NT = KC * 32;
-  const int M = n_tiles * KC;
+  const int n = blockIdx.x / P, patch = blockIdx.x - n * P;
   const int pp = ph * pw, K = C * pp, c4n = C >> 2, items = pp * c4n;
   float4* Q = sm4;
   float* cvs = reinterpret_cast<float*>(sm4 + items);
-  int* cis = reinterpret_cast<int*>(cvs + M);
-  const int n = blockIdx.x / P, patch = blockIdx.x - n * P;
+  int* cis = reinterpret_cast<int*>(cvs + kListCap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = n / q_repeat;
-  const int64_t co = ((int64_t)n * P + patch) * M;
+  const int cw = W - pw + 1;
   pdl_trigger();
   pdl_wait();
-  // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate lists.
-  // With several per-tile lists, warp 0 merges them while warps 1..KC-1 stage the patch. ----
-  if (n_tiles > 1) {
-    for (int i = threadIdx.x; i < M; i += NT) {
-      cvs[i] = cand_val[co + i];
-      cis[i] = cand_idx[co + i];
+  const bool scan = smap != nullptr;
+  int M = 0;          // collected candidates (scan mode)
+  bool exact_select = false;
+  if (scan) {
+    // ---- candidate selection from the screened score row (fp16, linear window origins, NaN = no window):
+    // pass 1 finds a threshold T0 with at least KC scores >= T0 (the KC-th largest of the per-thread maxima),
+    // pass 2 collects every score >= T0 (a few more than KC on average), warp 0 then takes the top-KC. ----
+    const uint4* rp = reinterpret_cast<const uint4*>(smap + ((long long)n * P + patch) * map_pitch);
+    const int n8 = (int)(map_pitch >> 3);
+    float lmax = -INFINITY;
+    for (int i = threadIdx.x; i < n8; i += NT) {
+      const uint4 u = __ldg(rp + i);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h[t]);
+        lmax = fmaxf(lmax, fmaxf(f.x, f.y));        // fmaxf drops NaN
+      }
+    }
+    {
+      // per-warp top-KC of the 32 lane maxima (KC rounds of max + remove), then warp 0 over the KC*KC survivors
+      float mine = lmax;
+      for (int t = 0; t < KC; ++t) {
+        const unsigned kmax = __reduce_max_sync(0xffffffffu, float_key(mine));
+        const unsigned who = __ballot_sync(0xffffffffu, float_key(mine) == kmax);
+        if (lane == (__ffs(who) - 1)) { wtop_v[warp * KC + t] = mine; mine = -INFINITY; }
+      }
+    }
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    if (warp == 0) {
+      constexpr int PL = KC * KC / 32;              // survivors per lane (2 or 8)
+      float mv[PL];
+#pragma unroll
+      for (int u = 0; u < PL; ++u) mv[u] = wtop_v[lane + 32 * u];
+      float t0 = -INFINITY;
+      for (int t = 0; t < KC; ++t) {
+        float lm = mv[0];
+#pragma unroll
+        for (int u = 1; u < PL; ++u) lm = fmaxf(lm, mv[u]);
+        const unsigned kmax = __reduce_max_sync(0xffffffffu, float_key(lm));
+        const unsigned who = __ballot_sync(0xffffffffu, float_key(lm) == kmax);
+        if (lane == (__ffs(who) - 1)) {
+          bool done = false;
+#pragma unroll
+          for (int u = 0; u < PL; ++u)
+            if (!done && float_key(mv[u]) == kmax) { mv[u] = -INFINITY; done = true; }
+        }
+        if (t == KC - 1) t0 = __shfl_sync(0xffffffffu, lm, __ffs(who) - 1);
+      }
+      if (lane == 0) thr_s = t0;                    // -inf when fewer than KC threads saw a score: collect all
     }
     __syncthreads();
+    const float T0 = thr_s;
+    for (int i = threadIdx.x; i < n8; i += NT) {
+      const uint4 u = __ldg(rp + i);
+      const __half* h = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float f = __half2float(h[t]);
+        if (f >= T0) {                               // NaN never passes
+          const int slot = atomicAdd(&cnt_s, 1);
+          if (slot < kListCap) {
+            const int pos = i * 8 + t;
+            const int oy = pos / W, ox = pos - oy * W;
+            cvs[slot] = f;
+            cis[slot] = oy * cw + ox;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    M = cnt_s;
+    if (M > kListCap) { exact_select = true; M = 0; }
+    if (exact_select) {
+      // More than kListCap scores tie at / above the threshold (e.g. a periodic reference): exact selection,
+      // KC rounds of a block-wide arg-max by (score desc, window id asc) over the whole row.
+      __shared__ float red_v[kMaxKC];
+      __shared__ int red_i[kMaxKC];
+      float pv = INFINITY;
+      int pid = -1;
+      for (int t = 0; t < KC; ++t) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = threadIdx.x; i < n8; i += NT) {
+          const uint4 u = __ldg(rp + i);
+          const __half* h = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float f = __half2float(h[e]);
+            if (!(f == f)) continue;
+            const int pos = i * 8 + e;
+            const int oy = pos / W, ox = pos - oy * W;
+            const int id = oy * cw + ox;
+            const bool after_prev = (f < pv) || (f == pv && id > pid);
+            if (after_prev && (f > bv || (f == bv && id < bi))) { bv = f; bi = id; }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+        __syncthreads();
+        bv = red_v[0]; bi = red_i[0];
+        for (int w = 1; w < KC; ++w)
+          if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+        __syncthreads();
+        const bool none = bi == 0x7fffffff;
+        if (threadIdx.x == 0) { sel_v[t] = none ? -INFINITY : bv; sel_i[t] = none ? -1 : bi; }
+        pv = bv; pid = bi;
+        if (none) { pv = -INFINITY; pid = 0x7fffffff; }
+      }
+    }
   }
-  const int sw = n_tiles > 1 ? warp - 1 : warp, snw = n_tiles > 1 ? KC - 1 : KC;   // staging warp id / count
+  // ---- stage the query patch (every shift is one contiguous row of C floats); in scan mode warp 0 selects
+  // the top-KC of the collected scores meanwhile ----
+  const bool w0_busy = scan && !exact_select;
+  const int sw = w0_busy ? warp - 1 : warp, snw = w0_busy ? KC - 1 : KC;   // staging warp id / count
   if (sw >= 0) {
     const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
     // two shifts x three float4 columns per warp-iteration: 6 loads in flight before the first store
@@ -1112,57 +1386,16 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         }
       }
   }
-  if (n_tiles == 1) {
+  if (!scan) {
     // a single candidate list (stacked kernel): already the screened top-KC in order
+    const int64_t co = ((int64_t)n * P + patch) * KC;
     if (threadIdx.x < KC) {
       sel_v[threadIdx.x] = cand_val[co + threadIdx.x];
       sel_i[threadIdx.x] = cand_idx[co + threadIdx.x];
     }
-  } else {
+  } else if (!exact_select) {
     if (warp == 0) {
-      constexpr int TL = 8;       // per-tile lists owned by one lane
-      if (n_tiles <= 32 * TL) {
-        // every per-tile list is already sorted (screened value desc, position asc), so the global
-        // top-KC is a KC-step multiway merge over the list HEADS: lane <-> lists lane, lane+32, ...;
-        // one redux.max over order-preserving keys + one redux.min over the tied ids per step
-        int head[TL];
-#pragma unroll
-        for (int u = 0; u < TL; ++u) head[u] = 0;
-        for (int t = 0; t < KC; ++t) {
-          unsigned bkey = 0u;
-          int bid = 0x7fffffff, bl = -1;
-          float bvv = -INFINITY;
-#pragma unroll
-          for (int u = 0; u < TL; ++u) {
-            const int li = lane + 32 * u;
-            if (li < n_tiles && head[u] < KC) {
-              const int id = cis[li * KC + head[u]];
-              if (id >= 0) {
-                const float v = cvs[li * KC + head[u]];
-                const unsigned uu = __float_as_uint(v);
-                unsigned key = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);
-                key = key ? key : 1u;                         // 0 is the "nothing left" sentinel
-                if (key > bkey || (key == bkey && id < bid)) { bkey = key; bid = id; bl = u; bvv = v; }
-              }
-            }
-          }
-          const unsigned kmax = __reduce_max_sync(0xffffffffu, bkey);
-          if (kmax == 0u) {                                   // fewer than KC candidates in total
-            if (lane == 0)
-              for (int tt = t; tt < KC; ++tt) { sel_v[tt] = -INFINITY; sel_i[tt] = -1; }
-            break;
-          }
-          const unsigned imin = __reduce_min_sync(0xffffffffu, bkey == kmax ? (unsigned)bid : 0x7fffffffu);
-          if (bkey == kmax && (unsigned)bid == imin) {        // ids are unique: exactly one winner
-            sel_v[t] = bvv;
-            sel_i[t] = bid;
-#pragma unroll
-            for (int u = 0; u < TL; ++u)
-              if (u == bl) ++head[u];
-          }
-        }
-      } else {
-      // KC rounds of warp arg-max over the merged list
+      // KC rounds of warp arg-max over the collected list, (score desc, window id asc)
       for (int t = 0; t < KC; ++t) {
         float bv = -INFINITY;
         int bi = 0x7fffffff, bslot = -1;
@@ -1186,12 +1419,11 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         }
         __syncwarp();
       }
-      }
     }
   }
   __syncthreads();
   // ---- exact re-scoring: warp c <-> candidate c ----
-  const int cw = W - pw + 1, L = (H - ph + 1) * cw;
+  const int L = (H - ph + 1) * cw;
   const int64_t HW = (int64_t)H * W;
   const int npx = W / pw;
   const int py = patch / npx, px = patch - py * npx;
@@ -1374,7 +1606,8 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     if (lane == 0 && n_uncertified != nullptr && L > KC) {
       // any window outside the candidate set has a screened score <= sel_v[KC-1]; the set provably
       // holds the exact top-k unless a screening error exceeds the margin to the k-th exact value.
-      const float eps = 0.03125f * sqrtf(2.0f / (float)K);  // 16 x the bf16 screening error model
+      // 16 x the bf16 screening error model, plus the fp16 rounding of the stored screened score
+      const float eps = 0.03125f * sqrtf(2.0f / (float)K) + (scan ? 4.9e-4f * fabsf(sel_v[KC - 1]) : 0.f);
       if (!(vk - sel_v[KC - 1] > eps)) atomicAdd(n_uncertified, 1);
     }
   }
@@ -1429,16 +1662,21 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct Plan {
-  int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks;
+  int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks, CK;
   int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid, a_rows, SB;
+  int units_per_group, total_units, halo;
   int stacked, st_rows, st_shifts, st_mt, st_stages, st_groups, zero_rows, n_lists;
   size_t smem_bytes;
   // workspace offsets (bytes)
-  size_t off_rT, off_A, off_r32, off_A32, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, total;
+  size_t off_rT, off_A, off_r32, off_A32, off_s1, off_s2, off_xs, off_sxx, off_cv, off_ci, off_map, total;
+  int64_t map_pitch;
   bool ok;
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Cycles the tensor pipe needs per 128 x N x 16 MMA (measured on B200, scripts/umma_bench.cu).
+static inline double mma_cycles(int N) { return N >= 96 ? 0.5 * N : 48.0; }
 
 static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int pw, int k) {
   Plan pl;
@@ -1458,24 +1696,30 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   // rows fetched per A stage: a small patch grid does not pay for the 128-row UMMA tile (the MMA
   // reads stale shared memory for the other rows; accumulator rows are independent and discarded)
   pl.a_rows = pl.m_tiles == 1 ? (pl.P + 7) / 8 * 8 : kTileM;
-  // shifts per A stage: as many whole shift sub-tiles as fit the 16 KB stage (fewer, fatter stages)
-  pl.SB = 1;
-  for (int d = pl.S; d >= 1; --d)
-    if (pl.S % d == 0 && d * pl.a_rows * kChunk * 2 <= kABytes && d <= 256) { pl.SB = d; break; }
-  pl.chunks = C / kChunk;
   const int halo = (ph - 1) * W + pw - 1;
   const int span = (H - ph + 1) * W;  // linear origins 0 .. span-1 cover every valid window
-  // tile shape: minimise waves x (tile width + fixed per-tile cost), prefer wider tiles on ties
-  static const int cand[5][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
+  pl.halo = halo;
+  // ---- tile shape: a small cost model per persistent CTA (cycles), over unit width TN, units per tile
+  // NACC and K-chunk width CK.  Terms: tensor-pipe time of the CTA's units; L2 -> shared-memory time of
+  // its operand stages (the patch operand is re-fetched per tile, so NACC = 2 halves it per flop; about
+  // 27 B/cycle/SM when every SM pulls); the epilogue (only exposed when a tile owns both TMEM slots); a
+  // single-buffered reference operand stalls the pipe for one buffer load per chunk. ----
+  static const int cand[7][3] = {{256, 2, 32}, {256, 2, 64}, {256, 1, 64}, {128, 2, 64}, {128, 1, 64},
+                                 {64, 1, 64}, {128, 2, 32}};
   double best = 1e300;
-  for (int i = 0; i < 5; ++i) {
-    const int TN = cand[i][0], NACC = cand[i][1], TNT = TN * NACC;
-    const int n_tiles = (span + TNT - 1) / TNT;
-    const int64_t tiles = NP * pl.m_tiles * (int64_t)n_tiles;
-    const int rowsB = TNT + halo;
+  for (int i = 0; i < 7; ++i) {
+    const int TN = cand[i][0], NACC = cand[i][1], CK = cand[i][2];
+    const int rowB = CK * 2;                                  // bytes per operand row
+    const int U = (span + TN - 1) / TN;
+    const int64_t T = NP * pl.m_tiles * (int64_t)U;
+    if (T > 0x7fffffff) continue;
+    const int grid = T < kNumSMs ? (int)T : kNumSMs;
+    const int units_cta = (int)((T + grid - 1) / grid);
+    const int nacc = NACC < units_cta ? NACC : units_cta;     // units a tile really gets
+    const int rowsB = NACC * TN + halo;
     const int nboxB = (rowsB + kBoxRowsB - 1) / kBoxRowsB;
-    const size_t bB = (size_t)nboxB * kBoxBytesB;
-    const size_t misc = (size_t)TNT * sizeof(ColStat) + 256 + 1024;
+    const size_t bB = (size_t)nboxB * kBoxRowsB * rowB;
+    const size_t misc = (size_t)NACC * TN * sizeof(ColStat) + 256 + 1024;
     const size_t lim = (size_t)kSmemLimit;
     int b_bufs = 2, a_stages = 0;
     if (lim >= misc + 2 * bB) a_stages = (int)((lim - misc - 2 * bB) / kABytes);
@@ -1486,25 +1730,37 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
       if (a_stages < 2) continue;
     }
     if (a_stages > 8) a_stages = 8;
-    const int64_t waves = (tiles + kNumSMs - 1) / kNumSMs;
-    const double cost = (double)waves * (TNT + 48);
+    const int chunks = C / CK;
+    const double l2_rate = fmin(64.0, 27.0 * kNumSMs / grid);          // B / cycle / SM
+    const double tiles_cta = ceil((double)units_cta / nacc);
+    const double mma = (double)units_cta * chunks * pl.S * (CK / 16) * mma_cycles(TN);
+    const double a_bytes = (double)chunks * pl.S * pl.a_rows * rowB;   // patch operand, per tile
+    const double b_bytes = (double)chunks * (nacc * TN + halo) * rowB; // reference operand, per tile
+    const double l2 = tiles_cta * (a_bytes + b_bytes) / l2_rate;
+    double cost = fmax(mma, l2) + tiles_cta * 2500.0;
+    const double epi = 12.0 * TN;                                      // cycles to drain one unit
+    cost += (NACC == 2) ? units_cta * epi : epi;
+    if (b_bufs == 1) cost += tiles_cta * chunks * (double)bB / l2_rate;
     if (cost < best) {
       best = cost;
-      pl.TN = TN; pl.NACC = NACC; pl.n_tiles = n_tiles; pl.total_tiles = (int)tiles;
+      pl.TN = TN; pl.NACC = NACC; pl.CK = CK; pl.chunks = chunks;
+      pl.units_per_group = U; pl.total_units = (int)T; pl.grid = grid;
+      pl.n_tiles = U; pl.total_tiles = (int)T;
       pl.rowsB = rowsB; pl.nboxB = nboxB; pl.a_stages = a_stages; pl.b_bufs = b_bufs;
-      pl.acc_stages = (TNT <= 256) ? 2 : 1;
-      int cols = pl.acc_stages * TNT, t = 32;
-      while (t < cols) t <<= 1;
-      pl.tmem_cols = t;
+      pl.acc_stages = 2;
+      pl.tmem_cols = 2 * TN < 32 ? 32 : 2 * TN;     // two unit slots (power of two: TN is one)
       pl.smem_bytes = (size_t)a_stages * kABytes + (size_t)b_bufs * bB + misc;
-      pl.ok = tiles <= 0x7fffffff;
+      pl.ok = true;
     }
   }
   if (!pl.ok) return pl;
-  pl.grid = pl.total_tiles < kNumSMs ? pl.total_tiles : kNumSMs;
+  // shifts per A stage: as many whole shift sub-tiles as fit the 16 KB stage (fewer, fatter stages)
+  pl.SB = 1;
+  for (int d = pl.S; d >= 1; --d)
+    if (pl.S % d == 0 && d * pl.a_rows * pl.CK * 2 <= kABytes && d <= 256) { pl.SB = d; break; }
   pl.zero_rows = pl.m_tiles == 1 ? pl.a_rows : pl.P_pad;   // rows of A the TMA boxes can reach
   // ---- small latents (<= 256 pixels): the stacked-shift kernel (match_gemm_stacked_kernel) ----
-  if (pl.HW <= 256 && pw <= 6 && !getenv("CLC_TC_NO_STACKED")) {
+  if (pl.HW <= 256 && pw <= 6 && !(dbg_bits() & 16)) {
     const int Npad = (pl.HW + 31) / 32 * 32;
     int rows = 16;
     if (pl.P <= 8 || NP * ((pl.P + 7) / 8) <= kNumSMs) rows = 8;
@@ -1514,10 +1770,11 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
     const size_t dump = (size_t)128 * (Npad + 4) * 4;
     const size_t misc = (size_t)24 * Npad + 4 * pl.S + 8 * (2 * 8 + 2) + 64 + 1024;
     int stages = (int)(((size_t)kSmemLimit - misc) / stage);
-    if (stages > pl.chunks) stages = pl.chunks;
+    if (stages > C / kChunk) stages = C / kChunk;
     if (stages > 8) stages = 8;
     if (mt * Npad <= 512 && stages >= 1 && dump + misc <= (size_t)kSmemLimit) {
       pl.stacked = 1;
+      pl.CK = kChunk; pl.chunks = C / kChunk;
       pl.st_rows = rows; pl.st_shifts = shifts; pl.st_mt = mt; pl.st_stages = stages;
       pl.st_groups = (pl.P + rows - 1) / rows;
       pl.zero_rows = pl.st_groups * rows;
@@ -1540,23 +1797,33 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   pl.off_A32 = o; o = align_up(o + (size_t)NQ * pl.S * pl.P_pad * C * 4, 256);
   pl.off_s1 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
-  pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * pl.chunks * 4, 256);
-  pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * pl.chunks * 4, 256);
-  pl.n_lists = pl.n_tiles;                         // candidate lists per (problem, patch)
-  pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_lists * pl.KC * 4, 256);
-  pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.n_lists * pl.KC * 4, 256);
+  pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * (C / kChunk) * 4, 256);
+  pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * (C / kChunk) * 4, 256);
+  // stacked kernel: one screened top-KC list per (problem, patch); general kernel: the fp16 screened score
+  // map [NP, P, map_pitch] (linear window origins, map_pitch = units * TN), scanned by the re-scoring kernel
+  pl.n_lists = 1;
+  pl.map_pitch = pl.stacked ? 0 : (int64_t)pl.units_per_group * pl.TN;
+  pl.off_cv = o;  o = align_up(o + (pl.stacked ? (size_t)NP * pl.P * pl.KC * 4 : 0), 256);
+  pl.off_ci = o;  o = align_up(o + (pl.stacked ? (size_t)NP * pl.P * pl.KC * 4 : 0), 256);
+  pl.off_map = o; o = align_up(o + (size_t)NP * pl.P * (size_t)pl.map_pitch * 2, 256);
   pl.total = o + 256;  // slack for aligning the caller's pointer
   return pl;
 }
 
-template <int KC, bool MASK>
+template <int KC, bool MASK, int CK>
 static int launch_gemm(const Plan& pl, const CUtensorMap& ta, const CUtensorMap& tb, const Params& prm,
                        cudaStream_t st) {
-  auto kern = match_gemm_kernel<KC, MASK>;
+  auto kern = match_gemm_kernel<KC, MASK, CK>;
   CLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CLC_CUDA(launch_pdl(kern, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, st, ta, tb, prm));
   CLC_CHECK_LAUNCH("clc_match_topk_tc(gemm)");
   return CLC_OK;
+}
+
+template <int KC, bool MASK>
+static int launch_gemm_ck(const Plan& pl, const CUtensorMap& ta, const CUtensorMap& tb, const Params& prm,
+                          cudaStream_t st) {
+  return pl.CK == 32 ? launch_gemm<KC, MASK, 32>(pl, ta, tb, prm, st) : launch_gemm<KC, MASK, 64>(pl, ta, tb, prm, st);
 }
 
 template <int KC, bool MASK>
@@ -1599,24 +1866,25 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
 
   // ---- tensor maps (host-side encode, no device work) ----
   CUtensorMap ta, tb;
+  const CUtensorMapSwizzle swz = pl.CK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)pl.P_pad, (cuuint64_t)(NQ * pl.S)};
     const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)pl.P_pad * C * 2};
-    const cuuint32_t box[3] = {kChunk, (cuuint32_t)(pl.stacked ? pl.st_rows : pl.a_rows),
+    const cuuint32_t box[3] = {(cuuint32_t)pl.CK, (cuuint32_t)(pl.stacked ? pl.st_rows : pl.a_rows),
                                (cuuint32_t)(pl.stacked ? (pl.st_shifts < pl.S ? pl.st_shifts : pl.S) : pl.SB)};
     const cuuint32_t es[3] = {1, 1, 1};
     CUresult cr = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Apk, dims, strides, box, es,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(A)");
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(NP * pl.HW)};
     const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    const cuuint32_t box[2] = {kChunk, kBoxRowsB};
+    const cuuint32_t box[2] = {(cuuint32_t)pl.CK, kBoxRowsB};
     const cuuint32_t es[2] = {1, 1};
     CUresult cr = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rT, dims, strides, box, es,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(B)");
   }
@@ -1627,17 +1895,18 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
     pp.r = r; pp.rT = rT; pp.rT32 = rT32; pp.s1 = s1; pp.s2 = s2;
     pp.q = q_img; pp.A = Apk; pp.A32 = A32; pp.xs_part = xs; pp.sxx_part = sxx;
     pp.C = C; pp.H = H; pp.W = W; pp.HW = pl.HW; pp.ph = ph; pp.pw = pw; pp.P = pl.P; pp.P_pad = pl.P_pad;
-    pp.chunks = pl.chunks;
+    pp.chunks = C / kChunk;         // query blocks / per-patch statistic partials: one per 64 channels
     pp.ref_tiles = (pl.HW + 31) / 32;
     pp.npy = H / ph;
     pp.zero_rows = pl.zero_rows;   // rows the A-operand TMA boxes read
     // query blocks: one patch row x 64 channels x seg_w columns (about 32, a whole number of patches)
     pp.seg_w = W <= 32 ? W : (32 / pw > 0 ? (32 / pw) * pw : pw);
     pp.n_seg = (W + pp.seg_w - 1) / pp.seg_w;
-    const int64_t n_ref = (int64_t)pp.ref_tiles * NP, n_q = (int64_t)pp.npy * pl.chunks * NQ * pp.n_seg;
+    const int64_t n_ref = (int64_t)pp.ref_tiles * NP, n_q = (int64_t)pp.npy * pp.chunks * NQ * pp.n_seg;
     if (n_ref + n_q > 0x7fffffffLL) return CLC_ERR_UNSUPPORTED;
     pp.n_ref_blocks = (int)n_ref;
-    pp.dbg = (g_stage_mask.load() >> 8) & 0xff;
+    pp.dbg = dbg_bits();
+    pp.n_uncert = n_uncertified;
     const size_t sm_r = ((size_t)C * 33 + (C >> 5) + 32 + 512) * sizeof(float);
     const size_t sm_q = ((size_t)64 * ph * (pp.seg_w | 1) + 32) * sizeof(float);
     const size_t sm = sm_r > sm_q ? sm_r : sm_q;
@@ -1657,42 +1926,52 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   prm.nboxB = pl.nboxB; prm.a_stages = pl.a_stages; prm.b_bufs = pl.b_bufs; prm.acc_stages = pl.acc_stages;
   prm.tmem_cols = pl.tmem_cols; prm.a_rows = pl.a_rows; prm.SB = pl.SB; prm.KC = pl.KC; prm.gaussian = gaussian;
   prm.s1 = s1; prm.s2 = s2; prm.xs = xs; prm.sxx = sxx; prm.cand_val = cand_val; prm.cand_idx = cand_idx;
-  prm.dump = dump;
+  prm.stat_chunks = C / kChunk;
+  prm.units_per_group = pl.units_per_group; prm.total_units = pl.total_units; prm.halo = pl.halo;
+  prm.map_pitch = pl.map_pitch;
+  prm.smap = reinterpret_cast<__half*>(ws + pl.off_map);
   prm.st_rows = pl.st_rows; prm.st_shifts = pl.st_shifts; prm.st_mt = pl.st_mt; prm.st_stages = pl.st_stages;
   prm.st_groups = pl.st_groups;
+#ifdef CLC_DEBUG_ABI
+  prm.dump = dump;
   prm.timing = timing;
   prm.dbg = 0;
-  if (timing) { const char* e = getenv("CLC_TC_DBG"); if (e) prm.dbg = atoi(e); }
   // bring-up (scripts/kernel_bench.py): when the stage mask selects the GEMM alone, its upper byte carries
-  // the GEMM experiment bits (1 = shifts rounded to 8 rows, 2 = no MMAs, 4 = no A loads); 0 in production
-  if ((g_stage_mask.load() & 0xff) == 2) prm.dbg = (g_stage_mask.load() >> 8) & 0xff;
+  // the GEMM experiment bits (1 = shifts rounded to 8 rows, 2 = no MMAs, 4 = no A loads)
+  if ((g_stage_mask.load() & 0xff) == 2) prm.dbg = dbg_bits();
+#else
+  (void)dump; (void)timing;
+#endif
   int rc;
   if (!stage_on(1)) rc = CLC_OK;
   else if (pl.stacked) {
     if (pl.KC == 8) rc = gaussian ? launch_gemm_stacked<8, true>(pl, ta, tb, prm, st) : launch_gemm_stacked<8, false>(pl, ta, tb, prm, st);
     else rc = gaussian ? launch_gemm_stacked<16, true>(pl, ta, tb, prm, st) : launch_gemm_stacked<16, false>(pl, ta, tb, prm, st);
-  } else if (pl.KC == 8) rc = gaussian ? launch_gemm<8, true>(pl, ta, tb, prm, st) : launch_gemm<8, false>(pl, ta, tb, prm, st);
-  else rc = gaussian ? launch_gemm<16, true>(pl, ta, tb, prm, st) : launch_gemm<16, false>(pl, ta, tb, prm, st);
+  } else if (pl.KC == 8) rc = gaussian ? launch_gemm_ck<8, true>(pl, ta, tb, prm, st) : launch_gemm_ck<8, false>(pl, ta, tb, prm, st);
+  else rc = gaussian ? launch_gemm_ck<16, true>(pl, ta, tb, prm, st) : launch_gemm_ck<16, false>(pl, ta, tb, prm, st);
   if (rc) return rc;
 
   // ---- merge + exact re-score + top-k (+ fused gather / blend) ----
   if (stage_on(2)) {
     const int64_t blocks = NP * pl.P;
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
-    const size_t sm = (size_t)pl.S * C * sizeof(float) + (size_t)pl.n_lists * pl.KC * 8;
+    const size_t sm = (size_t)pl.S * C * sizeof(float) + (size_t)kListCap * 8;
+    const __half* smap = pl.stacked ? nullptr : reinterpret_cast<const __half*>(ws + pl.off_map);
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
-    const int dbg = (g_stage_mask.load() >> 8) & 0xff;
+    const int dbg = dbg_bits();
     if (pl.KC == 8) {
       if (sm > 48 * 1024)
         CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CLC_CUDA(launch_pdl(rescore_kernel<8>, dim3((unsigned)blocks), dim3(256), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
-                          sxx, cand_val, cand_idx, pl.n_lists, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
+                          sxx, cand_val, cand_idx, smap, (long long)pl.map_pitch,
+                          q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, C / kChunk,
                           val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
     } else {
       if (sm > 48 * 1024)
         CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CLC_CUDA(launch_pdl(rescore_kernel<16>, dim3((unsigned)blocks), dim3(512), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
-                          sxx, cand_val, cand_idx, pl.n_lists, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, pl.chunks,
+                          sxx, cand_val, cand_idx, smap, (long long)pl.map_pitch,
+                          q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, C / kChunk,
                           val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
     }
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
@@ -1731,6 +2010,7 @@ extern "C" const float* clc_match_topk_tc_ref_cl(void* workspace, int64_t NP, in
   return reinterpret_cast<const float*>(ws + pl.off_r32);
 }
 
+#ifdef CLC_DEBUG_ABI
 // Bring-up / test hook: additionally dumps the raw bf16-GEMM accumulators
 // xy[NP, P, H*W] (linear window origins, wrapped ones included).
 extern "C" CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat, int32_t C,
@@ -1751,3 +2031,4 @@ extern "C" CLC_API int clc_debug_match_tc_timing(const float* q_img, const float
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, nullptr, nullptr,
                  timing, 0.f, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
+#endif  // CLC_DEBUG_ABI

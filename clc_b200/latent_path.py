@@ -29,7 +29,7 @@ class LatentPath:
 
     def __init__(self, B, H, W, n_refs=3, M=320, num_slices=5, z_channels=192, train=True, patch=4, k=4,
                  temperature=15.0, match_mode="tc", gaussian_mask=True, fused_slices=False,
-                 device="cuda", lmbda=0.013, data_parallel=False):
+                 device="cuda", lmbda=0.013, data_parallel=False, device_noise=False):
         assert H % 64 == 0 and W % 64 == 0, "latent geometry: h = H/16, hz = H/64"
         self.B, self.H, self.W, self.R, self.M = B, H, W, n_refs, M
         self.h, self.w = H // 16, W // 16
@@ -37,6 +37,7 @@ class LatentPath:
         self.num_slices, self.Cs = num_slices, M // num_slices
         self.train, self.patch, self.k, self.T = train, patch, k, float(temperature)
         self.match_mode, self.fused_slices = match_mode, fused_slices
+        self.device_noise = bool(device_noise) and train      # in-kernel Philox noise instead of noise tensors
         self.P = (self.h // patch) * (self.w // patch)
         self.corr_w = self.w - patch + 1
         self.num_pixels = B * H * W
@@ -82,6 +83,8 @@ class LatentPath:
         self.val = torch.empty(B * R, self.P, k, **f)
         self.idx = torch.empty(B * R, self.P, k, dtype=torch.int32, device=dev)
         self.weights = torch.empty(B * R, self.P, k, **f)
+        # patches whose bf16-screened candidate set could not be certified (tc mode; set by every match call)
+        self.n_uncert = torch.zeros(1, dtype=torch.int32, device=dev)
         self.aligned = torch.empty(B, R, M, h, w, **f)
         self.fused = torch.empty(B, M, h, w, **f)
         self.lik_z = torch.empty_like(self.z)
@@ -213,7 +216,7 @@ class LatentPath:
         if self.match_mode == "tc":
             # screening GEMM -> exact re-scoring + top-k + softmax + gather/blend (3 kernels, one call)
             call("clc_match_topk_tc", ptr(self.y), ptr(r), B * R, R, M, h, w, p, p, k,
-                 1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), None, self.T, ptr(self.aligned),
+                 1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), ptr(self.n_uncert), self.T, ptr(self.aligned),
                  ptr(self.weights), ptr(self.ws), self.ws.numel(), st)
             n = 1
         else:
@@ -404,13 +407,21 @@ class LatentPath:
         cur.synchronize()
         return -(self._host_out[0].item() + self._host_out[1].item()) / (self.num_pixels * self._world)
 
+    def n_uncertified(self):
+        """Patches of the last step whose top-k could not be certified against the bf16 screening error
+        (0 = indices provably equal the exact fp32 ranking).  Synchronises."""
+        return int(self.n_uncert.item())
+
     def bpp(self):
         """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels (over all ranks when data-parallel)."""
         return -(self.log2[0] + self.log2[1]) / (self.num_pixels * self._world)
 
     # ---- algorithmic work per kernel launch (SURVEY.md 8d; stated in DESIGN.md) ------------------
     def algorithmic_work(self):
-        """{trace label: ("bytes"|"flops", amount per launch)} for every kernel of one step.
+        """{trace label: ("bytes"|"flops", amount per launch)} for every kernel of one step, SURVEY.md 8(d)
+        figures only: COMPULSORY traffic (every tensor the operator must read or write, once).  Re-reads the
+        implementation causes (candidate windows re-scored from L2, read-modify-write scatters) are NOT
+        algorithmic work; they are listed separately in gathered_bytes() and reported as `l2_bytes`.
         Labels are the ones the library's per-kernel tracing reports (clc_trace_get)."""
         B, R, M, S, k, P = self.B, self.R, self.M, self.h * self.w, self.k, self.P
         NP = B * R
@@ -418,36 +429,53 @@ class LatentPath:
         n_slice = B * (M if self.fused_slices else self.Cs) * S
         nz = self.z.numel()
         t = self.train
-        KC = 8 if k <= 4 else 16
         L = (self.h - self.patch + 1) * (self.w - self.patch + 1)
+        noise_in = 4 if (t and not self.device_noise) else 0
         w = {
-            "clc_gc_fwd": ("bytes", n_slice * (20 + (4 if t else 0))),     # y,mu,scale(+noise) -> lik,y_hat
+            "clc_gc_fwd": ("bytes", n_slice * (20 + noise_in)),            # y,mu,scale(+noise) -> lik,y_hat
             "clc_lrp_add_fwd": ("bytes", n_slice * 12),
-            "clc_gc_bwd": ("bytes", n_slice * (20 + 4 + 12)),              # y,mu,scale,noise,lik,g_yhat -> 3 grads
+            "clc_gc_bwd": ("bytes", n_slice * (16 + noise_in + 12)),       # 8d E1 bwd: 28-32 B/elem
             "clc_lrp_add_bwd": ("bytes", n_slice * 12),
-            "clc_eb_fwd": ("bytes", nz * (12 + (4 if t else 0))),
-            "clc_eb_bwd": ("bytes", nz * (16 + 4)),
-            "clc_gather_blend_fwd": ("bytes", NP * (k * M * S * 4 + P * k * 8 + M * S * 4)),
+            "clc_eb_fwd": ("bytes", nz * (12 + noise_in)),
+            "clc_eb_bwd": ("bytes", nz * (8 + noise_in + 4)),              # 8d: 8 B read + 4 B write
+            # K6-K7 gather/blend: k windows + indices/values in, blended reference out, per (image, ref)
+            "clc_gather_blend_fwd": ("bytes", NP * ((k + 1) * M * S * 4 + P * k * 8)),
             "clc_clm_fuse_fwd": ("bytes", B * ((R * (M + 1) + M) * S * 4 + M * S * 4)),
             "clc_clm_fuse_bwd": ("bytes", B * ((R * (M + 1) + M) * S * 4 + R * (M + 1) * S * 4)),
             # tensor-core match: 2*P*L*C*ph*pw flop per (image, reference), counted once
             "clc_match_topk_tc(gemm)": ("flops", 2.0 * P * L * K * NP),
-            # pre-pass: read fp32 refs + queries once, write bf16 + fp32 channels-last copies, channel sums
-            "clc_match_topk_tc(prepass)": ("bytes", (NP + B) * M * S * (4 + 2 + 4) + NP * S * 8),
-            # re-score KC windows + the patch, write val/idx/weights and the blended reference
-            "clc_match_topk_tc(rescore)": ("bytes", NP * P * K * 4 * (KC + 1) + NP * P * k * 12 + NP * M * S * 4),
+            # pre-pass: read the fp32 refs + queries once, write the bf16 GEMM operands (the fp32 channels-last
+            # copy it also writes is this implementation's own extra traffic, not counted) + channel sums
+            "clc_match_topk_tc(prepass)": ("bytes", (NP + B) * M * S * (4 + 2) + NP * S * 8),
+            # re-score + top-k + softmax + gather/blend = 8d K6-K7: (k+1)*C*S*4 + P*k*8 per (image, ref)
+            "clc_match_topk_tc(rescore)": ("bytes", NP * ((k + 1) * M * S * 4 + P * k * 8)),
             "patch_stats": ("bytes", B * M * S * 4 + B * P * 8),
             "clc_pearson_corr": ("flops", 2.0 * P * L * K * NP),
             "clc_topk_rows": ("bytes", NP * P * L * 4 + NP * P * k * 8),
             "channel_sums": ("bytes", NP * M * S * 4 + NP * S * 8),
-            # fused match backward: patches of q and g once, k windows read once (kept in registers),
-            # k window read-modify-writes into the gradient scratch
             "clc_match_bwd(nchw_to_cl)": ("bytes", NP * M * S * 8),
-            "clc_match_bwd(main)": ("bytes", NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8),
+            # fused match backward, compulsory tensors: g_aligned + r in, g_r out per (image, ref); q in, g_q out
+            "clc_match_bwd(main)": ("bytes", NP * 3 * M * S * 4 + B * 2 * M * S * 4),
             "clc_match_bwd(cl_to_nchw)": ("bytes", NP * M * S * 8),
-            "clc_match_bwd": ("bytes", NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8),
+            "clc_match_bwd": ("bytes", NP * 3 * M * S * 4 + B * 2 * M * S * 4),
+            "clc_bpp_finalize": ("bytes", 64),
         }
         return w
+
+    def gathered_bytes(self):
+        """{trace label: bytes per launch} counting every window each time it is gathered (what the kernels
+        request from L2), for the kernels whose access pattern re-reads data; bench.py reports it as
+        `roofline.l2_bytes` next to the compulsory figure."""
+        B, R, M, S, k, P = self.B, self.R, self.M, self.h * self.w, self.k, self.P
+        NP = B * R
+        K = M * self.patch ** 2
+        KC = 8 if k <= 4 else 16
+        return {
+            "clc_match_topk_tc(rescore)": NP * P * K * 4 * (KC + 1 + k) + NP * P * k * 12 + NP * M * S * 4,
+            "clc_match_bwd(main)": NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8,
+            "clc_match_bwd": NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8,
+            "clc_gather_blend_fwd": NP * (k * P * K * 4 + P * k * 8 + M * S * 4),
+        }
 
     def algorithmic_bytes(self):
         """Back-compat view: {short name: bytes} + match_flops."""

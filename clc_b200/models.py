@@ -394,6 +394,10 @@ class CLC(_ChARMBase):
         filtered = {k: v for k, v in state_dict.items() if k in own}
         _update_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
                                    ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        # checkpoints saved after update() also carry the EntropyBottleneck tables (compressai's
+        # CompressionModel.load_state_dict resizes the buffers of every entropy model)
+        _update_registered_buffers(self.entropy_bottleneck, "entropy_bottleneck",
+                                   ["_quantized_cdf", "_offset", "_cdf_length"], state_dict)
         return super().load_state_dict(filtered, strict=False)
 
     @classmethod

@@ -201,8 +201,9 @@ CLC_API int clc_gaussian_mask(float* mask, int32_t img_h, int32_t img_w, int32_t
  *   r     : [NP, C, H, W] reference latents (same spatial size as the query)
  *   gaussian_mask : 0 = no mask, 1 = create_gaussian_masks(H, W, ph, pw)
  *   val, idx : out [NP, P, k], P = (H/ph)*(W/pw); idx = oy*(W-pw+1)+ox
- *   n_uncertified : optional device int32 counter += patches whose candidate set could not be
- *                   certified to contain the exact top-k (screening error bound), may be NULL */
+ *   n_uncertified : optional device int32, SET to the number of patches whose candidate set could not
+ *                   be certified to contain the exact top-k (margin below the bf16 screening error
+ *                   bound; such a patch may differ from the fp32 path at a near-tie), may be NULL */
 CLC_API int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
                       int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
                       int32_t gaussian_mask, float* val, int32_t* idx, int32_t* n_uncertified,
@@ -298,29 +299,6 @@ CLC_API int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb,
                              int64_t att_sr, int64_t att_sb, const float* g_out, float* g_ref_t,
                              float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
 
-/* ------------------------------------------------------------------------------------
- * Bring-up / test hooks of the tcgen05 match kernel (no reference counterpart; used by
- * tests/test_match_tc_gpu.py and scripts/tc_timing.py)
- * ---------------------------------------------------------------------------------- */
-
-/* Timing aid: bit i of `mask` enables the i-th kernel of the multi-kernel entry points
- * (clc_match_topk_tc: prepass, gemm, rescore; clc_match_bwd: main, transpose).  Default 0xff = all; bits 8-15 are kernel-specific experiment switches (0 in production).
- * Results are only meaningful with every stage on. */
-CLC_API void clc_debug_set_stage_mask(int mask);
-
-/* clc_match_topk_tc that additionally dumps the raw bf16-GEMM accumulators
- * xy[NP, P, H*W] (linear window origins oy*W+ox, wrapped ones included). */
-CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat, int32_t C,
-                                  int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
-                                  int32_t gaussian_mask, float* val, int32_t* idx, float* xy, void* workspace,
-                                  size_t workspace_bytes, void* stream);
-/* clc_match_topk_tc that additionally records per-CTA clock64 stamps of the GEMM kernel's
- * pipeline stages into timing[148][16] (int64). */
-CLC_API int clc_debug_match_tc_timing(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
-                                      int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
-                                      int32_t gaussian_mask, float* val, int32_t* idx, long long* timing,
-                                      void* workspace, size_t workspace_bytes, void* stream);
-
 /* ---- range coder: compress() / decompress() (CLC_run.py:629-716, :738-814) ----
  * HOST functions (no stream argument, plain host pointers): one rANS stream is a sequential
  * recurrence, so the state machine runs on the host; its inputs (symbols, scale-table indexes) come
@@ -348,6 +326,32 @@ CLC_API size_t clc_rans_encode_capacity(int64_t n);
 CLC_API int clc_rans_decode(const uint8_t* stream, size_t stream_bytes, uint64_t* state, const int32_t* indexes,
                             int64_t n, const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
                             const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out);
+
+#ifdef CLC_DEBUG_ABI
+/* ------------------------------------------------------------------------------------
+ * Bring-up / test hooks of the tcgen05 match kernel (no reference counterpart).  They exist ONLY in
+ * libclc_b200_dbg.so, the -DCLC_DEBUG_ABI build of the same sources that tests/test_match_tc_gpu.py and
+ * scripts/ load; the production library exports none of them and has no mutable global state.
+ * ---------------------------------------------------------------------------------- */
+
+/* Timing aid: bit i of `mask` enables the i-th kernel of the multi-kernel entry points
+ * (clc_match_topk_tc: prepass, gemm, rescore; clc_match_bwd: main, transpose).  Default 0xff = all; bits 8-15 are kernel-specific experiment switches (0 in production).
+ * Results are only meaningful with every stage on. */
+CLC_API void clc_debug_set_stage_mask(int mask);
+
+/* clc_match_topk_tc that additionally dumps the raw bf16-GEMM accumulators
+ * xy[NP, P, H*W] (linear window origins oy*W+ox, wrapped ones included). */
+CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r, int64_t NP, int32_t q_repeat, int32_t C,
+                                  int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                  int32_t gaussian_mask, float* val, int32_t* idx, float* xy, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+/* clc_match_topk_tc that additionally records per-CTA clock64 stamps of the GEMM kernel's
+ * pipeline stages into timing[148][16] (int64). */
+CLC_API int clc_debug_match_tc_timing(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
+                                      int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
+                                      int32_t gaussian_mask, float* val, int32_t* idx, long long* timing,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+#endif /* CLC_DEBUG_ABI */
 
 #ifdef __cplusplus
 }

@@ -33,12 +33,19 @@ torch.cuda.synchronize()
 
 # (a) record the C-ABI calls of one step, then replay each one REP times in a graph
 calls = []
-orig = _lib.call
+_real_call = _lib.call
+
+
+def orig(name, *args):
+    """Replays go through the bring-up build (stage masks / experiment bits only exist there)."""
+    rc = getattr(_lib.debug_lib(), name)(*args)
+    assert rc == 0, (name, rc)
+    return rc
 
 
 def rec(name, *args):
     calls.append((name, args))
-    return orig(name, *args)
+    return _real_call(name, *args)
 
 
 import clc_b200.latent_path as LPm  # noqa: E402
@@ -46,8 +53,8 @@ import clc_b200.ops as OPSm  # noqa: E402
 LPm.call = rec
 OPSm.call = rec
 lp.step()
-LPm.call = orig
-OPSm.call = orig
+LPm.call = _real_call
+OPSm.call = _real_call
 torch.cuda.synchronize()
 print(f"# {a.workload}: {len(calls)} C-ABI calls per step; per-call time, L2-warm, {a.rep} back-to-back in a graph")
 s = torch.cuda.Stream()
@@ -67,7 +74,7 @@ for name, args in calls:
     for st_, dbg, lab in VARIANTS.get(name, []):
         expanded.append((name, args, st_ | (dbg << 8), f"    dbg {lab}"))
 for name, args, mask, label in expanded:
-    _lib.lib().clc_debug_set_stage_mask(mask)
+    _lib.debug_lib().clc_debug_set_stage_mask(mask)
     with torch.cuda.stream(s):
         st = s.cuda_stream
         args2 = list(args)
@@ -92,7 +99,7 @@ for name, args, mask, label in expanded:
     if mask == 0xff:
         tot += us
     print(f"{label:40s} {us:8.2f} us/call")
-_lib.lib().clc_debug_set_stage_mask(0xff)
+_lib.debug_lib().clc_debug_set_stage_mask(0xff)
 print(f"{'sum':28s} {tot:8.2f} us")
 
 # (b) per-kernel trace, warm

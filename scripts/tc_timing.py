@@ -17,10 +17,8 @@ r = (0.5 * y.unsqueeze(1) + torch.randn(NQ, R, Cc, h, w, device=d, generator=g))
 P = (h // p) * (w // p)
 val = torch.empty(NQ * R, P, k, device=d)
 idx = torch.empty(NQ * R, P, k, dtype=torch.int32, device=d)
-H = _lib.lib()
+H = _lib.debug_lib()
 fn = H.clc_debug_match_tc_timing
-fn.restype = C.c_int
-fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 8 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
 nb = H.clc_match_topk_tc_workspace_bytes(NQ * R, R, Cc, h, w, p, p, k)
 ws = torch.empty(nb, dtype=torch.uint8, device=d)
 for it in range(3):

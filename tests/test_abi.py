@@ -10,9 +10,12 @@ import torch
 from conftest import ROOT
 
 
-def _header_symbols():
+def _header_symbols(debug=False):
+    """Symbols the header declares: the production ABI, or (debug=True) the CLC_DEBUG_ABI-only section."""
     src = open(os.path.join(ROOT, "include", "clc_b200.h")).read()
-    return sorted(set(re.findall(r"CLC_API\s+[\w\s\*]+?\b(clc_\w+)\s*\(", src)))
+    m = re.search(r"#ifdef CLC_DEBUG_ABI(.*?)#endif /\* CLC_DEBUG_ABI \*/", src, re.S)
+    part = m.group(1) if debug else src.replace(m.group(0), "")
+    return sorted(set(re.findall(r"CLC_API\s+[\w\s\*]+?\b(clc_\w+)\s*\(", part)))
 
 
 def test_build_and_exports():
@@ -28,6 +31,12 @@ def test_build_and_exports():
     assert not missing, f"declared in the header but not exported: {missing}"
     extra = [s for s in exported if s not in declared]
     assert not extra, f"exported but not declared: {extra}"
+    assert not [s for s in exported if "debug" in s], "the production library must not export bring-up hooks"
+    # the bring-up build exports the production ABI plus exactly the CLC_DEBUG_ABI section of the header
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.DEBUG_LIB_PATH], capture_output=True, text=True).stdout
+    exported_dbg = set(re.findall(r" T (clc_\w+)", out))
+    assert exported_dbg == set(declared) | set(_header_symbols(debug=True))
+    assert sorted(_lib.DEBUG_PROTOTYPES) == _header_symbols(debug=True)
 
 
 def test_prototypes_match_header_and_load():

@@ -23,10 +23,8 @@ def _inputs(NQ, R, Cc, h, w, seed):
 def _run_debug(y, refs, p, k, gauss):
     """Calls the bring-up hook: returns (val, idx, xy) with xy the raw accumulators [NP, P, h*w]."""
     from clc_b200 import _lib
-    h_ = _lib.lib()
+    h_ = _lib.debug_lib()          # bring-up build (-DCLC_DEBUG_ABI) of the same sources
     fn = h_.clc_debug_match_tc_xy
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 8 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
     NQ, R, Cc, h, w = refs.shape
     d = _dev()
     yq = y.to(d).contiguous()
@@ -65,6 +63,8 @@ def _xy_ref(y, refs, p):
     (1, 2, 320, 32, 48, 4),     # cfg3 latent
     (1, 1, 128, 12, 20, 2),     # 2x2 patches, P = 60
     (1, 2, 64, 12, 128, 4),     # wide latent (CLIC-shaped rows): large halo, several tiles per problem
+    (1, 1, 64, 80, 128, 4),     # cfg4 latent geometry: two-unit tiles, 32-channel (64-byte swizzle) K chunks
+    (1, 2, 128, 24, 128, 4),    # unit ranges that end inside a group: mixed one- and two-unit tiles
 ])
 def test_tc_gemm_accumulators(geom):
     NQ, R, Cc, h, w, p = geom
@@ -122,6 +122,39 @@ def test_tc_topk_equals_fp32_mode_and_oracle(geom):
     assert cnt.item() == 0, f"{cnt.item()} patches could not be certified"
 
 
+def test_tc_cfg4_indices_equal_fp32_mode_and_oracle():
+    """BASELINE configs[3] geometry (1 x 3 refs x 320 ch x 80 x 128 latent, P = 640, L = 9625): SURVEY 7.3-1
+    measured that this is where reduced-precision screening flips indices.  The tensor-core path must give
+    idx_tc == idx_fp32 == oracle SI_Finder (reference lines Patch_Matching.py:181-185, :224), values to fp32
+    round-off and every patch certified."""
+    import clc_b200
+    from oracle import clc_oracle as O
+    NQ, R, Cc, h, w, p, k = 1, 3, 320, 80, 128, 4, 4
+    y, refs = _inputs(NQ, R, Cc, h, w, seed=404)
+    d = _dev()
+    yq = y.to(d)
+    cnt = torch.full((1,), 7, dtype=torch.int32, device=d)           # the call resets it
+    from clc_b200 import _lib
+    from clc_b200.ops import _stream
+    r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
+    P = (h // p) * (w // p)
+    val = torch.empty(NQ * R, P, k, device=d)
+    idx = torch.empty(NQ * R, P, k, dtype=torch.int32, device=d)
+    nb = _lib.lib().clc_match_topk_tc_workspace_bytes(NQ * R, R, Cc, h, w, p, p, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device=d)
+    _lib.call("clc_match_topk_tc", yq.data_ptr(), r.data_ptr(), NQ * R, R, Cc, h, w, p, p, k, 1,
+              val.data_ptr(), idx.data_ptr(), cnt.data_ptr(), 0.0, None, None, ws.data_ptr(), ws.numel(), _stream())
+    v32, i32, _ = clc_b200.match_topk(yq, refs.to(d), p, p, k, gaussian_mask=True, mode="fp32")
+    assert torch.equal(idx.view(NQ, R, P, k), i32), "tc-mode indices differ from fp32 mode at cfg4"
+    assert torch.allclose(val.view(NQ, R, P, k), v32, atol=3e-6, rtol=0)
+    assert cnt.item() == 0, f"{cnt.item()} patches could not be certified"
+    mask = O.gaussian_masks(h, w, p, p)
+    for rr in range(R):
+        _, val_o, idx_o = O.si_finder(y, refs[:, rr], p, p, refs[:, rr], k, 15.0, mask=mask, return_index=True)
+        assert torch.equal(idx.view(NQ, R, P, k)[:, rr].cpu().long(), idx_o), "tc-mode indices differ from the oracle"
+        assert torch.allclose(val.view(NQ, R, P, k)[:, rr].cpu(), val_o, atol=3e-6)
+
+
 def test_tc_unsupported_shapes_fail_loudly():
     from clc_b200 import _lib
     h_ = _lib.lib()
@@ -135,7 +168,15 @@ def test_tc_unsupported_shapes_fail_loudly():
                   o.data_ptr(), None, 0.0, None, None, o.data_ptr(), 16, None)
 
 
-def _tc_call(yq, r, R, p, k, gauss, want_aligned):
+def _dcall(name, *args):
+    """Status-checked call into the bring-up library (stage masks / experiment bits live only there)."""
+    from clc_b200 import _lib
+    h_ = _lib.debug_lib()
+    rc = getattr(h_, name)(*args)
+    assert rc == 0, (name, rc, h_.clc_last_cuda_error())
+
+
+def _tc_call(yq, r, R, p, k, gauss, want_aligned, debug_build=False):
     from clc_b200 import _lib
     from clc_b200.ops import _stream
     NP, Cc, h, w = r.shape
@@ -147,8 +188,12 @@ def _tc_call(yq, r, R, p, k, gauss, want_aligned):
     weights = torch.empty(NP, P, k, device=d) if want_aligned else None
     nb = _lib.lib().clc_match_topk_tc_workspace_bytes(NP, R, Cc, h, w, p, p, k)
     ws = torch.empty(nb, dtype=torch.uint8, device=d)
-    _lib.call("clc_match_topk_tc", yq.data_ptr(), r.data_ptr(), NP, R, Cc, h, w, p, p, k, int(gauss), val.data_ptr(),
-              idx.data_ptr(), None, 15.0, _lib.ptr(aligned), _lib.ptr(weights), ws.data_ptr(), ws.numel(), _stream())
+    if debug_build:
+        nb = _lib.debug_lib().clc_match_topk_tc_workspace_bytes(NP, R, Cc, h, w, p, p, k)
+        ws = torch.empty(nb, dtype=torch.uint8, device=d)
+    (_dcall if debug_build else _lib.call)(
+        "clc_match_topk_tc", yq.data_ptr(), r.data_ptr(), NP, R, Cc, h, w, p, p, k, int(gauss), val.data_ptr(),
+        idx.data_ptr(), None, 15.0, _lib.ptr(aligned), _lib.ptr(weights), ws.data_ptr(), ws.numel(), _stream())
     return val, idx, aligned, weights, ws
 
 
@@ -173,17 +218,23 @@ def test_tc_fused_gather_equals_gather_kernel(geom):
     assert torch.allclose(aligned, out, atol=1e-6, rtol=0)
 
 
-def test_stacked_and_general_gemm_kernels_agree(monkeypatch):
-    """Small latents take the stacked-shift tcgen05 kernel; CLC_TC_NO_STACKED forces the general one."""
+def test_stacked_and_general_gemm_kernels_agree():
+    """Small latents take the stacked-shift tcgen05 kernel; experiment bit 16 of the bring-up build forces
+    the general one."""
+    from clc_b200 import _lib
     NQ, R, Cc, h, w, p, k = 3, 2, 320, 16, 16, 4, 4
     y, refs = _inputs(NQ, R, Cc, h, w, seed=123)
     d = _dev()
     yq = y.to(d)
     r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
     v1, i1, a1, _, _ = _tc_call(yq, r, R, p, k, True, True)
-    monkeypatch.setenv("CLC_TC_NO_STACKED", "1")
-    v2, i2, a2, _, _ = _tc_call(yq, r, R, p, k, True, True)
-    monkeypatch.delenv("CLC_TC_NO_STACKED")
+    H = _lib.debug_lib()
+    H.clc_debug_set_stage_mask(0xff | (16 << 8))
+    try:
+        v2, i2, a2, _, _ = _tc_call(yq, r, R, p, k, True, True, debug_build=True)
+        torch.cuda.synchronize()
+    finally:
+        H.clc_debug_set_stage_mask(0xff)
     assert torch.equal(i1, i2), "stacked / general screening must select the same windows"
     assert torch.equal(v1, v2) and torch.equal(a1, a2)      # final values come from the same fp32 re-scoring
 
@@ -207,7 +258,7 @@ def test_match_bwd_variants_agree(geom):
     NP, P = r.shape[0], idx.shape[1]
     g_out = torch.randn(r.shape, generator=torch.Generator().manual_seed(2)).to(d)
     view = _patch_view_from_image(yq, p, p, R)
-    H = _lib.lib()
+    H = _lib.debug_lib()
     r_cl = H.clc_match_topk_tc_ref_cl(ws_f.data_ptr(), NP, R, Cc, h, w, p, p, k)
     nb = H.clc_match_bwd_workspace_bytes(NP, Cc, h, w)
 
@@ -217,10 +268,10 @@ def test_match_bwd_variants_agree(geom):
         g_q = torch.zeros_like(yq)
         g_val = torch.empty_like(val)
         if zero_ws:
-            _lib.call("clc_match_bwd_zero_workspace", ws.data_ptr(), ws.numel(), NP, Cc, h, w, _stream())
+            _dcall("clc_match_bwd_zero_workspace", ws.data_ptr(), ws.numel(), NP, Cc, h, w, _stream())
         H.clc_debug_set_stage_mask(0xff | (dbg << 8))
         try:
-            _lib.call("clc_match_bwd", C.byref(view), r.data_ptr(), r_cl if use_cl else None, None, idx.data_ptr(),
+            _dcall("clc_match_bwd", C.byref(view), r.data_ptr(), r_cl if use_cl else None, None, idx.data_ptr(),
                       weights.data_ptr(), 15.0, g_out.data_ptr(), g_r.data_ptr(), g_q.data_ptr(), g_val.data_ptr(),
                       NP, P, Cc, p, p, h, w, k, flags, ws.data_ptr() if use_ws else None, ws.numel() if use_ws else 0,
                       _stream())

@@ -67,3 +67,21 @@ def test_tcm_backbone_reproduces_reference_forward():
     with torch.no_grad():
         out = to_oracle_mode(m).eval()(detfill.det_image((1, 3, 256, 256), 11))
     _check_against_golden(out, g)
+
+
+def test_clc_loads_checkpoint_saved_after_update():
+    """A checkpoint saved after update() carries non-empty CDF tables for BOTH entropy models; the
+    reference (compressai CompressionModel.load_state_dict, CLC_run.py:599-618) resizes the empty buffers so
+    that it loads.  Round trip through a fresh model."""
+    import clc_b200.models as M
+    src = M.CLC(N=64)
+    src.update()
+    sd = src.state_dict()
+    assert sd["entropy_bottleneck._quantized_cdf"].numel() > 0
+    assert sd["gaussian_conditional._quantized_cdf"].numel() > 0
+    dst = M.CLC(N=64)
+    dst.load_state_dict(sd)
+    for k in ("entropy_bottleneck._quantized_cdf", "entropy_bottleneck._offset", "entropy_bottleneck._cdf_length",
+              "gaussian_conditional._quantized_cdf", "gaussian_conditional._cdf_length",
+              "gaussian_conditional.scale_table"):
+        assert torch.equal(dst.state_dict()[k], sd[k]), k
