@@ -57,6 +57,8 @@ PROTOTYPES = {
     "clc_gaussian_mask": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p]),
     "clc_match_topk_tc": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                     _f, _p, _p, _p, _sz, _p]),
+    "clc_match_clm_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                    _f, _p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "clc_match_topk_tc_ref_cl": (_p, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "clc_match_topk_tc_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "clc_gather_blend_fwd": (C.c_int, [_p, _p, _p, _f, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
@@ -67,6 +69,8 @@ PROTOTYPES = {
                                        _i32, _i32, _i32, _i32, _p]),
     "clc_match_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i64, _i32, _i32, _i32,
                                 _i32, _i32, _i32, _i32, _i32, _p, _sz, _p]),
+    "clc_match_clm_bwd": (C.c_int, [C.POINTER(PatchView), _p, _p, _p, _p, _f, _p, _p, _i64, _i64, _p, _p, _p, _p, _p,
+                                    _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _sz, _p]),
     "clc_match_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "clc_match_bwd_zero_workspace": (C.c_int, [_p, _sz, _i64, _i32, _i32, _i32, _p]),
     "clc_pmf_to_quantized_cdf": (C.c_int, [_p, _i32, _i32, _p]),

@@ -9,6 +9,8 @@
 //   SI_Wraper ................. models/Patch_Matching.py:218-240
 #include "match.cuh"
 
+#include <cooperative_groups.h>
+
 namespace clc {
 
 // ------------------------------------------------------------------------------------------
@@ -1035,14 +1037,33 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
 // transposition happens in register naming, there is no shared-memory staging -- and every window
 // address is base + dx * C, so the kernel has no per-item index arithmetic.  Windows are processed
 // two at a time and read again for the scatter (L1 / L2 hits).
-template <int NT>
+// Fusion of the SimpleCLM elementwise backward (models/CLM.py:170-182) into the match backward: the kernel
+// then reads g_fused (the gradient of the FUSED feature) instead of g_aligned, forms
+//   g_aligned_r = g_fused * coef_r,  coef_r = softmax_r(att) * sigmoid(att_r)        (never written to HBM)
+// on the fly, and also produces g_att.  g_att_m = coef_m G_m - w_m sum_r G_r coef_r + G_m coef_m (1 - s_m) needs
+// G_r = sum_c g_fused_c * aligned_r,c of ALL references at a pixel: the R CTAs of one (image, patch) form a
+// thread-block cluster, each reduces its own G_r over the channels, rank 0 combines them through DSMEM.
+constexpr int kClmMaxRefs = 8;
+struct ClmBwdArgs {
+  const float* g_fused;     // [NQ, C, fh*fw]
+  const float* att;         // plane (r, b) of [fh*fw] logits at att + r*att_sr + b*att_sb
+  int64_t att_sr, att_sb;
+  const float* aligned;     // [NP, C, fh*fw] blended references of the forward pass
+  float* g_att;             // same addressing as att
+  int R;
+};
+
+template <int NT, bool CLM>
 __global__ void __launch_bounds__(NT, 2)
 match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __restrict__ mask,
                      const int32_t* __restrict__ idx, const float* __restrict__ weights, float temperature,
                      const float* __restrict__ g_out, float* __restrict__ g_rT, float* __restrict__ g_q,
-                     float* __restrict__ g_val_out, int P, int C, int ph, int fh, int fw, int k, int dbg) {
+                     float* __restrict__ g_val_out, int P, int C, int ph, int fh, int fw, int k, int dbg,
+                     const ClmBwdArgs ca) {
   constexpr int KK = 4, NV = 2 + 4 * KK, NW = NT / 32, pw = 4;
   __shared__ float red[NW][NV];
+  __shared__ float gpart[CLM ? NT : 1][4];     // per-thread partial G (its 4 channels) for the 4 pixels of its row
+  __shared__ float G_s[16];                    // this CTA's G_r at the 16 pixels of the patch (read through DSMEM)
   __shared__ float tot[NV];                 // xs, sxx, then per window: g_w, s1, s2, xy
   __shared__ float coef[KK][4];             // per window: w_j, g_xy, 2*g_dY, c_mean
   __shared__ float part[KK][3];             // per window: its terms of t_gxs, t_gsxx, t_gxm
@@ -1050,8 +1071,9 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
   __shared__ float w_s[KK], m_s[KK];
   const int cw = fw - pw + 1, L = (fh - ph + 1) * cw;
   const int HW = fh * fw;
-  const int n = blockIdx.x / P;
-  const int patch = blockIdx.x - n * P;
+  // CLM: the R problems (references) of one (image, patch) are consecutive blocks = one cluster
+  const int n = CLM ? (int)((blockIdx.x / ca.R / P) * ca.R + blockIdx.x % ca.R) : (int)(blockIdx.x / P);
+  const int patch = CLM ? (int)((blockIdx.x / ca.R) % P) : (int)(blockIdx.x - n * P);
   const int nq = n / qa.repeat;
   const int npx = fw / pw;
   const int py = patch / npx, px = patch - py * npx;
@@ -1078,17 +1100,75 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
   const float* qp = qa.q + (int64_t)nq * qa.sn + qa.patch_off(patch) + (int64_t)(4 * c4) * qa.sc + (int64_t)dy * qa.sy;
   const float* gp = g_out + ((int64_t)n * C + 4 * c4) * HW + (py * ph + dy) * fw + px * pw;
   float4 qc[4], gc[4];
+  if constexpr (!CLM) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    qc[i] = ld4(qp + (int64_t)i * qa.sc);
-    gc[i] = ld4(gp + (int64_t)i * HW);
+    for (int i = 0; i < 4; ++i) {
+      qc[i] = ld4(qp + (int64_t)i * qa.sc);
+      gc[i] = ld4(gp + (int64_t)i * HW);
+    }
+  } else {
+    // g_aligned = g_fused * coef_r on the 4 pixels of this thread's patch row; partial G_r over its 4 channels
+    const int r_own = n - nq * ca.R;
+    const int64_t s0 = (int64_t)(py * ph + dy) * fw + px * pw;
+    const float* gf = ca.g_fused + ((int64_t)nq * C + 4 * c4) * HW + s0;
+    const float* al = ca.aligned + ((int64_t)n * C + 4 * c4) * HW + s0;
+    float4 av[4], a4[kClmMaxRefs];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      qc[i] = ld4(qp + (int64_t)i * qa.sc);
+      gc[i] = ld4(gf + (int64_t)i * HW);
+      av[i] = ld4(al + (int64_t)i * HW);
+    }
+#pragma unroll
+    for (int r = 0; r < kClmMaxRefs; ++r)
+      if (r < ca.R) a4[r] = ld4(ca.att + (int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + s0);
+    float gp4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gp4[0] = fmaf(gc[i].x, av[i].x, gp4[0]); gp4[1] = fmaf(gc[i].y, av[i].y, gp4[1]);
+      gp4[2] = fmaf(gc[i].z, av[i].z, gp4[2]); gp4[3] = fmaf(gc[i].w, av[i].w, gp4[3]);
+    }
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) gpart[tid][dx] = gp4[dx];
+    float cf[4];
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      // coef_r = softmax_r(att)[r] * sigmoid(att_r), operation order of clm.cu::clm_coef
+      float mx = -INFINITY, den = 0.f, e_own = 0.f, a_own = 0.f;
+#pragma unroll
+      for (int r = 0; r < kClmMaxRefs; ++r)
+        if (r < ca.R) mx = fmaxf(mx, dx == 0 ? a4[r].x : dx == 1 ? a4[r].y : dx == 2 ? a4[r].z : a4[r].w);
+#pragma unroll
+      for (int r = 0; r < kClmMaxRefs; ++r)
+        if (r < ca.R) {
+          const float a = dx == 0 ? a4[r].x : dx == 1 ? a4[r].y : dx == 2 ? a4[r].z : a4[r].w;
+          const float e = expf(a - mx);
+          den += e;
+          if (r == r_own) { e_own = e; a_own = a; }
+        }
+      cf[dx] = (e_own / den) * (1.0f / (1.0f + expf(-a_own)));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { gc[i].x *= cf[0]; gc[i].y *= cf[1]; gc[i].z *= cf[2]; gc[i].w *= cf[3]; }
   }
   float4 q[4], g[4];   // [dx] -> float4 over the 4 channels
   q[0] = make_float4(qc[0].x, qc[1].x, qc[2].x, qc[3].x); q[1] = make_float4(qc[0].y, qc[1].y, qc[2].y, qc[3].y);
   q[2] = make_float4(qc[0].z, qc[1].z, qc[2].z, qc[3].z); q[3] = make_float4(qc[0].w, qc[1].w, qc[2].w, qc[3].w);
   g[0] = make_float4(gc[0].x, gc[1].x, gc[2].x, gc[3].x); g[1] = make_float4(gc[0].y, gc[1].y, gc[2].y, gc[3].y);
   g[2] = make_float4(gc[0].z, gc[1].z, gc[2].z, gc[3].z); g[3] = make_float4(gc[0].w, gc[1].w, gc[2].w, gc[3].w);
-  __syncthreads();    // src_s visible
+  __syncthreads();    // src_s (and gpart) visible
+  if constexpr (CLM) {
+    // G_r at the 16 pixels (dy, dx): fixed-order sum of the c4n per-thread partials of row dy
+    if (tid < 64) {
+      const int o = tid >> 2, qq = tid & 3, ody = o >> 2, odx = o & 3;
+      const int per = (c4n + 3) / 4;
+      float a = 0.f;
+      for (int t = qq * per; t < (qq + 1) * per && t < c4n; ++t) a += gpart[ody * c4n + t][odx];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (qq == 0) G_s[o] = a;
+    }
+  }
   const float* rbase = rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;    // + (src + dx) * C
   float* gbase = g_rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;
   float v[NV];
@@ -1204,15 +1284,64 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       red_add4(gqp + (int64_t)i * qa.sc, o);
     }
   }
+  if constexpr (CLM) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                  // every reference's G_r is in its CTA's shared memory
+    if (cluster.block_rank() == 0 && tid < 16) {
+      const int ody = tid >> 2, odx = tid & 3;
+      const int64_t s = (int64_t)(py * ph + ody) * fw + px * pw + odx;
+      float a[kClmMaxRefs], w[kClmMaxRefs], sg[kClmMaxRefs], Gt[kClmMaxRefs];
+      float mx = -INFINITY, den = 0.f, mix = 0.f;
+      for (int r = 0; r < ca.R; ++r) { a[r] = ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + s]; mx = fmaxf(mx, a[r]); }
+      for (int r = 0; r < ca.R; ++r) { w[r] = expf(a[r] - mx); den += w[r]; }
+      for (int r = 0; r < ca.R; ++r) {
+        w[r] = w[r] / den;
+        sg[r] = 1.0f / (1.0f + expf(-a[r]));
+        Gt[r] = cluster.map_shared_rank(&G_s[0], r)[tid];
+        mix = fmaf(Gt[r], w[r] * sg[r], mix);        // sum_r G_r s_r w_r
+      }
+      for (int m = 0; m < ca.R; ++m) {
+        const float cm = w[m] * sg[m];
+        ca.g_att[(int64_t)m * ca.att_sr + (int64_t)nq * ca.att_sb + s] = cm * Gt[m] - w[m] * mix + Gt[m] * cm * (1.f - sg[m]);
+      }
+    }
+    cluster.sync();                                  // keep every CTA's shared memory alive until rank 0 has read it
+  }
 }
 
 template <int NT>
 static int launch_bwd_own(unsigned blocks, cudaStream_t st, PatchAddr qa, const float* rT, const float* mask,
                           const int32_t* idx, const float* weights, float temperature, const float* g_out,
                           float* g_rT, float* g_q, float* g_val, int P, int C, int ph, int fh, int fw, int k) {
-  CLC_CUDA(launch_pdl(match_bwd_own_kernel<NT>, dim3(blocks), dim3(NT), 0, st, qa, rT, mask, idx, weights, temperature,
-                      g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, dbg_bits()));
+  CLC_CUDA(launch_pdl(match_bwd_own_kernel<NT, false>, dim3(blocks), dim3(NT), 0, st, qa, rT, mask, idx, weights, temperature,
+                      g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, dbg_bits(), ClmBwdArgs{}));
   CLC_CHECK_LAUNCH("clc_match_bwd(main)");
+  return CLC_OK;
+}
+// CLM-fused variant: clusters of R CTAs (the references of one (image, patch)), PDL.
+template <int NT>
+static int launch_bwd_own_clm(unsigned blocks, cudaStream_t st, PatchAddr qa, const float* rT, const float* mask,
+                              const int32_t* idx, const float* weights, float temperature, float* g_rT, float* g_q,
+                              float* g_val, int P, int C, int ph, int fh, int fw, int k, const ClmBwdArgs& ca) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ca.R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_on() ? 2 : 1;
+  const float* no_g_out = nullptr;
+  CLC_CUDA(cudaLaunchKernelEx(&cfg, match_bwd_own_kernel<NT, true>, qa, rT, mask, idx, weights, temperature, no_g_out,
+                              g_rT, g_q, g_val, P, C, ph, fh, fw, k, 0, ca));
+  CLC_CHECK_LAUNCH("clc_match_clm_bwd(main)");
   return CLC_OK;
 }
 
@@ -1479,5 +1608,49 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   if (overwrite) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
   else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
   CLC_CHECK_LAUNCH("clc_match_bwd(cl_to_nchw)");
+  return CLC_OK;
+}
+
+extern "C" int clc_match_clm_bwd(const clc_patch_view* qv, const float* r_cl, const float* mask, const int32_t* idx,
+                                 const float* weights, float temperature, const float* g_fused, const float* att,
+                                 int64_t att_sr, int64_t att_sb, const float* aligned, float* g_r, float* g_q,
+                                 float* g_val, float* g_att, int64_t NP, int32_t R, int32_t P, int32_t C, int32_t ph,
+                                 int32_t pw, int32_t fh, int32_t fw, int32_t k, int32_t flags, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!view_ok(qv) || !r_cl || !idx || !weights || !g_fused || !att || !aligned || !g_r || !g_att || !workspace)
+    return CLC_ERR_INVALID_ARGUMENT;
+  if (NP < 0 || R < 1 || P < 1 || C < 1 || ph < 1 || pw < 1 || fh < ph || fw < pw || k < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (fh % ph || fw % pw || P != (fh / ph) * (fw / pw) || NP % R || qv->q_repeat != R) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  if (NP * P > 2147483647LL || (int64_t)C * fh * fw > 0x7fffffffLL || NP > 65535) return CLC_ERR_UNSUPPORTED;
+  // the fused kernel is the thread-owns-items variant: 4x4 patches, k <= 4, one thread per (patch row, 4 channels)
+  const int nt_own = ph * (C / 4);
+  const PatchAddr qa = make_addr(qv);
+  const bool ok = R <= kClmMaxRefs && k <= 4 && pw == 4 && C % 4 == 0 && fw % 4 == 0 && ph == 4 &&
+                  (nt_own == 128 || nt_own == 192 || nt_own == 256 || nt_own == 320 || nt_own == 384) &&
+                  aligned16(qv->q) && aligned16(g_fused) && aligned16(att) && aligned16(aligned) && aligned16(r_cl) &&
+                  (!g_q || aligned16(g_q)) && qa.sy % 4 == 0 && qa.sc % 4 == 0 && qa.spx % 4 == 0 && qa.spy % 4 == 0 &&
+                  qa.sn % 4 == 0 && !((att_sr | att_sb) & 3);
+  if (!ok) return CLC_ERR_UNSUPPORTED;
+  if (workspace_bytes < clc_match_bwd_workspace_bytes(NP, C, fh, fw)) return CLC_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = fh * fw;
+  float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  if (!(flags & CLC_MATCH_BWD_WS_ZEROED))
+    CLC_CUDA(cudaMemsetAsync(g_rT, 0, sizeof(float) * (size_t)NP * C * HW, st));
+  ClmBwdArgs ca;
+  ca.g_fused = g_fused; ca.att = att; ca.att_sr = att_sr; ca.att_sb = att_sb; ca.aligned = aligned; ca.g_att = g_att;
+  ca.R = R;
+  const unsigned blocks = (unsigned)(NP * P);
+  int rc = CLC_OK;
+#define CLC_OWN_CASE(N) case N: rc = launch_bwd_own_clm<N>(blocks, st, qa, r_cl, mask, idx, weights, temperature, g_rT, \
+                                                            g_q, g_val, P, C, ph, fh, fw, k, ca); break;
+  switch (nt_own) { CLC_OWN_CASE(128) CLC_OWN_CASE(192) CLC_OWN_CASE(256) CLC_OWN_CASE(320) CLC_OWN_CASE(384) }
+#undef CLC_OWN_CASE
+  if (rc) return rc;
+  dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
+  if (flags & CLC_MATCH_BWD_OVERWRITE_G_R) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
+  else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
+  CLC_CHECK_LAUNCH("clc_match_clm_bwd(cl_to_nchw)");
   return CLC_OK;
 }

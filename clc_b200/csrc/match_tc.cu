@@ -23,6 +23,7 @@
 // warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (one TMEM lane quarter each).
 #include "match.cuh"
 
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -1199,7 +1200,7 @@ __device__ __forceinline__ void blend_rows(float4* T4, const float* __restrict__
   }
 }
 
-constexpr int kListCap = 256;   // screened scores collected per patch by the threshold scan
+constexpr int kListCap = 256;   // screened scores a warp collects per patch row in the threshold scan
 
 // Order-preserving integer key of a float (larger float <-> larger key; -0 < +0).
 __device__ __forceinline__ unsigned float_key(float v) {
@@ -1207,167 +1208,226 @@ __device__ __forceinline__ unsigned float_key(float v) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-template <int KC>
+// ------------------------------------------------------------------------------------------
+// Candidate selection from the screened score map (general GEMM kernel): one WARP per (problem, patch)
+// row of fp16 scores over linear window origins (NaN = no window there).  Lanes run across positions:
+//   pass 1  lane maxima; T0 = NC-th largest of them, so at least NC scores are >= T0
+//   pass 2  every score >= T0 is collected (ballot compaction, a few more than NC on average)
+//   then    NC rounds of warp arg-max by (score desc, window id asc) -> the sorted candidate list
+// i.e. the same [rows][NC] (value, id) lists the stacked kernel writes itself.
+// ------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256)
+select_kernel(const __half* __restrict__ smap, long long map_pitch, int rows, int W, int cw,
+              float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  __shared__ float lv[8][kListCap];
+  __shared__ int li[8][kListCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  pdl_trigger();
+  pdl_wait();
+  if (row >= rows) return;
+  const uint4* rp = reinterpret_cast<const uint4*>(smap + (long long)row * map_pitch);
+  const int n8 = (int)(map_pitch >> 3);
+  // Lane <-> position assignment: 16-byte piece i0 + ((lane + 5 * (i0 / 32)) & 31) of every group of 32, so a
+  // lane samples all column ranges of the latent (a fixed lane <-> column mapping would make the lane maxima
+  // follow the Gaussian mask -- the lanes near the patch centre would hold all the large scores -- and the
+  // threshold below would be far too low).
+  float m1 = -INFINITY, m2 = -INFINITY;            // this lane's two largest scores (distinct elements)
+  const uint4 kNaN4 = make_uint4(0x7e007e00u, 0x7e007e00u, 0x7e007e00u, 0x7e007e00u);   // 8 x fp16 NaN
+  for (int i0 = 0; i0 < n8; i0 += 128) {           // four 16-byte loads in flight per lane
+    uint4 u[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ib = i0 + 32 * b;
+      const int i = ib + ((lane + 5 * (ib >> 5)) & 31);
+      u[b] = i < n8 ? __ldg(rp + i) : kNaN4;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[b]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(h[t]);
+        // NaN (wrapped / out-of-range origins) -> -inf, then a branch-free top-2 update
+        f.x = (f.x == f.x) ? f.x : -INFINITY;
+        f.y = (f.y == f.y) ? f.y : -INFINITY;
+        m2 = fmaxf(m2, fminf(m1, f.x)); m1 = fmaxf(m1, f.x);
+        m2 = fmaxf(m2, fminf(m1, f.y)); m1 = fmaxf(m1, f.y);
+      }
+    }
+  }
+  float T0 = -INFINITY;                             // stays -inf when fewer than NC scores were seen: collect all
+  {
+    // NC-th largest of the 64 lane top-2 values: at least NC scores are >= T0
+    float a = m1, b = m2;
+    for (int t = 0; t < NC; ++t) {
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, float_key(a));
+      const unsigned who = __ballot_sync(0xffffffffu, float_key(a) == kmax);
+      const int src = __ffs(who) - 1;
+      if (t == NC - 1) T0 = __shfl_sync(0xffffffffu, a, src);
+      if (lane == src) { a = b; b = -INFINITY; }
+    }
+  }
+  float* mv = lv[warp];
+  int* mi = li[warp];
+  int M = 0;
+  bool overflow = false;
+  for (int i0 = 0; i0 < n8 && !overflow; i0 += 128) {
+    uint4 u4[4];
+    int ii[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ib = i0 + 32 * b;
+      ii[b] = ib + ((lane + 5 * (ib >> 5)) & 31);
+      u4[b] = ii[b] < n8 ? __ldg(rp + ii[b]) : kNaN4;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const __half* h = reinterpret_cast<const __half*>(&u4[b]);
+      float f[8];
+      bool any = false;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { f[t] = __half2float(h[t]); any |= f[t] >= T0; }   // NaN never passes
+      if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const bool hit = f[t] >= T0;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int slot = M + __popc(bal & ((1u << lane) - 1u));
+          if (slot < kListCap) {
+            mv[slot] = f[t];
+            mi[slot] = ii[b] * 8 + t;              // linear window origin (orders like the window id)
+          }
+        }
+        M += __popc(bal);
+      }
+    }
+    if (M > kListCap) overflow = true;
+  }
+  __syncwarp();
+  float* ov = cand_val + (long long)row * NC;
+  int32_t* oi = cand_idx + (long long)row * NC;
+  if (!overflow) {
+    // sorted top-NC of the M collected scores by RANK: entry e goes to slot #{entries ranking before e}
+    // ((score desc, position asc); positions are distinct, so the ranks are a permutation)
+    for (int t = lane; t < NC; t += 32) { ov[t] = -INFINITY; oi[t] = -1; }
+    __syncwarp();
+    for (int e0 = 0; e0 < M; e0 += 32) {
+      const int e = e0 + lane;
+      const float v = e < M ? mv[e] : 0.f;
+      const int pos = e < M ? mi[e] : 0;
+      int rank = 0;
+      for (int j = 0; j < M; ++j) {
+        const float xv = mv[j];
+        const int xp = mi[j];
+        rank += (xv > v || (xv == v && xp < pos)) ? 1 : 0;
+      }
+      if (e < M && rank < NC) {
+        const int oy = pos / W, ox = pos - oy * W;
+        ov[rank] = v;
+        oi[rank] = oy * cw + ox;
+      }
+    }
+  } else {
+    // more than kListCap scores tie at / above the threshold (e.g. a periodic reference): exact selection,
+    // NC rounds of a warp arg-max by (score desc, window id asc) over the whole row
+    // (linear window origins order exactly like window ids, so ties are broken on the position)
+    float pv = INFINITY;
+    int pid = -1;
+    for (int t = 0; t < NC; ++t) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int i = lane; i < n8; i += 32) {
+        const uint4 u = __ldg(rp + i);
+        const __half* h = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float f = __half2float(h[e]);
+          const int pos = i * 8 + e;
+          const bool after_prev = (f < pv) || (f == pv && pos > pid);      // false for NaN
+          if (after_prev && (f > bv || (f == bv && pos < bi))) { bv = f; bi = pos; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float xv = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int xi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (xv > bv || (xv == bv && xi < bi)) { bv = xv; bi = xi; }
+      }
+      const bool none = bi == 0x7fffffff;
+      if (lane == 0) {
+        const int oy = bi / W, ox = bi - oy * W;
+        ov[t] = none ? -INFINITY : bv;
+        oi[t] = none ? -1 : oy * cw + ox;
+      }
+      pv = none ? -INFINITY : bv;
+      pid = none ? 0x7fffffff : bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact fp32 re-scoring + final top-k (+ softmax, gather / blend).  One CTA per (problem, patch), KC
+// warps.  The patch's candidate list holds NC = 2*KC screened candidates in order; warp c re-scores
+// candidate c with fp32 FMAs over the C*ph*pw patch elements (lane-strided partial sums, xor-tree
+// combine), the masked Pearson value is formed exactly as in the fp32 path (match.cuh) and warp 0 takes
+// the top-k by (value desc, index asc).  The result is CERTIFIED when the k-th exact value clears the best
+// screened score outside the re-scored set by more than the screening error bound; otherwise the second
+// half of the list is re-scored as well (rare) and the test repeated against the NC-th screened score.
+// ------------------------------------------------------------------------------------------
+// CLM = true additionally fuses the SimpleCLM elementwise forward (models/CLM.py:170-182): the R CTAs (references)
+// of one (image, patch) run as a thread-block cluster; once every CTA holds its blended tile in shared memory
+// each of them forms 1/R of the channels of
+//   fused_c = sum_r aligned_r,c * softmax_r(att) * sigmoid(att_r) + y_c
+// reading the other references' tiles through distributed shared memory (y = the staged query patch).
+struct ClmFwdArgs {
+  const float* att;         // plane (r, b) of [H*W] logits at att + r*att_sr + b*att_sb
+  int64_t att_sr, att_sb;
+  float* fused;             // out [NP/R, C, H, W]
+  int R;
+};
+
+template <int KC, bool CLM>
 __global__ void __launch_bounds__(KC * 32, 768 / (KC * 32))
 rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, int P_pad,
                const float* __restrict__ s1,
                const float* __restrict__ s2, const float* __restrict__ xs_a, const float* __restrict__ sxx_a,
-               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
-               const __half* __restrict__ smap, long long map_pitch,
+               const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int NC, float score_rel_err,
                int q_repeat, int C, int H, int W, int ph, int pw, int P, int k, int gaussian, int chunks,
                float* __restrict__ val, int32_t* __restrict__ idx, int32_t* __restrict__ n_uncertified,
-               float temperature, float* __restrict__ aligned, float* __restrict__ weights_out, int dbg) {
-  // dynamic shared memory: query patch Q[S][C] fp32 (also reused as the blend tile [S][C]) | collected
-  // scores [kListCap] | their window ids [kListCap]
+               float temperature, float* __restrict__ aligned, float* __restrict__ weights_out, int dbg,
+               const ClmFwdArgs ca) {
+  // dynamic shared memory: query patch Q[S][C] fp32 (also reused as the blend tile [S][C]; CLM: a second
+  // [S][C] tile follows, so that the query patch survives the blend)
   extern __shared__ float4 sm4[];
-  __shared__ float sel_v[kMaxKC], ex_v[kMaxKC];
-  __shared__ int sel_i[kMaxKC];
+  __shared__ float sel_v[2 * kMaxKC], ex_v[2 * kMaxKC];
+  __shared__ int sel_i[2 * kMaxKC];
   __shared__ float top_w[8];
   __shared__ int top_src[8], top_id[8];
-  __shared__ float wtop_v[kMaxKC * kMaxKC];   // per-warp top-KC of the thread maxima (threshold selection)
-  __shared__ float thr_s;
-  __shared__ int cnt_s;
+  __shared__ int more_s;
   constexpr int NT = KC * 32;
-  const int n = blockIdx.x / P, patch = blockIdx.x - n * P;
-  const int pp = ph * pw, K = C * pp, c4n = C >> 2, items = pp * c4n;
+  // CLM: the R problems (references) of one (image, patch) are consecutive blocks = one cluster
+  const int n = CLM ? (int)((blockIdx.x / ca.R / P) * ca.R + blockIdx.x % ca.R) : (int)(blockIdx.x / P);
+  const int patch = CLM ? (int)((blockIdx.x / ca.R) % P) : (int)(blockIdx.x - n * P);
+  const int pp = ph * pw, K = C * pp, c4n = C >> 2;
   float4* Q = sm4;
-  float* cvs = reinterpret_cast<float*>(sm4 + items);
-  int* cis = reinterpret_cast<int*>(cvs + kListCap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = n / q_repeat;
   const int cw = W - pw + 1;
   pdl_trigger();
   pdl_wait();
-  const bool scan = smap != nullptr;
-  int M = 0;          // collected candidates (scan mode)
-  bool exact_select = false;
-  if (scan) {
-    // ---- candidate selection from the screened score row (fp16, linear window origins, NaN = no window):
-    // pass 1 finds a threshold T0 with at least KC scores >= T0 (the KC-th largest of the per-thread maxima),
-    // pass 2 collects every score >= T0 (a few more than KC on average), warp 0 then takes the top-KC. ----
-    const uint4* rp = reinterpret_cast<const uint4*>(smap + ((long long)n * P + patch) * map_pitch);
-    const int n8 = (int)(map_pitch >> 3);
-    float lmax = -INFINITY;
-    for (int i = threadIdx.x; i < n8; i += NT) {
-      const uint4 u = __ldg(rp + i);
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(h[t]);
-        lmax = fmaxf(lmax, fmaxf(f.x, f.y));        // fmaxf drops NaN
-      }
-    }
-    {
-      // per-warp top-KC of the 32 lane maxima (KC rounds of max + remove), then warp 0 over the KC*KC survivors
-      float mine = lmax;
-      for (int t = 0; t < KC; ++t) {
-        const unsigned kmax = __reduce_max_sync(0xffffffffu, float_key(mine));
-        const unsigned who = __ballot_sync(0xffffffffu, float_key(mine) == kmax);
-        if (lane == (__ffs(who) - 1)) { wtop_v[warp * KC + t] = mine; mine = -INFINITY; }
-      }
-    }
-    if (threadIdx.x == 0) cnt_s = 0;
-    __syncthreads();
-    if (warp == 0) {
-      constexpr int PL = KC * KC / 32;              // survivors per lane (2 or 8)
-      float mv[PL];
-#pragma unroll
-      for (int u = 0; u < PL; ++u) mv[u] = wtop_v[lane + 32 * u];
-      float t0 = -INFINITY;
-      for (int t = 0; t < KC; ++t) {
-        float lm = mv[0];
-#pragma unroll
-        for (int u = 1; u < PL; ++u) lm = fmaxf(lm, mv[u]);
-        const unsigned kmax = __reduce_max_sync(0xffffffffu, float_key(lm));
-        const unsigned who = __ballot_sync(0xffffffffu, float_key(lm) == kmax);
-        if (lane == (__ffs(who) - 1)) {
-          bool done = false;
-#pragma unroll
-          for (int u = 0; u < PL; ++u)
-            if (!done && float_key(mv[u]) == kmax) { mv[u] = -INFINITY; done = true; }
-        }
-        if (t == KC - 1) t0 = __shfl_sync(0xffffffffu, lm, __ffs(who) - 1);
-      }
-      if (lane == 0) thr_s = t0;                    // -inf when fewer than KC threads saw a score: collect all
-    }
-    __syncthreads();
-    const float T0 = thr_s;
-    for (int i = threadIdx.x; i < n8; i += NT) {
-      const uint4 u = __ldg(rp + i);
-      const __half* h = reinterpret_cast<const __half*>(&u);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float f = __half2float(h[t]);
-        if (f >= T0) {                               // NaN never passes
-          const int slot = atomicAdd(&cnt_s, 1);
-          if (slot < kListCap) {
-            const int pos = i * 8 + t;
-            const int oy = pos / W, ox = pos - oy * W;
-            cvs[slot] = f;
-            cis[slot] = oy * cw + ox;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    M = cnt_s;
-    if (M > kListCap) { exact_select = true; M = 0; }
-    if (exact_select) {
-      // More than kListCap scores tie at / above the threshold (e.g. a periodic reference): exact selection,
-      // KC rounds of a block-wide arg-max by (score desc, window id asc) over the whole row.
-      __shared__ float red_v[kMaxKC];
-      __shared__ int red_i[kMaxKC];
-      float pv = INFINITY;
-      int pid = -1;
-      for (int t = 0; t < KC; ++t) {
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int i = threadIdx.x; i < n8; i += NT) {
-          const uint4 u = __ldg(rp + i);
-          const __half* h = reinterpret_cast<const __half*>(&u);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float f = __half2float(h[e]);
-            if (!(f == f)) continue;
-            const int pos = i * 8 + e;
-            const int oy = pos / W, ox = pos - oy * W;
-            const int id = oy * cw + ox;
-            const bool after_prev = (f < pv) || (f == pv && id > pid);
-            if (after_prev && (f > bv || (f == bv && id < bi))) { bv = f; bi = id; }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
-        __syncthreads();
-        bv = red_v[0]; bi = red_i[0];
-        for (int w = 1; w < KC; ++w)
-          if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
-        __syncthreads();
-        const bool none = bi == 0x7fffffff;
-        if (threadIdx.x == 0) { sel_v[t] = none ? -INFINITY : bv; sel_i[t] = none ? -1 : bi; }
-        pv = bv; pid = bi;
-        if (none) { pv = -INFINITY; pid = 0x7fffffff; }
-      }
-    }
-  }
-  // ---- stage the query patch (every shift is one contiguous row of C floats); in scan mode warp 0 selects
-  // the top-KC of the collected scores meanwhile ----
-  const bool w0_busy = scan && !exact_select;
-  const int sw = w0_busy ? warp - 1 : warp, snw = w0_busy ? KC - 1 : KC;   // staging warp id / count
-  if (sw >= 0) {
+  // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate list ----
+  {
     const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
     // two shifts x three float4 columns per warp-iteration: 6 loads in flight before the first store
-    for (int s0 = sw; s0 < pp; s0 += 2 * snw)
+    for (int s0 = warp; s0 < pp; s0 += 2 * KC)
       for (int cb = 0; cb < c4n; cb += 96) {
         float4 t[2][3];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int sft = s0 + u * snw;
+          const int sft = s0 + u * KC;
           const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)sft * P_pad * C);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -1377,7 +1437,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int sft = s0 + u * snw;
+          const int sft = s0 + u * KC;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int c4 = cb + lane + 32 * i;
@@ -1386,49 +1446,25 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         }
       }
   }
-  if (!scan) {
-    // a single candidate list (stacked kernel): already the screened top-KC in order
-    const int64_t co = ((int64_t)n * P + patch) * KC;
-    if (threadIdx.x < KC) {
+  {
+    const int64_t co = ((int64_t)n * P + patch) * NC;
+    if (threadIdx.x < NC) {
       sel_v[threadIdx.x] = cand_val[co + threadIdx.x];
       sel_i[threadIdx.x] = cand_idx[co + threadIdx.x];
     }
-  } else if (!exact_select) {
-    if (warp == 0) {
-      // KC rounds of warp arg-max over the collected list, (score desc, window id asc)
-      for (int t = 0; t < KC; ++t) {
-        float bv = -INFINITY;
-        int bi = 0x7fffffff, bslot = -1;
-        for (int i = lane; i < M; i += 32) {
-          const int id = cis[i];
-          if (id < 0) continue;
-          const float v = cvs[i];
-          if (bslot < 0 || ranks_before(v, id, bv, bi)) { bv = v; bi = id; bslot = i; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
-          if (os >= 0 && (bslot < 0 || ranks_before(ov, oi, bv, bi))) { bv = ov; bi = oi; bslot = os; }
-        }
-        if (lane == 0) {
-          sel_v[t] = bslot >= 0 ? bv : -INFINITY;
-          sel_i[t] = bslot >= 0 ? bi : -1;
-          if (bslot >= 0) cis[bslot] = -1;  // taken
-        }
-        __syncwarp();
-      }
-    }
+    if (threadIdx.x == 0) more_s = 0;
   }
   __syncthreads();
-  // ---- exact re-scoring: warp c <-> candidate c ----
   const int L = (H - ph + 1) * cw;
   const int64_t HW = (int64_t)H * W;
   const int npx = W / pw;
   const int py = patch / npx, px = patch - py * npx;
+  float vk = 0.f;
+  for (int round = 0; round < 2; ++round) {
+  // ---- exact re-scoring: warp c <-> candidate round*KC + c ----
   {
-    const int id = sel_i[warp];
+    const int cslot = round * KC + warp;
+    const int id = cslot < NC ? sel_i[cslot] : -1;
     float out = -INFINITY;
     if (id >= 0 && !(dbg & 1)) {
       const int oy = id / cw, ox = id - oy * cw;
@@ -1502,13 +1538,14 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       const PosStat ps = pos_stat(b1, b2, 1.0f / Kf, Kf);
       out = pearson(acc, ps, xsum, sxxsum, Kf);
     }
-    if (lane == 0) ex_v[warp] = out;
+    if (lane == 0) ex_v[cslot] = out;
   }
   __syncthreads();
+  const int NE = (round + 1) * KC < NC ? (round + 1) * KC : NC;      // candidates with an exact value so far
   if (warp == 0) {
-    // final top-k among the KC exact values, (value desc, index asc); NaN ranks first like torch.topk
-    float myv = (lane < KC) ? ex_v[lane] : -INFINITY;
-    int myi = (lane < KC) ? sel_i[lane] : -1;
+    // final top-k among the NE exact values, (value desc, index asc); NaN ranks first like torch.topk
+    float myv = (lane < NE) ? ex_v[lane] : -INFINITY;
+    int myi = (lane < NE) ? sel_i[lane] : -1;
     if (gaussian && myi >= 0) {
       // create_gaussian_masks (:779-807): float64, rounded to fp32.  One lane per candidate.
       const int oy = myi / cw, ox = myi - oy * cw;
@@ -1521,11 +1558,10 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       myv *= (float)exp(-4.0 * 0.693147180559945309417232121458 * (rg + cg));
     }
     // final top-k by RANK: candidate j ranks before me iff it is valid and (I am not, or NaN first like
-    // torch.topk, or larger value, or equal value and smaller index).  KC independent shuffle pairs,
+    // torch.topk, or larger value, or equal value and smaller index).  Independent shuffle pairs,
     // no dependent reduction rounds; ids are distinct, so the valid ranks are a permutation.
     int rank = 0;
-#pragma unroll
-    for (int j = 0; j < KC; ++j) {
+    for (int j = 0; j < NE; ++j) {
       const float ov = __shfl_sync(0xffffffffu, myv, j);
       const int oi = __shfl_sync(0xffffffffu, myi, j);
       bool before = false;
@@ -1574,51 +1610,62 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       top_src[lane] = oy * W + ox;
     }
     __syncwarp();
-    const float vk = top_w[k - 1];
-    if (aligned != nullptr) {
-      // softmax(value * T) over the k selected positions (SI_Wraper, Patch_Matching.py:225): lanes
-      // 0..7 each form max and denominator in the reference's left-to-right order (identical bits in
-      // every lane) and their own weight
-      float tv[8];                                            // the k selected values
-#pragma unroll
-      for (int j = 0; j < 8; ++j) tv[j] = (j < k) ? top_w[j] : -INFINITY;
-      const int src0 = top_src[0];
-      __syncwarp();
-      float mx = -INFINITY, den = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < k) mx = fmaxf(mx, __fmul_rn(tv[j], temperature));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < k) den += expf(__fsub_rn(__fmul_rn(tv[j], temperature), mx));   // as torch: no FMA
-      if (lane < 8) {
-        float wj = 0.f;
-        if (lane < k) {
-          float mine = tv[0];
-#pragma unroll
-          for (int j = 1; j < 8; ++j) mine = (j == lane) ? tv[j] : mine;
-          wj = expf(__fsub_rn(__fmul_rn(mine, temperature), mx)) / den;
-          if (weights_out) weights_out[oo + lane] = wj;
-        } else {
-          top_src[lane] = src0;
-        }
-        top_w[lane] = wj;
-      }
+    vk = top_w[k - 1];
+    // ---- certification.  Every window that was NOT re-scored has a screened score <= sel_v[NE] (the list is
+    // sorted and holds the row's NC best), or <= sel_v[NC-1] once the whole list is re-scored; the re-scored
+    // set provably holds the exact top-k unless a screening error exceeds the margin to the k-th exact value.
+    // bound = 16 x the bf16 screening error model + the rounding of the stored screened score. ----
+    bool certified = true;
+    if (L > NE) {
+      const float outside = sel_v[NE < NC ? NE : NC - 1];
+      const float eps = 0.03125f * sqrtf(2.0f / (float)K) + score_rel_err * fabsf(outside);
+      certified = (vk - outside > eps) || !(outside == outside) || (NE < NC && sel_i[NE] < 0);
     }
-    if (lane == 0 && n_uncertified != nullptr && L > KC) {
-      // any window outside the candidate set has a screened score <= sel_v[KC-1]; the set provably
-      // holds the exact top-k unless a screening error exceeds the margin to the k-th exact value.
-      // 16 x the bf16 screening error model, plus the fp16 rounding of the stored screened score
-      const float eps = 0.03125f * sqrtf(2.0f / (float)K) + (scan ? 4.9e-4f * fabsf(sel_v[KC - 1]) : 0.f);
-      if (!(vk - sel_v[KC - 1] > eps)) atomicAdd(n_uncertified, 1);
+    if (lane == 0) {
+      more_s = (!certified && NE < NC) ? 1 : 0;
+      if (!certified && NE >= NC && n_uncertified != nullptr) atomicAdd(n_uncertified, 1);
     }
   }
-  if (aligned == nullptr || (dbg & 2)) return;
+  __syncthreads();
+  if (!more_s) break;
+  }   // rounds
+  if (warp == 0 && aligned != nullptr) {
+    // softmax(value * T) over the k selected positions (SI_Wraper, Patch_Matching.py:225): lanes
+    // 0..7 each form max and denominator in the reference's left-to-right order (identical bits in
+    // every lane) and their own weight
+    const int64_t oo = ((int64_t)n * P + patch) * k;
+    float tv[8];                                            // the k selected values
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tv[j] = (j < k) ? top_w[j] : -INFINITY;
+    const int src0 = top_src[0];
+    __syncwarp();
+    float mx = -INFINITY, den = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < k) mx = fmaxf(mx, __fmul_rn(tv[j], temperature));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < k) den += expf(__fsub_rn(__fmul_rn(tv[j], temperature), mx));   // as torch: no FMA
+    if (lane < 8) {
+      float wj = 0.f;
+      if (lane < k) {
+        float mine = tv[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) mine = (j == lane) ? tv[j] : mine;
+        wj = expf(__fsub_rn(__fmul_rn(mine, temperature), mx)) / den;
+        if (weights_out) weights_out[oo + lane] = wj;
+      } else {
+        top_src[lane] = src0;
+      }
+      top_w[lane] = wj;
+    }
+  }
+  if (!CLM && (aligned == nullptr || (dbg & 2))) return;
   // ---- fused gather + blend (SI_Wraper :226-238, is_stack = False): the k selected windows are read
   // again from the channels-last fp32 copy (coalesced float4, all k loads of an item in flight
   // together; they were just re-scored, so mostly L1/L2 hits), blended into a [S][C] shared tile and
   // written as 16-byte NCHW patch rows ----
   __syncthreads();
   {
-    float4* T4 = Q;                                          // the query patch is no longer needed
+    float4* T4 = CLM ? Q + pp * c4n : Q;                     // (not CLM: the query patch is no longer needed)
     const float* rn = rT32 + (int64_t)n * HW * C;
     if (k <= 4) blend_rows<4, 3, KC>(T4, rn, top_src, top_w, k, pp, pw, W, C, warp, lane);
     else blend_rows<8, 1, KC>(T4, rn, top_src, top_w, k, pp, pw, W, C, warp, lane);
@@ -1637,6 +1684,52 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
         const int dy = sft / pw, dx = sft - dy * pw;
         on[(int64_t)c * HW + dy * W + dx] = Tf[sft * C + c];
       }
+    }
+    if constexpr (CLM) {
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      __shared__ float coef_s[8][64];                        // [reference][pixel of the patch]
+      const unsigned rank = cluster.block_rank();
+      if ((int)threadIdx.x < pp) {
+        // coef_r = softmax_r(att)[r] * sigmoid(att_r) at this pixel, operation order of clm.cu::clm_coef
+        const int dy = threadIdx.x / pw, dx = threadIdx.x - dy * pw;
+        const int64_t sp = (int64_t)(py * ph + dy) * W + px * pw + dx;
+        float a[8], mx = -INFINITY, den = 0.f;
+        for (int r = 0; r < ca.R; ++r) { a[r] = ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + sp]; mx = fmaxf(mx, a[r]); }
+        for (int r = 0; r < ca.R; ++r) { const float e = expf(a[r] - mx); den += e; coef_s[r][threadIdx.x] = e; }
+        for (int r = 0; r < ca.R; ++r) coef_s[r][threadIdx.x] = (coef_s[r][threadIdx.x] / den) * (1.0f / (1.0f + expf(-a[r])));
+      }
+      cluster.sync();                                        // every reference's blended tile + the coefficients are in place
+      const float* Qf = reinterpret_cast<const float*>(Q);
+      float* fo = ca.fused + (int64_t)nq * C * HW + (int64_t)(py * ph) * W + px * pw;
+      // this CTA's channels: c = rank, rank + R, ...  (items = (channel, patch row) when pw == 4)
+      if (pw == 4) {
+        const int nc = (C - (int)rank + ca.R - 1) / ca.R;
+        for (int it = threadIdx.x; it < nc * ph; it += NT) {
+          const int dy = it / nc, c = (int)rank + (it - dy * nc) * ca.R;
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
+          // (aligned_stack * attention_weights).sum(dim=1): products summed left to right over r
+          for (int r = 0; r < ca.R; ++r) {
+            const float* t = reinterpret_cast<const float*>(cluster.map_shared_rank(T4, r)) + (dy * 4) * C + c;
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx) o[dx] += t[dx * C] * coef_s[r][dy * 4 + dx];
+          }
+#pragma unroll
+          for (int dx = 0; dx < 4; ++dx) o[dx] += Qf[(dy * 4 + dx) * C + c];
+          st4(fo + (int64_t)c * HW + dy * W, make_float4(o[0], o[1], o[2], o[3]));
+        }
+      } else {
+        for (int e = threadIdx.x; e < C * pp; e += NT) {
+          const int sft = e / C, c = e - sft * C;
+          if (c % ca.R != (int)rank) continue;
+          const int dy = sft / pw, dx = sft - dy * pw;
+          float acc = 0.f;
+          for (int r = 0; r < ca.R; ++r)
+            acc += reinterpret_cast<const float*>(cluster.map_shared_rank(T4, r))[sft * C + c] * coef_s[r][sft];
+          fo[(int64_t)c * HW + dy * W + dx] = acc + Qf[sft * C + c];
+        }
+      }
+      cluster.sync();                                        // keep every tile alive until all readers are done
     }
   }
 }
@@ -1664,7 +1757,7 @@ static EncodeTiledFn encode_fn() {
 struct Plan {
   int P, P_pad, S, HW, npx, m_tiles, n_tiles, total_tiles, TN, NACC, chunks, CK;
   int rowsB, nboxB, a_stages, b_bufs, acc_stages, tmem_cols, KC, grid, a_rows, SB;
-  int units_per_group, total_units, halo;
+  int units_per_group, total_units, halo, NC;
   int stacked, st_rows, st_shifts, st_mt, st_stages, st_groups, zero_rows, n_lists;
   size_t smem_bytes;
   // workspace offsets (bytes)
@@ -1799,12 +1892,14 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * (C / kChunk) * 4, 256);
   pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * (C / kChunk) * 4, 256);
-  // stacked kernel: one screened top-KC list per (problem, patch); general kernel: the fp16 screened score
-  // map [NP, P, map_pitch] (linear window origins, map_pitch = units * TN), scanned by the re-scoring kernel
+  // candidate lists [NP*P][NC] (screened value, window id), sorted: the stacked kernel writes its top-KC
+  // itself; the general kernel writes the fp16 screened score map [NP, P, map_pitch] (linear window origins,
+  // map_pitch = units * TN) and select_kernel extracts the top 2*KC of every row
   pl.n_lists = 1;
+  pl.NC = pl.stacked ? pl.KC : 2 * pl.KC;
   pl.map_pitch = pl.stacked ? 0 : (int64_t)pl.units_per_group * pl.TN;
-  pl.off_cv = o;  o = align_up(o + (pl.stacked ? (size_t)NP * pl.P * pl.KC * 4 : 0), 256);
-  pl.off_ci = o;  o = align_up(o + (pl.stacked ? (size_t)NP * pl.P * pl.KC * 4 : 0), 256);
+  pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.NC * 4, 256);
+  pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.NC * 4, 256);
   pl.off_map = o; o = align_up(o + (size_t)NP * pl.P * (size_t)pl.map_pitch * 2, 256);
   pl.total = o + 256;  // slack for aligning the caller's pointer
   return pl;
@@ -1836,10 +1931,41 @@ static int launch_gemm_stacked(const Plan& pl, const CUtensorMap& ta, const CUte
   return CLC_OK;
 }
 
+template <int KC, bool CLM, typename... Args>
+static cudaError_t launch_rescore(unsigned blocks, size_t sm, cudaStream_t st, int R, Args... args) {
+  auto kern = rescore_kernel<KC, CLM>;
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(KC * 32);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CLM) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)R;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_on()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int C, int H, int W, int ph,
                int pw, int k, int gaussian, float* val, int32_t* idx, int32_t* n_uncertified, float* dump,
                long long* timing, float temperature, float* aligned, float* weights_out, void* workspace,
-               size_t workspace_bytes, cudaStream_t st) {
+               size_t workspace_bytes, cudaStream_t st, const ClmFwdArgs* clm = nullptr) {
   const Plan pl = make_plan(NP, q_repeat, C, H, W, ph, pw, k);
   if (!pl.ok) return CLC_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < pl.total) return CLC_ERR_WORKSPACE;
@@ -1951,29 +2077,52 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   else rc = gaussian ? launch_gemm_ck<16, true>(pl, ta, tb, prm, st) : launch_gemm_ck<16, false>(pl, ta, tb, prm, st);
   if (rc) return rc;
 
-  // ---- merge + exact re-score + top-k (+ fused gather / blend) ----
+  // ---- candidate selection from the screened score map (general kernel only) ----
+  if (!pl.stacked && stage_on(1)) {
+    const int64_t rows = NP * pl.P;
+    if (rows > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
+    const __half* smap = reinterpret_cast<const __half*>(ws + pl.off_map);
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    if (pl.NC == 16)
+      CLC_CUDA(launch_pdl(select_kernel<16>, dim3(blocks), dim3(256), 0, st, smap, (long long)pl.map_pitch, (int)rows, W,
+                          W - pw + 1, cand_val, cand_idx));
+    else
+      CLC_CUDA(launch_pdl(select_kernel<32>, dim3(blocks), dim3(256), 0, st, smap, (long long)pl.map_pitch, (int)rows, W,
+                          W - pw + 1, cand_val, cand_idx));
+    CLC_CHECK_LAUNCH("clc_match_topk_tc(select)");
+  }
+
+  // ---- exact re-score + top-k (+ fused softmax / gather / blend, + CLM fusion) ----
   if (stage_on(2)) {
     const int64_t blocks = NP * pl.P;
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
-    const size_t sm = (size_t)pl.S * C * sizeof(float) + (size_t)kListCap * 8;
-    const __half* smap = pl.stacked ? nullptr : reinterpret_cast<const __half*>(ws + pl.off_map);
+    const size_t sm = (size_t)pl.S * C * sizeof(float) * (clm ? 2 : 1);
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
     const int dbg = dbg_bits();
-    if (pl.KC == 8) {
-      if (sm > 48 * 1024)
-        CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CLC_CUDA(launch_pdl(rescore_kernel<8>, dim3((unsigned)blocks), dim3(256), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
-                          sxx, cand_val, cand_idx, smap, (long long)pl.map_pitch,
-                          q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, C / kChunk,
-                          val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
+    const float rel = pl.stacked ? 0.f : 4.9e-4f;        // fp16 rounding of the stored screened scores
+    const int chunks64 = C / kChunk;
+    cudaError_t e;
+    if (clm) {
+      if (pl.KC == 8)
+        e = launch_rescore<8, true>((unsigned)blocks, sm, st, clm->R, (const float*)A32, (const float*)rT32, pl.P_pad, (const float*)s1, (const float*)s2, (const float*)xs, (const float*)sxx,
+                                    (const float*)cand_val, (const int32_t*)cand_idx, pl.NC, rel, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, chunks64, val, idx,
+                                    n_uncertified, temperature, aligned, weights_out, dbg, *clm);
+      else
+        e = launch_rescore<16, true>((unsigned)blocks, sm, st, clm->R, (const float*)A32, (const float*)rT32, pl.P_pad, (const float*)s1, (const float*)s2, (const float*)xs, (const float*)sxx,
+                                     (const float*)cand_val, (const int32_t*)cand_idx, pl.NC, rel, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, chunks64, val, idx,
+                                     n_uncertified, temperature, aligned, weights_out, dbg, *clm);
     } else {
-      if (sm > 48 * 1024)
-        CLC_CUDA(cudaFuncSetAttribute(rescore_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CLC_CUDA(launch_pdl(rescore_kernel<16>, dim3((unsigned)blocks), dim3(512), sm, st, A32, rT32, pl.P_pad, s1, s2, xs,
-                          sxx, cand_val, cand_idx, smap, (long long)pl.map_pitch,
-                          q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, C / kChunk,
-                          val, idx, n_uncertified, temperature, aligned, weights_out, dbg));
+      const ClmFwdArgs none = {};
+      if (pl.KC == 8)
+        e = launch_rescore<8, false>((unsigned)blocks, sm, st, 1, (const float*)A32, (const float*)rT32, pl.P_pad, (const float*)s1, (const float*)s2, (const float*)xs, (const float*)sxx,
+                                     (const float*)cand_val, (const int32_t*)cand_idx, pl.NC, rel, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, chunks64, val, idx,
+                                     n_uncertified, temperature, aligned, weights_out, dbg, none);
+      else
+        e = launch_rescore<16, false>((unsigned)blocks, sm, st, 1, (const float*)A32, (const float*)rT32, pl.P_pad, (const float*)s1, (const float*)s2, (const float*)xs, (const float*)sxx,
+                                      (const float*)cand_val, (const int32_t*)cand_idx, pl.NC, rel, q_repeat, C, H, W, ph, pw, pl.P, k, gaussian, chunks64, val, idx,
+                                      n_uncertified, temperature, aligned, weights_out, dbg, none);
     }
+    CLC_CUDA(e);
     CLC_CHECK_LAUNCH("clc_match_topk_tc(rescore)");
   }
   return CLC_OK;
@@ -2000,6 +2149,22 @@ extern "C" int clc_match_topk_tc(const float* q_img, const float* r, int64_t NP,
   if (k > (H - ph + 1) * (W - pw + 1)) return CLC_ERR_INVALID_ARGUMENT;
   return tc::run(q_img, r, NP, q_repeat, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, n_uncertified,
                  nullptr, nullptr, temperature, aligned, weights, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int clc_match_clm_fwd(const float* q_img, const float* r, int64_t NP, int32_t R, int32_t C, int32_t H,
+                                int32_t W, int32_t ph, int32_t pw, int32_t k, int32_t gaussian_mask, float* val,
+                                int32_t* idx, int32_t* n_uncertified, float temperature, float* aligned,
+                                float* weights, const float* att, int64_t att_sr, int64_t att_sb, float* fused,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q_img || !r || !val || !idx || !aligned || !att || !fused || NP < 0 || R < 1) return CLC_ERR_INVALID_ARGUMENT;
+  if (NP == 0) return CLC_OK;
+  if (NP % R || k > (H - ph + 1) * (W - pw + 1)) return CLC_ERR_INVALID_ARGUMENT;
+  if (R > 8 || ph * pw > 64) return CLC_ERR_UNSUPPORTED;    // portable cluster size; coefficient table
+  if (!aligned16(fused)) return CLC_ERR_INVALID_ARGUMENT;
+  tc::ClmFwdArgs ca;
+  ca.att = att; ca.att_sr = att_sr; ca.att_sb = att_sb; ca.fused = fused; ca.R = R;
+  return tc::run(q_img, r, NP, R, C, H, W, ph, pw, k, gaussian_mask ? 1 : 0, val, idx, n_uncertified, nullptr, nullptr,
+                 temperature, aligned, weights, workspace, workspace_bytes, (cudaStream_t)stream, &ca);
 }
 
 extern "C" const float* clc_match_topk_tc_ref_cl(void* workspace, int64_t NP, int32_t q_repeat, int32_t C,

@@ -29,7 +29,7 @@ class LatentPath:
 
     def __init__(self, B, H, W, n_refs=3, M=320, num_slices=5, z_channels=192, train=True, patch=4, k=4,
                  temperature=15.0, match_mode="tc", gaussian_mask=True, fused_slices=False,
-                 device="cuda", lmbda=0.013, data_parallel=False, device_noise=False):
+                 device="cuda", lmbda=0.013, data_parallel=False, device_noise=False, fuse_chain=True):
         assert H % 64 == 0 and W % 64 == 0, "latent geometry: h = H/16, hz = H/64"
         self.B, self.H, self.W, self.R, self.M = B, H, W, n_refs, M
         self.h, self.w = H // 16, W // 16
@@ -132,6 +132,10 @@ class LatentPath:
         # channels-last fp32 copy of the references that the forward leaves in its workspace
         self._r_cl = (lib().clc_match_topk_tc_ref_cl(ptr(self.ws), B * R, R, M, h, w, patch, patch, k)
                       if match_mode == "tc" else None)
+        # shapes the CLM-fused match backward kernel covers (clc_match_clm_bwd); others use the two-call sequence
+        self._fused_bwd = (fuse_chain and match_mode == "tc" and patch == 4 and k <= 4 and n_refs <= 8 and
+                           M % 4 == 0 and patch * (M // 4) in (128, 192, 256, 320, 384) and w % 4 == 0)
+        self._fused_fwd = fuse_chain and match_mode == "tc" and n_refs <= 8 and patch * patch <= 64
         self._qview = matching._patch_view_from_image(self.y, patch, patch, R)
         self._gqview = self._qview
         self._graph = self._g_match = self._g_entropy = None
@@ -213,8 +217,15 @@ class LatentPath:
                      ops._stream())
         # 1. match: masked Pearson correlation + top-k over all B*R (image, reference) problems
         r = self.refs.view(B * R, M, h, w)
-        if self.match_mode == "tc":
-            # screening GEMM -> exact re-scoring + top-k + softmax + gather/blend (3 kernels, one call)
+        if self.match_mode == "tc" and self._fused_fwd:
+            # screening GEMM -> exact re-scoring + top-k + softmax + gather/blend + CLM fusion, one call
+            call("clc_match_clm_fwd", ptr(self.y), ptr(r), B * R, R, M, h, w, p, p, k,
+                 1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), ptr(self.n_uncert), self.T,
+                 ptr(self.aligned), ptr(self.weights), ptr(self.att), S, R * S, ptr(self.fused), ptr(self.ws),
+                 self.ws.numel(), st)
+            n = 1
+        elif self.match_mode == "tc":
+            # screening GEMM -> exact re-scoring + top-k + softmax + gather/blend (one call)
             call("clc_match_topk_tc", ptr(self.y), ptr(r), B * R, R, M, h, w, p, p, k,
                  1 if self.gaussian_mask else 0, ptr(self.val), ptr(self.idx), ptr(self.n_uncert), self.T, ptr(self.aligned),
                  ptr(self.weights), ptr(self.ws), self.ws.numel(), st)
@@ -229,17 +240,26 @@ class LatentPath:
                  ptr(self.weights), B * R, M, h, w, p, p, self.corr_w, k, 0, st)
             n = 3
         # 3. CLM fusion over the aligned references ([B,R,C,S] layout, strided -- no transpose)
-        call("clc_clm_fuse_fwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S, ptr(self.y),
-             ptr(self.fused), R, B, M, S, st)
-        n += 1
+        if not (self.match_mode == "tc" and self._fused_fwd):
+            call("clc_clm_fuse_fwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S, ptr(self.y),
+                 ptr(self.fused), R, B, M, S, st)
+            n += 1
         if self.train:
-            call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
-                 ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
             cur.wait_stream(zs)
-            call("clc_match_bwd", C.byref(self._qview), ptr(r), self._r_cl, ptr(self.mask), ptr(self.idx),
-                 ptr(self.weights), self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val),
-                 B * R, self.P, M, p, p, h, w, k, 3, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
-            n += 2
+            if self._fused_bwd:
+                # CLM elementwise backward folded into the match backward: g_aligned is never materialised
+                call("clc_match_clm_bwd", C.byref(self._qview), self._r_cl, ptr(self.mask), ptr(self.idx),
+                     ptr(self.weights), self.T, ptr(self.g_fused), ptr(self.att), S, R * S, ptr(self.aligned),
+                     ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val), ptr(self.g_att), B * R, R, self.P, M, p, p,
+                     h, w, k, 3, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
+                n += 1
+            else:
+                call("clc_clm_fuse_bwd", ptr(self.aligned), M * S, R * M * S, ptr(self.att), S, R * S,
+                     ptr(self.g_fused), ptr(self.g_aligned), ptr(self.g_att), R, B, M, S, st)
+                call("clc_match_bwd", C.byref(self._qview), ptr(r), self._r_cl, ptr(self.mask), ptr(self.idx),
+                     ptr(self.weights), self.T, ptr(self.g_aligned), ptr(self.g_refs), ptr(self.g_q), ptr(self.g_val),
+                     B * R, self.P, M, p, p, h, w, k, 3, ptr(self.ws_bwd), self.ws_bwd.numel(), st)
+                n += 2
         return n
 
     def hyper_chain(self):
@@ -449,6 +469,8 @@ class LatentPath:
             "clc_match_topk_tc(prepass)": ("bytes", (NP + B) * M * S * (4 + 2) + NP * S * 8),
             # re-score + top-k + softmax + gather/blend = 8d K6-K7: (k+1)*C*S*4 + P*k*8 per (image, ref)
             "clc_match_topk_tc(rescore)": ("bytes", NP * ((k + 1) * M * S * 4 + P * k * 8)),
+            # candidate selection: one pass over the fp16 screened score map, 2*KC (value, id) pairs out per patch
+            "clc_match_topk_tc(select)": ("bytes", NP * P * L * 2 + NP * P * (16 if k <= 4 else 32) * 8),
             "patch_stats": ("bytes", B * M * S * 4 + B * P * 8),
             "clc_pearson_corr": ("flops", 2.0 * P * L * K * NP),
             "clc_topk_rows": ("bytes", NP * P * L * 4 + NP * P * k * 8),

@@ -223,6 +223,18 @@ CLC_API size_t clc_match_topk_tc_workspace_bytes(int64_t NP, int32_t q_repeat, i
 CLC_API const float* clc_match_topk_tc_ref_cl(void* workspace, int64_t NP, int32_t q_repeat, int32_t C,
                                               int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k);
 
+/* clc_match_topk_tc with the SimpleCLM elementwise fusion (models/CLM.py:170-182; clc_clm_fuse_fwd) folded into its
+ * last kernel: problem n = image * R + reference (q_repeat = R); the R references of one (image, patch) run as a
+ * thread-block cluster and exchange their blended tiles through distributed shared memory.
+ *   aligned : out [NP, C, H, W] (required);  att : plane (r, b) of [H*W] logits at att + r*att_sr + b*att_sb
+ *   fused   : out [NP/R, C, H, W] = sum_r aligned_r * softmax_r(att) * sigmoid(att_r) + q_img
+ * Identical results to clc_match_topk_tc followed by clc_clm_fuse_fwd.  R <= 8. */
+CLC_API int clc_match_clm_fwd(const float* q_img, const float* r, int64_t NP, int32_t R, int32_t C, int32_t H,
+                              int32_t W, int32_t ph, int32_t pw, int32_t k, int32_t gaussian_mask, float* val,
+                              int32_t* idx, int32_t* n_uncertified, float temperature, float* aligned,
+                              float* weights, const float* att, int64_t att_sr, int64_t att_sb, float* fused,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* softmax(value*T) weights + gather of the k matched patches + weighted sum + tile
  * reassembly (or channel stacking).
  * Replaces: SI_Wraper Patch_Matching.py:226-238.
@@ -279,6 +291,25 @@ CLC_API size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, 
  * pass CLC_MATCH_BWD_WS_ZEROED. */
 CLC_API int clc_match_bwd_zero_workspace(void* workspace, size_t workspace_bytes, int64_t NP, int32_t C,
                                          int32_t fh, int32_t fw, void* stream);
+
+/* Backward of [match -> SimpleCLM elementwise fusion] in one call: clc_clm_fuse_bwd folded into clc_match_bwd
+ * (models/CLM.py:170-182 + Patch_Matching.py:218-240, :854-910, reference autograd semantics as above).
+ * The gradient of the aligned references, g_aligned_r = g_fused * softmax_r(att) * sigmoid(att_r), is formed on
+ * the fly and never written; the R references of one (image, patch) run as one thread-block cluster and combine
+ * their G_r = sum_c g_fused_c * aligned_r,c through distributed shared memory to produce g_att.
+ *   qv      : query patches addressed in place, q_repeat == R (problem n = image * R + reference)
+ *   r_cl    : channels-last fp32 copy of the references [NP, fh*fw, C] (clc_match_topk_tc_ref_cl), required
+ *   g_fused : [NP/R, C, fh, fw] dL/d(fused feature);  att / g_att : plane (r, b) at + r*att_sr + b*att_sb
+ *   aligned : [NP, C, fh, fw] blended references of the forward pass
+ *   g_r, g_q, g_val, flags, workspace : as clc_match_bwd (workspace required)
+ * Shapes outside the fused kernel (patches other than 4x4, k > 4, C/4*ph not in {128,...,384}, R > 8) return
+ * CLC_ERR_UNSUPPORTED: call clc_clm_fuse_bwd + clc_match_bwd instead. */
+CLC_API int clc_match_clm_bwd(const clc_patch_view* qv, const float* r_cl, const float* mask, const int32_t* idx,
+                              const float* weights, float temperature, const float* g_fused, const float* att,
+                              int64_t att_sr, int64_t att_sb, const float* aligned, float* g_r, float* g_q,
+                              float* g_val, float* g_att, int64_t NP, int32_t R, int32_t P, int32_t C, int32_t ph,
+                              int32_t pw, int32_t fh, int32_t fw, int32_t k, int32_t flags, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * CLM conditional fusion (elementwise part; the 1x1 / 3x3 convolutions stay nn.Conv2d)

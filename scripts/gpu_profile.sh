@@ -12,7 +12,7 @@ for wl in "$@"; do
       --log-file gpurun_out/${tag}_launches_${wl}.csv \
       python scripts/profile_step.py --workload $wl --steps 3 > gpurun_out/${tag}_launches_${wl}.log 2>&1
   # full set: only this library's kernels (base-name filter skips the ATen randomize()/fill kernels)
-  ncu --set full --clock-control none --import-source on -k regex:'^(prepass|rescore|match_|clm_|eb_|gc_|lrp_|cl_to|nchw_|gather|patch_stats|channel|topk|pearson)' \
+  ncu --set full --clock-control none --import-source on -k regex:'^(prepass|rescore|select|match_|clm_|eb_|gc_|lrp_|cl_to|nchw_|gather|patch_stats|channel|topk|pearson|bpp)' \
       -c 60 -o gpurun_out/${tag}_full_${wl} -f \
       python scripts/profile_step.py --workload $wl --steps 1 > gpurun_out/${tag}_full_${wl}.log 2>&1
 done

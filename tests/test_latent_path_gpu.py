@@ -141,3 +141,26 @@ def test_host_pipeline_matches_step_host():
     ref.step()
     torch.cuda.synchronize()
     assert torch.equal(a.idx, ref.idx) and torch.equal(a.y_hat, ref.y_hat) and torch.equal(a.lik_y, ref.lik_y)
+
+
+@pytest.mark.parametrize("geom", [(2, 256, 256, 3, 4), (1, 256, 320, 5, 2), (2, 256, 256, 1, 4), (1, 512, 768, 2, 4)])
+def test_fused_chain_equals_separate_kernels(geom):
+    """clc_match_clm_fwd / clc_match_clm_bwd (CLM elementwise fusion folded into the re-scoring kernel and into
+    the match backward, cluster of R CTAs per (image, patch)) == the separate clc_match_topk_tc -> clc_clm_fuse_fwd
+    and clc_clm_fuse_bwd -> clc_match_bwd call sequences."""
+    from clc_b200.latent_path import LatentPath
+    B, H, W, R, k = geom
+    outs = []
+    for fuse in (True, False):
+        lp = LatentPath(B, H, W, n_refs=R, train=True, match_mode="tc", k=k, device="cuda:0", fuse_chain=fuse)
+        assert lp._fused_fwd == fuse and lp._fused_bwd == fuse
+        lp.randomize(seed=17)
+        lp.step()
+        torch.cuda.synchronize()
+        outs.append(lp)
+    a, b = outs
+    assert torch.equal(a.idx, b.idx) and torch.equal(a.val, b.val) and torch.equal(a.aligned, b.aligned)
+    assert torch.allclose(a.fused, b.fused, rtol=0, atol=1e-6)
+    for n in ("g_refs", "g_q", "g_att", "g_val"):
+        x, y = getattr(a, n), getattr(b, n)
+        assert (x - y).abs().max().item() <= 2e-5 * max(y.abs().max().item(), 1e-6), n

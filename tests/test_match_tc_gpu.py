@@ -155,6 +155,37 @@ def test_tc_cfg4_indices_equal_fp32_mode_and_oracle():
         assert torch.allclose(val.view(NQ, R, P, k)[:, rr].cpu(), val_o, atol=3e-6)
 
 
+def test_tc_many_exact_ties_take_the_exact_selection_path():
+    """A reference that is periodic with the patch size makes hundreds of windows IDENTICAL, so their screened
+    scores tie exactly and the threshold scan of select_kernel overflows its list: the exact arg-max fallback
+    must still return the fp32 path's indices (ties -> lowest window index, as torch.topk does on the
+    reference's map) -- nothing can be certified, and the counter must say so."""
+    import clc_b200
+    NQ, R, Cc, h, w, p, k = 1, 1, 64, 48, 96, 4, 4
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(NQ, Cc, h, w, generator=g)
+    tile = torch.randn(NQ, R, Cc, p, p, generator=g)
+    refs = tile.repeat(1, 1, 1, h // p, w // p)                   # period p in both directions
+    d = _dev()
+    yq = y.to(d)
+    r = refs.to(d).reshape(NQ * R, Cc, h, w).contiguous()
+    cnt = torch.zeros(1, dtype=torch.int32, device=d)
+    from clc_b200 import _lib
+    from clc_b200.ops import _stream
+    P = (h // p) * (w // p)
+    val = torch.empty(NQ * R, P, k, device=d)
+    idx = torch.empty(NQ * R, P, k, dtype=torch.int32, device=d)
+    nb = _lib.lib().clc_match_topk_tc_workspace_bytes(NQ * R, R, Cc, h, w, p, p, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device=d)
+    _lib.call("clc_match_topk_tc", yq.data_ptr(), r.data_ptr(), NQ * R, R, Cc, h, w, p, p, k, 0,
+              val.data_ptr(), idx.data_ptr(), cnt.data_ptr(), 0.0, None, None, ws.data_ptr(), ws.numel(), _stream())
+    v32, i32, _ = clc_b200.match_topk(yq, refs.to(d), p, p, k, gaussian_mask=False, mode="fp32")
+    # identical windows: the 16 distinct shifts of the tile repeat (h/p-1)*(w/p-1)+ times each
+    assert torch.equal(idx.view(NQ, R, P, k), i32)
+    assert torch.allclose(val.view(NQ, R, P, k), v32, atol=3e-6, rtol=0)
+    assert cnt.item() > 0           # exact ties cannot be certified against the screening error
+
+
 def test_tc_unsupported_shapes_fail_loudly():
     from clc_b200 import _lib
     h_ = _lib.lib()
