@@ -63,7 +63,9 @@ def make_config(args, cfg, world):
             "slice_launches": "fused" if fused else "per-slice", "cuda_graph": use_graph,
             "graph_branches": "serial" if args.no_fork else ("match | hyper -> slices" if world == 1
                                                               else "match | hyper | slices -> all-reduce"),
-            "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4}
+            "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4,
+            "noise": "uploaded tensors" if args.host_noise else "generated in-kernel (Philox), like the reference's "
+                     "on-device uniform_()"}
 
 
 def peaks():
@@ -178,12 +180,13 @@ class PublicPath:
         t = {k: (v.requires_grad_(True) if (train and k in grad) else v) for k, v in d.items()}
         aligned = c.match_and_gather(t["y"], t["refs"], 4, 4, 4, 15.0, True, False, self.mode)   # [B,R,C,h,w]
         fused = c.clm_fuse(aligned.transpose(0, 1), t["att"].transpose(0, 1), t["y"])
-        _, lik_z, z_hat = self.eb(t["z"], noise=t["noise_z"] if train else None, ste=True, want_outputs=False)
+        _, lik_z, z_hat = self.eb(t["z"], noise=t.get("noise_z") if train else None, ste=True, want_outputs=False)
         liks, yh = [], []
         for i in range(5):
             sl = slice(64 * i, 64 * (i + 1))
             _, lik, y_hat = self.gc(t["y"][:, sl], t["scale"][:, sl], t["mu"][:, sl],
-                                    noise=t["noise_y"][:, sl] if train else None, ste=True, want_outputs=False)
+                                    noise=t["noise_y"][:, sl] if (train and "noise_y" in t) else None, ste=True,
+                                    want_outputs=False)
             yh.append(ops.lrp_add_(y_hat, t["lrp"][:, sl]))
             liks.append(lik)
         bpp = -(ops.log2_sum(torch.cat(liks, 1)) + ops.log2_sum(lik_z)) / self.npix
@@ -197,7 +200,7 @@ class PublicPath:
 def _make_path(cfg, args, dev, fused, rank):
     from clc_b200.latent_path import LatentPath
     lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=args.match_mode,
-                    fused_slices=fused, device=dev, data_parallel=True)
+                    fused_slices=fused, device=dev, data_parallel=True, device_noise=not args.host_noise)
     lp.randomize(seed=1 + rank)
     return lp
 
@@ -503,6 +506,9 @@ def main():
     ap.add_argument("--per-slice", action="store_true",
                     help="launch the GaussianConditional / LRP kernels once per channel slice (the model's call "
                          "pattern) instead of once over all slices (the isolated path's all-slices entry point)")
+    ap.add_argument("--host-noise", action="store_true",
+                    help="upload the U(-1/2,1/2) quantisation noise as tensors (bit-reproducible parity runs) instead "
+                         "of generating it inside the kernels, as the reference generates it on the device")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fork", action="store_true", help="capture the step as one serial chain instead of two branches")
     ap.add_argument("--no-cpu-baseline", action="store_true")

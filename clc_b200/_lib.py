@@ -41,6 +41,16 @@ PROTOTYPES = {
                              _i64, _i64, _f, _f, _p]),
     "clc_gc_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _f, _p, _i64,
                              _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _f, _f, _p]),
+    "clc_gc_fwd_rng": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, C.c_uint64, _p, _i64, _p, _i64, _p, _i64, _p,
+                                 _i64, _i64, _f, _f, _p]),
+    "clc_gc_bwd_rng": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, C.c_uint64, _p, _i64, _p, _i64, _f, _p, _i64,
+                                 _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _f, _f, _p]),
+    "clc_rng_advance": (C.c_int, [_p, C.c_uint64, _p]),
+    "clc_eb_fwd_rng": (C.c_int, [_p, _p, C.c_uint64, _PTR5, _PTR5, _PTR4, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p]),
+    "clc_eb_bwd_rng": (C.c_int, [_p, _p, C.c_uint64, _PTR5, _PTR5, _PTR4, _p, _p, _p, _f, _p, _p, _p, _p, _p,
+                                 _i64, _i64, _i64, _f, _p]),
+    "clc_bpp_finalize": (C.c_int, [_p, _i32, C.c_double, _p, _p, C.c_uint64, _p]),
+    "clc_zero": (C.c_int, [_p, _sz, _p]),
     "clc_lrp_add_fwd": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "clc_lrp_add_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p]),
     "clc_gc_symbols_indexes": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _p, C.c_int, _p, _i64, _p, _i64,

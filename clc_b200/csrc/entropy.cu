@@ -18,6 +18,66 @@ constexpr float kNegInvSqrt2 = -0.70710678118654752440f;  // const = -(2 ** -0.5
 constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
 
 // ------------------------------------------------------------------------------------------
+// In-kernel quantisation noise (training-mode `inputs + U(-1/2, 1/2)`, compressai EntropyModel.quantize
+// "noise" as reached from CLC_run.py:526 / :569): Philox4x32-10, counter = (element index / 4, stream offset),
+// key = seed.  The state {seed, base offset} lives in DEVICE memory, so a captured CUDA graph draws fresh noise
+// on every replay once its owner advances the base offset (clc_rng_advance); `offset` separates the calls of
+// one step.  Forward and backward regenerate the same sample from (state, offset, element index).
+// ------------------------------------------------------------------------------------------
+struct RngArg {
+  const unsigned long long* state;   // device: {seed, base offset}; NULL = no in-kernel noise
+  unsigned long long offset;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+// 24-bit mantissa sample in the OPEN interval (-1/2, 1/2), symmetric around 0
+__device__ __forceinline__ float u_centered(uint32_t r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-8f - 0.5f; }
+
+struct RngCtx {
+  uint2 key;
+  uint32_t off_lo, off_hi;
+  __device__ __forceinline__ explicit RngCtx(const RngArg& a) {
+    const unsigned long long seed = a.state ? a.state[0] : 0ull, off = (a.state ? a.state[1] : 0ull) + a.offset;
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    off_lo = (uint32_t)off;
+    off_hi = (uint32_t)(off >> 32);
+  }
+  // the four samples of elements 4*i4 .. 4*i4+3
+  __device__ __forceinline__ float4 noise4(unsigned long long i4) const {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i4, (uint32_t)(i4 >> 32), off_lo, off_hi), key);
+    return make_float4(u_centered(r.x), u_centered(r.y), u_centered(r.z), u_centered(r.w));
+  }
+  __device__ __forceinline__ float noise1(unsigned long long e) const {
+    const float4 n = noise4(e >> 2);
+    const int c = (int)(e & 3);
+    return c == 0 ? n.x : c == 1 ? n.y : c == 2 ? n.z : n.w;
+  }
+};
+
+__global__ void rng_advance_kernel(unsigned long long* state, unsigned long long n) { state[1] += n; }
+
+// bpp = -(sum_i log2_sums[i]) / num_pixels  (train_CLC.py:48-51 with the log2 sums the kernels accumulated);
+// optionally advances the noise stream for the next step.  One thread.
+__global__ void bpp_finalize_kernel(const double* log2_sums, int n, double num_pixels, double* bpp,
+                                    unsigned long long* rng_state, unsigned long long rng_advance) {
+  double a = 0.0;
+  for (int i = 0; i < n; ++i) a += log2_sums[i];
+  *bpp = -a / num_pixels;
+  if (rng_state) rng_state[1] += rng_advance;
+}
+
+// ------------------------------------------------------------------------------------------
 // GaussianConditional
 // ------------------------------------------------------------------------------------------
 // Phi(u) - Phi(l) with u - l = 1/s loses ~1.25*s ulps to cancellation when formed as a
@@ -79,12 +139,15 @@ struct GcFwdParams {
   int64_t y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs;
   int64_t B, CS;
   float scale_bound, lik_bound;
+  RngArg rng;
 };
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) gc_fwd_kernel(const GcFwdParams p) {
   __shared__ float red[32];
-  const bool train = p.noise != nullptr;
+  const bool use_rng = p.rng.state != nullptr;
+  const bool train = p.noise != nullptr || use_rng;
+  const RngCtx rc(p.rng);
   constexpr int W = VEC ? 4 : 1;
   const int64_t per_b = p.CS / W;
   const int64_t total = p.B * per_b;
@@ -97,7 +160,8 @@ __global__ void __launch_bounds__(256) gc_fwd_kernel(const GcFwdParams p) {
       const float4 y4 = ld4_stream(p.y + b * p.y_bs + j);
       const float4 s4 = ld4_stream(p.scale + b * p.scale_bs + j);
       const float4 m4 = p.mean ? ld4_stream(p.mean + b * p.mean_bs + j) : make_float4(0, 0, 0, 0);
-      const float4 n4 = train ? ld4_stream(p.noise + b * p.noise_bs + j) : make_float4(0, 0, 0, 0);
+      const float4 n4 = use_rng ? rc.noise4((unsigned long long)(b * p.CS + j) >> 2)
+                                : (train ? ld4_stream(p.noise + b * p.noise_bs + j) : make_float4(0, 0, 0, 0));
       const GcOut o0 = gc_elem(y4.x, s4.x, m4.x, n4.x, train, p.scale_bound, p.lik_bound);
       const GcOut o1 = gc_elem(y4.y, s4.y, m4.y, n4.y, train, p.scale_bound, p.lik_bound);
       const GcOut o2 = gc_elem(y4.z, s4.z, m4.z, n4.z, train, p.scale_bound, p.lik_bound);
@@ -113,7 +177,7 @@ __global__ void __launch_bounds__(256) gc_fwd_kernel(const GcFwdParams p) {
       const float y = p.y[b * p.y_bs + j];
       const float s = p.scale[b * p.scale_bs + j];
       const float m = p.mean ? p.mean[b * p.mean_bs + j] : 0.f;
-      const float n = train ? p.noise[b * p.noise_bs + j] : 0.f;
+      const float n = use_rng ? rc.noise1((unsigned long long)(b * p.CS + j)) : (train ? p.noise[b * p.noise_bs + j] : 0.f);
       const GcOut o = gc_elem(y, s, m, n, train, p.scale_bound, p.lik_bound);
       p.lik[b * p.lik_bs + j] = o.lik;
       if (p.y_hat) p.y_hat[b * p.y_hat_bs + j] = o.y_hat;
@@ -133,6 +197,7 @@ struct GcBwdParams {
   int64_t y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs;
   int64_t B, CS;
   float bpp_coef, scale_bound, lik_bound;
+  RngArg rng;
 };
 
 struct GcGrad {
@@ -179,7 +244,9 @@ __device__ __forceinline__ GcGrad gc_elem_bwd(float y, float s, float m, float n
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) gc_bwd_kernel(const GcBwdParams p) {
-  const bool train = p.noise != nullptr;
+  const bool use_rng = p.rng.state != nullptr;
+  const bool train = p.noise != nullptr || use_rng;
+  const RngCtx rc(p.rng);
   const bool has_gl = p.g_lik != nullptr;
   constexpr int W = VEC ? 4 : 1;
   const int64_t per_b = p.CS / W;
@@ -193,7 +260,8 @@ __global__ void __launch_bounds__(256) gc_bwd_kernel(const GcBwdParams p) {
       const float4 y4 = ld4_stream(p.y + b * p.y_bs + j);
       const float4 s4 = ld4_stream(p.scale + b * p.scale_bs + j);
       const float4 m4 = p.mean ? ld4_stream(p.mean + b * p.mean_bs + j) : z4;
-      const float4 n4 = train ? ld4_stream(p.noise + b * p.noise_bs + j) : z4;
+      const float4 n4 = use_rng ? rc.noise4((unsigned long long)(b * p.CS + j) >> 2)
+                                : (train ? ld4_stream(p.noise + b * p.noise_bs + j) : z4);
       const float4 l4 = ld4_stream(p.lik + b * p.lik_bs + j);
       const float4 gl4 = has_gl ? ld4_stream(p.g_lik + b * p.g_lik_bs + j) : z4;
       const float4 gy4 = p.g_y_hat ? ld4_stream(p.g_y_hat + b * p.g_y_hat_bs + j) : z4;
@@ -209,7 +277,7 @@ __global__ void __launch_bounds__(256) gc_bwd_kernel(const GcBwdParams p) {
       const float y = p.y[b * p.y_bs + j];
       const float s = p.scale[b * p.scale_bs + j];
       const float m = p.mean ? p.mean[b * p.mean_bs + j] : 0.f;
-      const float n = train ? p.noise[b * p.noise_bs + j] : 0.f;
+      const float n = use_rng ? rc.noise1((unsigned long long)(b * p.CS + j)) : (train ? p.noise[b * p.noise_bs + j] : 0.f);
       const float l = p.lik[b * p.lik_bs + j];
       const float gl = has_gl ? p.g_lik[b * p.g_lik_bs + j] : 0.f;
       const float gy = p.g_y_hat ? p.g_y_hat[b * p.g_y_hat_bs + j] : 0.f;
@@ -378,6 +446,7 @@ struct EbFwdParams {
   int64_t B, C, S;
   float lik_bound;
   EbPtrs P;
+  RngArg rng;
 };
 
 // grid = (C, chunks): CTA (c, k) handles elements k, k+chunks, ... of channel c's B*S values.
@@ -388,7 +457,9 @@ __global__ void __launch_bounds__(128) eb_fwd_kernel(const EbFwdParams p) {
   eb_load_pack(p.P, c, pk);
   __syncthreads();
   const float med = p.quantiles[c * 3 + 1];
-  const bool train = p.noise != nullptr;
+  const bool use_rng = p.rng.state != nullptr;
+  const bool train = p.noise != nullptr || use_rng;
+  const RngCtx rc(p.rng);
   const int64_t n = p.B * p.S;
   float acc = 0.f;
   for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n;
@@ -397,7 +468,7 @@ __global__ void __launch_bounds__(128) eb_fwd_kernel(const EbFwdParams p) {
     const int64_t off = (b * p.C + c) * p.S + s;
     const float z = p.z[off];
     const float zh = rintf(z - med) + med;
-    const float x = train ? (z + p.noise[off]) : zh;
+    const float x = train ? (z + (use_rng ? rc.noise1((unsigned long long)off) : p.noise[off])) : zh;
     const float lo = eb_logits<false>(pk, x - 0.5f, nullptr, nullptr);
     const float up = eb_logits<false>(pk, x + 0.5f, nullptr, nullptr);
     const float t = lo + up;
@@ -422,6 +493,7 @@ struct EbBwdParams {
   bool param_grads;
   EbPtrs P;
   EbGradPtrs G;
+  RngArg rng;
 };
 
 // Reverse-mode through one logits chain.  g_out = dL/dlogit.  Accumulates transformed-parameter
@@ -477,7 +549,9 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
   if (threadIdx.x < 64) gsum[threadIdx.x] = 0.f;
   __syncthreads();
   const float med = p.quantiles[c * 3 + 1];
-  const bool train = p.noise != nullptr;
+  const bool use_rng = p.rng.state != nullptr;
+  const bool train = p.noise != nullptr || use_rng;
+  const RngCtx rc(p.rng);
   const int64_t n = p.B * p.S;
   float gp[kEbPack];
 #pragma unroll
@@ -487,7 +561,7 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
     const int64_t b = e / p.S, s = e - b * p.S;
     const int64_t off = (b * p.C + c) * p.S + s;
     const float z = p.z[off];
-    const float x = train ? (z + p.noise[off]) : (rintf(z - med) + med);
+    const float x = train ? (z + (use_rng ? rc.noise1((unsigned long long)off) : p.noise[off])) : (rintf(z - med) + med);
     float a_lo[4][3], in_lo[5][3], a_up[4][3], in_up[5][3];
     const float lo = eb_logits<true>(pk, x - 0.5f, a_lo, in_lo);
     const float up = eb_logits<true>(pk, x + 0.5f, a_up, in_up);
@@ -585,21 +659,85 @@ static bool vec_ok(int64_t CS, std::initializer_list<const void*> ptrs, std::ini
   return true;
 }
 
-extern "C" int clc_gc_fwd(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
-                          const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs,
-                          float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
-                          float* outputs, int64_t outputs_bs, double* log2_sum,
-                          int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+static int gc_fwd_impl(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                       const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs, RngArg rng,
+                       float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
+                       float* outputs, int64_t outputs_bs, double* log2_sum,
+                       int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
   if (!y || !scale || !lik || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
   if (B == 0 || CS == 0) return CLC_OK;
   GcFwdParams p{y, scale, mean, noise, lik, y_hat, outputs, log2_sum,
-                y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs, B, CS, scale_bound, lik_bound};
+                y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs, B, CS, scale_bound, lik_bound, rng};
   const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, y_hat, outputs},
                           {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs});
   cudaStream_t st = (cudaStream_t)stream;
   if (vec) gc_fwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
   else gc_fwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
   CLC_CHECK_LAUNCH("clc_gc_fwd");
+  return CLC_OK;
+}
+
+extern "C" int clc_gc_fwd(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                          const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs,
+                          float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
+                          float* outputs, int64_t outputs_bs, double* log2_sum,
+                          int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+  return gc_fwd_impl(y, y_bs, scale, scale_bs, mean, mean_bs, noise, noise_bs, RngArg{nullptr, 0}, lik, lik_bs, y_hat,
+                     y_hat_bs, outputs, outputs_bs, log2_sum, B, CS, scale_bound, lik_bound, stream);
+}
+
+extern "C" int clc_gc_fwd_rng(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                              const float* mean, int64_t mean_bs, const uint64_t* rng_state, uint64_t rng_offset,
+                              float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
+                              float* outputs, int64_t outputs_bs, double* log2_sum,
+                              int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+  if (!rng_state) return CLC_ERR_INVALID_ARGUMENT;
+  return gc_fwd_impl(y, y_bs, scale, scale_bs, mean, mean_bs, nullptr, 0,
+                     RngArg{reinterpret_cast<const unsigned long long*>(rng_state), rng_offset}, lik, lik_bs, y_hat,
+                     y_hat_bs, outputs, outputs_bs, log2_sum, B, CS, scale_bound, lik_bound, stream);
+}
+
+extern "C" int clc_bpp_finalize(const double* log2_sums, int32_t n, double num_pixels, double* bpp,
+                                uint64_t* rng_state, uint64_t rng_advance, void* stream) {
+  if (!log2_sums || !bpp || n < 0 || !(num_pixels > 0)) return CLC_ERR_INVALID_ARGUMENT;
+  bpp_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(log2_sums, n, num_pixels, bpp,
+                                                         reinterpret_cast<unsigned long long*>(rng_state), rng_advance);
+  CLC_CHECK_LAUNCH("clc_bpp_finalize");
+  return CLC_OK;
+}
+
+extern "C" int clc_zero(void* p, size_t bytes, void* stream) {
+  if (!p && bytes) return CLC_ERR_INVALID_ARGUMENT;
+  if (bytes) CLC_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return CLC_OK;
+}
+
+extern "C" int clc_rng_advance(uint64_t* rng_state, uint64_t n, void* stream) {
+  if (!rng_state) return CLC_ERR_INVALID_ARGUMENT;
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(rng_state), n);
+  CLC_CHECK_LAUNCH("clc_rng_advance");
+  return CLC_OK;
+}
+
+static int gc_bwd_impl(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                       const float* mean, int64_t mean_bs, const float* noise, int64_t noise_bs, RngArg rng,
+                       const float* lik, int64_t lik_bs, const float* g_lik, int64_t g_lik_bs,
+                       float bpp_coef, const float* g_y_hat, int64_t g_y_hat_bs,
+                       float* g_y, int64_t g_y_bs, float* g_scale, int64_t g_scale_bs,
+                       float* g_mean, int64_t g_mean_bs,
+                       int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+  if (!y || !scale || !lik || !g_y || !g_scale || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
+  if (mean && !g_mean) return CLC_ERR_INVALID_ARGUMENT;
+  if (B == 0 || CS == 0) return CLC_OK;
+  GcBwdParams p{y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean,
+                y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs,
+                B, CS, bpp_coef, scale_bound, lik_bound, rng};
+  const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean},
+                          {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs});
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) gc_bwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
+  else gc_bwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
+  CLC_CHECK_LAUNCH("clc_gc_bwd");
   return CLC_OK;
 }
 
@@ -610,19 +748,23 @@ extern "C" int clc_gc_bwd(const float* y, int64_t y_bs, const float* scale, int6
                           float* g_y, int64_t g_y_bs, float* g_scale, int64_t g_scale_bs,
                           float* g_mean, int64_t g_mean_bs,
                           int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
-  if (!y || !scale || !lik || !g_y || !g_scale || B < 0 || CS < 0) return CLC_ERR_INVALID_ARGUMENT;
-  if (mean && !g_mean) return CLC_ERR_INVALID_ARGUMENT;
-  if (B == 0 || CS == 0) return CLC_OK;
-  GcBwdParams p{y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean,
-                y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs,
-                B, CS, bpp_coef, scale_bound, lik_bound};
-  const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean},
-                          {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs});
-  cudaStream_t st = (cudaStream_t)stream;
-  if (vec) gc_bwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
-  else gc_bwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
-  CLC_CHECK_LAUNCH("clc_gc_bwd");
-  return CLC_OK;
+  return gc_bwd_impl(y, y_bs, scale, scale_bs, mean, mean_bs, noise, noise_bs, RngArg{nullptr, 0}, lik, lik_bs, g_lik,
+                     g_lik_bs, bpp_coef, g_y_hat, g_y_hat_bs, g_y, g_y_bs, g_scale, g_scale_bs, g_mean, g_mean_bs, B, CS,
+                     scale_bound, lik_bound, stream);
+}
+
+extern "C" int clc_gc_bwd_rng(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                              const float* mean, int64_t mean_bs, const uint64_t* rng_state, uint64_t rng_offset,
+                              const float* lik, int64_t lik_bs, const float* g_lik, int64_t g_lik_bs,
+                              float bpp_coef, const float* g_y_hat, int64_t g_y_hat_bs,
+                              float* g_y, int64_t g_y_bs, float* g_scale, int64_t g_scale_bs,
+                              float* g_mean, int64_t g_mean_bs,
+                              int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream) {
+  if (!rng_state) return CLC_ERR_INVALID_ARGUMENT;
+  return gc_bwd_impl(y, y_bs, scale, scale_bs, mean, mean_bs, nullptr, 0,
+                     RngArg{reinterpret_cast<const unsigned long long*>(rng_state), rng_offset}, lik, lik_bs, g_lik,
+                     g_lik_bs, bpp_coef, g_y_hat, g_y_hat_bs, g_y, g_y_bs, g_scale, g_scale_bs, g_mean, g_mean_bs, B, CS,
+                     scale_bound, lik_bound, stream);
 }
 
 extern "C" int clc_lrp_add_fwd(float* y_hat, int64_t y_hat_bs, const float* lrp, int64_t lrp_bs,
@@ -678,17 +820,17 @@ static int eb_grid_y(int64_t C, int64_t n) {
   return (int)(chunks < 1 ? 1 : chunks);
 }
 
-extern "C" int clc_eb_fwd(const float* z, const float* noise, const float* const matrix[5],
-                          const float* const bias[5], const float* const factor[4], const float* quantiles,
-                          float* lik, float* z_hat, float* outputs, double* log2_sum,
-                          int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+static int eb_fwd_impl(const float* z, const float* noise, RngArg rng, const float* const matrix[5],
+                       const float* const bias[5], const float* const factor[4], const float* quantiles,
+                       float* lik, float* z_hat, float* outputs, double* log2_sum,
+                       int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
   if (!z || !matrix || !bias || !factor || !quantiles || !lik || B < 0 || C < 0 || S < 0)
     return CLC_ERR_INVALID_ARGUMENT;
   if (B == 0 || C == 0 || S == 0) return CLC_OK;
   if (C > 2147483647LL) return CLC_ERR_UNSUPPORTED;
   EbFwdParams p;
   p.z = z; p.noise = noise; p.quantiles = quantiles; p.lik = lik; p.z_hat = z_hat; p.outputs = outputs;
-  p.log2_sum = log2_sum; p.B = B; p.C = C; p.S = S; p.lik_bound = lik_bound;
+  p.log2_sum = log2_sum; p.B = B; p.C = C; p.S = S; p.lik_bound = lik_bound; p.rng = rng;
   for (int i = 0; i < 5; ++i) { p.P.matrix[i] = matrix[i]; p.P.bias[i] = bias[i]; if (!matrix[i] || !bias[i]) return CLC_ERR_INVALID_ARGUMENT; }
   for (int i = 0; i < 4; ++i) { p.P.factor[i] = factor[i]; if (!factor[i]) return CLC_ERR_INVALID_ARGUMENT; }
   dim3 grid((unsigned)C, (unsigned)eb_grid_y(C, B * S));
@@ -697,17 +839,34 @@ extern "C" int clc_eb_fwd(const float* z, const float* noise, const float* const
   return CLC_OK;
 }
 
-extern "C" int clc_eb_bwd(const float* z, const float* noise, const float* const matrix[5],
+extern "C" int clc_eb_fwd(const float* z, const float* noise, const float* const matrix[5],
                           const float* const bias[5], const float* const factor[4], const float* quantiles,
-                          const float* lik, const float* g_lik, float bpp_coef, const float* g_z_hat,
-                          float* g_z, float* const g_matrix[5], float* const g_bias[5], float* const g_factor[4],
+                          float* lik, float* z_hat, float* outputs, double* log2_sum,
                           int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+  return eb_fwd_impl(z, noise, RngArg{nullptr, 0}, matrix, bias, factor, quantiles, lik, z_hat, outputs, log2_sum, B, C, S,
+                     lik_bound, stream);
+}
+
+extern "C" int clc_eb_fwd_rng(const float* z, const uint64_t* rng_state, uint64_t rng_offset,
+                              const float* const matrix[5], const float* const bias[5], const float* const factor[4],
+                              const float* quantiles, float* lik, float* z_hat, float* outputs, double* log2_sum,
+                              int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+  if (!rng_state) return CLC_ERR_INVALID_ARGUMENT;
+  return eb_fwd_impl(z, nullptr, RngArg{reinterpret_cast<const unsigned long long*>(rng_state), rng_offset}, matrix, bias,
+                     factor, quantiles, lik, z_hat, outputs, log2_sum, B, C, S, lik_bound, stream);
+}
+
+static int eb_bwd_impl(const float* z, const float* noise, RngArg rng, const float* const matrix[5],
+                       const float* const bias[5], const float* const factor[4], const float* quantiles,
+                       const float* lik, const float* g_lik, float bpp_coef, const float* g_z_hat,
+                       float* g_z, float* const g_matrix[5], float* const g_bias[5], float* const g_factor[4],
+                       int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
   if (!z || !matrix || !bias || !factor || !quantiles || !lik || !g_z || B < 0 || C < 0 || S < 0)
     return CLC_ERR_INVALID_ARGUMENT;
   if (B == 0 || C == 0 || S == 0) return CLC_OK;
   EbBwdParams p;
   p.z = z; p.noise = noise; p.quantiles = quantiles; p.lik = lik; p.g_lik = g_lik; p.g_z_hat = g_z_hat;
-  p.g_z = g_z; p.B = B; p.C = C; p.S = S; p.bpp_coef = bpp_coef; p.lik_bound = lik_bound;
+  p.g_z = g_z; p.B = B; p.C = C; p.S = S; p.bpp_coef = bpp_coef; p.lik_bound = lik_bound; p.rng = rng;
   p.param_grads = g_matrix && g_bias && g_factor;
   for (int i = 0; i < 5; ++i) {
     p.P.matrix[i] = matrix[i]; p.P.bias[i] = bias[i];
@@ -726,6 +885,26 @@ extern "C" int clc_eb_bwd(const float* z, const float* noise, const float* const
   eb_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
   CLC_CHECK_LAUNCH("clc_eb_bwd");
   return CLC_OK;
+}
+
+extern "C" int clc_eb_bwd(const float* z, const float* noise, const float* const matrix[5],
+                          const float* const bias[5], const float* const factor[4], const float* quantiles,
+                          const float* lik, const float* g_lik, float bpp_coef, const float* g_z_hat,
+                          float* g_z, float* const g_matrix[5], float* const g_bias[5], float* const g_factor[4],
+                          int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+  return eb_bwd_impl(z, noise, RngArg{nullptr, 0}, matrix, bias, factor, quantiles, lik, g_lik, bpp_coef, g_z_hat, g_z,
+                     g_matrix, g_bias, g_factor, B, C, S, lik_bound, stream);
+}
+
+extern "C" int clc_eb_bwd_rng(const float* z, const uint64_t* rng_state, uint64_t rng_offset,
+                              const float* const matrix[5], const float* const bias[5], const float* const factor[4],
+                              const float* quantiles, const float* lik, const float* g_lik, float bpp_coef,
+                              const float* g_z_hat, float* g_z, float* const g_matrix[5], float* const g_bias[5],
+                              float* const g_factor[4], int64_t B, int64_t C, int64_t S, float lik_bound, void* stream) {
+  if (!rng_state) return CLC_ERR_INVALID_ARGUMENT;
+  return eb_bwd_impl(z, nullptr, RngArg{reinterpret_cast<const unsigned long long*>(rng_state), rng_offset}, matrix, bias,
+                     factor, quantiles, lik, g_lik, bpp_coef, g_z_hat, g_z, g_matrix, g_bias, g_factor, B, C, S, lik_bound,
+                     stream);
 }
 
 extern "C" int clc_log2_sum_fwd(const float* lik, int64_t n, double* log2_sum, void* stream) {

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from . import ops
+from . import ops, rng
 
 
 class LowerBound(nn.Module):
@@ -228,16 +228,16 @@ class GaussianConditional(EntropyModel):
         self._cdf_length = (pmf_length + 2).to(dev)
 
     def forward(self, inputs, scales, means=None, training=None, *, noise=None, ste=False,
-                want_outputs=True, log2_acc=None):
+                want_outputs=True, log2_acc=None, out=None):
         if training is None:
             training = self.training
         if training and noise is None:
-            noise = _uniform_noise_like(inputs)
+            noise = rng.ticket(inputs.device)        # U(-1/2, 1/2) generated inside the kernel (Philox)
         if not training:
             noise = None
         lik, y_hat, outputs = ops.gaussian_conditional(
             inputs, scales, means, noise, self._scale_bound, self._lik_bound, want_outputs=want_outputs,
-            log2_acc=log2_acc)
+            log2_acc=log2_acc, out=out)
         if ste:
             return outputs, lik, y_hat
         return outputs, lik
@@ -309,7 +309,7 @@ class EntropyBottleneck(EntropyModel):
         if training is None:
             training = self.training
         if training and noise is None:
-            noise = _uniform_noise_like(x)
+            noise = rng.ticket(x.device)             # U(-1/2, 1/2) generated inside the kernel (Philox)
         if not training:
             noise = None
         ms, bs, fs = self._params()

@@ -52,21 +52,27 @@ class LatentPath:
                   "z": (B, z_channels, self.hz, self.wz), "mu": (B, M, h, w), "scale": (B, M, h, w),
                   "lrp": (B, M, h, w), "noise_y": (B, M, h, w), "noise_z": (B, z_channels, self.hz, self.wz),
                   "g_y_hat": (B, M, h, w)}
-        self.step_inputs = [n for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS
-                            if train or n not in self.TRAIN_ONLY]
+        # (device_noise: the U(-1/2, 1/2) samples are generated inside the kernels -- as the reference draws them
+        # on the device -- so no noise tensors exist or are uploaded)
+        skip = set() if train else set(self.TRAIN_ONLY)
+        if self.device_noise:
+            skip |= {"noise_y", "noise_z"}
+        self.step_inputs = [n for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS if n not in skip]
         offs, off = {}, 0
         for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS:
             if n == self.ENTROPY_INPUTS[0]:
                 self._n_match_in = off
             offs[n] = off
             off += (math.prod(shapes[n]) + 63) // 64 * 64       # 256-byte aligned segments
-            if not train and n in self.TRAIN_ONLY:
-                off = offs[n]                                   # eval: no noise / upstream gradients uploaded
+            if n in skip:
+                off = offs[n]                                   # not part of a step's inputs: not uploaded
         self._in = torch.zeros(off, **f)
         self._in_offsets, self._in_shapes = offs, shapes
         for n in self.MATCH_INPUTS + self.ENTROPY_INPUTS:
             if n in self.step_inputs:
                 setattr(self, n, self._in[offs[n]:offs[n] + math.prod(shapes[n])].view(shapes[n]))
+            elif n in ("noise_y", "noise_z") and self.device_noise:
+                setattr(self, n, None)
             else:
                 setattr(self, n, torch.empty(shapes[n], **f))   # unused in eval; kept for API symmetry
         # ---- EntropyBottleneck parameters ----
@@ -149,6 +155,9 @@ class LatentPath:
         self._eb_grads_flat = self._acc[4:4 + n_eb]
         self._dp_buf = torch.zeros(2 + n_eb, dtype=torch.float64, device=dev) if self.data_parallel else None
         self._world = torch.distributed.get_world_size() if self.data_parallel else 1
+        # device-resident noise stream {seed, base offset} (clc_gc_fwd_rng) + the step's bpp (clc_bpp_finalize)
+        self.rng_state = torch.tensor([0x5DEECE66D + 7919 * (id(self) & 0xFFFF), 0], dtype=torch.int64, device=dev)
+        self._bpp_dev = torch.zeros(1, dtype=torch.float64, device=dev)
 
     # -------------------------------------------------------------------------------------
     def randomize(self, seed=1):
@@ -163,13 +172,28 @@ class LatentPath:
         self.scale.uniform_(math.log(0.05), math.log(300.0), generator=g).exp_()
         rn(self.lrp)
         rn(self.att)
-        self.noise_y.uniform_(-0.5, 0.5, generator=g)
-        self.noise_z.uniform_(-0.5, 0.5, generator=g)
+        if not self.device_noise:
+            self.noise_y.uniform_(-0.5, 0.5, generator=g)
+            self.noise_z.uniform_(-0.5, 0.5, generator=g)
         rn(self.g_y_hat).mul_(1e-3)
         rn(self.g_fused).mul_(1e-3)
 
     def inputs(self):
-        return {n: getattr(self, n) for n in self.INPUT_NAMES}
+        return {n: getattr(self, n) for n in self.INPUT_NAMES if getattr(self, n) is not None}
+
+    _RNG_STRIDE = 1 << 32
+
+    def _noise(self, name, call_index, sl=None):
+        """Noise argument of one kernel launch: the uploaded tensor (slice), or an rng ticket."""
+        if not self.train:
+            return None
+        if self.device_noise:
+            return (self.rng_state, call_index * self._RNG_STRIDE)
+        t = getattr(self, name)
+        return t if sl is None else sl(t)
+
+    def _zero(self, t):
+        call("clc_zero", ptr(t), t.numel() * t.element_size(), ops._stream())
 
     # ---- host staging (end-to-end path) ------------------------------------------------------
     def host_staging(self):
@@ -212,7 +236,7 @@ class LatentPath:
             zs = self._zero_stream()
             zs.wait_stream(cur)
             with torch.cuda.stream(zs):
-                self._acc_match.zero_()
+                self._zero(self._acc_match)
                 call("clc_match_bwd_zero_workspace", ptr(self.ws_bwd), self.ws_bwd.numel(), B * R, M, h, w,
                      ops._stream())
         # 1. match: masked Pearson correlation + top-k over all B*R (image, reference) problems
@@ -264,23 +288,29 @@ class LatentPath:
 
     def hyper_chain(self):
         """EntropyBottleneck on z (+ STE round, bpp partial) and its backward.  Reads z / noise_z."""
-        self._acc_eb.zero_()
-        ops.eb_fwd_raw(self.z, self.noise_z if self.train else None, self.eb_m, self.eb_b, self.eb_f,
+        self._zero(self._acc_eb)
+        nz = self._noise("noise_z", 0)
+        ops.eb_fwd_raw(self.z, nz, self.eb_m, self.eb_b, self.eb_f,
                        self.quantiles, self.lik_z, self.z_hat, None, self.log2[1:2])
         if not self.train:
             return 1
-        ops.eb_bwd_raw(self.z, self.noise_z, self.eb_m, self.eb_b, self.eb_f, self.quantiles, self.lik_z,
+        ops.eb_bwd_raw(self.z, nz, self.eb_m, self.eb_b, self.eb_f, self.quantiles, self.lik_z,
                        None, self.bpp_coef, None, self.g_z, self.g_eb[0:5], self.g_eb[5:10], self.g_eb[10:14])
         return 2      # (data-parallel: the EB parameter gradients are all-reduced in _exchange_stats)
 
     def slice_chain(self):
         """Slice loop: GaussianConditional + STE round (+ bpp partial), LRP add, and their backward."""
         n = 0
-        self._acc_y.zero_()
-        noise = self._slices(self.noise_y) if self.train else None
+        self._zero(self._acc_y)
+        if not self.train:
+            noise = [None] * self.num_slices
+        elif self.device_noise:
+            noise = [self._noise("noise_y", 1 + i) for i in range(self.num_slices)]
+        else:
+            noise = self._slices(self.noise_y)
         for i, (ys, ss, ms, ls, yh, lr) in enumerate(zip(*(self._slices(t) for t in (
                 self.y, self.scale, self.mu, self.lik_y, self.y_hat, self.lrp)))):
-            ops.gc_fwd_raw(ys, ss, ms, noise[i] if self.train else None, ls, yh, None, self.log2[0:1])
+            ops.gc_fwd_raw(ys, ss, ms, noise[i], ls, yh, None, self.log2[0:1])
             ops.lrp_add_fwd_raw(yh, lr)
             n += 2
         if not self.train:
@@ -308,6 +338,7 @@ class LatentPath:
         if not fork:
             n = self.match_chain() + self.hyper_chain() + self.slice_chain()
             self._exchange_stats()
+            self._finalize()
             return n
         cur = torch.cuda.current_stream(self.device)
         s1, s2 = self._side_streams()
@@ -330,6 +361,7 @@ class LatentPath:
                 n += self.slice_chain()
         n += self.match_chain()
         cur.wait_stream(s1)
+        self._finalize()
         return n
 
     def _exchange_stats(self):
@@ -347,6 +379,12 @@ class LatentPath:
         self.log2.copy_(buf[:2])
         if self.train:
             self._eb_grads_flat.copy_(buf[2:])
+
+    def _finalize(self):
+        """bpp of the step from the two accumulated log2 sums (train_CLC.py:48-51) and, with in-kernel noise,
+        the advance of the noise stream -- one one-thread kernel at the join of the chains."""
+        call("clc_bpp_finalize", ptr(self.log2), 2, float(self.num_pixels * self._world), ptr(self._bpp_dev),
+             ptr(self.rng_state) if self.device_noise else None, 16 * self._RNG_STRIDE, ops._stream())
 
     def _zero_stream(self):
         if self._zs is None:
@@ -399,6 +437,7 @@ class LatentPath:
         n += self.slice_chain()
         cur.wait_stream(s1)
         self._exchange_stats()
+        self._finalize()
         return n
 
     def step_host(self, host_flat):
@@ -433,8 +472,9 @@ class LatentPath:
         return int(self.n_uncert.item())
 
     def bpp(self):
-        """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels (over all ranks when data-parallel)."""
-        return -(self.log2[0] + self.log2[1]) / (self.num_pixels * self._world)
+        """Device scalar: -(sum log2 lik_y + sum log2 lik_z) / num_pixels (over all ranks when data-parallel),
+        written by clc_bpp_finalize at the end of the step."""
+        return self._bpp_dev[0]
 
     # ---- algorithmic work per kernel launch (SURVEY.md 8d; stated in DESIGN.md) ------------------
     def algorithmic_work(self):

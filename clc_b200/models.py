@@ -130,6 +130,11 @@ class _ChARMBase(CompressionModel):
         y_shape = y.shape[2:]
         y_hat_slices, liks, mus, scales = [], [], [], []
         use_ref = ref_features is not None
+        # likelihoods and y_hat of every slice are written in place into [B, 320, h, w] buffers by the
+        # per-slice launches (batch-strided kernel arguments): no torch.cat of them (CLC_run.py:587,:590)
+        inplace = getattr(self, "_inplace_slices", True)     # (the CPU oracle adapters of the tests turn it off)
+        bufs = ops.SliceBuffers(y.shape[0], y.shape[1], y_shape[0], y_shape[1], y.device) if inplace else None
+        c0 = 0
         for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
             support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[:self.max_support_slices]
             mean_support = self.atten_mean[i](torch.cat([latent_means] + support, dim=1))
@@ -146,8 +151,14 @@ class _ChARMBase(CompressionModel):
             scales.append(scale)
             # one launch: likelihood (train: y + U(-.5,.5); eval: round) AND ste_round(y - mu) + mu
             n_i = None if noise is None else noise["y"][:, i * y_slice.shape[1]:(i + 1) * y_slice.shape[1]]
-            _, lik_i, y_hat_i = self.gaussian_conditional(y_slice, scale, mu, noise=n_i, ste=True,
-                                                          want_outputs=False)
+            if inplace:
+                _, lik_i, y_hat_i = self.gaussian_conditional(y_slice, scale, mu, noise=n_i, ste=True,
+                                                              want_outputs=False,
+                                                              out=bufs.take(c0, c0 + y_slice.shape[1]))
+            else:
+                _, lik_i, y_hat_i = self.gaussian_conditional(y_slice, scale, mu, noise=n_i, ste=True,
+                                                              want_outputs=False)
+            c0 += y_slice.shape[1]
             liks.append(lik_i)
             if use_ref:
                 lrp = self.ref_lrp_transforms[i](torch.cat([mean_support, y_hat_i, ref_features], dim=1))
@@ -155,8 +166,11 @@ class _ChARMBase(CompressionModel):
                 lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_i], dim=1))
             y_hat_i = self._lrp_add(y_hat_i, lrp)  # y_hat += 0.5 * tanh(lrp), in place
             y_hat_slices.append(y_hat_i)
-        return (torch.cat(y_hat_slices, dim=1), torch.cat(mus, dim=1), torch.cat(scales, dim=1),
-                torch.cat(liks, dim=1))
+        if not inplace:
+            return (torch.cat(y_hat_slices, dim=1), torch.cat(mus, dim=1), torch.cat(scales, dim=1),
+                    torch.cat(liks, dim=1))
+        return (ops.assemble(bufs, "y_hat", y_hat_slices), torch.cat(mus, dim=1), torch.cat(scales, dim=1),
+                ops.assemble(bufs, "lik", liks))
 
     @staticmethod
     def _lrp_add(y_hat, lrp):
@@ -319,9 +333,15 @@ class CLC(_ChARMBase):
         if self.match_refs:
             if y is None:
                 raise ValueError("match_refs needs the image latent y")
-            feats = match_and_gather(y, feats.contiguous(), self.match_patch, self.match_patch, self.match_k,
-                                     self.match_temperature, True, False, self.match_mode)
+            feats = self._align_refs(y, feats.contiguous())
         return self.ref_feature_adapter(feats.reshape(B, R * feats.shape[2], *feats.shape[3:]))
+
+    def _align_refs(self, y, feats):
+        """Level-C wiring: every reference latent is replaced by its patch-matched, softmax-blended
+        version, SI_Finder_at_Decoder_Feature_Domain(y, ref, ...)['1'] (Patch_Matching.py:157-216) with
+        ph = pw = match_patch, num_k = match_k, temperature, Gaussian mask on.  feats [B, R, M, h, w]."""
+        return match_and_gather(y, feats, self.match_patch, self.match_patch, self.match_k,
+                                self.match_temperature, True, False, self.match_mode)
 
     def forward(self, x, ref_frames=None, noise=None):
         """`noise` (optional dict {"y": [B,320,h,w], "z": [B,192,h/4,w/4]}) injects the training

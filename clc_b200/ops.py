@@ -54,15 +54,22 @@ def _bcs(t):
 # ---------------------------------------------------------------------------------------------
 # raw (no autograd) entry points -- used by the autograd Functions below and by bench.py
 # ---------------------------------------------------------------------------------------------
+def _is_ticket(noise):
+    """In-kernel noise request: (device state tensor int64[2], host offset) from clc_b200.rng.ticket()."""
+    return isinstance(noise, tuple)
+
+
 def gc_fwd_raw(y, scale, mean, noise, lik, y_hat=None, outputs=None, log2_sum=None,
                scale_bound=SCALE_BOUND, lik_bound=LIKELIHOOD_BOUND):
+    """`noise`: None (eval), a tensor (explicit sample) or an rng ticket (generated in the kernel)."""
     y, y_bs = _rows(y, "y")
     scale, s_bs = _rows(scale, "scale")
     B, CS = _bcs(y)
     m_bs = n_bs = yh_bs = o_bs = 0
     if mean is not None:
         mean, m_bs = _rows(mean, "mean")
-    if noise is not None:
+    tk = noise if _is_ticket(noise) else None
+    if noise is not None and tk is None:
         noise, n_bs = _rows(noise, "noise")
     lik_, l_bs = _rows(lik, "lik")
     assert lik_ is lik, "lik output must be row-dense"
@@ -72,6 +79,11 @@ def gc_fwd_raw(y, scale, mean, noise, lik, y_hat=None, outputs=None, log2_sum=No
     if outputs is not None:
         oo, o_bs = _rows(outputs, "outputs")
         assert oo is outputs
+    if tk is not None:
+        call("clc_gc_fwd_rng", ptr(y), y_bs, ptr(scale), s_bs, ptr(mean), m_bs, ptr(tk[0]), tk[1],
+             ptr(lik), l_bs, ptr(y_hat), yh_bs, ptr(outputs), o_bs, ptr(log2_sum), B, CS,
+             scale_bound, lik_bound, _stream())
+        return
     call("clc_gc_fwd", ptr(y), y_bs, ptr(scale), s_bs, ptr(mean), m_bs, ptr(noise), n_bs,
          ptr(lik), l_bs, ptr(y_hat), yh_bs, ptr(outputs), o_bs, ptr(log2_sum), B, CS,
          scale_bound, lik_bound, _stream())
@@ -86,7 +98,8 @@ def gc_bwd_raw(y, scale, mean, noise, lik, g_lik, bpp_coef, g_y_hat, g_y, g_scal
     m_bs = n_bs = gl_bs = gy_bs = gm_bs = 0
     if mean is not None:
         mean, m_bs = _rows(mean, "mean")
-    if noise is not None:
+    tk = noise if _is_ticket(noise) else None
+    if noise is not None and tk is None:
         noise, n_bs = _rows(noise, "noise")
     if g_lik is not None:
         g_lik, gl_bs = _rows(g_lik, "g_lik")
@@ -96,6 +109,12 @@ def gc_bwd_raw(y, scale, mean, noise, lik, g_lik, bpp_coef, g_y_hat, g_y, g_scal
     _, gs_bs = _rows(g_scale, "g_scale")
     if g_mean is not None:
         _, gm_bs = _rows(g_mean, "g_mean")
+    if tk is not None:
+        call("clc_gc_bwd_rng", ptr(y), y_bs, ptr(scale), s_bs, ptr(mean), m_bs, ptr(tk[0]), tk[1],
+             ptr(lik), l_bs, ptr(g_lik), gl_bs, float(bpp_coef), ptr(g_y_hat), gy_bs,
+             ptr(g_y), go_bs, ptr(g_scale), gs_bs, ptr(g_mean), gm_bs, B, CS, scale_bound, lik_bound,
+             _stream())
+        return
     call("clc_gc_bwd", ptr(y), y_bs, ptr(scale), s_bs, ptr(mean), m_bs, ptr(noise), n_bs,
          ptr(lik), l_bs, ptr(g_lik), gl_bs, float(bpp_coef), ptr(g_y_hat), gy_bs,
          ptr(g_y), go_bs, ptr(g_scale), gs_bs, ptr(g_mean), gm_bs, B, CS, scale_bound, lik_bound,
@@ -129,6 +148,10 @@ def eb_fwd_raw(z, noise, matrices, biases, factors, quantiles, lik, z_hat=None, 
     B, Cc = z.shape[0], z.shape[1]
     S = z.numel() // max(B * Cc, 1)
     pm, pb, pf = eb_param_arrays(matrices, biases, factors)
+    if _is_ticket(noise):
+        call("clc_eb_fwd_rng", ptr(z), ptr(noise[0]), noise[1], pm, pb, pf, ptr(quantiles), ptr(lik), ptr(z_hat),
+             ptr(outputs), ptr(log2_sum), B, Cc, S, lik_bound, _stream())
+        return
     call("clc_eb_fwd", ptr(z), ptr(noise), pm, pb, pf, ptr(quantiles), ptr(lik), ptr(z_hat),
          ptr(outputs), ptr(log2_sum), B, Cc, S, lik_bound, _stream())
 
@@ -143,6 +166,10 @@ def eb_bwd_raw(z, noise, matrices, biases, factors, quantiles, lik, g_lik, bpp_c
         gm, gb, gf = eb_param_arrays(g_matrices, g_biases, g_factors)
     else:
         gm = gb = gf = None
+    if _is_ticket(noise):
+        call("clc_eb_bwd_rng", ptr(z), ptr(noise[0]), noise[1], pm, pb, pf, ptr(quantiles), ptr(lik), ptr(g_lik),
+             float(bpp_coef), ptr(g_z_hat), ptr(g_z), gm, gb, gf, B, Cc, S, lik_bound, _stream())
+        return
     call("clc_eb_bwd", ptr(z), ptr(noise), pm, pb, pf, ptr(quantiles), ptr(lik), ptr(g_lik),
          float(bpp_coef), ptr(g_z_hat), ptr(g_z), gm, gb, gf, B, Cc, S, lik_bound, _stream())
 
@@ -156,17 +183,66 @@ def log2_sum_fwd_raw(lik, acc):
 # ---------------------------------------------------------------------------------------------
 # autograd Functions
 # ---------------------------------------------------------------------------------------------
+class SliceBuffers:
+    """Preallocated [B, C, h, w] likelihood / y_hat buffers that the per-slice GaussianConditional launches
+    write IN PLACE (channel-slice views, batch-strided kernel arguments), so that the ChARM loop needs no
+    `torch.cat` of its outputs (CLC_run.py:587-590).  Deliberately not a tensor: autograd
+    must not see the buffers as inputs of the per-slice Functions (their outputs are later modified in place
+    by the LRP add)."""
+
+    def __init__(self, B, C, h, w, device):
+        self.lik = torch.empty((B, C, h, w), dtype=torch.float32, device=device)
+        self.y_hat = torch.empty((B, C, h, w), dtype=torch.float32, device=device)
+        self.views = {"lik": [], "y_hat": []}
+
+    @staticmethod
+    def _alias(v):
+        # same memory as the channel-slice view `v`, but not a view in autograd's eyes (outputs of a custom
+        # Function that are views may not be modified in place; y_hat is, by the LRP add)
+        return torch.empty(0, dtype=v.dtype, device=v.device).set_(v.untyped_storage(), v.storage_offset(),
+                                                                   v.size(), v.stride())
+
+    def take(self, c0, c1):
+        return self._alias(self.lik[:, c0:c1]), self._alias(self.y_hat[:, c0:c1])
+
+
+class _AssembleFn(torch.autograd.Function):
+    """The concatenation of slice tensors that already live in one buffer: forward returns the buffer,
+    backward hands every slice a channel-slice VIEW of the incoming gradient (no copies either way)."""
+
+    @staticmethod
+    def forward(ctx, holder, which, *slices):
+        ctx.widths = [t.shape[1] for t in slices]
+        return SliceBuffers._alias(getattr(holder, which))
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, c = [], 0
+        for w in ctx.widths:
+            outs.append(g[:, c:c + w])
+            c += w
+        return (None, None, *outs)
+
+
+def assemble(holder, which, slices):
+    return _AssembleFn.apply(holder, which, *slices)
+
+
 class _GaussianConditionalFn(torch.autograd.Function):
     """(y, scale, mean, noise) -> (lik, y_hat, outputs).  See clc_gc_fwd / clc_gc_bwd."""
 
     @staticmethod
-    def forward(ctx, y, scale, mean, noise, scale_bound, lik_bound, want_outputs, log2_acc):
-        lik = torch.empty(y.shape, dtype=torch.float32, device=y.device)
-        y_hat = torch.empty_like(lik)
+    def forward(ctx, y, scale, mean, noise, scale_bound, lik_bound, want_outputs, log2_acc, out=None):
+        if out is not None:
+            lik, y_hat = out                     # channel-slice views of SliceBuffers (written in place)
+        else:
+            lik = torch.empty(y.shape, dtype=torch.float32, device=y.device)
+            y_hat = torch.empty_like(lik)
         outputs = torch.empty_like(lik) if want_outputs else None
         if y.numel():
             gc_fwd_raw(y, scale, mean, noise, lik, y_hat, outputs, log2_acc, scale_bound, lik_bound)
-        ctx.save_for_backward(y, scale, mean, noise, lik)
+        ctx.ticket = noise if _is_ticket(noise) else None
+        ctx.save_for_backward(y, scale, mean, None if ctx.ticket else noise, lik)
         ctx.bounds = (scale_bound, lik_bound)
         ctx.train = noise is not None
         if not want_outputs:
@@ -177,6 +253,8 @@ class _GaussianConditionalFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_lik, g_y_hat, g_outputs):
         y, scale, mean, noise, lik = ctx.saved_tensors
+        if ctx.ticket is not None:
+            noise = ctx.ticket          # the backward regenerates the forward's sample from the same ticket
         sb, lb = ctx.bounds
         g_y = torch.empty(y.shape, dtype=torch.float32, device=y.device)
         g_scale = torch.empty_like(g_y)
@@ -190,15 +268,23 @@ class _GaussianConditionalFn(torch.autograd.Function):
                 g_y = g_y + g_outputs
             elif g_mean is not None:
                 g_mean = g_mean + g_outputs
-        return g_y, g_scale, g_mean, None, None, None, None, None
+        return g_y, g_scale, g_mean, None, None, None, None, None, None
 
 
 def gaussian_conditional(y, scale, mean=None, noise=None, scale_bound=SCALE_BOUND,
-                         lik_bound=LIKELIHOOD_BOUND, want_outputs=False, log2_acc=None):
-    """Fused GaussianConditional.forward + ste_round.  Returns (lik, y_hat, outputs|None)."""
+                         lik_bound=LIKELIHOOD_BOUND, want_outputs=False, log2_acc=None, out=None):
+    """Fused GaussianConditional.forward + ste_round.  Returns (lik, y_hat, outputs|None).
+    `out`: an `_OutViews` pair from SliceBuffers.take() -- the kernel then writes there."""
     lik, y_hat, outputs = _GaussianConditionalFn.apply(y, scale, mean, noise, float(scale_bound),
-                                                       float(lik_bound), bool(want_outputs), log2_acc)
+                                                       float(lik_bound), bool(want_outputs), log2_acc,
+                                                       _OutViews(out) if out is not None else None)
     return lik, y_hat, (outputs if want_outputs else None)
+
+
+class _OutViews(tuple):
+    """(lik_view, y_hat_view) wrapped in a non-tensor container so autograd does not treat the views as inputs."""
+    def __new__(cls, pair):
+        return super().__new__(cls, pair)
 
 
 class _LrpAddFn(torch.autograd.Function):
@@ -265,7 +351,8 @@ class _EntropyBottleneckFn(torch.autograd.Function):
         z_hat = torch.empty_like(lik)
         outputs = torch.empty_like(lik) if want_outputs else None
         eb_fwd_raw(z, noise, ms, bs, fs, quantiles, lik, z_hat, outputs, log2_acc, lik_bound)
-        ctx.save_for_backward(z, noise, quantiles, lik, *params)
+        ctx.ticket = noise if _is_ticket(noise) else None
+        ctx.save_for_backward(z, None if ctx.ticket else noise, quantiles, lik, *params)
         ctx.lik_bound = lik_bound
         ctx.train = noise is not None
         if not want_outputs:
@@ -276,6 +363,8 @@ class _EntropyBottleneckFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_lik, g_z_hat, g_outputs):
         z, noise, quantiles, lik, *params = ctx.saved_tensors
+        if ctx.ticket is not None:
+            noise = ctx.ticket
         ms, bs, fs = params[0:5], params[5:10], params[10:14]
         g_z = torch.empty(z.shape, dtype=torch.float32, device=z.device)
         need_p = any(ctx.needs_input_grad[6:])

@@ -101,6 +101,29 @@ CLC_API int clc_gc_bwd(const float* y, int64_t y_bs, const float* scale, int64_t
                float* g_mean, int64_t g_mean_bs,
                int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream);
 
+/* Training-mode quantisation noise generated INSIDE the kernels (compressai EntropyModel.quantize "noise",
+ * `inputs + U(-1/2, 1/2)`, as reached from CLC_run.py:526 / :569) instead of read from a tensor: saves the
+ * uniform_() launch and 8 B per element.  Philox4x32-10, counter = (element index / 4, state[1] + rng_offset),
+ * key = state[0].  `rng_state` is a DEVICE uint64[2] {seed, base offset}: a captured CUDA graph draws fresh
+ * noise on every replay once its owner advances the base (clc_rng_advance / clc_bpp_finalize); `rng_offset`
+ * separates the calls of one step.  The backward regenerates the forward's sample from the same
+ * (rng_state contents, rng_offset).  Same distribution as torch's uniform_(-.5, .5), not the same bits: pass an
+ * explicit `noise` tensor to the plain entry points for bit-reproducible parity runs. */
+CLC_API int clc_gc_fwd_rng(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                   const float* mean, int64_t mean_bs, const uint64_t* rng_state, uint64_t rng_offset,
+                   float* lik, int64_t lik_bs, float* y_hat, int64_t y_hat_bs,
+                   float* outputs, int64_t outputs_bs, double* log2_sum,
+                   int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream);
+CLC_API int clc_gc_bwd_rng(const float* y, int64_t y_bs, const float* scale, int64_t scale_bs,
+                   const float* mean, int64_t mean_bs, const uint64_t* rng_state, uint64_t rng_offset,
+                   const float* lik, int64_t lik_bs, const float* g_lik, int64_t g_lik_bs,
+                   float bpp_coef, const float* g_y_hat, int64_t g_y_hat_bs,
+                   float* g_y, int64_t g_y_bs, float* g_scale, int64_t g_scale_bs,
+                   float* g_mean, int64_t g_mean_bs,
+                   int64_t B, int64_t CS, float scale_bound, float lik_bound, void* stream);
+/* state[1] += n (one-thread kernel; capturable). */
+CLC_API int clc_rng_advance(uint64_t* rng_state, uint64_t n, void* stream);
+
 /* Latent residual prediction add:  y_hat += 0.5 * tanh(lrp)   (CLC_run.py:582-583). */
 CLC_API int clc_lrp_add_fwd(float* y_hat, int64_t y_hat_bs, const float* lrp, int64_t lrp_bs,
                     int64_t B, int64_t CS, void* stream);
@@ -142,6 +165,25 @@ CLC_API int clc_eb_bwd(const float* z, const float* noise, const float* const ma
                const float* lik, const float* g_lik, float bpp_coef, const float* g_z_hat,
                float* g_z, float* const g_matrix[5], float* const g_bias[5], float* const g_factor[4],
                int64_t B, int64_t C, int64_t S, float lik_bound, void* stream);
+
+/* clc_eb_fwd / clc_eb_bwd with in-kernel noise (see clc_gc_fwd_rng); element index = offset inside z. */
+CLC_API int clc_eb_fwd_rng(const float* z, const uint64_t* rng_state, uint64_t rng_offset,
+                   const float* const matrix[5], const float* const bias[5], const float* const factor[4],
+                   const float* quantiles, float* lik, float* z_hat, float* outputs, double* log2_sum,
+                   int64_t B, int64_t C, int64_t S, float lik_bound, void* stream);
+CLC_API int clc_eb_bwd_rng(const float* z, const uint64_t* rng_state, uint64_t rng_offset,
+                   const float* const matrix[5], const float* const bias[5], const float* const factor[4],
+                   const float* quantiles, const float* lik, const float* g_lik, float bpp_coef,
+                   const float* g_z_hat, float* g_z, float* const g_matrix[5], float* const g_bias[5],
+                   float* const g_factor[4], int64_t B, int64_t C, int64_t S, float lik_bound, void* stream);
+
+/* bpp of RateDistortionLoss from the accumulated log2 sums (train_CLC.py:48-51, eval.py:27-31):
+ *   *bpp = -(log2_sums[0] + ... + log2_sums[n-1]) / num_pixels      (device doubles, one-thread kernel)
+ * and, when rng_state != NULL, rng_state[1] += rng_advance (next step's noise). */
+CLC_API int clc_bpp_finalize(const double* log2_sums, int32_t n, double num_pixels, double* bpp,
+                             uint64_t* rng_state, uint64_t rng_advance, void* stream);
+/* Zero-fill of an accumulator (cudaMemsetAsync on `stream`: a memset node, not a kernel). */
+CLC_API int clc_zero(void* p, size_t bytes, void* stream);
 
 /* Rate term of RateDistortionLoss for an arbitrary likelihood tensor.
  * Replaces: `torch.log(likelihoods).sum()` train_CLC.py:48-51, eval.py:27-31.

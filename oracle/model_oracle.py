@@ -19,7 +19,8 @@ class _OracleGC(nn.Module):
         self.inner.load_state_dict(src.state_dict(), strict=False)
 
     def forward(self, inputs, scales, means=None, training=None, *, noise=None, ste=False, want_outputs=True,
-                log2_acc=None):
+                log2_acc=None, out=None):
+        assert out is None, "oracle mode runs the slice loop with plain tensors (model._inplace_slices = False)"
         training = self.training if training is None else training
         self.inner.train(training)
         if training and noise is not None:
@@ -71,6 +72,24 @@ def to_oracle_mode(model):
     m.gaussian_conditional = _OracleGC(model.gaussian_conditional).to(dev)
     m.entropy_bottleneck = _OracleEB(model.entropy_bottleneck).to(dev)
     m._lrp_add = lambda y_hat, lrp: O.lrp_add(y_hat, lrp)
+    m._inplace_slices = False
     if getattr(m, "match_refs", False):
-        raise NotImplementedError("oracle mode covers the shipped forward (match_refs=False)")
+        # Level-C wiring: the oracle's SI_Finder (Patch_Matching.py:157-216 restated) per reference, on the
+        # CPU in fp32 exactly as the reference would run it; indices are kept for the parity test
+        p, k, T = m.match_patch, m.match_k, m.match_temperature
+        m.oracle_match_idx = []
+
+        def align(y, feats):
+            yc = y.detach().float().cpu()
+            fc = feats.detach().float().cpu()
+            mask = O.gaussian_masks(fc.shape[-2], fc.shape[-1], p, p)
+            outs, idxs = [], []
+            for r in range(fc.shape[1]):
+                (o,), _, idx = O.si_finder(yc, fc[:, r], p, p, fc[:, r], k, T, mask=mask, return_index=True)
+                outs.append(o)
+                idxs.append(idx)
+            m.oracle_match_idx.append(torch.stack(idxs, 1))          # [B, R, P, k]
+            return torch.stack(outs, 1).to(feats.device)
+
+        m._align_refs = align
     return m

@@ -143,3 +143,36 @@ def test_clc_match_refs_extended_wiring_and_symbols():
     assert sym["indexes"].min().item() >= 0 and sym["indexes"].max().item() <= 63
     y, mu = out["para"]["y"], out["para"]["means"]
     assert torch.equal(sym["symbols"], torch.round(y - mu).int())
+
+
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_clc_match_refs_model_parity_vs_oracle_si_finder(mode):
+    """Level-C wiring at MODEL level: CLC(match_refs=True) with the tensor-core match path (the default) vs the
+    same weights in oracle mode, where the alignment is the oracle's SI_Finder_at_Decoder_Feature_Domain
+    (Patch_Matching.py:157-216 restated, CPU fp32).  Match indices bit-exact, aligned context / likelihoods /
+    x_hat to conv round-off."""
+    import clc_b200.models as M
+    from clc_b200 import matching
+    from oracle import detfill
+    from oracle.model_oracle import to_oracle_mode
+    d = torch.device("cuda:0")
+    m = detfill.fill_(M.CLC(N=64, match_refs=True, match_mode=mode), seed=2).eval().to(d)
+    mo = to_oracle_mode(m).eval()
+    x = detfill.det_image((2, 3, 256, 256), 41).to(d)
+    refs = [detfill.det_image((2, 3, 256, 256), 42 + i).to(d) for i in range(3)]
+    with torch.no_grad():
+        out = m(x, refs)
+        out_o = mo(x, refs)
+        # the indices the product path selected, on the same latents the oracle saw
+        y = m.g_a(x)
+        feats = m.ref_encoder(torch.cat(refs, 0)).view(3, 2, 320, 16, 16).transpose(0, 1).contiguous()
+        _, idx, _ = matching.match_topk(y, feats, 4, 4, 4, gaussian_mask=True, mode=mode)
+    assert torch.equal(idx.cpu().long(), mo.oracle_match_idx[0]), "model-level match indices differ from the oracle"
+    lik, lik_o = out["likelihoods"]["y"], out_o["likelihoods"]["y"]
+    close = ((lik - lik_o).abs() <= 1e-3 * lik_o + 1e-9).float().mean().item()
+    assert close > 0.995, close                                    # conv round-off may flip a few symbols
+    assert torch.allclose(out["likelihoods"]["z"], out_o["likelihoods"]["z"], rtol=1e-3, atol=1e-9)
+    mse = torch.mean((out["x_hat"] - out_o["x_hat"]) ** 2).item()
+    psnr_gap = abs(10 * math.log10(1.0 / max(torch.mean((out["x_hat"] - x) ** 2).item(), 1e-12)) -
+                   10 * math.log10(1.0 / max(torch.mean((out_o["x_hat"] - x) ** 2).item(), 1e-12)))
+    assert mse < 1e-6 and psnr_gap < 0.01
