@@ -171,6 +171,7 @@ class PublicPath:
         self.gc = clc_b200.GaussianConditional(None).to(device).train(cfg["train"])
         self.eb = clc_b200.EntropyBottleneck(192).to(device).train(cfg["train"])
         self.npix = cfg["B"] * cfg["H"] * cfg["W"]
+        self.functional_grads = False
 
     def step(self, d):
         from clc_b200 import ops
@@ -192,9 +193,56 @@ class PublicPath:
         bpp = -(ops.log2_sum(torch.cat(liks, 1)) + ops.log2_sum(lik_z)) / self.npix
         if train:
             loss = bpp.float() + (torch.cat(yh, 1) * t["g_y_hat"]).sum() + (fused * t["g_fused"]).sum()
-            loss.backward()
+            if self.functional_grads:
+                # graph capture: gradients as returned tensors (no AccumulateGrad nodes tied to another stream)
+                self.grads = torch.autograd.grad(loss, [t[k] for k in grad])
+            else:
+                loss.backward()
             return loss
         return bpp
+
+
+class GraphedPublicPath:
+    """The module-API step (PublicPath.step: forward AND backward through the drop-in autograd modules) captured
+    once into a CUDA graph, the standard PyTorch recipe for a launch-bound training step (whole-network
+    capture): per step the host inputs are copied into the graph's static tensors, the graph is replayed and the
+    result read back.  In-kernel noise: the captured step advances the device noise stream, so every replay
+    draws a fresh sample."""
+
+    def __init__(self, pub, example):
+        from clc_b200 import rng
+        self.pub = pub
+        pub.functional_grads = True
+        self.static = {k: v.detach().clone() for k, v in example.items()}
+        dev = next(iter(self.static.values())).device
+
+        def step():
+            for v in self.static.values():
+                v.grad = None
+            out = pub.step(self.static)
+            rng.advance(dev)
+            return out
+
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        for v in self.static.values():
+            v.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = pub.step(self.static)
+            rng.advance(dev)
+
+    def step(self, host_views):
+        with torch.no_grad():
+            for n, t in self.static.items():
+                t.copy_(host_views[n], non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 def _make_path(cfg, args, dev, fused, rank):
@@ -387,6 +435,27 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(mod_ms, op=torch.distributed.ReduceOp.MAX)
     e2e_modules_value = pix_per_step * K / (mod_ms.item() * 1e-3) / 1e6
+
+    # the same module-API step, captured once into a CUDA graph (whole-step capture, fwd + bwd)
+    gpub = GraphedPublicPath(pub, {n: host_views[n].to(dev) for n in names})
+    for _ in range(Wm):
+        gpub.step(host_views).item()
+    torch.cuda.synchronize()
+    barrier()
+    gmod_ev = []
+    for _ in range(K):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res_host = gpub.step(host_views).item()          # uploads + replay + device -> host read of the result
+        b.record()
+        gmod_ev.append((a, b))
+    torch.cuda.synchronize()
+    gmod_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in gmod_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(gmod_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_gmodules_value = pix_per_step * K / (gmod_ms.item() * 1e-3) / 1e6
+    del gpub
     clocks = sampler.stop()
 
     # ---- per-kernel pass: the library records a CUDA event after EVERY kernel of the same step ---
@@ -457,7 +526,10 @@ def run_ours(args):
                 "single_buffered": {"value": e2e_single_value, "ms_per_step": e2e1_ms.item() / K,
                                     "api": "clc_b200.LatentPath.step_host (no overlap between steps)"},
                 "autograd_modules": {"value": e2e_modules_value, "ms_per_step": mod_ms.item() / K,
-                                     "api": "clc_b200 per-operator autograd modules, eager, per-slice calls"}},
+                                     "api": "clc_b200 per-operator autograd modules, eager, per-slice calls"},
+                "autograd_modules_graphed": {"value": e2e_gmodules_value, "ms_per_step": gmod_ms.item() / K,
+                                             "api": "the same per-operator autograd modules (fwd + bwd), step captured "
+                                                    "once with torch.cuda.graph and replayed"}},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": rooflines[dom],

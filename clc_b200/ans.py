@@ -63,10 +63,13 @@ def _encode(symbols, indexes, tables):
 
 
 class BufferedRansEncoder:
-    """encode_with_indexes() may be called several times; flush() codes everything as ONE stream."""
+    """encode_with_indexes() may be called several times; flush() codes everything as ONE stream.  Every call's
+    symbols are coded against the tables passed IN THAT CALL (as compressai's encoder resolves them): calls with
+    different tables -- e.g. EntropyBottleneck and GaussianConditional symbols in one stream -- are merged into
+    one combined table with the later calls' indexes shifted accordingly."""
 
     def __init__(self):
-        self._sym, self._idx, self._tables = [], [], None
+        self._sym, self._idx, self._tabs = [], [], []
 
     def encode_with_indexes(self, symbols, indexes, cdfs, cdfs_sizes, offsets):
         s, i = _host_i32(symbols).reshape(-1), _host_i32(indexes).reshape(-1)
@@ -74,15 +77,40 @@ class BufferedRansEncoder:
             raise ValueError("symbols and indexes must have the same length")
         self._sym.append(s)
         self._idx.append(i)
-        self._tables = cdfs if isinstance(cdfs, _Tables) else _Tables(cdfs, cdfs_sizes, offsets)
+        self._tabs.append(cdfs if isinstance(cdfs, _Tables) else _Tables(cdfs, cdfs_sizes, offsets))
+
+    @staticmethod
+    def _same(a, b):
+        return a is b or (a.cdfs.shape == b.cdfs.shape and np.array_equal(a.cdfs, b.cdfs) and
+                          np.array_equal(a.sizes, b.sizes) and np.array_equal(a.offsets, b.offsets))
 
     def flush(self):
-        if self._tables is None:
+        if not self._tabs:
             s = i = np.empty(0, dtype=np.int32)
             tables = _Tables(np.array([[0, 1 << 16]], dtype=np.int32), [2], [0])
         else:
-            s, i, tables = np.concatenate(self._sym), np.concatenate(self._idx), self._tables
-        self._sym, self._idx, self._tables = [], [], None
+            distinct, row0, idx = [], [], []
+            for i_call, t in zip(self._idx, self._tabs):
+                for j, u in enumerate(distinct):
+                    if self._same(t, u):
+                        base = row0[j]
+                        break
+                else:
+                    base = sum(u.cdfs.shape[0] for u in distinct)
+                    distinct.append(t)
+                    row0.append(base)
+                idx.append(i_call + base if base else i_call)
+            if len(distinct) == 1:
+                tables = distinct[0]
+            else:
+                stride = max(u.cdfs.shape[1] for u in distinct)
+                cdfs = np.zeros((sum(u.cdfs.shape[0] for u in distinct), stride), dtype=np.int32)
+                for u, b in zip(distinct, row0):
+                    cdfs[b:b + u.cdfs.shape[0], :u.cdfs.shape[1]] = u.cdfs
+                tables = _Tables(cdfs, np.concatenate([u.sizes for u in distinct]),
+                                 np.concatenate([u.offsets for u in distinct]))
+            s, i = np.concatenate(self._sym), np.concatenate(idx).astype(np.int32)
+        self._sym, self._idx, self._tabs = [], [], []
         return _encode(s, i, tables)
 
 

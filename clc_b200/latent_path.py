@@ -521,7 +521,14 @@ class LatentPath:
             "clc_match_bwd(cl_to_nchw)": ("bytes", NP * M * S * 8),
             "clc_match_bwd": ("bytes", NP * 3 * M * S * 4 + B * 2 * M * S * 4),
             "clc_bpp_finalize": ("bytes", 64),
+            # CLM-fused match backward: g_fused, att, aligned, r, q in; g_r, g_q, g_att out (g_aligned never exists)
+            "clc_match_clm_bwd(main)": ("bytes", NP * 3 * M * S * 4 + B * 3 * M * S * 4 + 2 * NP * S * 4),
+            "clc_match_clm_bwd(cl_to_nchw)": ("bytes", NP * M * S * 8),
         }
+        if self.match_mode == "tc" and self._fused_fwd:
+            # re-scoring kernel with the CLM fusion folded in: + query latent and attention logits in, fused out
+            kind, v = w["clc_match_topk_tc(rescore)"]
+            w["clc_match_topk_tc(rescore)"] = (kind, v + B * 2 * M * S * 4 + NP * S * 4)
         return w
 
     def gathered_bytes(self):
@@ -536,6 +543,7 @@ class LatentPath:
             "clc_match_topk_tc(rescore)": NP * P * K * 4 * (KC + 1 + k) + NP * P * k * 12 + NP * M * S * 4,
             "clc_match_bwd(main)": NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8,
             "clc_match_bwd": NP * P * K * 4 * (2 + k + 2 * k) + B * M * S * 8,
+            "clc_match_clm_bwd(main)": NP * P * K * 4 * (3 + k + 2 * k) + B * M * S * 8,
             "clc_gather_blend_fwd": NP * (k * P * K * 4 + P * k * 8 + M * S * 4),
         }
 

@@ -49,6 +49,40 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# ---- certification of the tensor-core path ---------------------------------------------------------------
+# clc_match_topk_tc screens with a bf16 GEMM and re-scores the best candidates exactly; a patch whose margin
+# is below the screening-error bound even after the second re-scoring round is counted as "uncertified" (its
+# indices may differ from the exact fp32 ranking at a near-tie).  The counter of the LAST tc call on a device is
+# kept here; `strict=True` on the public functions reads it (one host sync) and re-runs the call in fp32 mode.
+_UNCERT = {}
+_WARNED = set()
+
+
+def _uncert_counter(device):
+    idx = torch.device(device).index
+    if idx not in _UNCERT:
+        _UNCERT[idx] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _UNCERT[idx]
+
+
+def last_uncertified(device=None):
+    """Patches of the last tensor-core match call on `device` whose top-k could not be certified against the
+    screening error (0 = indices provably equal the exact fp32 ranking).  Synchronises."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return int(_uncert_counter(dev).item())
+
+
+def _tc_supported(NP, q_repeat, Cc, H, W, ph, pw, k):
+    """Shapes the tensor-core path implements (C a multiple of 64, k <= 8, ...); others take the fp32 path."""
+    ok = lib().clc_match_topk_tc_workspace_bytes(NP, q_repeat, Cc, H, W, ph, pw, k) > 0
+    if not ok and (Cc, H, W, ph, pw, k) not in _WARNED:
+        _WARNED.add((Cc, H, W, ph, pw, k))
+        import warnings
+        warnings.warn(f"clc_b200: match shape C={Cc} {H}x{W} patch {ph}x{pw} k={k} is outside the tensor-core "
+                      "kernels; using the exact fp32 path")
+    return ok
+
+
 def _corr_raw(view, r, P, ph, pw, mask=None):
     NP, Cc, fh, fw = r.shape
     ch, cw = fh - ph + 1, fw - pw + 1
@@ -97,6 +131,8 @@ class _PearsonTopkFn(torch.autograd.Function):
             L = corr.shape[2] * corr.shape[3]
             val, idx = topk_rows(corr.view(NP * P, L), k)
             val, idx = val.view(NP, P, k), idx.view(NP, P, k)
+        elif mode == "tc" and not _tc_supported(NP, q_repeat, Cc, H, W, ph, pw, k) and (fh, fw) == (H, W):
+            return _PearsonTopkFn.forward(ctx, q_img, r, mask, ph, pw, k, q_repeat, "fp32")
         elif mode == "tc":
             if (fh, fw) != (H, W):
                 raise ValueError("tc mode needs query and reference latents of the same spatial size")
@@ -110,7 +146,7 @@ class _PearsonTopkFn(torch.autograd.Function):
             nb = lib().clc_match_topk_tc_workspace_bytes(NP, q_repeat, Cc, H, W, ph, pw, k)
             ws = _workspace(nb, r.device)
             call("clc_match_topk_tc", ptr(q_img), ptr(r), NP, q_repeat, Cc, H, W, ph, pw, k, gauss,
-                 ptr(val), ptr(idx), None, 0.0, None, None, ptr(ws), ws.numel(), _stream())
+                 ptr(val), ptr(idx), ptr(_uncert_counter(r.device)), 0.0, None, None, ptr(ws), ws.numel(), _stream())
         else:
             raise ValueError(f'Invalid match mode "{mode}" (expected "fp32" or "tc")')
         ctx.save_for_backward(q_img, r, mask, idx)
@@ -266,10 +302,12 @@ def SI_Finder_at_Decoder_Feature_Domain(x_decs, ys, patch_h, patch_w, y_decs, la
     return out
 
 
-def match_topk(y, refs, patch_h=4, patch_w=4, k=4, gaussian_mask=True, mode="tc"):
+def match_topk(y, refs, patch_h=4, patch_w=4, k=4, gaussian_mask=True, mode="tc", strict=False):
     """Fused match for a batch of images against R references each.
     y [B,C,h,w]; refs: list of R tensors [B,C,h,w] or a stacked [B,R,C,h,w] tensor.
-    Returns (val [B,R,P,k], idx int32 [B,R,P,k], refs_stacked [B*R,C,h,w])."""
+    Returns (val [B,R,P,k], idx int32 [B,R,P,k], refs_stacked [B*R,C,h,w]).
+    mode="tc": indices equal the exact fp32 ranking whenever last_uncertified() == 0 (always on the shapes and
+    data of the test-suite); strict=True checks that (one host sync) and re-runs in fp32 mode otherwise."""
     _check(y, "y")
     if isinstance(refs, (list, tuple)):
         refs = torch.stack(list(refs), dim=1)
@@ -279,6 +317,8 @@ def match_topk(y, refs, patch_h=4, patch_w=4, k=4, gaussian_mask=True, mode="tc"
     if gaussian_mask:
         mask = _cached_mask(h, w, patch_h, patch_w, y.device)
     val, idx = _PearsonTopkFn.apply(y.contiguous(), r, mask, patch_h, patch_w, int(k), R, mode)
+    if strict and mode == "tc" and last_uncertified(y.device) > 0:
+        val, idx = _PearsonTopkFn.apply(y.contiguous(), r, mask, patch_h, patch_w, int(k), R, "fp32")
     P = val.shape[1]
     return val.view(B, R, P, k), idx.view(B, R, P, k), r
 
@@ -305,6 +345,9 @@ class _MatchGatherFn(torch.autograd.Function):
     def forward(ctx, q_img, r, mask, ph, pw, k, q_repeat, temperature, mode):
         NP, Cc, fh, fw = r.shape
         r_cl = ws = None
+        if mode == "tc" and r.shape[2:] == q_img.shape[2:] and \
+                not _tc_supported(NP, q_repeat, Cc, q_img.shape[2], q_img.shape[3], ph, pw, k):
+            mode = "fp32"
         if mode == "tc":
             # fused: screening GEMM -> exact re-scoring + top-k + softmax + gather/blend in one C call
             NQ, _, H, W = q_img.shape
@@ -323,7 +366,8 @@ class _MatchGatherFn(torch.autograd.Function):
             nb = lib().clc_match_topk_tc_workspace_bytes(NP, q_repeat, Cc, H, W, ph, pw, k)
             ws = _workspace(nb, r.device)
             call("clc_match_topk_tc", ptr(q_img), ptr(r), NP, q_repeat, Cc, H, W, ph, pw, k, gauss, ptr(val), ptr(idx),
-                 None, float(temperature), ptr(out), ptr(weights), ptr(ws), ws.numel(), _stream())
+                 ptr(_uncert_counter(r.device)), float(temperature), ptr(out), ptr(weights), ptr(ws), ws.numel(),
+                 _stream())
             if any(ctx.needs_input_grad[:2]):
                 # channels-last fp32 copy of r left in the workspace: the backward reuses it
                 r_cl = lib().clc_match_topk_tc_ref_cl(ptr(ws), NP, q_repeat, Cc, H, W, ph, pw, k)
@@ -358,8 +402,8 @@ class _MatchGatherFn(torch.autograd.Function):
 
 
 def match_and_gather(y, refs, patch_h=4, patch_w=4, k=4, temperature=15.0, gaussian_mask=True,
-                     is_stack=False, mode="tc"):
-    """match_topk + gather/blend: aligned references [B, R, C(*k), h, w]."""
+                     is_stack=False, mode="tc", strict=False):
+    """match_topk + gather/blend: aligned references [B, R, C(*k), h, w].  `strict`: see match_topk."""
     if is_stack:
         val, idx, r = match_topk(y, refs, patch_h, patch_w, k, gaussian_mask, mode)
         B, R, P, _ = val.shape
@@ -374,4 +418,6 @@ def match_and_gather(y, refs, patch_h=4, patch_w=4, k=4, temperature=15.0, gauss
     r = refs.reshape(B * R, Cc, h, w).contiguous()
     mask = _cached_mask(h, w, patch_h, patch_w, y.device) if gaussian_mask else None
     out, _, _ = _MatchGatherFn.apply(y.contiguous(), r, mask, patch_h, patch_w, int(k), R, float(temperature), mode)
+    if strict and mode == "tc" and last_uncertified(y.device) > 0:
+        out, _, _ = _MatchGatherFn.apply(y.contiguous(), r, mask, patch_h, patch_w, int(k), R, float(temperature), "fp32")
     return out.view(B, R, Cc, h, w)

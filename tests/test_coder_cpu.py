@@ -222,3 +222,106 @@ def test_coder_property_random_tables_vs_oracle():
         assert O.RansDecoder().decode_with_indexes(got, idx, cdfs, sizes, offsets) == sym
 
     run()
+
+
+def test_quantized_cdf_invariants_on_adversarial_pmfs():
+    """clc_pmf_to_quantized_cdf against the INVARIANTS any 16-bit rANS table must satisfy (an authority that does
+    not depend on the in-tree shim): cdf[0] = 0, cdf[-1] = 2^16, strictly increasing (every symbol keeps a
+    non-zero frequency, also when its mass rounds to 0), and -- where no stealing was needed -- frequencies equal
+    round(p * 2^16).  Adversarial inputs: masses straddling the 1/65536 boundary, one dominant symbol, many
+    zero-mass symbols, EntropyBottleneck tables from perturbed parameters."""
+    from hypothesis import given, settings, strategies as st
+    from clc_b200.ans import pmf_to_quantized_cdf
+    O = _oracle_ans()
+    unit = 1.0 / 65536
+
+    @st.composite
+    def pmf(draw):
+        kind = draw(st.integers(0, 3))
+        m = draw(st.integers(1, 60))
+        if kind == 0:      # masses around the quantisation step
+            w = [draw(st.sampled_from([0.0, 0.49 * unit, 0.5 * unit, 0.51 * unit, unit, 1.5 * unit])) for _ in range(m)]
+            w.append(max(1.0 - sum(w), unit))
+        elif kind == 1:    # one dominant symbol, the rest tiny
+            w = [draw(st.floats(0.0, 3e-6)) for _ in range(m)] + [1.0]
+        elif kind == 2:    # smooth bell (what update() produces)
+            s = draw(st.floats(0.3, 12.0))
+            c = draw(st.floats(0, m))
+            w = [np.exp(-0.5 * ((i - c) / s) ** 2) + 1e-12 for i in range(m + 1)]
+        else:
+            w = [draw(st.floats(1e-9, 1.0)) for _ in range(m + 1)]
+        tot = sum(w)
+        return [x / tot for x in w]
+
+    @settings(max_examples=300, deadline=None)
+    @given(pmf())
+    def run(p):
+        cdf = pmf_to_quantized_cdf(p, 16)
+        assert len(cdf) == len(p) + 1 and cdf[0] == 0 and cdf[-1] == 65536
+        freq = np.diff(np.asarray(cdf, dtype=np.int64))
+        assert (freq >= 1).all(), "every symbol must stay decodable"
+        assert cdf == O.pmf_to_quantized_cdf(p, 16)
+        want = np.floor(np.asarray(p, dtype=np.float32).astype(np.float64) * 65536 + 0.5)
+        if int(want.sum()) == 65536 and (want >= 1).all():   # no renormalisation, nothing stolen
+            assert (freq == want).all()
+
+    run()
+
+
+def test_eb_tables_from_perturbed_parameters_round_trip():
+    """EntropyBottleneck.update() tables built from perturbed parameters: quantised CDF rows are valid rANS
+    tables, equal the oracle's update(), and symbols over (and beyond) the support survive encode -> decode."""
+    import clc_b200
+    from clc_b200 import ans as A
+    from oracle import clc_oracle as O
+    g = torch.Generator().manual_seed(3)
+    eb = clc_b200.EntropyBottleneck(12)
+    with torch.no_grad():
+        for n, p in eb.named_parameters():
+            if n == "quantiles":
+                p[:, 0, 0] -= 4 * torch.rand(12, generator=g)
+                p[:, 0, 1] += torch.randn(12, generator=g)
+                p[:, 0, 2] += 4 * torch.rand(12, generator=g)
+            else:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+    eb.update(force=True)
+    ob = O.EntropyBottleneck(12)
+    ob.load_state_dict({k: v for k, v in eb.state_dict().items() if not k.startswith("_") or "matrix" in k
+                        or "bias" in k or "factor" in k}, strict=False)
+    ob.update(force=True)
+    assert torch.equal(eb._quantized_cdf.cpu(), ob._quantized_cdf.cpu())
+    assert torch.equal(eb._offset.cpu(), ob._offset.cpu()) and torch.equal(eb._cdf_length.cpu(), ob._cdf_length.cpu())
+    tab = eb.coder_tables()
+    cdf, ln = eb._quantized_cdf.numpy(), eb._cdf_length.numpy()
+    for c in range(12):
+        row = cdf[c, :ln[c]]
+        assert row[0] == 0 and row[-1] == 65536 and (np.diff(row) >= 1).all()
+    rng = np.random.default_rng(5)
+    n = 20000
+    idx = rng.integers(0, 12, n).astype(np.int32)
+    sym = (eb._offset.numpy()[idx] + rng.integers(-3, ln[idx] + 1)).astype(np.int32)   # incl. out-of-support (bypass)
+    s = A.RansEncoder().encode_with_indexes(sym, idx, tab, None, None)
+    out = A.RansDecoder().decode_with_indexes(s, idx, tab, None, None, as_tensor=True).numpy()
+    assert (out == sym).all()
+
+
+def test_buffered_encoder_resolves_each_call_against_its_own_tables():
+    """compressai's BufferedRansEncoder codes every call's symbols with the cdfs passed in THAT call; buffering
+    calls with different tables must give the stream of the oracle coder fed the same calls."""
+    O = _oracle_ans()
+    from clc_b200 import ans as A
+    t1 = ([O.pmf_to_quantized_cdf([0.2, 0.5, 0.3, 1e-9], 16)], [5], [-1])
+    c2 = [O.pmf_to_quantized_cdf([0.1, 0.1, 0.6, 0.2, 1e-9], 16), O.pmf_to_quantized_cdf([0.7, 0.3, 1e-9], 16) + [0, 0]]
+    t2 = (c2, [6, 4], [0, -3])
+    s1, i1 = [0, 1, -1, 1, 0, 5], [0, 0, 0, 0, 0, 0]
+    s2, i2 = [2, -3, 1, -2, 3, 0, 9], [0, 1, 0, 1, 0, 0, 1]
+    want_e = O.BufferedRansEncoder()
+    got_e = A.BufferedRansEncoder()
+    for sy, ix, t in ((s1, i1, t1), (s2, i2, t2), (s1, i1, t1)):
+        want_e.encode_with_indexes(sy, ix, *t)
+        got_e.encode_with_indexes(sy, ix, *t)
+    want, got = want_e.flush(), got_e.flush()
+    assert got == want
+    d = A.RansDecoder()
+    d.set_stream(got)
+    assert d.decode_stream(i1, *t1) == s1 and d.decode_stream(i2, *t2) == s2 and d.decode_stream(i1, *t1) == s1

@@ -353,3 +353,29 @@ def test_degenerate_inputs_keep_indices_in_bounds():
     # x/0, every other patch is untouched
     assert not torch.isfinite(val[:, 6]).any()
     assert torch.isfinite(val[:, :6]).all() and torch.isfinite(val[:, 7:]).all()
+
+
+def test_public_api_falls_back_to_fp32_outside_the_tc_kernels_and_strict_mode():
+    """The public functions route shapes the tensor-core kernels do not cover (C % 64 != 0) to the exact fp32
+    path (with a warning) instead of raising; strict=True re-runs a tc call in fp32 mode when the certification
+    counter is non-zero (exact ties cannot be certified)."""
+    import clc_b200
+    from clc_b200 import matching
+    d = _dev()
+    y, refs = _inputs(1, 2, 100, 8, 12, seed=3)
+    with pytest.warns(UserWarning, match="outside the tensor-core"):
+        v_t, i_t, _ = clc_b200.match_topk(y.to(d), refs.to(d), 4, 4, 2, mode="tc")
+    v_f, i_f, _ = clc_b200.match_topk(y.to(d), refs.to(d), 4, 4, 2, mode="fp32")
+    assert torch.equal(i_t, i_f) and torch.equal(v_t, v_f)
+    a_t = clc_b200.match_and_gather(y.to(d), refs.to(d), 4, 4, 2, mode="tc")
+    a_f = clc_b200.match_and_gather(y.to(d), refs.to(d), 4, 4, 2, mode="fp32")
+    assert torch.equal(a_t, a_f)
+    # periodic reference: exact ties -> uncertified -> strict mode answers with the fp32 path's result
+    g = torch.Generator().manual_seed(5)
+    yq = torch.randn(1, 64, 16, 32, generator=g)
+    tile = torch.randn(1, 1, 64, 4, 4, generator=g)
+    rp = tile.repeat(1, 1, 1, 4, 8)
+    v_s, i_s, _ = clc_b200.match_topk(yq.to(d), rp.to(d), 4, 4, 4, gaussian_mask=False, mode="tc", strict=True)
+    assert matching.last_uncertified(d) > 0
+    v_e, i_e, _ = clc_b200.match_topk(yq.to(d), rp.to(d), 4, 4, 4, gaussian_mask=False, mode="fp32")
+    assert torch.equal(i_s, i_e) and torch.equal(v_s, v_e)
