@@ -87,6 +87,13 @@ PROTOTYPES = {
     "clc_rans_encode": (C.c_int, [_p, _p, _i64, _p, _i32, _i32, _p, _p, _p, _sz, C.POINTER(_sz)]),
     "clc_rans_encode_capacity": (_sz, [_i64]),
     "clc_rans_decode": (C.c_int, [_p, _sz, _p, _p, _i64, _p, _i32, _i32, _p, _p, _p]),
+    "clc_peer_alloc": (C.c_int, [_sz, C.POINTER(_p)]),
+    "clc_peer_free": (C.c_int, [_p]),
+    "clc_peer_export": (C.c_int, [_p, _p]),
+    "clc_peer_open": (C.c_int, [_p, C.POINTER(_p)]),
+    "clc_peer_close": (C.c_int, [_p]),
+    "clc_peer_allreduce_bytes": (_sz, [_i32, _i32, _i32]),
+    "clc_peer_allreduce": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _f, _p, _p]),
     "clc_clm_fuse_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i32, _i64, _i32, _i64, _p]),
     "clc_clm_fuse_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
 }

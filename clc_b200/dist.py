@@ -31,6 +31,63 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+class PeerAllReduce:
+    """One-shot all-reduce of {n_stat doubles (sum), n_grads floats (mean)} over NVLink peer memory
+    (clc_peer_allreduce: one kernel per rank, no ring latency; capturable into CUDA graphs).  torch.distributed
+    is the plumbing only: it carries the 64-byte CUDA IPC handles of the per-rank regions once, at
+    construction.  All ranks must be on one node with peer access (one NVSwitch domain), world <= 8."""
+
+    def __init__(self, n_stat, n_grads, device, group=None):
+        import ctypes as C
+        from ._lib import call, lib
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_stat, self.n_grads = int(n_stat), int(n_grads)
+        nbytes = lib().clc_peer_allreduce_bytes(self.n_stat, self.n_grads, self.world)
+        if nbytes == 0:
+            raise RuntimeError("clc_peer_allreduce supports at most 8 ranks")
+        with torch.cuda.device(device):
+            mine = C.c_void_p()
+            call("clc_peer_alloc", nbytes, C.byref(mine))
+            handle = (C.c_uint8 * 64)()
+            call("clc_peer_export", mine, handle)
+            on_gpu = dist.get_backend(group) == "nccl"      # (gloo, used by the tests, gathers host tensors)
+            t = torch.tensor(list(handle), dtype=torch.uint8, device=device if on_gpu else "cpu")
+            gathered = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(gathered, t, group=group)
+            self._mine, self._opened = mine, []
+            self._regions = (C.c_void_p * self.world)()
+            for r, g in enumerate(gathered):
+                if r == self.rank:
+                    self._regions[r] = mine.value
+                else:
+                    h = (C.c_uint8 * 64)(*g.cpu().tolist())
+                    p = C.c_void_p()
+                    call("clc_peer_open", h, C.byref(p))
+                    self._opened.append(p)
+                    self._regions[r] = p.value
+            self.state = torch.zeros(3, dtype=torch.int64, device=device)
+            dist.barrier(group=group)          # every region is open everywhere before the first kernel
+
+    def __call__(self, stat, grads, stream=None):
+        """stat: float64[n_stat] (summed in place); grads: float32[n_grads] (replaced by the cross-rank mean)."""
+        from ._lib import call, ptr
+        assert stat.dtype == torch.float64 and stat.numel() == self.n_stat and stat.is_contiguous()
+        assert grads is None or (grads.dtype == torch.float32 and grads.numel() == self.n_grads and grads.is_contiguous())
+        st = torch.cuda.current_stream(stat.device).cuda_stream if stream is None else stream
+        call("clc_peer_allreduce", self._regions, self.rank, self.world, ptr(stat), self.n_stat,
+             ptr(grads), self.n_grads if grads is not None else 0, 1.0 / self.world, ptr(self.state), st)
+
+    def close(self):
+        from ._lib import call
+        for p in self._opened:
+            call("clc_peer_close", p)
+        self._opened = []
+        if self._mine is not None:
+            call("clc_peer_free", self._mine)
+            self._mine = None
+
+
 def shard_range(n_items, rank, world):
     """Contiguous, balanced [start, stop) of `n_items` independent units (images) for `rank`."""
     base, rem = divmod(n_items, world)

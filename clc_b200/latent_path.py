@@ -29,7 +29,7 @@ class LatentPath:
 
     def __init__(self, B, H, W, n_refs=3, M=320, num_slices=5, z_channels=192, train=True, patch=4, k=4,
                  temperature=15.0, match_mode="tc", gaussian_mask=True, fused_slices=False,
-                 device="cuda", lmbda=0.013, data_parallel=False, device_noise=False, fuse_chain=True):
+                 device="cuda", lmbda=0.013, data_parallel=False, device_noise=False, fuse_chain=True, collective="peer"):
         assert H % 64 == 0 and W % 64 == 0, "latent geometry: h = H/16, hz = H/64"
         self.B, self.H, self.W, self.R, self.M = B, H, W, n_refs, M
         self.h, self.w = H // 16, W // 16
@@ -155,6 +155,11 @@ class LatentPath:
         self._eb_grads_flat = self._acc[4:4 + n_eb]
         self._dp_buf = torch.zeros(2 + n_eb, dtype=torch.float64, device=dev) if self.data_parallel else None
         self._world = torch.distributed.get_world_size() if self.data_parallel else 1
+        # the exchange itself: one-shot kernel over NVLink peer memory (default on NCCL / one node), or NCCL
+        self._peer = None
+        if self.data_parallel and collective == "peer" and self._world <= 8:
+            from .dist import PeerAllReduce
+            self._peer = PeerAllReduce(2, n_eb if train else 0, dev)
         # device-resident noise stream {seed, base offset} (clc_gc_fwd_rng) + the step's bpp (clc_bpp_finalize)
         self.rng_state = torch.tensor([0x5DEECE66D + 7919 * (id(self) & 0xFFFF), 0], dtype=torch.int64, device=dev)
         self._bpp_dev = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -371,10 +376,16 @@ class LatentPath:
         Enqueued at the end of the entropy branch, where it overlaps the match chain."""
         if not self.data_parallel:
             return
+        if self._peer is not None:
+            # one kernel: pack -> publish over NVLink -> wait -> fixed-order sum; statistic summed, EB parameter
+            # gradients averaged (the gradient of the GLOBAL-batch bpp, like every other data-parallel gradient)
+            self._peer(self.log2, self._eb_grads_flat if self.train else None)
+            return
         buf = self._dp_buf if self.train else self._dp_buf[:2]
         buf[:2].copy_(self.log2)
         if self.train:
-            buf[2:].copy_(self._eb_grads_flat)
+            # mean over ranks: the EB gradients were formed with the per-rank 1/(B_local H W) normalisation
+            torch.mul(self._eb_grads_flat, 1.0 / self._world, out=buf[2:])
         torch.distributed.all_reduce(buf)
         self.log2.copy_(buf[:2])
         if self.train:

@@ -400,6 +400,32 @@ CLC_API int clc_rans_decode(const uint8_t* stream, size_t stream_bytes, uint64_t
                             int64_t n, const int32_t* cdfs, int32_t n_cdfs, int32_t cdf_stride,
                             const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out);
 
+/* ------------------------------------------------------------------------------------
+ * Data-parallel exchange over NVLink peer memory (the reference trains with threaded
+ * nn.DataParallel, train_CLC.py:74-79,:472-473, whose gradient is the mean over the global batch)
+ * ---------------------------------------------------------------------------------- */
+
+/* Peer-visible device memory: a zero-filled cudaMalloc region exported / opened through CUDA IPC (HOST
+ * functions; the 64-byte handles travel over the caller's own transport, e.g. torch.distributed). */
+CLC_API int clc_peer_alloc(size_t bytes, void** ptr);
+CLC_API int clc_peer_free(void* ptr);
+CLC_API int clc_peer_export(void* ptr, uint8_t handle[64]);
+CLC_API int clc_peer_open(const uint8_t handle[64], void** ptr);
+CLC_API int clc_peer_close(void* ptr);
+/* Bytes of the peer region clc_peer_allreduce needs on every rank (0 = unsupported arguments). */
+CLC_API size_t clc_peer_allreduce_bytes(int32_t n_stat, int32_t n_grads, int32_t world);
+
+/* One-shot all-reduce of the path's per-step exchange in ONE kernel per rank (no ring): every rank publishes
+ * {stat[n_stat] doubles, grads[n_grads] floats} in its peer region, signals all ranks through NVLink, waits
+ * for all of them and sums the world's contributions in fixed rank order (identical bits on every rank):
+ *   stat  <- sum over ranks            (the bpp statistic: sum log2 likelihoods)
+ *   grads <- grad_scale * sum over ranks  (1/world: the mean gradient of the EntropyBottleneck parameters)
+ *   regions : HOST array of `world` device pointers, regions[r] = rank r's region (own or clc_peer_open'ed)
+ *   state   : device uint64[3], zero-initialised once; the kernel keeps its step counter there, so the launch can
+ *             be captured into a CUDA graph.  Every rank must enqueue the same sequence of calls.  world <= 8. */
+CLC_API int clc_peer_allreduce(void* const* regions, int32_t rank, int32_t world, double* stat, int32_t n_stat,
+                               float* grads, int32_t n_grads, float grad_scale, uint64_t* state, void* stream);
+
 #ifdef CLC_DEBUG_ABI
 /* ------------------------------------------------------------------------------------
  * Bring-up / test hooks of the tcgen05 match kernel (no reference counterpart).  They exist ONLY in
