@@ -64,6 +64,8 @@ def make_config(args, cfg, world):
             "graph_branches": "serial" if args.no_fork else ("match | hyper -> slices" if world == 1
                                                               else "match | hyper | slices -> all-reduce"),
             "l2": "flushed between timed iterations (256 MB write)", "patch": 4, "k": 4,
+            "collective": ("none" if world == 1 else
+                           ("one-shot all-reduce kernel over NVLink peer memory" if args.collective == "peer" else "NCCL all-reduce")),
             "noise": "uploaded tensors" if args.host_noise else "generated in-kernel (Philox), like the reference's "
                      "on-device uniform_()"}
 
@@ -248,7 +250,8 @@ class GraphedPublicPath:
 def _make_path(cfg, args, dev, fused, rank):
     from clc_b200.latent_path import LatentPath
     lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], match_mode=args.match_mode,
-                    fused_slices=fused, device=dev, data_parallel=True, device_noise=not args.host_noise)
+                    fused_slices=fused, device=dev, data_parallel=True, device_noise=not args.host_noise,
+                    collective=args.collective)
     lp.randomize(seed=1 + rank)
     return lp
 
@@ -547,6 +550,103 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def run_model_step(args):
+    """Context run (NOT the latent-path metric): the reference's data-parallel TRAINING step at model level
+    (train_CLC.py:119-184 with CLC(N=128, num_ref_frames=n), AdamW, grad clip 1.0, aux loss), one process per GPU,
+    bucketed gradient all-reduce (clc_b200.dist.GradAllReducer, NCCL over NVLink) overlapped with the backward.
+    Reports the step time, the same step without the all-reduce, and the bare all-reduce of the same buckets, i.e.
+    how much of the exchange the backward hides."""
+    from clc_b200 import dist as cdist
+    from clc_b200.loss import RateDistortionLoss
+    from clc_b200.models import CLC
+    rank, world, local = cdist.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = workload(args, world)
+    B, H, W, R = cfg["B"], cfg["H"], cfg["W"], cfg["R"]
+    torch.manual_seed(0)
+    model = CLC(N=128, num_ref_frames=R).to(dev).train()
+    crit = RateDistortionLoss(lmbda=0.013)
+    main = [p for n, p in model.named_parameters() if not n.endswith(".quantiles")]
+    aux = [p for n, p in model.named_parameters() if n.endswith(".quantiles")]
+    opt, aux_opt = torch.optim.AdamW(main, lr=1e-4), torch.optim.AdamW(aux, lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.rand(B, 3, H, W, device=dev, generator=g)
+    refs = [torch.rand(B, 3, H, W, device=dev, generator=g) for _ in range(R)]
+
+    def step(red):
+        if red is not None:
+            red.zero_grad()                              # gradients live in the communication buckets
+        else:
+            opt.zero_grad(set_to_none=True)
+            aux_opt.zero_grad(set_to_none=True)
+        out = model(x, refs)
+        loss = crit(out, x)["loss"]
+        loss.backward()
+        model.aux_loss().backward()                     # (train_CLC.py:181-183; its 192x3 gradients ride the last bucket)
+        if red is not None:
+            red.finish()
+        torch.nn.utils.clip_grad_norm_(main, 1.0)
+        opt.step()
+        aux_opt.step()
+        return loss
+
+    def timed(red, K, Wm):
+        for _ in range(Wm):
+            step(red)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            loss = step(red)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / K], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return t.item(), loss.item()
+
+    K, Wm = args.steps, max(args.warmup, 2)
+    ms_nodp, _ = timed(None, K, Wm)                       # local step, no exchange (each rank drifts apart: timing only)
+    red = cdist.GradAllReducer(model, bucket_mb=args.bucket_mb) if world > 1 else None
+    ms_dp, loss = timed(red, K, Wm)
+    n_grad = sum(p.grad.numel() for p in model.parameters() if p.grad is not None)
+    ms_ar = None
+    if world > 1:
+        flat = torch.zeros(n_grad, device=dev)
+        for _ in range(3):
+            torch.distributed.all_reduce(flat)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            torch.distributed.all_reduce(flat)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 5], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_ar = t.item()
+    if rank != 0:
+        return
+    pix = world * B * H * W
+    exposed = max(ms_dp - ms_nodp, 0.0)
+    line = {"impl": "ours", "mode": "model-step (context, not the latent-path metric)",
+            "metric": "Mpix/s of the CLC(N=128) data-parallel training step", "value": pix / (ms_dp * 1e-3) / 1e6,
+            "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_dp,
+            "ms_per_step_without_allreduce": ms_nodp, "higher_is_better": True,
+            "scaling": "strong" if "global_batch" in cfg else "weak", "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg['desc']}", "model": "CLC(N=128, M=320)", "per_gpu_batch": B,
+                       "global_batch": B * world, "image": [H, W], "n_refs": R, "optimizer": "AdamW + aux AdamW, clip 1.0",
+                       "bucket_mb": args.bucket_mb},
+            "grad_allreduce": {"elements": n_grad, "bytes": 4 * n_grad, "bare_ms": ms_ar, "exposed_ms": exposed,
+                               "hidden_fraction": (1.0 - exposed / ms_ar) if ms_ar else None,
+                               "bus_gbs": (2 * (world - 1) / world * 4 * n_grad / (ms_ar * 1e-3) / 1e9) if ms_ar else None},
+            "loss": loss}
+    print(json.dumps(line))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -581,6 +681,12 @@ def main():
     ap.add_argument("--host-noise", action="store_true",
                     help="upload the U(-1/2,1/2) quantisation noise as tensors (bit-reproducible parity runs) instead "
                          "of generating it inside the kernels, as the reference generates it on the device")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="the latent path's per-step exchange: one-shot kernel over NVLink peer memory, or NCCL all-reduce")
+    ap.add_argument("--model-step", action="store_true",
+                    help="context run: CLC(N=128) model-level data-parallel training step with the bucketed gradient "
+                         "all-reduce (not the latent-path metric)")
+    ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fork", action="store_true", help="capture the step as one serial chain instead of two branches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -588,6 +694,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.model_step:
+        run_model_step(args)
     else:
         run_ours(args)
     if torch.distributed.is_initialized():

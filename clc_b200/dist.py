@@ -98,52 +98,112 @@ def shard_range(n_items, rank, world):
 class GradAllReducer:
     """Bucketed, overlapped gradient all-reduce (mean) for a replicated model.
 
-    Gradient hooks fire as autograd produces each parameter's gradient; parameters are packed
-    into flat buckets of ~`bucket_mb` in reverse registration order and each full bucket is
-    all-reduced asynchronously while the backward pass continues.  `finish()` flushes the last
-    bucket, waits, divides by world size and scatters the results back.  Parameters that receive
-    no gradient (the reference's unused `feature_alignment`, `multi_ref_fusion`, ... modules)
-    are simply absent from every rank's buckets, which keeps the ranks consistent because the
-    set is a property of the graph, not of the data."""
+    Gradients live IN the buckets: after a first (discovery) backward has shown which parameters receive a
+    gradient and in which order, every such parameter's `.grad` is a view into a flat fp32 bucket of
+    ~`bucket_mb`, so autograd accumulates straight into the communication buffer (no flatten / scatter copies).
+    A post-accumulate hook counts the bucket's parameters as they become ready; the moment a bucket is complete
+    it is all-reduced asynchronously (NCCL: ReduceOp.AVG, in place) while the backward pass continues.
+    `finish()` waits.  Parameters that receive no gradient (the reference's unused `feature_alignment`,
+    `multi_ref_fusion`, `cc_*`, `lrp_transforms` modules: 310 tensors) are in no bucket on any rank
+    -- the set is a property of the graph, not of the data.  Call `zero_grad()` (instead of the optimiser's)
+    between steps: it clears the buckets and keeps the views."""
 
-    def __init__(self, module, bucket_mb=64.0, group=None):
+    def __init__(self, module, bucket_mb=32.0, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = int(bucket_mb * 1024 * 1024 // 4)
         self.params = [p for p in module.parameters() if p.requires_grad]
-        self._pending, self._pending_elems, self._inflight = [], 0, []
+        self._order = []                 # discovery pass: parameters in the order their gradients became ready
+        self._buckets = None             # [(flat, [params], n_params)]
+        self._bucket_of, self._ready, self._inflight = {}, [], []
+        self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
 
-    def _hook(self, p):
-        if self.world == 1 or p.grad is None:
-            return
-        self._pending.append(p)
-        self._pending_elems += p.grad.numel()
-        if self._pending_elems >= self.bucket_elems:
-            self._launch()
-
-    def _launch(self):
-        if not self._pending:
-            return
-        ps, self._pending, self._pending_elems = self._pending, [], 0
-        flat = torch.cat([p.grad.reshape(-1) for p in ps])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._inflight.append((work, flat, ps))
-
-    def finish(self):
-        """Call after backward(): completes all buckets; gradients become the cross-rank mean."""
-        if self.world == 1:
-            return
-        self._launch()
-        for work, flat, ps in self._inflight:
-            work.wait()
+    # ---- discovery step: plain flatten -> all-reduce -> scatter (runs once) ----
+    def _finish_discovery(self):
+        ps = [p for p in self._order if p.grad is not None]
+        if ps and self.world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in ps])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.div_(self.world)
             off = 0
             for p in ps:
                 n = p.grad.numel()
                 p.grad.copy_(flat[off:off + n].view_as(p.grad))
                 off += n
+        # build the buckets in ready order and move the gradients into them
+        self._buckets, cur, cur_n = [], [], 0
+        for p in ps:
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n >= self.bucket_elems:
+                self._buckets.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            self._buckets.append(cur)
+        built = []
+        for bi, plist in enumerate(self._buckets):
+            flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=plist[0].device)
+            off = 0
+            for p in plist:
+                n = p.numel()
+                view = flat[off:off + n].view_as(p)
+                view.copy_(p.grad)
+                p.grad = view
+                self._bucket_of[p] = bi
+                off += n
+            built.append((flat, plist))
+        self._buckets = built
+        self._ready = [0] * len(built)
+
+    def _hook(self, p):
+        if self._buckets is None:
+            self._order.append(p)
+            return
+        bi = self._bucket_of.get(p)
+        if bi is None or self.world == 1:
+            return
+        self._ready[bi] += 1
+        if self._ready[bi] == len(self._buckets[bi][1]):
+            self._launch(bi)
+
+    def _launch(self, bi):
+        flat = self._buckets[bi][0]
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._inflight.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
+        self._ready[bi] = -(1 << 30)     # launched
+
+    def finish(self):
+        """Call after backward(): completes all buckets; gradients become the cross-rank mean."""
+        if self._buckets is None:
+            self._finish_discovery()
+            self._order = []
+            return
+        if self.world == 1:
+            return
+        for bi in range(len(self._buckets)):
+            if self._ready[bi] >= 0:     # a bucket some parameter of which got no gradient this step
+                self._launch(bi)
+        for work, flat in self._inflight:
+            work.wait()
+            if not self._avg:
+                flat.div_(self.world)
         self._inflight = []
+        self._ready = [0] * len(self._buckets)
+
+    def zero_grad(self):
+        """Clears the gradient buckets (one memset each) and keeps every `.grad` a view into its bucket."""
+        if self._buckets is None:
+            for p in self.params:
+                p.grad = None
+            return
+        for flat, plist in self._buckets:
+            flat.zero_()
+            off = 0
+            for p in plist:
+                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
 
     def remove(self):
         for h in self._handles:

