@@ -20,7 +20,9 @@ hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 
 # kernel function name -> the trace label bench.py uses
-LABELS = [("prepass", "clc_match_topk_tc(prepass)"), ("match_bwd_own", "clc_match_bwd(main)"),
+LABELS = [("prepass", "clc_match_topk_tc(prepass)"), ("select_kernel", "clc_match_topk_tc(select)"),
+          ("match_bwd_own_kernel<320, 1>", "clc_match_clm_bwd(main)"), ("match_bwd_own_kernel<320, 0>", "clc_match_bwd(main)"),
+          ("match_bwd_own", "clc_match_bwd(main)"), ("bpp_finalize", "clc_bpp_finalize"),
           ("cl_to_nchw_kernel", "clc_match_bwd(cl_to_nchw)"),
           ("pack_ref", "clc_match_topk_tc(pack_ref)"), ("pack_query", "clc_match_topk_tc(pack_query)"),
           ("patch_stats", "patch_stats"), ("match_gemm", "clc_match_topk_tc(gemm)"),
