@@ -130,4 +130,15 @@ inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8, int 
   return (int)(need < cap ? need : cap);
 }
 
+// 2-D grid for [B rows] x [items per row] elementwise kernels: x covers one row in `per_block` chunks, y the rows,
+// the whole grid capped at ~ctas_per_sm CTAs per SM (kernels stride over both dimensions).
+inline dim3 grid_rows(int64_t rows, int64_t items_per_row, int per_block, int ctas_per_sm = 8) {
+  int64_t gy = rows < 1 ? 1 : (rows > 65535 ? 65535 : rows);
+  int64_t need = (items_per_row + per_block - 1) / per_block;
+  if (need < 1) need = 1;
+  int64_t cap = ((int64_t)kNumSMs * ctas_per_sm + gy - 1) / gy;
+  if (cap < 1) cap = 1;
+  return dim3((unsigned)(need < cap ? need : cap), (unsigned)gy, 1);
+}
+
 }  // namespace clc

@@ -14,7 +14,7 @@
 
 namespace clc {
 
-constexpr float kNegInvSqrt2 = -0.70710678118654752440f;  // const = -(2 ** -0.5)
+constexpr float kInvSqrt2 = 0.70710678118654752440f;     // -const, const = -(2 ** -0.5) of CLC_run.py:729
 constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
 
 // ------------------------------------------------------------------------------------------
@@ -92,12 +92,33 @@ constexpr float kSeriesMinScale = 4.0f;
 __device__ __forceinline__ float gauss_mass_series(float v, float d) {   // d = 1 / scale
   const float t = v * d;
   const float a = t * t, d2 = d * d;
-  const float phi = kInvSqrt2Pi * expf(-0.5f * a);
+  const float phi = kInvSqrt2Pi * __expf(-0.5f * a);
   const float h2 = a - 1.f;
   const float h4 = (a - 6.f) * a + 3.f;
   const float h6 = ((a - 15.f) * a + 45.f) * a - 15.f;
   const float poly = 1.f + d2 * (h2 * (1.f / 24.f) + d2 * (h4 * (1.f / 1920.f) + d2 * (h6 * (1.f / 322560.f))));
   return d * phi * poly;
+}
+
+// erfc(z) for z >= 0 with fractional error < 1.1e-7 in exact arithmetic everywhere (so the far tail keeps its
+// relative accuracy, which a fit of erfc itself would not): erfc(z) = t * exp(-z^2 + P9(t)), t = 1 / (1 + z/2),
+// the classic Chebyshev fit of log(erfc(z) e^{z^2} / t) (Numerical Recipes "erfcc").  One MUFU.RCP, one MUFU.EX2,
+// eleven FMAs -- a third of the instructions of libdevice's erfcf, which made the forward kernel issue-bound
+// (profiles/r2_full_cfg4: 81 % issue slots busy).  In fp32 with ex2.approx the relative error is < 4e-6 down to
+// erfc = 1e-19, the fp64 leg of tests/test_entropy_gpu.py::test_gc_golden_reference_vectors.
+__device__ __forceinline__ float erfc_pos(float z) {
+  const float t = __fdividef(1.0f, fmaf(0.5f, z, 1.0f));
+  float p = 0.17087277f;
+  p = fmaf(p, t, -0.82215223f);
+  p = fmaf(p, t, 1.48851587f);
+  p = fmaf(p, t, -1.13520398f);
+  p = fmaf(p, t, 0.27886807f);
+  p = fmaf(p, t, -0.18628806f);
+  p = fmaf(p, t, 0.09678418f);
+  p = fmaf(p, t, 0.37409196f);
+  p = fmaf(p, t, 1.00002368f);
+  p = fmaf(p, t, -1.26551223f);
+  return t * __expf(fmaf(-z, z, p));
 }
 
 struct GcOut {
@@ -118,17 +139,20 @@ __device__ __forceinline__ GcOut gc_elem(float y, float s, float m, float n, boo
   const float values = o.outputs - m;
   const float sc = fmaxf(s, scale_bound);
   const float v = fabsf(values);
-  // one IEEE reciprocal shared by both bin edges (and by the series): (half - v) * (1/s) differs from the
-  // reference's true division (half - v) / s by at most 1 ulp, i.e. ~1e-7 relative in the likelihood --
-  // three orders below the 1e-4 bar -- and saves a division per element on a kernel that is ALU-bound
-  const float inv = 1.0f / sc;
+  // one reciprocal (MUFU.RCP, 1 ulp) shared by both bin edges and by the series: (half - v) * (1/s) differs
+  // from the reference's true division (half - v) / s by ~2 ulp, i.e. < 5e-6 relative in the likelihood even at
+  // the 1e-9 floor -- more than an order below the 1e-4 bar -- on a kernel that is instruction-issue-bound
+  const float inv = __fdividef(1.0f, sc);
   if (sc >= kSeriesMinScale) {
     o.lik_raw = gauss_mass_series(v, inv);
   } else {
+    // Phi(up) - Phi(lo) with both erfc arguments taken POSITIVE (lo < 0 always; up < 0 unless |values| < 1/2),
+    // which is also what the reference's half * erfc(-x / sqrt 2) evaluates for the tail side
     const float up = (0.5f - v) * inv;
     const float lo = (-0.5f - v) * inv;
-    const float U = 0.5f * erfcf(kNegInvSqrt2 * up);
-    const float L = 0.5f * erfcf(kNegInvSqrt2 * lo);
+    const float eu = 0.5f * erfc_pos(fabsf(up) * kInvSqrt2);
+    const float L = 0.5f * erfc_pos(-lo * kInvSqrt2);
+    const float U = up < 0.f ? eu : 1.0f - eu;
     o.lik_raw = U - L;
   }
   o.lik = fmaxf(o.lik_raw, lik_bound);
@@ -153,12 +177,11 @@ __global__ void __launch_bounds__(256) gc_fwd_kernel(const GcFwdParams p) {
   const RngCtx rc(p.rng);
   constexpr int W = VEC ? 4 : 1;
   const int64_t per_b = p.CS / W;
-  const int64_t total = p.B * per_b;
   float acc = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / per_b;
-    const int64_t j = (i - b * per_b) * W;
+  // grid = (blocks per batch row, batch rows): no 64-bit division per item
+  for (int64_t b = blockIdx.y; b < p.B; b += gridDim.y)
+  for (int64_t jj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; jj < per_b; jj += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = jj * W;
     if constexpr (VEC) {
       const float4 y4 = ld4_stream(p.y + b * p.y_bs + j);
       const float4 s4 = ld4_stream(p.scale + b * p.scale_bs + j);
@@ -226,15 +249,15 @@ __device__ __forceinline__ GcGrad gc_elem_bwd(float y, float s, float m, float n
   }
   const float sc = fmaxf(s, scale_bound);
   const float v = fabsf(values);
-  const float up = (0.5f - v) / sc;
-  const float lo = (-0.5f - v) / sc;
-  const float pu = kInvSqrt2Pi * expf(-0.5f * up * up);
-  const float pl = kInvSqrt2Pi * expf(-0.5f * lo * lo);
+  const float inv = __fdividef(1.0f, sc);          // same shared reciprocal as the forward (gc_elem)
+  const float up = (0.5f - v) * inv;
+  const float lo = (-0.5f - v) * inv;
+  const float pu = kInvSqrt2Pi * __expf(-0.5f * up * up);
+  const float pl = kInvSqrt2Pi * __expf(-0.5f * lo * lo);
   float gl = has_g_lik ? g_lik : (bpp_coef / lik);
   // likelihood LowerBound gate: lik > bound means the raw value was above the floor.
   const bool pass_l = (lik > lik_bound) || (gl < 0.f);
   gl = pass_l ? gl : 0.f;
-  const float inv = 1.0f / sc;
   const float dv = (pl - pu) * inv;
   const float ds = (lo * pl - up * pu) * inv;
   const float sgn = (values > 0.f) ? 1.f : ((values < 0.f) ? -1.f : 0.f);
@@ -254,11 +277,10 @@ __global__ void __launch_bounds__(256) gc_bwd_kernel(const GcBwdParams p) {
   const bool has_gl = p.g_lik != nullptr;
   constexpr int W = VEC ? 4 : 1;
   const int64_t per_b = p.CS / W;
-  const int64_t total = p.B * per_b;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / per_b;
-    const int64_t j = (i - b * per_b) * W;
+  // grid = (blocks per batch row, batch rows): no 64-bit division per item
+  for (int64_t b = blockIdx.y; b < p.B; b += gridDim.y)
+  for (int64_t jj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; jj < per_b; jj += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = jj * W;
     if constexpr (VEC) {
       const float4 z4 = make_float4(0, 0, 0, 0);
       const float4 y4 = ld4_stream(p.y + b * p.y_bs + j);
@@ -302,11 +324,10 @@ lrp_kernel(float* __restrict__ io, int64_t io_bs, const float* __restrict__ lrp,
            const float* __restrict__ g, int64_t g_bs, int64_t B, int64_t CS) {
   constexpr int W = VEC ? 4 : 1;
   const int64_t per_b = CS / W;
-  const int64_t total = B * per_b;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / per_b;
-    const int64_t j = (i - b * per_b) * W;
+  // grid = (blocks per batch row, batch rows): no 64-bit division per item
+  for (int64_t b = blockIdx.y; b < B; b += gridDim.y)
+  for (int64_t jj = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; jj < per_b; jj += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = jj * W;
     if constexpr (VEC) {
       const float4 l4 = ld4_stream(lrp + b * lrp_bs + j);
       const float t0 = tanhf(l4.x), t1 = tanhf(l4.y), t2 = tanhf(l4.z), t3 = tanhf(l4.w);
@@ -387,23 +408,33 @@ __device__ __forceinline__ float softplusf(float x) {
   return x > 20.f ? x : log1pf(expf(x));
 }
 
-__device__ __forceinline__ void eb_load_pack(const EbPtrs& P, int c, float* pk) {
-  // raw -> transformed parameters of channel c (58 values), done by the first 58 threads
+// raw -> transformed parameters of channel c (58 values), done by the first 58 threads.  The source address is
+// SELECTED per thread and loaded once after the selection: a 14-way if-chain with one load per arm serialises
+// 14 global-load latencies inside the two warps (it was ~6 us of the 10 us this kernel took at cfg2).
+// Returns the thread's raw parameter (the backward's softplus / tanh chain rule needs it again).
+__device__ __forceinline__ float eb_load_pack(const EbPtrs& P, int c, float* pk) {
   const int t = threadIdx.x;
-  if (t < 3) pk[t] = softplusf(P.matrix[0][c * 3 + t]);
-  else if (t < 12) pk[t] = softplusf(P.matrix[1][c * 9 + (t - 3)]);
-  else if (t < 21) pk[t] = softplusf(P.matrix[2][c * 9 + (t - 12)]);
-  else if (t < 30) pk[t] = softplusf(P.matrix[3][c * 9 + (t - 21)]);
-  else if (t < 33) pk[t] = softplusf(P.matrix[4][c * 3 + (t - 30)]);
-  else if (t < 36) pk[t] = P.bias[0][c * 3 + (t - 33)];
-  else if (t < 39) pk[t] = P.bias[1][c * 3 + (t - 36)];
-  else if (t < 42) pk[t] = P.bias[2][c * 3 + (t - 39)];
-  else if (t < 45) pk[t] = P.bias[3][c * 3 + (t - 42)];
-  else if (t < 46) pk[t] = P.bias[4][c];
-  else if (t < 49) pk[t] = tanhf(P.factor[0][c * 3 + (t - 46)]);
-  else if (t < 52) pk[t] = tanhf(P.factor[1][c * 3 + (t - 49)]);
-  else if (t < 55) pk[t] = tanhf(P.factor[2][c * 3 + (t - 52)]);
-  else if (t < 58) pk[t] = tanhf(P.factor[3][c * 3 + (t - 55)]);
+  float raw = 0.f;
+  if (t < kEbPack) {
+    const float* src = P.matrix[0];
+    int i = c * 3 + t;
+    if (t >= 3) { src = P.matrix[1]; i = c * 9 + (t - 3); }
+    if (t >= 12) { src = P.matrix[2]; i = c * 9 + (t - 12); }
+    if (t >= 21) { src = P.matrix[3]; i = c * 9 + (t - 21); }
+    if (t >= 30) { src = P.matrix[4]; i = c * 3 + (t - 30); }
+    if (t >= 33) { src = P.bias[0]; i = c * 3 + (t - 33); }
+    if (t >= 36) { src = P.bias[1]; i = c * 3 + (t - 36); }
+    if (t >= 39) { src = P.bias[2]; i = c * 3 + (t - 39); }
+    if (t >= 42) { src = P.bias[3]; i = c * 3 + (t - 42); }
+    if (t >= 45) { src = P.bias[4]; i = c; }
+    if (t >= 46) { src = P.factor[0]; i = c * 3 + (t - 46); }
+    if (t >= 49) { src = P.factor[1]; i = c * 3 + (t - 49); }
+    if (t >= 52) { src = P.factor[2]; i = c * 3 + (t - 52); }
+    if (t >= 55) { src = P.factor[3]; i = c * 3 + (t - 55); }
+    raw = __ldg(src + i);
+    pk[t] = t < 33 ? softplusf(raw) : (t < 46 ? raw : tanhf(raw));
+  }
+  return raw;
 }
 
 // logits = _logits_cumulative(x) for one scalar input.  Operation order follows upstream:
@@ -458,21 +489,28 @@ __global__ void __launch_bounds__(128) eb_fwd_kernel(const EbFwdParams p) {
   __shared__ float pk[64];
   __shared__ float red[32];
   const int c = blockIdx.x;
-  eb_load_pack(p.P, c, pk);
-  __syncthreads();
-  const float med = p.quantiles[c * 3 + 1];
+  // everything that does not depend on the parameter pack is loaded first, so its latency overlaps the pack's
+  const float med = __ldg(p.quantiles + c * 3 + 1);
   const bool use_rng = p.rng.state != nullptr;
   const bool train = p.noise != nullptr || use_rng;
   const RngCtx rc(p.rng);
   const int64_t n = p.B * p.S;
+  const int64_t e0 = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  float z_pre = 0.f, n_pre = 0.f;
+  if (e0 < n) {
+    const int64_t off0 = ((e0 / p.S) * p.C + c) * p.S + e0 % p.S;
+    z_pre = p.z[off0];
+    if (p.noise) n_pre = p.noise[off0];
+  }
+  eb_load_pack(p.P, c, pk);
+  __syncthreads();
   float acc = 0.f;
-  for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n;
-       e += (int64_t)gridDim.y * blockDim.x) {
+  for (int64_t e = e0; e < n; e += (int64_t)gridDim.y * blockDim.x) {
     const int64_t b = e / p.S, s = e - b * p.S;
     const int64_t off = (b * p.C + c) * p.S + s;
-    const float z = p.z[off];
+    const float z = e == e0 ? z_pre : p.z[off];
     const float zh = rintf(z - med) + med;
-    const float x = train ? (z + (use_rng ? rc.noise1((unsigned long long)off) : p.noise[off])) : zh;
+    const float x = train ? (z + (use_rng ? rc.noise1((unsigned long long)off) : (e == e0 ? n_pre : p.noise[off]))) : zh;
     const float lo = eb_logits<false>(pk, x - 0.5f, nullptr, nullptr);
     const float up = eb_logits<false>(pk, x + 0.5f, nullptr, nullptr);
     const float t = lo + up;
@@ -549,23 +587,33 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
   __shared__ float pk[64];
   __shared__ float gsum[64];
   const int c = blockIdx.x;
-  eb_load_pack(p.P, c, pk);
-  if (threadIdx.x < 64) gsum[threadIdx.x] = 0.f;
-  __syncthreads();
-  const float med = p.quantiles[c * 3 + 1];
+  const float med = __ldg(p.quantiles + c * 3 + 1);
   const bool use_rng = p.rng.state != nullptr;
   const bool train = p.noise != nullptr || use_rng;
   const RngCtx rc(p.rng);
   const int64_t n = p.B * p.S;
+  const int64_t e0 = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  float z_pre = 0.f, n_pre = 0.f, lik_pre = 1.f, gl_pre = 0.f, gzh_pre = 0.f;   // first element: loads ahead of the pack
+  if (e0 < n) {
+    const int64_t off0 = ((e0 / p.S) * p.C + c) * p.S + e0 % p.S;
+    z_pre = p.z[off0];
+    if (p.noise) n_pre = p.noise[off0];
+    lik_pre = p.lik[off0];
+    if (p.g_lik) gl_pre = p.g_lik[off0];
+    if (p.g_z_hat) gzh_pre = p.g_z_hat[off0];
+  }
+  const float raw = eb_load_pack(p.P, c, pk);
+  if (threadIdx.x < 64) gsum[threadIdx.x] = 0.f;
+  __syncthreads();
   float gp[kEbPack];
 #pragma unroll
   for (int i = 0; i < kEbPack; ++i) gp[i] = 0.f;
-  for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n;
-       e += (int64_t)gridDim.y * blockDim.x) {
+  for (int64_t e = e0; e < n; e += (int64_t)gridDim.y * blockDim.x) {
     const int64_t b = e / p.S, s = e - b * p.S;
     const int64_t off = (b * p.C + c) * p.S + s;
-    const float z = p.z[off];
-    const float x = train ? (z + (use_rng ? rc.noise1((unsigned long long)off) : p.noise[off])) : (rintf(z - med) + med);
+    const bool first = e == e0;
+    const float z = first ? z_pre : p.z[off];
+    const float x = train ? (z + (use_rng ? rc.noise1((unsigned long long)off) : (first ? n_pre : p.noise[off]))) : (rintf(z - med) + med);
     float a_lo[4][3], in_lo[5][3], a_up[4][3], in_up[5][3];
     const float lo = eb_logits<true>(pk, x - 0.5f, a_lo, in_lo);
     const float up = eb_logits<true>(pk, x + 0.5f, a_up, in_up);
@@ -573,15 +621,15 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
     const float sg = (t > 0.f) ? -1.f : ((t < 0.f) ? 1.f : 0.f);
     const float su = sigmoidf_(sg * up), sl = sigmoidf_(sg * lo);
     const float D = su - sl;
-    const float lik = p.lik[off];
-    float gl = p.g_lik ? p.g_lik[off] : (p.bpp_coef / lik);
+    const float lik = first ? lik_pre : p.lik[off];
+    float gl = p.g_lik ? (first ? gl_pre : p.g_lik[off]) : (p.bpp_coef / lik);
     gl = ((lik > p.lik_bound) || (gl < 0.f)) ? gl : 0.f;
     const float sd = (D > 0.f) ? 1.f : ((D < 0.f) ? -1.f : 0.f);  // d|D|/dD
     const float g_up = gl * sd * su * (1.f - su) * sg;
     const float g_lo = -gl * sd * sl * (1.f - sl) * sg;
     float gx = eb_logits_bwd(pk, x + 0.5f, a_up, in_up, g_up, gp);
     gx += eb_logits_bwd(pk, x - 0.5f, a_lo, in_lo, g_lo, gp);
-    const float gzh = p.g_z_hat ? p.g_z_hat[off] : 0.f;  // STE: d z_hat / d z = 1
+    const float gzh = p.g_z_hat ? (first ? gzh_pre : p.g_z_hat[off]) : 0.f;  // STE: d z_hat / d z = 1
     p.g_z[off] = gzh + (train ? gx : 0.f);
   }
   if (!p.param_grads) return;
@@ -601,7 +649,6 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
       if (t < 3) { l = 0; k = t; } else if (t < 12) { l = 1; k = t - 3; } else if (t < 21) { l = 2; k = t - 12; }
       else if (t < 30) { l = 3; k = t - 21; } else { l = 4; k = t - 30; }
       const int per = (l == 0 || l == 4) ? 3 : 9;
-      const float raw = p.P.matrix[l][c * per + k];
       atomicAdd(&p.G.matrix[l][c * per + k], g * sigmoidf_(raw));  // d softplus = sigmoid
     } else if (t < 46) {
       const int l = (t - 33) / 3, k = (t - 33) % 3;
@@ -675,8 +722,8 @@ static int gc_fwd_impl(const float* y, int64_t y_bs, const float* scale, int64_t
   const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, y_hat, outputs},
                           {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, y_hat_bs, outputs_bs});
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) gc_fwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
-  else gc_fwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
+  if (vec) gc_fwd_kernel<true><<<grid_rows(B, CS / 4, 256), 256, 0, st>>>(p);
+  else gc_fwd_kernel<false><<<grid_rows(B, CS, 256), 256, 0, st>>>(p);
   CLC_CHECK_LAUNCH("clc_gc_fwd");
   return CLC_OK;
 }
@@ -739,8 +786,8 @@ static int gc_bwd_impl(const float* y, int64_t y_bs, const float* scale, int64_t
   const bool vec = vec_ok(CS, {y, scale, mean, noise, lik, g_lik, g_y_hat, g_y, g_scale, g_mean},
                           {y_bs, scale_bs, mean_bs, noise_bs, lik_bs, g_lik_bs, g_y_hat_bs, g_y_bs, g_scale_bs, g_mean_bs});
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) gc_bwd_kernel<true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(p);
-  else gc_bwd_kernel<false><<<grid_for(B * CS, 256), 256, 0, st>>>(p);
+  if (vec) gc_bwd_kernel<true><<<grid_rows(B, CS / 4, 256), 256, 0, st>>>(p);
+  else gc_bwd_kernel<false><<<grid_rows(B, CS, 256), 256, 0, st>>>(p);
   CLC_CHECK_LAUNCH("clc_gc_bwd");
   return CLC_OK;
 }
@@ -777,9 +824,9 @@ extern "C" int clc_lrp_add_fwd(float* y_hat, int64_t y_hat_bs, const float* lrp,
   if (B == 0 || CS == 0) return CLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (vec_ok(CS, {y_hat, lrp}, {y_hat_bs, lrp_bs}))
-    lrp_kernel<true, false><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(y_hat, y_hat_bs, lrp, lrp_bs, nullptr, 0, B, CS);
+    lrp_kernel<true, false><<<grid_rows(B, CS / 4, 256), 256, 0, st>>>(y_hat, y_hat_bs, lrp, lrp_bs, nullptr, 0, B, CS);
   else
-    lrp_kernel<false, false><<<grid_for(B * CS, 256), 256, 0, st>>>(y_hat, y_hat_bs, lrp, lrp_bs, nullptr, 0, B, CS);
+    lrp_kernel<false, false><<<grid_rows(B, CS, 256), 256, 0, st>>>(y_hat, y_hat_bs, lrp, lrp_bs, nullptr, 0, B, CS);
   CLC_CHECK_LAUNCH("clc_lrp_add_fwd");
   return CLC_OK;
 }
@@ -790,9 +837,9 @@ extern "C" int clc_lrp_add_bwd(const float* g, int64_t g_bs, const float* lrp, i
   if (B == 0 || CS == 0) return CLC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (vec_ok(CS, {g, lrp, g_lrp}, {g_bs, lrp_bs, g_lrp_bs}))
-    lrp_kernel<true, true><<<grid_for(B * CS / 4, 256), 256, 0, st>>>(g_lrp, g_lrp_bs, lrp, lrp_bs, g, g_bs, B, CS);
+    lrp_kernel<true, true><<<grid_rows(B, CS / 4, 256), 256, 0, st>>>(g_lrp, g_lrp_bs, lrp, lrp_bs, g, g_bs, B, CS);
   else
-    lrp_kernel<false, true><<<grid_for(B * CS, 256), 256, 0, st>>>(g_lrp, g_lrp_bs, lrp, lrp_bs, g, g_bs, B, CS);
+    lrp_kernel<false, true><<<grid_rows(B, CS, 256), 256, 0, st>>>(g_lrp, g_lrp_bs, lrp, lrp_bs, g, g_bs, B, CS);
   CLC_CHECK_LAUNCH("clc_lrp_add_bwd");
   return CLC_OK;
 }
