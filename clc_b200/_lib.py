@@ -96,6 +96,11 @@ PROTOTYPES = {
     "clc_peer_allreduce": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _f, _p, _p]),
     "clc_clm_fuse_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i32, _i64, _i32, _i64, _p]),
     "clc_clm_fuse_bwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
+    "clc_clm_sim_colsum_workspace_bytes": (C.c_size_t, [_i64, _i64]),
+    "clc_clm_sim_colsum": (C.c_int, [_p, _p, _i64, _i64, _i32, _i64, C.c_float, _p, _p, C.c_size_t, _p]),
+    "clc_clm_weighted_concat": (C.c_int, [_p, _p, _p, _i64, _i32, _i64, _p]),
+    "clc_clm_deform_fwd": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p]),
+    "clc_clm_attention_sum_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
 }
 
 # Bring-up entry points: only in libclc_b200_dbg.so (the -DCLC_DEBUG_ABI build), see debug_lib().

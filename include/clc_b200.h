@@ -372,6 +372,34 @@ CLC_API int clc_clm_fuse_bwd(const float* ref_t, int64_t ref_sr, int64_t ref_sb,
                              int64_t att_sr, int64_t att_sb, const float* g_out, float* g_ref_t,
                              float* g_att, int32_t R, int64_t B, int32_t C, int64_t S, void* stream);
 
+/* ---- CLM variant (a): similarity-softmax alignment (models/CLM.py:5-128), forward ----
+ * Batch index nb = r*B + b over the R references of B images ([R, B, ...] stacking); NB = R*B. */
+
+/* Replaces: the HW x HW `torch.bmm(y_t^T, y_ref_t) / T` + softmax (CLM.py:104-107) as consumed by
+ * DeformableAlignment.forward's accumulation loop (:16-20), which only ever uses the COLUMN SUMS of the map:
+ *   colsum[nb, p] = sum_q softmax_p(y_t[nb % B_y][:, q] . ref_t[nb][:, :] / T)[p]
+ *   y_t [B_y, C, HW], ref_t [NB, C, HW] -> colsum [NB, HW].  Two passes over register tiles; the map is never
+ *   written.  workspace: clc_clm_sim_colsum_workspace_bytes(NB, HW) (row max / row sum). */
+CLC_API size_t clc_clm_sim_colsum_workspace_bytes(int64_t NB, int64_t HW);
+CLC_API int clc_clm_sim_colsum(const float* y_t, const float* ref_t, int64_t NB, int64_t B_y, int32_t C, int64_t HW,
+                               float temperature, float* colsum, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* Replaces: weighted_x (CLM.py:16-20) + torch.cat([x, weighted_x], 1) (:22):
+ *   out[nb, 0:C] = x[nb],  out[nb, C:2C] = x[nb] * colsum[nb]      x [NB, C, HW] -> out [NB, 2C, HW] */
+CLC_API int clc_clm_weighted_concat(const float* x, const float* colsum, float* out, int64_t NB, int32_t C,
+                                    int64_t HW, void* stream);
+/* Replaces: DeformableAlignment.deform_conv (CLM.py:35-60), the Python loops over B*H*W*9 taps.
+ *   x [NB, C, H, W]; offset [NB, 18, H, W] (channel 2k = dh, 2k+1 = dw of tap k, the view of :29);
+ *   modulation [NB, 9, H, W] -- the convolution output when modulation_is_logit (sigmoid fused, :25), else
+ *   already sigmoided;  out [NB, C, H, W]. */
+CLC_API int clc_clm_deform_fwd(const float* x, const float* offset, const float* modulation,
+                               int32_t modulation_is_logit, float* out, int64_t NB, int32_t C, int32_t H, int32_t W,
+                               void* stream);
+/* Replaces: CLM.py:117-126  out = sum_r softmax_r(att)[r] * aligned[r] + y.
+ *   aligned [R, B, C, S], att [R, B, S], y [B, C, S] -> out [B, C, S].  R <= 8. */
+CLC_API int clc_clm_attention_sum_fwd(const float* aligned, const float* att, const float* y, float* out, int32_t R,
+                                      int64_t B, int32_t C, int64_t S, void* stream);
+
 /* ---- range coder: compress() / decompress() (CLC_run.py:629-716, :738-814) ----
  * HOST functions (no stream argument, plain host pointers): one rANS stream is a sequential
  * recurrence, so the state machine runs on the host; its inputs (symbols, scale-table indexes) come

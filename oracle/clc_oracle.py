@@ -264,3 +264,101 @@ class SimpleCLM(torch.nn.Module):
         ref_t = torch.stack([self.feature_transform(r) for r in y_refs], 0)
         att = torch.stack([self.attention_conv(t) for t in ref_t], 0)
         return self.fusion_conv(clm_fuse(ref_t, att, y))
+
+
+# ----------------------------------------------------------------------------------------------
+# CLM variant (a): similarity-softmax alignment (models/CLM.py:5-128)
+# ----------------------------------------------------------------------------------------------
+def clm_sim_colsum(y_t, ref_t, temperature):
+    """Column sums of the row-softmax of the HW x HW similarity (CLM.py:104-107 feeding :16-20).
+
+    DeformableAlignment.forward accumulates `weighted_x += sim[:, i, j, :, :] * x` over every query position
+    (i, j) (:17-20), i.e. weighted_x[b, c, p] = x[b, c, p] * sum_q softmax_p(sim[b, q, :])[p]: only the column
+    sums of the similarity map are ever used.  y_t, ref_t [B, C, H, W] -> [B, H*W]."""
+    B, C = y_t.shape[:2]
+    sim = torch.bmm(y_t.reshape(B, C, -1).transpose(1, 2), ref_t.reshape(B, C, -1)) / temperature
+    return F.softmax(sim, dim=-1).sum(dim=1)
+
+
+def clm_deform_sample(x, offset, modulation):
+    """DeformableAlignment.deform_conv (CLM.py:35-60), vectorised; same arithmetic order per element.
+    x [B, C, H, W]; offset [B, 9, 2, H, W]; modulation [B, 9, 1, H, W] (already sigmoided) -> [B, C, H, W].
+    Quirks kept: no kernel-tap base offsets (every tap samples around (h, w) itself), taps outside
+    [0, H-1] x [0, W-1] contribute nothing, int() truncation == floor on the valid range, (h1, w1) clamped."""
+    B, C, H, W = x.shape
+    hh = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    ww = torch.arange(W, dtype=torch.float32).view(1, 1, W)
+    xf = x.reshape(B, C, H * W)
+    result = torch.zeros_like(x)
+    for k in range(9):
+        off_h = hh + offset[:, k, 0]
+        off_w = ww + offset[:, k, 1]
+        valid = (off_h >= 0) & (off_h <= H - 1) & (off_w >= 0) & (off_w <= W - 1)
+        h0 = off_h.nan_to_num(0.0).clamp(0, H - 1).long()       # (invalid / NaN taps are masked out below)
+        w0 = off_w.nan_to_num(0.0).clamp(0, W - 1).long()
+        h1 = (h0 + 1).clamp_max(H - 1)
+        w1 = (w0 + 1).clamp_max(W - 1)
+        lh = (off_h - h0).unsqueeze(1)
+        lw = (off_w - w0).unsqueeze(1)
+
+        def at(hi, wi):
+            return torch.gather(xf, 2, (hi * W + wi).view(B, 1, H * W).expand(B, C, H * W)).view(B, C, H, W)
+
+        val = (1 - lh) * (1 - lw) * at(h0, w0) + lh * (1 - lw) * at(h1, w0) + (1 - lh) * lw * at(h0, w1) \
+            + lh * lw * at(h1, w1)
+        result = result + torch.where(valid.unsqueeze(1), val * modulation[:, k], torch.zeros_like(val))
+    return result
+
+
+def clm_attention_sum(aligned, att, y):
+    """CLM.py:117-126: softmax over the references of the 1-channel attention, weighted sum, + y.
+    aligned [R, B, C, H, W], att [R, B, 1, H, W]."""
+    w = F.softmax(att.permute(1, 0, 2, 3, 4), dim=1)
+    return (aligned.permute(1, 0, 2, 3, 4) * w).sum(dim=1) + y
+
+
+class DeformableAlignment(torch.nn.Module):
+    """CLM.py:5-33 (same parameter names)."""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        self.offset_conv = torch.nn.Conv2d(input_dim * 2, 2 * 3 * 3, kernel_size=3, padding=1)
+        self.modulation_conv = torch.nn.Conv2d(input_dim * 2, 3 * 3, kernel_size=3, padding=1)
+
+    def forward(self, x, colsum):
+        B, C, H, W = x.shape
+        weighted_x = x * colsum.view(B, 1, H, W)
+        cat = torch.cat([x, weighted_x], dim=1)
+        offset = self.offset_conv(cat).view(B, 9, 2, H, W)
+        modulation = torch.sigmoid(self.modulation_conv(cat)).view(B, 9, 1, H, W)
+        return clm_deform_sample(x, offset, modulation)
+
+
+class CLM(torch.nn.Module):
+    """CLM, CLM.py:62-128 (same parameter names)."""
+
+    def __init__(self, input_dim, temperature=0.5):
+        super().__init__()
+        self.temperature = temperature
+        self.feature_transform = torch.nn.Sequential(torch.nn.Conv2d(input_dim, input_dim, 1),
+                                                     torch.nn.ReLU(inplace=True),
+                                                     torch.nn.Conv2d(input_dim, input_dim, 1))
+        self.alignment = DeformableAlignment(input_dim)
+        self.attention_conv = torch.nn.Conv2d(input_dim, 1, 1)
+        self.fusion_conv = torch.nn.Sequential(torch.nn.Conv2d(input_dim, input_dim, 3, padding=1),
+                                               torch.nn.ReLU(inplace=True),
+                                               torch.nn.Conv2d(input_dim, input_dim, 3, padding=1))
+
+    def forward(self, y, y_refs, return_parts=False):
+        y_t = self.feature_transform(y)
+        colsums, aligned, att = [], [], []
+        for y_ref in y_refs:
+            cs = clm_sim_colsum(y_t, self.feature_transform(y_ref), self.temperature)
+            al = self.alignment(y_ref, cs)
+            colsums.append(cs)
+            aligned.append(al)
+            att.append(self.attention_conv(al))
+        fused = self.fusion_conv(clm_attention_sum(torch.stack(aligned), torch.stack(att), y))
+        if return_parts:
+            return fused, torch.stack(colsums), torch.stack(aligned)
+        return fused

@@ -97,6 +97,34 @@ def golden_clm():
     _save("clm.npz", y=y, refs=torch.stack(refs), out=out, **sd)
 
 
+def golden_clm_full():
+    """CLM variant (a) forward (models/CLM.py:62-128, DeformableAlignment :5-60), seed 42 as in its __main__.
+    The offset convolution is scaled up (weights are data) so that the sampled taps leave their cell, cross
+    integer boundaries and fall outside the image; intermediates are taken with forward hooks."""
+    clm = ref_loader.load_clm()
+    torch.manual_seed(42)
+    B, C, H, W, M = 2, 16, 8, 12, 3
+    m = clm.CLM(C, temperature=0.5)
+    with torch.no_grad():
+        m.alignment.offset_conv.weight.mul_(8.0)
+        m.alignment.offset_conv.bias.add_(0.7)
+    y = torch.randn(B, C, H, W)
+    refs = [torch.randn(B, C, H, W) for _ in range(M)]
+    colsums, aligned = [], []
+
+    def tap(mod, inp, out):
+        colsums.append(inp[1].sum(dim=1))
+        aligned.append(out)
+
+    hook = m.alignment.register_forward_hook(tap)
+    with torch.no_grad():
+        out = m(y, refs)
+    hook.remove()
+    sd = {"sd_" + k.replace(".", "__"): v for k, v in m.state_dict().items()}
+    _save("clm_full.npz", y=y, refs=torch.stack(refs), out=out, colsum=torch.stack(colsums),
+          aligned=torch.stack(aligned), **sd)
+
+
 def golden_rd_loss():
     RD = ref_loader.load_rd_loss()
     g = torch.Generator().manual_seed(3)
@@ -199,6 +227,7 @@ def main():
     golden_gaussian(CLC)
     golden_match()
     golden_clm()
+    golden_clm_full()
     golden_rd_loss()
     golden_model(CLC, TCM)
     golden_coder(CLC, TCM)

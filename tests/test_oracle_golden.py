@@ -104,6 +104,26 @@ def test_clm_oracle_vs_reference_golden():
     assert torch.allclose(out, g["out"], atol=1e-6)
 
 
+def test_clm_variant_a_oracle_vs_reference_golden():
+    """CLM.forward (models/CLM.py:84-128) incl. the Python-loop DeformableAlignment (:5-60): vectorised
+    restatement vs the reference's own output and hooked intermediates."""
+    g = load_golden("clm_full.npz")
+    m = O.CLM(16, temperature=0.5)
+    m.load_state_dict({k[3:].replace("__", "."): v for k, v in g.items() if k.startswith("sd_")})
+    with torch.no_grad():
+        out, colsum, aligned = m(g["y"], list(g["refs"]), return_parts=True)
+    assert torch.allclose(colsum, g["colsum"], rtol=1e-5, atol=1e-6)
+    # (the x8 offsets amplify the 1e-7 summation-order difference of weighted_x into ~1e-5 in the samples)
+    assert torch.allclose(aligned, g["aligned"], atol=2e-5)
+    assert torch.allclose(out, g["out"], atol=5e-6)
+    # the taps really exercise the quirks: some fall outside the image, some leave their own cell
+    B, C, H, W = g["y"].shape
+    ws = g["refs"][0] * g["colsum"][0].view(B, 1, H, W)
+    off = m.alignment.offset_conv(torch.cat([g["refs"][0], ws], 1)).view(B, 9, 2, H, W)
+    oh = off[:, :, 0] + torch.arange(H).view(1, 1, H, 1)
+    assert (oh < 0).any() and (oh > H - 1).any() and (off.abs() > 1).any()
+
+
 def test_rd_loss_oracle_vs_reference_golden():
     g = load_golden("rd_loss.npz")
     out = O.rate_distortion_loss({"likelihoods": {"y": g["lik_y"], "z": g["lik_z"]}, "x_hat": g["x_hat"]},
