@@ -1041,8 +1041,12 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
 // then reads g_fused (the gradient of the FUSED feature) instead of g_aligned, forms
 //   g_aligned_r = g_fused * coef_r,  coef_r = softmax_r(att) * sigmoid(att_r)        (never written to HBM)
 // on the fly, and also produces g_att.  g_att_m = coef_m G_m - w_m sum_r G_r coef_r + G_m coef_m (1 - s_m) needs
-// G_r = sum_c g_fused_c * aligned_r,c of ALL references at a pixel: the R CTAs of one (image, patch) form a
-// thread-block cluster, each reduces its own G_r over the channels, rank 0 combines them through DSMEM.
+// G_r = sum_c g_fused_c * aligned_r,c of ALL references at a pixel.  Each of the R CTAs of one (image, patch) reduces
+// its own G_r over the channels at the START of the kernel, publishes the 16 values to a global scratch and bumps
+// the group's arrival counter; whichever CTA arrives last combines the R contributions (fixed order r = 0..R-1,
+// so the result does not depend on who that is) and writes g_att, then carries on with its own match backward.
+// Nobody waits: the first version ran the R CTAs as a thread-block cluster and exchanged G_r through DSMEM, and
+// its two cluster barriers were 36 % of the kernel's stall samples at cfg2 (profiles/r2_full_cfg2).
 constexpr int kClmMaxRefs = 8;
 struct ClmBwdArgs {
   const float* g_fused;     // [NQ, C, fh*fw]
@@ -1051,6 +1055,8 @@ struct ClmBwdArgs {
   const float* aligned;     // [NP, C, fh*fw] blended references of the forward pass
   float* g_att;             // same addressing as att
   int R;
+  float* g_scratch;         // [NQ*P][R][16] published G_r
+  int* arrivals;            // [NQ*P] arrival counters, zero on entry (the last CTA re-zeroes its own)
 };
 
 template <int NT, bool CLM>
@@ -1063,7 +1069,6 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
   constexpr int KK = 4, NV = 2 + 4 * KK, NW = NT / 32, pw = 4;
   __shared__ float red[NW][NV];
   __shared__ float gpart[CLM ? NT : 1][4];     // per-thread partial G (its 4 channels) for the 4 pixels of its row
-  __shared__ float G_s[16];                    // this CTA's G_r at the 16 pixels of the patch (read through DSMEM)
   __shared__ float tot[NV];                 // xs, sxx, then per window: g_w, s1, s2, xy
   __shared__ float coef[KK][4];             // per window: w_j, g_xy, 2*g_dY, c_mean
   __shared__ float part[KK][3];             // per window: its terms of t_gxs, t_gsxx, t_gxm
@@ -1166,7 +1171,39 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       for (int t = qq * per; t < (qq + 1) * per && t < c4n; ++t) a += gpart[ody * c4n + t][odx];
       a += __shfl_xor_sync(0xffffffffu, a, 1);
       a += __shfl_xor_sync(0xffffffffu, a, 2);
-      if (qq == 0) G_s[o] = a;
+      const int r_own = n - nq * ca.R;
+      const int64_t grp = (int64_t)nq * P + patch;
+      float* gs = ca.g_scratch + grp * ca.R * 16;
+      if (qq == 0) gs[r_own * 16 + o] = a;
+      __threadfence();                                     // the 16 values are visible device-wide ...
+      asm volatile("bar.sync 1, 64;" ::: "memory");        // ... for both warps, before warp 0 announces them
+      if (tid < 32) {
+        int last = 0;
+        if (tid == 0) {
+          last = atomicAdd(ca.arrivals + grp, 1) == ca.R - 1;
+          if (last) ca.arrivals[grp] = 0;                  // ready for the next launch on this workspace
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && tid < 16) {
+          __threadfence();
+          const int tdy = tid >> 2, tdx = tid & 3;
+          const int64_t sp = (int64_t)(py * ph + tdy) * fw + px * pw + tdx;
+          float av[kClmMaxRefs], w[kClmMaxRefs], sg[kClmMaxRefs], Gt[kClmMaxRefs];
+          float mx = -INFINITY, den = 0.f, mix = 0.f;
+          for (int r = 0; r < ca.R; ++r) { av[r] = ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + sp]; mx = fmaxf(mx, av[r]); }
+          for (int r = 0; r < ca.R; ++r) { w[r] = expf(av[r] - mx); den += w[r]; }
+          for (int r = 0; r < ca.R; ++r) {
+            w[r] = w[r] / den;
+            sg[r] = 1.0f / (1.0f + expf(-av[r]));
+            Gt[r] = __ldcg(gs + r * 16 + tid);
+            mix = fmaf(Gt[r], w[r] * sg[r], mix);          // sum_r G_r s_r w_r
+          }
+          for (int m = 0; m < ca.R; ++m) {
+            const float cm = w[m] * sg[m];
+            ca.g_att[(int64_t)m * ca.att_sr + (int64_t)nq * ca.att_sb + sp] = cm * Gt[m] - w[m] * mix + Gt[m] * cm * (1.f - sg[m]);
+          }
+        }
+      }
     }
   }
   const float* rbase = rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;    // + (src + dx) * C
@@ -1284,30 +1321,6 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       red_add4(gqp + (int64_t)i * qa.sc, o);
     }
   }
-  if constexpr (CLM) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();                                  // every reference's G_r is in its CTA's shared memory
-    if (cluster.block_rank() == 0 && tid < 16) {
-      const int ody = tid >> 2, odx = tid & 3;
-      const int64_t s = (int64_t)(py * ph + ody) * fw + px * pw + odx;
-      float a[kClmMaxRefs], w[kClmMaxRefs], sg[kClmMaxRefs], Gt[kClmMaxRefs];
-      float mx = -INFINITY, den = 0.f, mix = 0.f;
-      for (int r = 0; r < ca.R; ++r) { a[r] = ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + s]; mx = fmaxf(mx, a[r]); }
-      for (int r = 0; r < ca.R; ++r) { w[r] = expf(a[r] - mx); den += w[r]; }
-      for (int r = 0; r < ca.R; ++r) {
-        w[r] = w[r] / den;
-        sg[r] = 1.0f / (1.0f + expf(-a[r]));
-        Gt[r] = cluster.map_shared_rank(&G_s[0], r)[tid];
-        mix = fmaf(Gt[r], w[r] * sg[r], mix);        // sum_r G_r s_r w_r
-      }
-      for (int m = 0; m < ca.R; ++m) {
-        const float cm = w[m] * sg[m];
-        ca.g_att[(int64_t)m * ca.att_sr + (int64_t)nq * ca.att_sb + s] = cm * Gt[m] - w[m] * mix + Gt[m] * cm * (1.f - sg[m]);
-      }
-    }
-    cluster.sync();                                  // keep every CTA's shared memory alive until rank 0 has read it
-  }
 }
 
 template <int NT>
@@ -1319,28 +1332,14 @@ static int launch_bwd_own(unsigned blocks, cudaStream_t st, PatchAddr qa, const 
   CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   return CLC_OK;
 }
-// CLM-fused variant: clusters of R CTAs (the references of one (image, patch)), PDL.
+// CLM-fused variant: the R CTAs of one (image, patch) are consecutive blocks; PDL.
 template <int NT>
 static int launch_bwd_own_clm(unsigned blocks, cudaStream_t st, PatchAddr qa, const float* rT, const float* mask,
                               const int32_t* idx, const float* weights, float temperature, float* g_rT, float* g_q,
                               float* g_val, int P, int C, int ph, int fh, int fw, int k, const ClmBwdArgs& ca) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks);
-  cfg.blockDim = dim3(NT);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)ca.R;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_on() ? 2 : 1;
   const float* no_g_out = nullptr;
-  CLC_CUDA(cudaLaunchKernelEx(&cfg, match_bwd_own_kernel<NT, true>, qa, rT, mask, idx, weights, temperature, no_g_out,
-                              g_rT, g_q, g_val, P, C, ph, fh, fw, k, 0, ca));
+  CLC_CUDA(launch_pdl(match_bwd_own_kernel<NT, true>, dim3(blocks), dim3(NT), 0, st, qa, rT, mask, idx, weights, temperature,
+                      no_g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, 0, ca));
   CLC_CHECK_LAUNCH("clc_match_clm_bwd(main)");
   return CLC_OK;
 }
@@ -1522,9 +1521,19 @@ extern "C" int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, co
   return CLC_OK;
 }
 
+// One memset clears the gradient scratch AND the counters behind it.
+static inline size_t bwd_ws_counter_bytes(int64_t NP, int fh, int fw) {
+  return ((size_t)NP * fh * fw * sizeof(int) + 255) / 256 * 256;      // >= NQ * P counters for any patch size
+}
+static inline size_t bwd_ws_zero_bytes(int64_t NP, int C, int fh, int fw) {
+  return sizeof(float) * (size_t)NP * C * fh * fw + bwd_ws_counter_bytes(NP, fh, fw);
+}
+
 extern "C" size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw) {
   if (NP < 0 || C < 1 || fh < 1 || fw < 1) return 0;
-  return 2 * sizeof(float) * (size_t)NP * C * fh * fw + 512;  // channels-last copy of r + gradient scratch
+  // gradient scratch (channels-last g_r) | arrival counters of the CLM-fused kernel | channels-last copy of r
+  // (or, when the caller supplies that copy, the fused kernel's published G_r)
+  return bwd_ws_counter_bytes(NP, fh, fw) + 2 * sizeof(float) * (size_t)NP * C * fh * fw + 512;
 }
 
 extern "C" int clc_match_bwd_zero_workspace(void* workspace, size_t workspace_bytes, int64_t NP, int32_t C,
@@ -1532,7 +1541,7 @@ extern "C" int clc_match_bwd_zero_workspace(void* workspace, size_t workspace_by
   if (!workspace || NP < 0 || C < 1 || fh < 1 || fw < 1) return CLC_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < clc_match_bwd_workspace_bytes(NP, C, fh, fw)) return CLC_ERR_WORKSPACE;
   float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  CLC_CUDA(cudaMemsetAsync(g_rT, 0, sizeof(float) * (size_t)NP * C * fh * fw, (cudaStream_t)stream));
+  CLC_CUDA(cudaMemsetAsync(g_rT, 0, bwd_ws_zero_bytes(NP, C, fh, fw), (cudaStream_t)stream));
   return CLC_OK;
 }
 
@@ -1566,7 +1575,7 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
   }
   if (workspace_bytes < clc_match_bwd_workspace_bytes(NP, C, fh, fw)) return CLC_ERR_WORKSPACE;
   float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  float* rT_own = g_rT + (size_t)NP * C * HW;
+  float* rT_own = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_rT) + bwd_ws_zero_bytes(NP, C, fh, fw));
   dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
   if (!(flags & CLC_MATCH_BWD_WS_ZEROED)) CLC_CUDA(cudaMemsetAsync(g_rT, 0, plane, st));
   const float* rT = r_cl;
@@ -1636,11 +1645,12 @@ extern "C" int clc_match_clm_bwd(const clc_patch_view* qv, const float* r_cl, co
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = fh * fw;
   float* g_rT = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  if (!(flags & CLC_MATCH_BWD_WS_ZEROED))
-    CLC_CUDA(cudaMemsetAsync(g_rT, 0, sizeof(float) * (size_t)NP * C * HW, st));
+  if (!(flags & CLC_MATCH_BWD_WS_ZEROED)) CLC_CUDA(cudaMemsetAsync(g_rT, 0, bwd_ws_zero_bytes(NP, C, fh, fw), st));
   ClmBwdArgs ca;
   ca.g_fused = g_fused; ca.att = att; ca.att_sr = att_sr; ca.att_sb = att_sb; ca.aligned = aligned; ca.g_att = g_att;
   ca.R = R;
+  ca.arrivals = reinterpret_cast<int*>(g_rT + (size_t)NP * C * HW);
+  ca.g_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_rT) + bwd_ws_zero_bytes(NP, C, fh, fw));
   const unsigned blocks = (unsigned)(NP * P);
   int rc = CLC_OK;
 #define CLC_OWN_CASE(N) case N: rc = launch_bwd_own_clm<N>(blocks, st, qa, r_cl, mask, idx, weights, temperature, g_rT, \

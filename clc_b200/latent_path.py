@@ -139,14 +139,15 @@ class LatentPath:
         self._r_cl = (lib().clc_match_topk_tc_ref_cl(ptr(self.ws), B * R, R, M, h, w, patch, patch, k)
                       if match_mode == "tc" else None)
         # shapes the CLM-fused match backward kernel covers (clc_match_clm_bwd); others use the two-call sequence
-        self._fused_bwd = (fuse_chain and match_mode == "tc" and patch == 4 and k <= 4 and n_refs <= 8 and
+        self._fused_bwd = (bool(fuse_chain) and match_mode == "tc" and patch == 4 and k <= 4 and n_refs <= 8 and
                            M % 4 == 0 and patch * (M // 4) in (128, 192, 256, 320, 384) and w % 4 == 0)
         # forward CLM fusion (clusters of R CTAs per (image, patch)) pays only for small latents: measured on B200
         # (scripts/chain_timing.py [--no-fuse]) the match chain is 96 vs 98 us at 16 x 16 latents (cfg2) but
         # 133 vs 107 us at 32 x 48 (cfg3) and 336 vs 299 us at 80 x 128 (cfg4) -- with thousands of clusters the
         # two cluster barriers cost more than the 5 x C x H x W floats of HBM traffic the fusion saves
-        self._fused_fwd = (fuse_chain and match_mode == "tc" and n_refs <= 8 and patch * patch <= 64 and
-                           h * w <= 512)
+        # (fuse_chain="all" forces it at any size: tests, measurements)
+        self._fused_fwd = (bool(fuse_chain) and match_mode == "tc" and n_refs <= 8 and patch * patch <= 64 and
+                           (h * w <= 512 or fuse_chain == "all"))
         self._qview = matching._patch_view_from_image(self.y, patch, patch, R)
         self._gqview = self._qview
         self._graph = self._g_match = self._g_entropy = None

@@ -146,14 +146,14 @@ def test_host_pipeline_matches_step_host():
 @pytest.mark.parametrize("geom", [(2, 256, 256, 3, 4), (1, 256, 320, 5, 2), (2, 256, 256, 1, 4), (1, 512, 768, 2, 4)])
 def test_fused_chain_equals_separate_kernels(geom):
     """clc_match_clm_fwd / clc_match_clm_bwd (CLM elementwise fusion folded into the re-scoring kernel and into
-    the match backward, cluster of R CTAs per (image, patch)) == the separate clc_match_topk_tc -> clc_clm_fuse_fwd
+    the match backward; the R CTAs of an (image, patch) exchange through a cluster / a last-arrival scratch) == the separate clc_match_topk_tc -> clc_clm_fuse_fwd
     and clc_clm_fuse_bwd -> clc_match_bwd call sequences."""
     from clc_b200.latent_path import LatentPath
     B, H, W, R, k = geom
     outs = []
-    for fuse in (True, False):
+    for fuse in ("all", False):       # "all": forward fusion also at latent sizes where it is off by default
         lp = LatentPath(B, H, W, n_refs=R, train=True, match_mode="tc", k=k, device="cuda:0", fuse_chain=fuse)
-        assert lp._fused_fwd == fuse and lp._fused_bwd == fuse
+        assert lp._fused_fwd == bool(fuse) and lp._fused_bwd == bool(fuse)
         lp.randomize(seed=17)
         lp.step()
         torch.cuda.synchronize()
