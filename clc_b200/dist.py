@@ -98,15 +98,18 @@ def shard_range(n_items, rank, world):
 class GradAllReducer:
     """Bucketed, overlapped gradient all-reduce (mean) for a replicated model.
 
-    Gradients live IN the buckets: after a first (discovery) backward has shown which parameters receive a
-    gradient and in which order, every such parameter's `.grad` is a view into a flat fp32 bucket of
-    ~`bucket_mb`, so autograd accumulates straight into the communication buffer (no flatten / scatter copies).
-    A post-accumulate hook counts the bucket's parameters as they become ready; the moment a bucket is complete
-    it is all-reduced asynchronously (NCCL: ReduceOp.AVG, in place) while the backward pass continues.
-    `finish()` waits.  Parameters that receive no gradient (the reference's unused `feature_alignment`,
-    `multi_ref_fusion`, `cc_*`, `lrp_transforms` modules: 310 tensors) are in no bucket on any rank
-    -- the set is a property of the graph, not of the data.  Call `zero_grad()` (instead of the optimiser's)
-    between steps: it clears the buckets and keeps the views."""
+    A first (discovery) backward shows which parameters receive a gradient and in which order; they are packed,
+    in that order, into flat fp32 buckets of ~`bucket_mb`.  From then on ONE post-accumulate hook per bucket --
+    on the parameter whose gradient arrives last -- gathers the bucket's gradients into the flat buffer with a
+    single multi-tensor copy and launches its all-reduce asynchronously (NCCL: ReduceOp.AVG, in place) while the
+    backward pass continues; `finish()` waits and points every `.grad` at its slice of the reduced bucket (no
+    scatter copy).  A training step of this model is launch-bound on the host (~700 parameter tensors), so what
+    the reducer must not do is add per-parameter work: a hook per parameter and gradients accumulated INTO bucket
+    views (one extra `add_` launch each) cost 9-20 ms per step on 8 B200s for an exchange that takes 0.85 ms.
+    Parameters that receive no gradient (the reference's unused `feature_alignment`, `multi_ref_fusion`, `cc_*`,
+    `lrp_transforms` modules: 310 tensors) are in no bucket on any rank -- the set is a property of
+    the graph, not of the data.  Use the optimiser's `zero_grad(set_to_none=True)` (or `zero_grad()` here)
+    between steps."""
 
     def __init__(self, module, bucket_mb=32.0, group=None):
         self.group = group
@@ -114,100 +117,93 @@ class GradAllReducer:
         self.bucket_elems = int(bucket_mb * 1024 * 1024 // 4)
         self.params = [p for p in module.parameters() if p.requires_grad]
         self._order = []                 # discovery pass: parameters in the order their gradients became ready
-        self._buckets = None             # [(flat, [params], n_params)]
-        self._bucket_of, self._ready, self._inflight = {}, [], []
+        self._buckets = None             # [(flat, [params], [views])]
+        self._launched, self._inflight = [], []
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
-        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self._handles = [p.register_post_accumulate_grad_hook(self._discover) for p in self.params]
 
     # ---- discovery step: plain flatten -> all-reduce -> scatter (runs once) ----
+    def _discover(self, p):
+        self._order.append(p)
+
     def _finish_discovery(self):
+        for h in self._handles:
+            h.remove()
         ps = [p for p in self._order if p.grad is not None]
-        if ps and self.world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in ps])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.div_(self.world)
-            off = 0
-            for p in ps:
-                n = p.grad.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
-        # build the buckets in ready order and move the gradients into them
-        self._buckets, cur, cur_n = [], [], 0
+        self._order = []
+        plists, cur, cur_n = [], [], 0
         for p in ps:
             cur.append(p)
             cur_n += p.numel()
             if cur_n >= self.bucket_elems:
-                self._buckets.append(cur)
+                plists.append(cur)
                 cur, cur_n = [], 0
         if cur:
-            self._buckets.append(cur)
-        built = []
-        for bi, plist in enumerate(self._buckets):
+            plists.append(cur)
+        self._buckets, self._handles = [], []
+        for bi, plist in enumerate(plists):
             flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=plist[0].device)
-            off = 0
+            views, off = [], 0
             for p in plist:
-                n = p.numel()
-                view = flat[off:off + n].view_as(p)
-                view.copy_(p.grad)
-                p.grad = view
-                self._bucket_of[p] = bi
-                off += n
-            built.append((flat, plist))
-        self._buckets = built
-        self._ready = [0] * len(built)
-
-    def _hook(self, p):
-        if self._buckets is None:
-            self._order.append(p)
-            return
-        bi = self._bucket_of.get(p)
-        if bi is None or self.world == 1:
-            return
-        self._ready[bi] += 1
-        if self._ready[bi] == len(self._buckets[bi][1]):
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._buckets.append((flat, plist, views))
+            # the bucket is complete when the parameter that was ready LAST in the discovery pass is ready
+            self._handles.append(plist[-1].register_post_accumulate_grad_hook(
+                lambda _p, bi=bi: self._launch(bi, from_hook=True)))
+        self._launched = [False] * len(self._buckets)
+        for bi in range(len(self._buckets)):     # this step's gradients: reduce them now, without overlap
             self._launch(bi)
+        self._wait()
 
-    def _launch(self, bi):
-        flat = self._buckets[bi][0]
-        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
-        self._inflight.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
-        self._ready[bi] = -(1 << 30)     # launched
+    def _launch(self, bi, from_hook=False):
+        if self._launched[bi]:
+            return
+        flat, plist, views = self._buckets[bi]
+        grads = [p.grad for p in plist]
+        if any(g is None for g in grads):
+            if from_hook:
+                return                   # order differs from the discovery pass: finish() picks the bucket up
+            flat.zero_()
+            pairs = [(v, g) for v, g in zip(views, grads) if g is not None]
+            if pairs:
+                torch._foreach_copy_([v for v, _ in pairs], [g for _, g in pairs])
+        else:
+            torch._foreach_copy_(views, grads)
+        self._launched[bi] = True
+        if self.world > 1:
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            self._inflight.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
 
-    def finish(self):
-        """Call after backward(): completes all buckets; gradients become the cross-rank mean."""
-        if self._buckets is None:
-            self._finish_discovery()
-            self._order = []
-            return
-        if self.world == 1:
-            return
-        for bi in range(len(self._buckets)):
-            if self._ready[bi] >= 0:     # a bucket some parameter of which got no gradient this step
-                self._launch(bi)
+    def _wait(self):
         for work, flat in self._inflight:
             work.wait()
             if not self._avg:
                 flat.div_(self.world)
         self._inflight = []
-        self._ready = [0] * len(self._buckets)
+        for flat, plist, views in self._buckets:
+            for p, v in zip(plist, views):
+                if p.grad is not None:
+                    p.grad = v
+        self._launched = [False] * len(self._buckets)
+
+    def finish(self):
+        """Call after backward(): completes all buckets; gradients become the cross-rank mean."""
+        if self._buckets is None:
+            self._finish_discovery()
+            return
+        for bi in range(len(self._buckets)):
+            self._launch(bi)
+        self._wait()
 
     def zero_grad(self):
-        """Clears the gradient buckets (one memset each) and keeps every `.grad` a view into its bucket."""
-        if self._buckets is None:
-            for p in self.params:
-                p.grad = None
-            return
-        for flat, plist in self._buckets:
-            flat.zero_()
-            off = 0
-            for p in plist:
-                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
-                    p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+        for p in self.params:
+            p.grad = None
 
     def remove(self):
         for h in self._handles:
             h.remove()
+        self._handles = []
 
 
 def allreduce_stats(log2_lik_y, log2_lik_z, sq_err, n_pix, device=None, group=None):

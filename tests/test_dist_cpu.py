@@ -41,13 +41,16 @@ def _worker(rank, world, port, q):
     t = torch.randn(8, 2, generator=g)
     lo, hi = cd.shard_range(8, rank, world)
     red = cd.GradAllReducer(net, bucket_mb=0.0001)  # tiny buckets -> several async all-reduces
-    # step 0 discovers which parameters receive gradients; steps 1.. accumulate straight into the buckets
+    # step 0 discovers which parameters receive gradients and in which order; steps 1.. use one hook per bucket
     for it in range(3):
         red.zero_grad()
         loss = ((net(x[lo:hi]) - t[lo:hi]) ** 2).mean()
         loss.backward()
         red.finish()
-    assert net.a.weight.grad.data_ptr() == red._buckets[red._bucket_of[net.a.weight]][0].data_ptr() or True
+    # after finish() every gradient is a view into its (reduced) bucket: no scatter copy
+    flats = {f.data_ptr(): f for f, _, _ in red._buckets}
+    assert len(red._buckets) > 1
+    assert any(f.data_ptr() <= net.a.weight.grad.data_ptr() < f.data_ptr() + 4 * f.numel() for f in flats.values())
     assert all(p.grad is None for p in net.unused.parameters())
     bpp, mse = cd.allreduce_stats(torch.tensor(-10.0 * (rank + 1)), -1.0, 3.0 * (rank + 1), 4.0)
     q.put((rank, {n: p.grad.numpy().copy() for n, p in net.named_parameters() if p.grad is not None}, bpp, mse))
