@@ -135,16 +135,34 @@ class _ChARMBase(CompressionModel):
         inplace = getattr(self, "_inplace_slices", True)     # (the CPU oracle adapters of the tests turn it off)
         bufs = ops.SliceBuffers(y.shape[0], y.shape[1], y_shape[0], y_shape[1], y.device) if inplace else None
         c0 = 0
+        # the mean and the scale branch of a slice (SWAtten + 3 convolutions each, CLC_run.py:537-566) are
+        # independent: with `fork_branches` the scale branch runs on a side stream -- two parallel branches once
+        # the forward is captured into a CUDA graph (make_graphed_forward)
+        fork = getattr(self, "fork_branches", False) and y.is_cuda and not torch.is_grad_enabled()
         for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
             support = y_hat_slices if self.max_support_slices < 0 else y_hat_slices[:self.max_support_slices]
+
+            def scale_branch():
+                ss = self.atten_scale[i](torch.cat([latent_scales] + support, dim=1))
+                if use_ref:
+                    return self.ref_cc_scale_transforms[i](torch.cat([ss, ref_features], dim=1))
+                return self.cc_scale_transforms[i](ss)
+
+            if fork:
+                cur, side = torch.cuda.current_stream(y.device), self._side_stream(y.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    scale = scale_branch()
+                    scale.record_stream(cur)
             mean_support = self.atten_mean[i](torch.cat([latent_means] + support, dim=1))
-            scale_support = self.atten_scale[i](torch.cat([latent_scales] + support, dim=1))
             if use_ref:
                 mu = self.ref_cc_mean_transforms[i](torch.cat([mean_support, ref_features], dim=1))
-                scale = self.ref_cc_scale_transforms[i](torch.cat([scale_support, ref_features], dim=1))
             else:
                 mu = self.cc_mean_transforms[i](mean_support)
-                scale = self.cc_scale_transforms[i](scale_support)
+            if fork:
+                cur.wait_stream(side)
+            else:
+                scale = scale_branch()
             mu = mu[:, :, :y_shape[0], :y_shape[1]]
             scale = scale[:, :, :y_shape[0], :y_shape[1]]
             mus.append(mu)
@@ -175,6 +193,67 @@ class _ChARMBase(CompressionModel):
     @staticmethod
     def _lrp_add(y_hat, lrp):
         return ops.lrp_add_(y_hat, lrp)
+
+    def _side_stream(self, device):
+        st = getattr(self, "_side", None)
+        if st is None or st.device != device:
+            st = self._side = torch.cuda.Stream(device=device)
+        return st
+
+    def make_graphed_forward(self, *example_inputs, fork_branches=True, warmup=3):
+        """Inference: capture `forward` for these input shapes into ONE CUDA graph and return `run(*inputs) ->
+        the same output dict` (tensors are static buffers, overwritten by the next call).  The reference's
+        forward is ~1 500 eager launches (SWAtten blocks, the 5-slice ChARM loop with 10 parameter networks),
+        launch-bound at every image size it is evaluated on; the graph removes the host from the loop and, with
+        `fork_branches`, runs each slice's mean and scale branch in parallel."""
+        if self.training:
+            raise RuntimeError("make_graphed_forward is for eval mode (training draws fresh noise per step: use "
+                               "clc_b200.latent_path.LatentPath for a captured training step)")
+
+        def clone(a):
+            if isinstance(a, torch.Tensor):
+                return a.detach().clone()
+            if isinstance(a, (list, tuple)):
+                return [clone(t) for t in a]
+            return a
+
+        def copy_in(dst, src):
+            if isinstance(dst, torch.Tensor):
+                dst.copy_(src)
+            elif isinstance(dst, list):
+                if len(dst) != len(src):
+                    raise ValueError("graphed forward: number of reference frames differs from the captured call")
+                for d, t in zip(dst, src):
+                    copy_in(d, t)
+
+        static = [clone(a) for a in example_inputs]
+        dev = next(self.parameters()).device
+        prev, self.fork_branches = getattr(self, "fork_branches", False), bool(fork_branches)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(warmup):
+                    self(*static)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                out = self(*static)
+        finally:
+            self.fork_branches = prev
+
+        def run(*inputs):
+            if len(inputs) != len(static):
+                raise ValueError("graphed forward: call with the same arguments as the captured example")
+            with torch.no_grad():
+                for d, t in zip(static, inputs):
+                    copy_in(d, t)
+            graph.replay()
+            return out
+
+        run.graph = graph
+        return run
 
     # -- bitstreams (CLC_run.py:629-716, :738-814; tcm.py compress / decompress) ---------------------
     def _slice_params(self, i, latent_means, latent_scales, y_hat_slices, ref_features, y_shape):

@@ -176,3 +176,31 @@ def test_clc_match_refs_model_parity_vs_oracle_si_finder(mode):
     psnr_gap = abs(10 * math.log10(1.0 / max(torch.mean((out["x_hat"] - x) ** 2).item(), 1e-12)) -
                    10 * math.log10(1.0 / max(torch.mean((out_o["x_hat"] - x) ** 2).item(), 1e-12)))
     assert mse < 1e-6 and psnr_gap < 0.01
+
+
+def test_graphed_forward_equals_eager_forward():
+    """make_graphed_forward (whole CLC.forward in one CUDA graph, mean / scale branches forked) returns what the
+    eager forward returns, for new inputs too (static buffers are refilled), with and without references."""
+    from clc_b200.models import CLC
+    from oracle import detfill
+    d = torch.device("cuda:0")
+    m = detfill.fill_(CLC(N=64), seed=0).eval().to(d)
+    x = detfill.det_image((1, 3, 256, 256), 11).to(d)
+    refs = [detfill.det_image((1, 3, 256, 256), 12 + i).to(d) for i in range(3)]
+    run = m.make_graphed_forward(x, refs)
+    x2 = detfill.det_image((1, 3, 256, 256), 41).to(d)
+    refs2 = [detfill.det_image((1, 3, 256, 256), 42 + i).to(d) for i in range(3)]
+    for xi, ri in ((x, refs), (x2, refs2)):
+        with torch.no_grad():
+            want = m(xi, ri)
+        got = run(xi, ri)
+        torch.cuda.synchronize()
+        assert torch.equal(got["para"]["y"], want["para"]["y"])
+        assert torch.equal(got["x_hat"], want["x_hat"])
+        for key in ("y", "z"):
+            assert torch.equal(got["likelihoods"][key], want["likelihoods"][key])
+    with pytest.raises(ValueError):
+        run(x, refs[:2])
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.make_graphed_forward(x, refs)
