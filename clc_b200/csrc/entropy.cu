@@ -439,15 +439,17 @@ __device__ __forceinline__ float eb_load_pack(const EbPtrs& P, int c, float* pk)
 
 // logits = _logits_cumulative(x) for one scalar input.  Operation order follows upstream:
 // matmul(softplus(M), x) accumulated left to right, + bias, + tanh(factor) * tanh(logits).
-// When KEEP, the pre-gate activations a[l][j] (after bias) of layers 0..3 are kept for backward.
+// When KEEP, th[l][j] = tanh(pre-gate activation) of layers 0..3 and the layer inputs are kept for backward (the
+// backward needs the activation only through its tanh: keeping that saves 24 tanhf per element).
 template <bool KEEP>
 __device__ __forceinline__ float eb_logits(const float* pk, float x, float (*a)[3], float (*in)[3]) {
   float h[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     float t = pk[j] * x + pk[33 + j];
-    if (KEEP) a[0][j] = t;
-    h[j] = t + pk[46 + j] * tanhf(t);
+    const float th = tanhf(t);
+    if (KEEP) a[0][j] = th;
+    h[j] = t + pk[46 + j] * th;
   }
 #pragma unroll
   for (int l = 1; l < 4; ++l) {
@@ -460,8 +462,9 @@ __device__ __forceinline__ float eb_logits(const float* pk, float x, float (*a)[
       t = fmaf(mrow[1], h[1], t);
       t = fmaf(mrow[2], h[2], t);
       t += pk[33 + 3 * l + j];
-      if (KEEP) a[l][j] = t;
-      o[j] = t + pk[46 + 3 * l + j] * tanhf(t);
+      const float th = tanhf(t);
+      if (KEEP) a[l][j] = th;
+      o[j] = t + pk[46 + 3 * l + j] * th;
     }
     h[0] = o[0]; h[1] = o[1]; h[2] = o[2];
   }
@@ -555,7 +558,7 @@ __device__ __forceinline__ float eb_logits_bwd(const float* pk, float x, const f
     float gin[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float th = tanhf(a[l][j]);
+      const float th = a[l][j];                         // tanh of the activation, kept by eb_logits<true>
       const float tf = pk[46 + 3 * l + j];
       gp[46 + 3 * l + j] += gh[j] * th;                 // d/d tanh(f)
       const float ga = gh[j] * (1.f + tf * (1.f - th * th));  // through h = a + tf*tanh(a)
@@ -572,7 +575,7 @@ __device__ __forceinline__ float eb_logits_bwd(const float* pk, float x, const f
   float gx = 0.f;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const float th = tanhf(a[0][j]);
+    const float th = a[0][j];
     const float tf = pk[46 + j];
     gp[46 + j] += gh[j] * th;
     const float ga = gh[j] * (1.f + tf * (1.f - th * th));
@@ -585,7 +588,8 @@ __device__ __forceinline__ float eb_logits_bwd(const float* pk, float x, const f
 
 __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
   __shared__ float pk[64];
-  __shared__ float gsum[64];
+  __shared__ float gsum[2][64];
+  __shared__ float gred[kEbPack][129];         // [parameter][thread], odd pitch: conflict-free both ways
   const int c = blockIdx.x;
   const float med = __ldg(p.quantiles + c * 3 + 1);
   const bool use_rng = p.rng.state != nullptr;
@@ -603,7 +607,6 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
     if (p.g_z_hat) gzh_pre = p.g_z_hat[off0];
   }
   const float raw = eb_load_pack(p.P, c, pk);
-  if (threadIdx.x < 64) gsum[threadIdx.x] = 0.f;
   __syncthreads();
   float gp[kEbPack];
 #pragma unroll
@@ -633,17 +636,26 @@ __global__ void __launch_bounds__(128) eb_bwd_kernel(const EbBwdParams p) {
     p.g_z[off] = gzh + (train ? gx : 0.f);
   }
   if (!p.param_grads) return;
-  // CTA reduction of the 58 transformed-parameter gradients: warp shuffle, then shared atomics.
+  // CTA reduction of the 58 transformed-parameter gradients through shared memory: every thread parks its 58
+  // partials, then thread (half, parameter) adds 64 of the 128 columns in fixed order (58 STS + 64 LDS/FADD per
+  // thread instead of 58 five-step shuffle trees; deterministic within the CTA).
 #pragma unroll
-  for (int i = 0; i < kEbPack; ++i) {
-    const float v = warp_sum(gp[i]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&gsum[i], v);
+  for (int i = 0; i < kEbPack; ++i) gred[i][threadIdx.x] = gp[i];
+  __syncthreads();
+  {
+    const int prm = threadIdx.x & 63, half = threadIdx.x >> 6;
+    if (prm < kEbPack) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) a += gred[prm][half * 64 + i];
+      gsum[half][prm] = a;
+    }
   }
   __syncthreads();
   // Chain through softplus / tanh of the raw parameters and add to global (one atomic each).
   const int t = threadIdx.x;
   if (t < kEbPack) {
-    const float g = gsum[t];
+    const float g = gsum[0][t] + gsum[1][t];
     if (t < 33) {
       int l, k;
       if (t < 3) { l = 0; k = t; } else if (t < 12) { l = 1; k = t - 3; } else if (t < 21) { l = 2; k = t - 12; }

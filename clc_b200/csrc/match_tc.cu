@@ -1235,16 +1235,18 @@ select_kernel(const __half* __restrict__ smap, long long map_pitch, int rows, in
   // threshold below would be far too low).
   float m1 = -INFINITY, m2 = -INFINITY;            // this lane's two largest scores (distinct elements)
   const uint4 kNaN4 = make_uint4(0x7e007e00u, 0x7e007e00u, 0x7e007e00u, 0x7e007e00u);   // 8 x fp16 NaN
-  for (int i0 = 0; i0 < n8; i0 += 128) {           // four 16-byte loads in flight per lane
-    uint4 u[4];
+  // eight 16-byte loads in flight per lane: with one warp per row only ~13 warps are resident per SM at cfg4
+  // (1 920 rows), and this pass streams the map from HBM -- 4 loads left the SM at 26 KB in flight (22 us)
+  for (int i0 = 0; i0 < n8; i0 += 256) {
+    uint4 u[8];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 8; ++b) {
       const int ib = i0 + 32 * b;
       const int i = ib + ((lane + 5 * (ib >> 5)) & 31);
       u[b] = i < n8 ? __ldg(rp + i) : kNaN4;
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 8; ++b) {
       const __half2* h = reinterpret_cast<const __half2*>(&u[b]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
