@@ -927,10 +927,11 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
           acc[pi][m] = (sv == sv) ? sv : -INFINITY;   // wrapped origins (NaN) never win
         }
       }
-      // ---- per-patch candidate top-KC: KC rounds of a warp arg-max (redux.sync on order-preserving
-      // integer keys; ties -> lowest position); the winning lane writes the candidate ----
+      // ---- per-patch candidate list, NC = 2*KC entries: NC rounds of a warp arg-max (redux.sync on
+      // order-preserving integer keys; ties -> lowest position); the winning lane writes the candidate.  The
+      // second half is only re-scored when the first KC do not certify the top-k (rescore_kernel) ----
       constexpr unsigned kNegInfKey = 0x007fffffu;           // key of -inf
-      for (int j = 0; j < KC; ++j) {
+      for (int j = 0; j < 2 * KC; ++j) {
 #pragma unroll
         for (int pi = 0; pi < kStPW; ++pi) {
           if (pi >= rows_pw) break;
@@ -946,7 +947,7 @@ match_gemm_stacked_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
           const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
           const unsigned cand = (key == kmax) ? (unsigned)(lane + 32 * bm) : 0x7fffffffu;
           const unsigned wpos = __reduce_min_sync(0xffffffffu, cand);
-          const int64_t o = ((int64_t)n * p.P + patch) * KC + j;   // n_tiles == 1
+          const int64_t o = ((int64_t)n * p.P + patch) * (2 * KC) + j;   // n_tiles == 1
           if (kmax == kNegInfKey) {                          // fewer than KC valid windows
             if (lane == 0) { p.cand_val[o] = -INFINITY; p.cand_idx[o] = -1; }
           } else if ((int)(wpos & 31u) == lane) {
@@ -1894,11 +1895,11 @@ static Plan make_plan(int64_t NP, int q_repeat, int C, int H, int W, int ph, int
   pl.off_s2 = o;  o = align_up(o + (size_t)NP * pl.HW * 4, 256);
   pl.off_xs = o;  o = align_up(o + (size_t)NQ * pl.P * (C / kChunk) * 4, 256);
   pl.off_sxx = o; o = align_up(o + (size_t)NQ * pl.P * (C / kChunk) * 4, 256);
-  // candidate lists [NP*P][NC] (screened value, window id), sorted: the stacked kernel writes its top-KC
+  // candidate lists [NP*P][NC] (screened value, window id), sorted: the stacked kernel writes its top-2*KC
   // itself; the general kernel writes the fp16 screened score map [NP, P, map_pitch] (linear window origins,
   // map_pitch = units * TN) and select_kernel extracts the top 2*KC of every row
   pl.n_lists = 1;
-  pl.NC = pl.stacked ? pl.KC : 2 * pl.KC;
+  pl.NC = 2 * pl.KC;
   pl.map_pitch = pl.stacked ? 0 : (int64_t)pl.units_per_group * pl.TN;
   pl.off_cv = o;  o = align_up(o + (size_t)NP * pl.P * pl.NC * 4, 256);
   pl.off_ci = o;  o = align_up(o + (size_t)NP * pl.P * pl.NC * 4, 256);
