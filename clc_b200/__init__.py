@@ -14,4 +14,4 @@ __all__ = [
     "SimpleCLM", "CLM", "DeformableAlignment", "clm_fuse", "L2_or_pearson_corr", "SI_Finder_at_Decoder_Feature_Domain", "SI_Wraper",
     "create_gaussian_masks", "match_and_gather", "match_topk", "topk_rows",
 ]
-from . import ans, ops  # noqa: E402,F401  (range coder behind compress()/decompress(); raw op wrappers)
+from . import ans, ops, retrieval  # noqa: E402,F401  (range coder behind compress()/decompress(); raw op wrappers)

@@ -400,6 +400,14 @@ CLC_API int clc_clm_deform_fwd(const float* x, const float* offset, const float*
 CLC_API int clc_clm_attention_sum_fwd(const float* aligned, const float* att, const float* y, float* out, int32_t R,
                                       int64_t B, int32_t C, int64_t S, void* stream);
 
+/* ---- reference retrieval, search half (dataloader_ref_cluster.py:64, :162) ----
+ * Replaces: sklearn NearestNeighbors(algorithm='ball_tree').kneighbors, called per sample on the host.
+ *   queries [Q, D], dict [N, D] (fp32, D % 4 == 0, D <= 6400) -> neg_d2 [Q, N] = -(squared Euclidean distance);
+ *   follow with clc_topk_rows(neg_d2, Q, N, k, val, idx): idx = the k nearest entries (nearest first, ties ->
+ *   lowest index), distance = sqrt(-val). */
+CLC_API int clc_knn_neg_sqdist(const float* queries, const float* dict, int32_t Q, int32_t N, int32_t D,
+                               float* neg_d2, void* stream);
+
 /* ---- range coder: compress() / decompress() (CLC_run.py:629-716, :738-814) ----
  * HOST functions (no stream argument, plain host pointers): one rANS stream is a sequential
  * recurrence, so the state machine runs on the host; its inputs (symbols, scale-table indexes) come
