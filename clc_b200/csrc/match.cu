@@ -1339,7 +1339,7 @@ static int launch_bwd_own_clm(unsigned blocks, cudaStream_t st, PatchAddr qa, co
                               float* g_val, int P, int C, int ph, int fh, int fw, int k, const ClmBwdArgs& ca) {
   const float* no_g_out = nullptr;
   CLC_CUDA(launch_pdl(match_bwd_own_kernel<NT, true>, dim3(blocks), dim3(NT), 0, st, qa, rT, mask, idx, weights, temperature,
-                      no_g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, 0, ca));
+                      no_g_out, g_rT, g_q, g_val, P, C, ph, fh, fw, k, dbg_bits(), ca));
   CLC_CHECK_LAUNCH("clc_match_clm_bwd(main)");
   return CLC_OK;
 }
@@ -1655,9 +1655,10 @@ extern "C" int clc_match_clm_bwd(const clc_patch_view* qv, const float* r_cl, co
   int rc = CLC_OK;
 #define CLC_OWN_CASE(N) case N: rc = launch_bwd_own_clm<N>(blocks, st, qa, r_cl, mask, idx, weights, temperature, g_rT, \
                                                             g_q, g_val, P, C, ph, fh, fw, k, ca); break;
-  switch (nt_own) { CLC_OWN_CASE(128) CLC_OWN_CASE(192) CLC_OWN_CASE(256) CLC_OWN_CASE(320) CLC_OWN_CASE(384) }
+  if (stage_on(0)) switch (nt_own) { CLC_OWN_CASE(128) CLC_OWN_CASE(192) CLC_OWN_CASE(256) CLC_OWN_CASE(320) CLC_OWN_CASE(384) }
 #undef CLC_OWN_CASE
   if (rc) return rc;
+  if (!stage_on(1)) return CLC_OK;
   dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
   if (flags & CLC_MATCH_BWD_OVERWRITE_G_R) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
   else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));

@@ -1385,6 +1385,15 @@ select_kernel(const __half* __restrict__ smap, long long map_pitch, int rows, in
 // each of them forms 1/R of the channels of
 //   fused_c = sum_r aligned_r,c * softmax_r(att) * sigmoid(att_r) + y_c
 // reading the other references' tiles through distributed shared memory (y = the staged query patch).
+#ifdef CLC_DEBUG_ABI
+// bring-up: wall-clock (ns) phase stamps of the first 64 CTAs of the re-scoring kernel
+__device__ long long g_rescore_stamps[64][16];
+#define RS_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) { long long t_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_rescore_stamps[blockIdx.x][(i)] = t_; } } while (0)
+#else
+#define RS_STAMP(i) do { } while (0)
+#endif
+
 struct ClmFwdArgs {
   const float* att;         // plane (r, b) of [H*W] logits at att + r*att_sr + b*att_sb
   int64_t att_sr, att_sb;
@@ -1410,6 +1419,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   __shared__ float top_w[8];
   __shared__ int top_src[8], top_id[8];
   __shared__ int more_s;
+  __shared__ float coef_s[CLM ? 8 : 1][64];                  // CLM: [reference][pixel of the patch]
   constexpr int NT = KC * 32;
   // CLM: the R problems (references) of one (image, patch) are consecutive blocks = one cluster
   const int n = CLM ? (int)((blockIdx.x / ca.R / P) * ca.R + blockIdx.x % ca.R) : (int)(blockIdx.x / P);
@@ -1419,8 +1429,26 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = n / q_repeat;
   const int cw = W - pw + 1;
+  RS_STAMP(0);
   pdl_trigger();
   pdl_wait();
+  RS_STAMP(1);
+  // CLM: split-phase cluster barrier #1 -- arrive now, wait right before the first remote shared-memory access:
+  // a peer's shared memory may only be touched once that CTA is known to have started
+  if constexpr (CLM) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  // CLM: the attention logits of this patch's pixels are requested now and turned into coefficients after the
+  // query staging below, so their L2 round trip hides under it
+  float att_a[CLM ? 8 : 1];
+  if constexpr (CLM) {
+    if ((int)threadIdx.x < pp) {
+      const int npx_ = W / pw, py_ = patch / npx_, px_ = patch - py_ * npx_;
+      const int dy = threadIdx.x / pw, dx = threadIdx.x - dy * pw;
+      const int64_t sp = (int64_t)(py_ * ph + dy) * W + px_ * pw + dx;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        att_a[r] = r < ca.R ? ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + sp] : 0.f;
+    }
+  }
   // ---- stage the query patch (every shift is one contiguous row of C floats) + the candidate list ----
   {
     const float* qb = A32 + ((int64_t)nq * pp * P_pad + patch) * C;
@@ -1457,7 +1485,21 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     }
     if (threadIdx.x == 0) more_s = 0;
   }
+  if constexpr (CLM) {
+    // coef_r = softmax_r(att)[r] * sigmoid(att_r), operation order of clm.cu::clm_coef
+    if ((int)threadIdx.x < pp) {
+      float mx = -INFINITY, den = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) if (r < ca.R) mx = fmaxf(mx, att_a[r]);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) if (r < ca.R) { const float e = expf(att_a[r] - mx); den += e; coef_s[r][threadIdx.x] = e; }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < ca.R) coef_s[r][threadIdx.x] = (coef_s[r][threadIdx.x] / den) * (1.0f / (1.0f + expf(-att_a[r])));
+    }
+  }
   __syncthreads();
+  RS_STAMP(2);
   const int L = (H - ph + 1) * cw;
   const int64_t HW = (int64_t)H * W;
   const int npx = W / pw;
@@ -1474,6 +1516,24 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       // window rows are contiguous runs of C floats in the channels-last copy; the patch comes from
       // shared memory.  8 float4 window loads are in flight per lane.
       const float* rb = rT32 + ((int64_t)n * HW + (int64_t)oy * W + ox) * C;
+      // the window / patch statistics are requested BEFORE the window itself, so their two L2 round trips
+      // overlap the re-scoring loads instead of following them (1.5-2 us of a 7 us phase at cfg2)
+      const float* s1n = s1 + (int64_t)n * HW;
+      const float* s2n = s2 + (int64_t)n * HW;
+      const int64_t qi = (int64_t)nq * P + patch;
+      const bool pre = pp <= 32 && chunks <= 32;
+      float px1 = 0.f, px2 = 0.f, pc1 = 0.f, pc2 = 0.f;
+      if (pre) {
+        if (lane < pp) {
+          const int dy = lane / pw, dx = lane - dy * pw;
+          px1 = __ldg(s1n + (oy + dy) * W + ox + dx);
+          px2 = __ldg(s2n + (oy + dy) * W + ox + dx);
+        }
+        if (lane < chunks) {
+          pc1 = __ldg(xs_a + qi * chunks + lane);
+          pc2 = __ldg(sxx_a + qi * chunks + lane);
+        }
+      }
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       // loads of 4 shifts x 3 float4 columns are issued together (12 LDG.128 in flight per lane);
       // no per-item integer division: shifts advance by counters, channels by lane strides
@@ -1509,13 +1569,11 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
       // window / patch statistics: the lanes fetch the terms in parallel, the sums are then formed in
       // the reference's sequential order (same bits as the fp32 path) with warp shuffles
       const float Kf = (float)K;
-      const float* s1n = s1 + (int64_t)n * HW;
-      const float* s2n = s2 + (int64_t)n * HW;
       float b1 = 0.f, b2 = 0.f;
       for (int e0 = 0; e0 < pp; e0 += 32) {
         const int e = e0 + lane;
-        float x1 = 0.f, x2 = 0.f;
-        if (e < pp) {
+        float x1 = px1, x2 = px2;
+        if (!pre && e < pp) {
           const int dy = e / pw, dx = e - dy * pw;
           x1 = __ldg(s1n + (oy + dy) * W + ox + dx);
           x2 = __ldg(s2n + (oy + dy) * W + ox + dx);
@@ -1526,12 +1584,11 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
           b2 += __shfl_sync(0xffffffffu, x2, j);
         }
       }
-      const int64_t qi = (int64_t)nq * P + patch;
       float xsum = 0.f, sxxsum = 0.f;
       for (int c0 = 0; c0 < chunks; c0 += 32) {
         const int c = c0 + lane;
-        const float x1 = c < chunks ? __ldg(xs_a + qi * chunks + c) : 0.f;
-        const float x2 = c < chunks ? __ldg(sxx_a + qi * chunks + c) : 0.f;
+        const float x1 = pre ? pc1 : (c < chunks ? __ldg(xs_a + qi * chunks + c) : 0.f);
+        const float x2 = pre ? pc2 : (c < chunks ? __ldg(sxx_a + qi * chunks + c) : 0.f);
         const int cnt = chunks - c0 < 32 ? chunks - c0 : 32;
         for (int j = 0; j < cnt; ++j) {
           xsum += __shfl_sync(0xffffffffu, x1, j);
@@ -1544,6 +1601,7 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     if (lane == 0) ex_v[cslot] = out;
   }
   __syncthreads();
+  if (round == 0) RS_STAMP(3);
   const int NE = (round + 1) * KC < NC ? (round + 1) * KC : NC;      // candidates with an exact value so far
   if (warp == 0) {
     // final top-k among the NE exact values, (value desc, index asc); NaN ranks first like torch.topk
@@ -1630,8 +1688,10 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     }
   }
   __syncthreads();
+  if (round == 0) RS_STAMP(4);
   if (!more_s) break;
   }   // rounds
+  RS_STAMP(5);
   if (warp == 0 && aligned != nullptr) {
     // softmax(value * T) over the k selected positions (SI_Wraper, Patch_Matching.py:225): lanes
     // 0..7 each form max and denominator in the reference's left-to-right order (identical bits in
@@ -1667,12 +1727,14 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
   // together; they were just re-scored, so mostly L1/L2 hits), blended into a [S][C] shared tile and
   // written as 16-byte NCHW patch rows ----
   __syncthreads();
+  RS_STAMP(6);
   {
     float4* T4 = CLM ? Q + pp * c4n : Q;                     // (not CLM: the query patch is no longer needed)
     const float* rn = rT32 + (int64_t)n * HW * C;
     if (k <= 4) blend_rows<4, 3, KC>(T4, rn, top_src, top_w, k, pp, pw, W, C, warp, lane);
     else blend_rows<8, 1, KC>(T4, rn, top_src, top_w, k, pp, pw, W, C, warp, lane);
     __syncthreads();
+    RS_STAMP(7);
     const float* Tf = reinterpret_cast<const float*>(T4);
     float* on = aligned + (int64_t)n * C * HW + (int64_t)(py * ph) * W + px * pw;
     if (pw == 4) {
@@ -1691,37 +1753,56 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
     if constexpr (CLM) {
       namespace cg = cooperative_groups;
       cg::cluster_group cluster = cg::this_cluster();
-      __shared__ float coef_s[8][64];                        // [reference][pixel of the patch]
       const unsigned rank = cluster.block_rank();
-      if ((int)threadIdx.x < pp) {
-        // coef_r = softmax_r(att)[r] * sigmoid(att_r) at this pixel, operation order of clm.cu::clm_coef
-        const int dy = threadIdx.x / pw, dx = threadIdx.x - dy * pw;
-        const int64_t sp = (int64_t)(py * ph + dy) * W + px * pw + dx;
-        float a[8], mx = -INFINITY, den = 0.f;
-        for (int r = 0; r < ca.R; ++r) { a[r] = ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + sp]; mx = fmaxf(mx, a[r]); }
-        for (int r = 0; r < ca.R; ++r) { const float e = expf(a[r] - mx); den += e; coef_s[r][threadIdx.x] = e; }
-        for (int r = 0; r < ca.R; ++r) coef_s[r][threadIdx.x] = (coef_s[r][threadIdx.x] / den) * (1.0f / (1.0f + expf(-a[r])));
-      }
-      cluster.sync();                                        // every reference's blended tile + the coefficients are in place
       const float* Qf = reinterpret_cast<const float*>(Q);
       float* fo = ca.fused + (int64_t)nq * C * HW + (int64_t)(py * ph) * W + px * pw;
+      asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // barrier #1: every peer CTA is running
       // this CTA's channels: c = rank, rank + R, ...  (items = (channel, patch row) when pw == 4)
       if (pw == 4) {
-        const int nc = (C - (int)rank + ca.R - 1) / ca.R;
+        // PUSH exchange: every CTA stores, into each peer's receive buffer, the channels of its blended tile that
+        // the peer will fuse (remote shared-memory stores are fire-and-forget; the cluster barrier's
+        // release/acquire makes them visible).  After the barrier every CTA reads local shared memory only, so
+        // no second barrier is needed to keep tiles alive -- the pull version (remote loads + a closing barrier)
+        // spent 3.7 + 1.8 us of a 25 us kernel there at cfg2.
+        const int R = ca.R, ncmax = (((C + R - 1) / R) + 3) & ~3;      // peer channels per shift, padded to 4
+        float* recv = reinterpret_cast<float*>(T4 + pp * c4n);          // [R][pp][ncmax]
+        for (int m = 0; m < R; ++m) {
+          if (m == (int)rank) continue;
+          float* dst = cluster.map_shared_rank(recv, m) + (size_t)rank * pp * ncmax;
+          const int ncm = (C - m + R - 1) / R, n4 = (ncm + 3) >> 2;
+          for (int it = threadIdx.x; it < pp * n4; it += NT) {          // 16-byte remote stores
+            const int sft = it / n4, j = (it - sft * n4) * 4;
+            const float* src = Tf + sft * C + m + j * R;
+            float4 v;
+            v.x = src[0];
+            v.y = j + 1 < ncm ? src[R] : 0.f;
+            v.z = j + 2 < ncm ? src[2 * R] : 0.f;
+            v.w = j + 3 < ncm ? src[3 * R] : 0.f;
+            *reinterpret_cast<float4*>(dst + sft * ncmax + j) = v;
+          }
+        }
+        RS_STAMP(8);
+        cluster.sync();                                      // every peer's channels have landed
+        RS_STAMP(9);
+        const int nc = (C - (int)rank + R - 1) / R;
         for (int it = threadIdx.x; it < nc * ph; it += NT) {
-          const int dy = it / nc, c = (int)rank + (it - dy * nc) * ca.R;
+          const int dy = it / nc, j = it - dy * nc, c = (int)rank + j * R;
           float o[4] = {0.f, 0.f, 0.f, 0.f};
           // (aligned_stack * attention_weights).sum(dim=1): products summed left to right over r
-          for (int r = 0; r < ca.R; ++r) {
-            const float* t = reinterpret_cast<const float*>(cluster.map_shared_rank(T4, r)) + (dy * 4) * C + c;
+          for (int r = 0; r < R; ++r) {
+            const float* t = (r == (int)rank) ? Tf + (dy * 4) * C + c : recv + ((size_t)r * pp + dy * 4) * ncmax + j;
+            const int st_ = (r == (int)rank) ? C : ncmax;
 #pragma unroll
-            for (int dx = 0; dx < 4; ++dx) o[dx] += t[dx * C] * coef_s[r][dy * 4 + dx];
+            for (int dx = 0; dx < 4; ++dx) o[dx] += t[dx * st_] * coef_s[r][dy * 4 + dx];
           }
 #pragma unroll
           for (int dx = 0; dx < 4; ++dx) o[dx] += Qf[(dy * 4 + dx) * C + c];
           st4(fo + (int64_t)c * HW + dy * W, make_float4(o[0], o[1], o[2], o[3]));
         }
+        RS_STAMP(10);
+        RS_STAMP(11);
       } else {
+        cluster.sync();                                      // every reference's blended tile is in place (pull)
         for (int e = threadIdx.x; e < C * pp; e += NT) {
           const int sft = e / C, c = e - sft * C;
           if (c % ca.R != (int)rank) continue;
@@ -1731,8 +1812,8 @@ rescore_kernel(const float* __restrict__ A32, const float* __restrict__ rT32, in
             acc += reinterpret_cast<const float*>(cluster.map_shared_rank(T4, r))[sft * C + c] * coef_s[r][sft];
           fo[(int64_t)c * HW + dy * W + dx] = acc + Qf[sft * C + c];
         }
+        cluster.sync();                                      // keep every tile alive until all readers are done
       }
-      cluster.sync();                                        // keep every tile alive until all readers are done
     }
   }
 }
@@ -2099,7 +2180,9 @@ static int run(const float* q_img, const float* r, int64_t NP, int q_repeat, int
   if (stage_on(2)) {
     const int64_t blocks = NP * pl.P;
     if (blocks > 0x7fffffff) return CLC_ERR_UNSUPPORTED;
-    const size_t sm = (size_t)pl.S * C * sizeof(float) * (clm ? 2 : 1);
+    // query patch [S][C] (+ CLM: blended tile [S][C] + receive buffer [R][S][ceil(C/R)] of the push exchange)
+    size_t sm = (size_t)pl.S * C * sizeof(float) * (clm ? 2 : 1);
+    if (clm) sm += (size_t)clm->R * pl.S * ((((C + clm->R - 1) / clm->R) + 3) & ~3) * sizeof(float);
     if (sm > 200 * 1024) return CLC_ERR_UNSUPPORTED;
     const int dbg = dbg_bits();
     const float rel = pl.stacked ? 0.f : 4.9e-4f;        // fp16 rounding of the stored screened scores
@@ -2191,6 +2274,12 @@ extern "C" CLC_API int clc_debug_match_tc_xy(const float* q_img, const float* r,
 }
 
 // Bring-up hook: per-CTA clock64 stamps of the GEMM kernel's pipeline stages ([148][16] int64).
+extern "C" CLC_API int clc_debug_rescore_stamps(long long* host_out /* [64][16] */) {
+  if (!host_out) return CLC_ERR_INVALID_ARGUMENT;
+  CLC_CUDA(cudaMemcpyFromSymbol(host_out, clc::tc::g_rescore_stamps, sizeof(long long) * 64 * 16));
+  return CLC_OK;
+}
+
 extern "C" CLC_API int clc_debug_match_tc_timing(const float* q_img, const float* r, int64_t NP, int32_t q_repeat,
                                                  int32_t C, int32_t H, int32_t W, int32_t ph, int32_t pw, int32_t k,
                                                  int32_t gaussian_mask, float* val, int32_t* idx, long long* timing,

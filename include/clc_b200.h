@@ -473,6 +473,8 @@ CLC_API int clc_peer_allreduce(void* const* regions, int32_t rank, int32_t world
  * (clc_match_topk_tc: prepass, gemm, rescore; clc_match_bwd: main, transpose).  Default 0xff = all; bits 8-15 are kernel-specific experiment switches (0 in production).
  * Results are only meaningful with every stage on. */
 CLC_API void clc_debug_set_stage_mask(int mask);
+/* wall-clock (ns, %globaltimer) phase stamps of the first 64 CTAs of the last re-scoring kernel: [64][16] */
+CLC_API int clc_debug_rescore_stamps(long long* host_out);
 
 /* clc_match_topk_tc that additionally dumps the raw bf16-GEMM accumulators
  * xy[NP, P, H*W] (linear window origins oy*W+ox, wrapped ones included). */

@@ -59,13 +59,16 @@ torch.cuda.synchronize()
 print(f"# {a.workload}: {len(calls)} C-ABI calls per step; per-call time, L2-warm, {a.rep} back-to-back in a graph")
 s = torch.cuda.Stream()
 tot = 0.0
-STAGES = {"clc_match_topk_tc": ["prepass", "gemm", "rescore+blend"], "clc_match_bwd": ["memset+main", "cl_to_nchw"]}
+STAGES = {"clc_match_topk_tc": ["prepass", "gemm", "rescore+blend"], "clc_match_bwd": ["memset+main", "cl_to_nchw"],
+          "clc_match_clm_fwd": ["prepass", "gemm", "rescore+blend+clm"], "clc_match_clm_bwd": ["main", "cl_to_nchw"]}
 # debug variants: (stage bit, dbg bits << 8, label)
 VARIANTS = {"clc_match_topk_tc": [(1, 1, "prepass: query role only"), (1, 2, "prepass: ref role only"),
                                   (2, 1, "gemm: shifts rounded to 8 rows (aligned descriptors)"),
                                   (2, 2, "gemm: no MMAs (TMA + epilogue only)"), (2, 4, "gemm: no A loads"),
                                   (4, 1, "rescore: no re-scoring loads"), (4, 2, "rescore: no blend")],
-            "clc_match_bwd": [(1, 1, "main: no window atomics"), (1, 2, "main: no g_q atomics"), (1, 3, "main: no atomics")]}
+            "clc_match_bwd": [(1, 1, "main: no window atomics"), (1, 2, "main: no g_q atomics"), (1, 3, "main: no atomics")],
+            "clc_match_clm_fwd": [(4, 1, "rescore: no re-scoring loads"), (4, 2, "rescore: no blend")],
+            "clc_match_clm_bwd": [(1, 1, "main: no window atomics"), (1, 2, "main: no g_q atomics"), (1, 3, "main: no atomics")]}
 expanded = []
 for name, args in calls:
     expanded.append((name, args, 0xff, name))
