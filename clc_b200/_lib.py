@@ -108,6 +108,7 @@ PROTOTYPES = {
 DEBUG_PROTOTYPES = {
     "clc_debug_set_stage_mask": (None, [C.c_int]),
     "clc_debug_rescore_stamps": (C.c_int, [_p]),
+    "clc_debug_bwd_stamps": (C.c_int, [_p]),
     "clc_debug_match_tc_xy": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,
                                         _p, _sz, _p]),
     "clc_debug_match_tc_timing": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p,

@@ -643,14 +643,50 @@ nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ xT, int C, in
   }
 }
 
-// x[n][c][p] (+)= xT[n][p][c]
+// SimpleCLM attention-logit gradient from the per-reference G_r = sum_c g_fused_c * aligned_r,c the CLM-fused match
+// backward published ([NQ*P][R][16], 4 x 4 patches):
+//   g_att_m = w_m s_m G_m - w_m sum_r G_r s_r w_r + G_m w_m s_m (1 - s_m),   w = softmax_r(att), s = sigmoid(att)
+struct ClmAttGrad {
+  const float* g_scratch;   // NULL = nothing to do
+  const float* att;
+  float* g_att;
+  int64_t att_sr, att_sb;
+  int R, P, fw;
+};
+
+// x[n][c][p] (+)= xT[n][p][c].  With `ga`, the blocks (*, 0, first reference of an image) also form g_att for their
+// 32 pixels: the R CTAs of a patch in the backward kernel only publish their G_r -- no fence, no arrival counter,
+// no cluster barrier on that kernel's critical path (each of those cost 2-3.4 us per CTA there).
 template <bool ADD>
 __global__ void __launch_bounds__(256)
-cl_to_nchw_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, int HW) {
+cl_to_nchw_kernel(const float* __restrict__ xT, float* __restrict__ x, int C, int HW, const ClmAttGrad ga) {
   __shared__ float t[32][33];
   pdl_trigger();
   pdl_wait();
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (ga.g_scratch != nullptr && blockIdx.y == 0 && n % ga.R == 0 && threadIdx.y == 0 && p0 + (int)threadIdx.x < HW) {
+    const int nq = n / ga.R, pix = p0 + threadIdx.x;
+    const int y = pix / ga.fw, xx = pix - y * ga.fw;
+    const int patch = (y >> 2) * (ga.fw >> 2) + (xx >> 2), o = (y & 3) * 4 + (xx & 3);
+    const float* gs = ga.g_scratch + ((int64_t)nq * ga.P + patch) * ga.R * 16 + o;
+    float av[8], w[8], sg[8], Gt[8];
+    float mx = -INFINITY, den = 0.f, mix = 0.f;
+    for (int r = 0; r < ga.R; ++r) {
+      av[r] = ga.att[(int64_t)r * ga.att_sr + (int64_t)nq * ga.att_sb + pix];
+      Gt[r] = gs[r * 16];
+      mx = fmaxf(mx, av[r]);
+    }
+    for (int r = 0; r < ga.R; ++r) { w[r] = expf(av[r] - mx); den += w[r]; }
+    for (int r = 0; r < ga.R; ++r) {
+      w[r] = w[r] / den;
+      sg[r] = 1.0f / (1.0f + expf(-av[r]));
+      mix = fmaf(Gt[r], w[r] * sg[r], mix);          // sum_r G_r s_r w_r
+    }
+    for (int m = 0; m < ga.R; ++m) {
+      const float cm = w[m] * sg[m];
+      ga.g_att[(int64_t)m * ga.att_sr + (int64_t)nq * ga.att_sb + pix] = cm * Gt[m] - w[m] * mix + Gt[m] * cm * (1.f - sg[m]);
+    }
+  }
   const float* xTn = xT + (int64_t)n * C * HW;
   float* xn = x + (int64_t)n * C * HW;
   float v[4];
@@ -1042,11 +1078,20 @@ match_bwd_cl_reg_kernel(PatchAddr qa, const float* __restrict__ rT, const float*
 //   g_aligned_r = g_fused * coef_r,  coef_r = softmax_r(att) * sigmoid(att_r)        (never written to HBM)
 // on the fly, and also produces g_att.  g_att_m = coef_m G_m - w_m sum_r G_r coef_r + G_m coef_m (1 - s_m) needs
 // G_r = sum_c g_fused_c * aligned_r,c of ALL references at a pixel.  Each of the R CTAs of one (image, patch) reduces
-// its own G_r over the channels at the START of the kernel, publishes the 16 values to a global scratch and bumps
-// the group's arrival counter; whichever CTA arrives last combines the R contributions (fixed order r = 0..R-1,
-// so the result does not depend on who that is) and writes g_att, then carries on with its own match backward.
-// Nobody waits: the first version ran the R CTAs as a thread-block cluster and exchanged G_r through DSMEM, and
-// its two cluster barriers were 36 % of the kernel's stall samples at cfg2 (profiles/r2_full_cfg2).
+// its own G_r over the channels and publishes the 16 values to a global scratch; g_att itself is formed by a few
+// blocks of the cl_to_nchw launch that follows (ClmAttGrad), in fixed order r = 0..R-1.  Nothing on this kernel's
+// critical path waits for a peer: the first version ran the R CTAs as a thread-block cluster and exchanged G_r
+// through DSMEM (its two cluster barriers were 36 % of the stall samples at cfg2), the second let the last CTA to
+// arrive do it (fence + arrival atomic: 2-3.4 us of warp 0's time ahead of a block-wide barrier).
+#ifdef CLC_DEBUG_ABI
+// bring-up: wall-clock (ns) phase stamps of the first 64 CTAs of the thread-owns-items backward kernel
+__device__ long long g_bwd_stamps[64][16];
+#define BW_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) { long long t_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_bwd_stamps[blockIdx.x][(i)] = t_; } } while (0)
+#else
+#define BW_STAMP(i) do { } while (0)
+#endif
+
 constexpr int kClmMaxRefs = 8;
 struct ClmBwdArgs {
   const float* g_fused;     // [NQ, C, fh*fw]
@@ -1087,8 +1132,10 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
   const int64_t po = ((int64_t)n * P + patch) * k;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int dy = tid / c4n, c4 = tid - dy * c4n;
+  BW_STAMP(0);
   pdl_trigger();
   pdl_wait();
+  BW_STAMP(1);
   if (tid < KK) {
     int src = 0;
     float wj = 0.f, mj = 1.f;
@@ -1162,6 +1209,7 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
   g[0] = make_float4(gc[0].x, gc[1].x, gc[2].x, gc[3].x); g[1] = make_float4(gc[0].y, gc[1].y, gc[2].y, gc[3].y);
   g[2] = make_float4(gc[0].z, gc[1].z, gc[2].z, gc[3].z); g[3] = make_float4(gc[0].w, gc[1].w, gc[2].w, gc[3].w);
   __syncthreads();    // src_s (and gpart) visible
+  BW_STAMP(2);
   if constexpr (CLM) {
     // G_r at the 16 pixels (dy, dx): fixed-order sum of the c4n per-thread partials of row dy
     if (tid < 64) {
@@ -1174,38 +1222,10 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       const int r_own = n - nq * ca.R;
       const int64_t grp = (int64_t)nq * P + patch;
       float* gs = ca.g_scratch + grp * ca.R * 16;
-      if (qq == 0) gs[r_own * 16 + o] = a;
-      __threadfence();                                     // the 16 values are visible device-wide ...
-      asm volatile("bar.sync 1, 64;" ::: "memory");        // ... for both warps, before warp 0 announces them
-      if (tid < 32) {
-        int last = 0;
-        if (tid == 0) {
-          last = atomicAdd(ca.arrivals + grp, 1) == ca.R - 1;
-          if (last) ca.arrivals[grp] = 0;                  // ready for the next launch on this workspace
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last && tid < 16) {
-          __threadfence();
-          const int tdy = tid >> 2, tdx = tid & 3;
-          const int64_t sp = (int64_t)(py * ph + tdy) * fw + px * pw + tdx;
-          float av[kClmMaxRefs], w[kClmMaxRefs], sg[kClmMaxRefs], Gt[kClmMaxRefs];
-          float mx = -INFINITY, den = 0.f, mix = 0.f;
-          for (int r = 0; r < ca.R; ++r) { av[r] = ca.att[(int64_t)r * ca.att_sr + (int64_t)nq * ca.att_sb + sp]; mx = fmaxf(mx, av[r]); }
-          for (int r = 0; r < ca.R; ++r) { w[r] = expf(av[r] - mx); den += w[r]; }
-          for (int r = 0; r < ca.R; ++r) {
-            w[r] = w[r] / den;
-            sg[r] = 1.0f / (1.0f + expf(-av[r]));
-            Gt[r] = __ldcg(gs + r * 16 + tid);
-            mix = fmaf(Gt[r], w[r] * sg[r], mix);          // sum_r G_r s_r w_r
-          }
-          for (int m = 0; m < ca.R; ++m) {
-            const float cm = w[m] * sg[m];
-            ca.g_att[(int64_t)m * ca.att_sr + (int64_t)nq * ca.att_sb + sp] = cm * Gt[m] - w[m] * mix + Gt[m] * cm * (1.f - sg[m]);
-          }
-        }
-      }
+      if (qq == 0) gs[r_own * 16 + o] = a;                 // published; g_att is formed by the cl_to_nchw launch
     }
   }
+  BW_STAMP(3);
   const float* rbase = rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;    // + (src + dx) * C
   float* gbase = g_rT + ((int64_t)n * HW + dy * fw) * C + 4 * c4;
   float v[NV];
@@ -1239,6 +1259,7 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       }
     }
   }
+  BW_STAMP(4);
 #pragma unroll
   for (int t = 0; t < NV; ++t) {
     v[t] = warp_sum(v[t]);
@@ -1252,6 +1273,7 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
     tot[tid] = a;
   }
   __syncthreads();
+  BW_STAMP(5);
   if (tid < k) {
     const int j = tid;
     const float xs = tot[0], sxx = tot[1];
@@ -1280,6 +1302,7 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
     coef[j][0] = wj; coef[j][1] = g_num; coef[j][2] = 2.f * g_dY; coef[j][3] = g_ym * inv_k;
   }
   __syncthreads();
+  BW_STAMP(6);
 #pragma unroll
   for (int j0 = 0; j0 < KK; j0 += 2) {
     if (j0 >= k) break;
@@ -1309,6 +1332,7 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       }
     }
   }
+  BW_STAMP(7);
   if (g_q && !(dbg & 2)) {
     float t_gxs = 0.f, t_gsxx = 0.f, t_gxm = 0.f;
     for (int j = 0; j < k; ++j) { t_gxs += part[j][0]; t_gsxx += part[j][1]; t_gxm += part[j][2]; }
@@ -1321,6 +1345,7 @@ match_bwd_own_kernel(PatchAddr qa, const float* __restrict__ rT, const float* __
       red_add4(gqp + (int64_t)i * qa.sc, o);
     }
   }
+  BW_STAMP(8);
 }
 
 template <int NT>
@@ -1529,6 +1554,14 @@ static inline size_t bwd_ws_zero_bytes(int64_t NP, int C, int fh, int fw) {
   return sizeof(float) * (size_t)NP * C * fh * fw + bwd_ws_counter_bytes(NP, fh, fw);
 }
 
+#ifdef CLC_DEBUG_ABI
+extern "C" CLC_API int clc_debug_bwd_stamps(long long* host_out /* [64][16] */) {
+  if (!host_out) return CLC_ERR_INVALID_ARGUMENT;
+  CLC_CUDA(cudaMemcpyFromSymbol(host_out, clc::g_bwd_stamps, sizeof(long long) * 64 * 16));
+  return CLC_OK;
+}
+#endif
+
 extern "C" size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw) {
   if (NP < 0 || C < 1 || fh < 1 || fw < 1) return 0;
   // gradient scratch (channels-last g_r) | arrival counters of the CLM-fused kernel | channels-last copy of r
@@ -1614,8 +1647,8 @@ extern "C" int clc_match_bwd(const clc_patch_view* qv, const float* r, const flo
     CLC_CHECK_LAUNCH("clc_match_bwd(main)");
   }
   if (!stage_on(1)) return CLC_OK;
-  if (overwrite) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
-  else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
+  if (overwrite) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW, ClmAttGrad{}));
+  else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW, ClmAttGrad{}));
   CLC_CHECK_LAUNCH("clc_match_bwd(cl_to_nchw)");
   return CLC_OK;
 }
@@ -1660,8 +1693,11 @@ extern "C" int clc_match_clm_bwd(const clc_patch_view* qv, const float* r_cl, co
   if (rc) return rc;
   if (!stage_on(1)) return CLC_OK;
   dim3 tgrid((HW + 31) / 32, (C + 31) / 32, (unsigned)NP), tblock(32, 8);
-  if (flags & CLC_MATCH_BWD_OVERWRITE_G_R) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
-  else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW));
+  ClmAttGrad ga;
+  ga.g_scratch = ca.g_scratch; ga.att = att; ga.g_att = g_att; ga.att_sr = att_sr; ga.att_sb = att_sb;
+  ga.R = R; ga.P = P; ga.fw = fw;
+  if (flags & CLC_MATCH_BWD_OVERWRITE_G_R) CLC_CUDA(launch_pdl(cl_to_nchw_kernel<false>, tgrid, tblock, 0, st, g_rT, g_r, C, HW, ga));
+  else CLC_CUDA(launch_pdl(cl_to_nchw_kernel<true>, tgrid, tblock, 0, st, g_rT, g_r, C, HW, ga));
   CLC_CHECK_LAUNCH("clc_match_clm_bwd(cl_to_nchw)");
   return CLC_OK;
 }

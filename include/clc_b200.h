@@ -475,6 +475,7 @@ CLC_API int clc_peer_allreduce(void* const* regions, int32_t rank, int32_t world
 CLC_API void clc_debug_set_stage_mask(int mask);
 /* wall-clock (ns, %globaltimer) phase stamps of the first 64 CTAs of the last re-scoring kernel: [64][16] */
 CLC_API int clc_debug_rescore_stamps(long long* host_out);
+CLC_API int clc_debug_bwd_stamps(long long* host_out);      /* same for the match backward kernel */
 
 /* clc_match_topk_tc that additionally dumps the raw bf16-GEMM accumulators
  * xy[NP, P, H*W] (linear window origins oy*W+ox, wrapped ones included). */

@@ -47,3 +47,15 @@ for i, n in enumerate(names):
     col = d[:, i]
     print(f"{n:24s} median {np.median(col):7.2f}  min {col.min():7.2f}  max {col.max():7.2f} us")
 print(f"{'total':24s} median {np.median((out[:, 11] - out[:, 0]) / 1e3):7.2f} us; last end - first start {(out[:, :12].max() - t0) / 1e3:.2f} us")
+if lp.train:
+    out = np.zeros((64, 16), dtype=np.int64)
+    assert H.clc_debug_bwd_stamps(out.ctypes.data_as(C.c_void_p)) == 0
+    names = ["launch->pdl_wait", "idx/q/g/aligned/att loads", "G_r reduce+publish (w0-1)", "window pass 1 (loads+FMA)",
+             "block reduction", "coefficients", "window pass 2 + red.add", "g_q red.add"]
+    t0 = out[:, 0].min()
+    print("\nmatch backward -- CTA start spread (us):", (out[:, 0].max() - t0) / 1e3)
+    d = np.diff(out[:, :9], axis=1) / 1e3
+    for i, n in enumerate(names):
+        col = d[:, i]
+        print(f"{n:28s} median {np.median(col):7.2f}  min {col.min():7.2f}  max {col.max():7.2f} us")
+    print(f"{'total':28s} median {np.median((out[:, 8] - out[:, 0]) / 1e3):7.2f} us; last end - first start {(out[:, :9].max() - t0) / 1e3:.2f} us")
