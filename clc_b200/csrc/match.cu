@@ -1101,7 +1101,6 @@ struct ClmBwdArgs {
   float* g_att;             // same addressing as att
   int R;
   float* g_scratch;         // [NQ*P][R][16] published G_r
-  int* arrivals;            // [NQ*P] arrival counters, zero on entry (the last CTA re-zeroes its own)
 };
 
 template <int NT, bool CLM>
@@ -1546,9 +1545,9 @@ extern "C" int clc_pearson_topk_bwd(const clc_patch_view* qv, const float* r, co
   return CLC_OK;
 }
 
-// One memset clears the gradient scratch AND the counters behind it.
+// (a 256-byte-aligned pad of NP*fh*fw ints sits behind the gradient scratch: reserved, cleared with it)
 static inline size_t bwd_ws_counter_bytes(int64_t NP, int fh, int fw) {
-  return ((size_t)NP * fh * fw * sizeof(int) + 255) / 256 * 256;      // >= NQ * P counters for any patch size
+  return ((size_t)NP * fh * fw * sizeof(int) + 255) / 256 * 256;
 }
 static inline size_t bwd_ws_zero_bytes(int64_t NP, int C, int fh, int fw) {
   return sizeof(float) * (size_t)NP * C * fh * fw + bwd_ws_counter_bytes(NP, fh, fw);
@@ -1564,8 +1563,8 @@ extern "C" CLC_API int clc_debug_bwd_stamps(long long* host_out /* [64][16] */) 
 
 extern "C" size_t clc_match_bwd_workspace_bytes(int64_t NP, int32_t C, int32_t fh, int32_t fw) {
   if (NP < 0 || C < 1 || fh < 1 || fw < 1) return 0;
-  // gradient scratch (channels-last g_r) | arrival counters of the CLM-fused kernel | channels-last copy of r
-  // (or, when the caller supplies that copy, the fused kernel's published G_r)
+  // gradient scratch (channels-last g_r) | reserved pad | channels-last copy of r (or, when the caller supplies
+  // that copy, the CLM-fused kernel's published G_r)
   return bwd_ws_counter_bytes(NP, fh, fw) + 2 * sizeof(float) * (size_t)NP * C * fh * fw + 512;
 }
 
@@ -1682,7 +1681,6 @@ extern "C" int clc_match_clm_bwd(const clc_patch_view* qv, const float* r_cl, co
   ClmBwdArgs ca;
   ca.g_fused = g_fused; ca.att = att; ca.att_sr = att_sr; ca.att_sb = att_sb; ca.aligned = aligned; ca.g_att = g_att;
   ca.R = R;
-  ca.arrivals = reinterpret_cast<int*>(g_rT + (size_t)NP * C * HW);
   ca.g_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_rT) + bwd_ws_zero_bytes(NP, C, fh, fw));
   const unsigned blocks = (unsigned)(NP * P);
   int rc = CLC_OK;
