@@ -142,9 +142,10 @@ class LatentPath:
         self._fused_bwd = (bool(fuse_chain) and match_mode == "tc" and patch == 4 and k <= 4 and n_refs <= 8 and
                            M % 4 == 0 and patch * (M // 4) in (128, 192, 256, 320, 384) and w % 4 == 0)
         # forward CLM fusion (clusters of R CTAs per (image, patch)) pays only for small latents: measured on B200
-        # (scripts/chain_timing.py [--no-fuse]) the match chain is 96 vs 98 us at 16 x 16 latents (cfg2) but
-        # 133 vs 107 us at 32 x 48 (cfg3) and 336 vs 299 us at 80 x 128 (cfg4) -- with thousands of clusters the
-        # two cluster barriers cost more than the 5 x C x H x W floats of HBM traffic the fusion saves
+        # (scripts/chain_timing.py [--no-fuse | --fuse-all]) it wins ~2 us at 16 x 16 latents (cfg2) but loses
+        # 12 us at 32 x 48 (cfg3: 121 vs 109 us) and 16 us at 80 x 128 (cfg4: 317 vs 301 us) -- with thousands of
+        # clusters, each gated on its slowest CTA, the barrier costs more than the 5 x C x H x W floats of HBM
+        # traffic the fusion saves
         # (fuse_chain="all" forces it at any size: tests, measurements)
         self._fused_fwd = (bool(fuse_chain) and match_mode == "tc" and n_refs <= 8 and patch * patch <= 64 and
                            (h * w <= 512 or fuse_chain == "all"))

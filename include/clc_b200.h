@@ -337,8 +337,8 @@ CLC_API int clc_match_bwd_zero_workspace(void* workspace, size_t workspace_bytes
 /* Backward of [match -> SimpleCLM elementwise fusion] in one call: clc_clm_fuse_bwd folded into clc_match_bwd
  * (models/CLM.py:170-182 + Patch_Matching.py:218-240, :854-910, reference autograd semantics as above).
  * The gradient of the aligned references, g_aligned_r = g_fused * softmax_r(att) * sigmoid(att_r), is formed on
- * the fly and never written; the R references of one (image, patch) run as one thread-block cluster and combine
- * their G_r = sum_c g_fused_c * aligned_r,c through distributed shared memory to produce g_att.
+ * the fly and never written; the R CTAs of one (image, patch) publish their G_r = sum_c g_fused_c * aligned_r,c to
+ * the workspace and the transposing kernel that ends the call forms g_att from them (fixed order r = 0..R-1).
  *   qv      : query patches addressed in place, q_repeat == R (problem n = image * R + reference)
  *   r_cl    : channels-last fp32 copy of the references [NP, fh*fw, C] (clc_match_topk_tc_ref_cl), required
  *   g_fused : [NP/R, C, fh, fw] dL/d(fused feature);  att / g_att : plane (r, b) at + r*att_sr + b*att_sb

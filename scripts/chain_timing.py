@@ -15,10 +15,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--no-fuse", action="store_true", help="separate CLM kernels instead of the fused chain")
+ap.add_argument("--fuse-all", action="store_true", help="forward CLM fusion at any latent size (default: <= 512 pixels)")
 a = ap.parse_args()
 cfg = WORKLOADS[a.workload]
 lp = LatentPath(cfg["B"], cfg["H"], cfg["W"], n_refs=cfg["R"], train=cfg["train"], fused_slices=True, device="cuda:0",
-                fuse_chain=not a.no_fuse)
+                fuse_chain=("all" if a.fuse_all else not a.no_fuse))
 lp.randomize(seed=1)
 lp.step()
 torch.cuda.synchronize()
