@@ -102,6 +102,7 @@ PROTOTYPES = {
     "clc_clm_deform_fwd": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p]),
     "clc_clm_attention_sum_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i64, _p]),
     "clc_knn_neg_sqdist": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "clc_window_attention_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f, _p]),
 }
 
 # Bring-up entry points: only in libclc_b200_dbg.so (the -DCLC_DEBUG_ABI build), see debug_lib().

@@ -187,8 +187,23 @@ class WMSA(nn.Module):
             self._mask_cache[key] = m
         return m
 
+    def _fused_ok(self, x):
+        """Inference on the GPU: everything between the two Linear layers is one kernel (clc_window_attention_fwd)."""
+        return (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and self.window_size == 8
+                and self.head_dim in (8, 16, 32) and x.shape[1] % 8 == 0 and x.shape[2] % 8 == 0
+                and getattr(self, "fused_attention", True))
+
     def forward(self, x):  # x: [B, H, W, C]
         p, shifted = self.window_size, self.type != "W"
+        if self._fused_ok(x):
+            from ._lib import call, ptr
+            from .ops import _stream
+            B, H, W, C = x.shape
+            qkv = self.embedding_layer(x.contiguous())          # per-token: no roll / window partition needed first
+            out = torch.empty(B, H, W, C, dtype=torch.float32, device=x.device)
+            call("clc_window_attention_fwd", ptr(qkv), ptr(self.relative_position_params.detach().contiguous()),
+                 ptr(out), B, H, W, C, self.head_dim, p, 1 if shifted else 0, float(self.scale), _stream())
+            return self.linear(out)
         if shifted:
             x = torch.roll(x, shifts=(-(p // 2), -(p // 2)), dims=(1, 2))
         B, H, W, C = x.shape

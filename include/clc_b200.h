@@ -400,6 +400,17 @@ CLC_API int clc_clm_deform_fwd(const float* x, const float* offset, const float*
 CLC_API int clc_clm_attention_sum_fwd(const float* aligned, const float* att, const float* y, float* out, int32_t R,
                                       int64_t B, int32_t C, int64_t S, void* stream);
 
+/* ---- Swin window attention core (WMSA inside the SWAtten parameter networks, CLC_run.py:107-193,
+ * :399-409, and inside g_a / g_s / h_a / h_s), forward ----
+ * Replaces everything between WMSA's two Linear layers: roll, window partition, q/k/v slicing, q k^T * scale +
+ * relative-position bias, the shifted-window mask, softmax, . v, window reverse, roll back.
+ *   qkv [B, H, W, 3C] = embedding_layer(x) on the UN-rolled, UN-partitioned tokens (channel (t*heads + h)*head_dim + d,
+ *   t = q, k, v);  rel_table [heads, 2*window-1, 2*window-1] (the module's relative_position_params);
+ *   out [B, H, W, C] (channel h*head_dim + d), ready for the output Linear.  window == 8, head_dim in {8, 16, 32}. */
+CLC_API int clc_window_attention_fwd(const float* qkv, const float* rel_table, float* out, int64_t B, int32_t H,
+                                     int32_t W, int32_t C, int32_t head_dim, int32_t window, int32_t shifted,
+                                     float scale, void* stream);
+
 /* ---- reference retrieval, search half (dataloader_ref_cluster.py:64, :162) ----
  * Replaces: sklearn NearestNeighbors(algorithm='ball_tree').kneighbors, called per sample on the host.
  *   queries [Q, D], dict [N, D] (fp32, D % 4 == 0, D <= 6400) -> neg_d2 [Q, N] = -(squared Euclidean distance);
