@@ -200,18 +200,27 @@ class _ChARMBase(CompressionModel):
             st = self._side = torch.cuda.Stream(device=device)
         return st
 
-    def make_graphed_forward(self, *example_inputs, fork_branches=True, warmup=3):
+    def make_graphed_forward(self, *example_inputs, fork_branches=True, channels_last=False, warmup=3):
         """Inference: capture `forward` for these input shapes into ONE CUDA graph and return `run(*inputs) ->
         the same output dict` (tensors are static buffers, overwritten by the next call).  The reference's
         forward is ~1 500 eager launches (SWAtten blocks, the 5-slice ChARM loop with 10 parameter networks),
         launch-bound at every image size it is evaluated on; the graph removes the host from the loop and, with
-        `fork_branches`, runs each slice's mean and scale branch in parallel."""
+        `fork_branches`, runs each slice's mean and scale branch in parallel.  `channels_last=True` additionally
+        converts the weights (in place) and the static inputs to torch.channels_last: cuDNN then runs its NHWC
+        kernels without the per-call NCHW<->NHWC conversion kernels (1.4 ms of 12 ms at 256 x 256) and the Swin
+        blocks' 'b c h w -> b h w c' rearranges become views; results then differ from the NCHW forward by
+        convolution round-off (other algorithms), not bit for bit."""
         if self.training:
             raise RuntimeError("make_graphed_forward is for eval mode (training draws fresh noise per step: use "
                                "clc_b200.latent_path.LatentPath for a captured training step)")
 
+        if channels_last:
+            self.to(memory_format=torch.channels_last)
+
         def clone(a):
             if isinstance(a, torch.Tensor):
+                if channels_last and a.dim() == 4:
+                    return a.detach().clone(memory_format=torch.channels_last)
                 return a.detach().clone()
             if isinstance(a, (list, tuple)):
                 return [clone(t) for t in a]

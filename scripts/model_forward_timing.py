@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--refs", type=int, default=3)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--channels-last", action="store_true", help="weights and images in torch.channels_last")
     a = ap.parse_args()
     from clc_b200.models import CLC
     d = torch.device("cuda:0")
@@ -40,15 +41,19 @@ def main():
     H, W = a.size
     x = torch.rand(a.batch, 3, H, W, device=d)
     refs = [torch.rand(a.batch, 3, H, W, device=d) for _ in range(a.refs)]
+    if a.channels_last:
+        m = m.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+        refs = [r.contiguous(memory_format=torch.channels_last) for r in refs]
 
     def eager():
         with torch.no_grad():
             return m(x, refs)
 
-    res = {"model": f"CLC(N={a.N})", "batch": a.batch, "image": [H, W], "n_refs": a.refs,
+    res = {"model": f"CLC(N={a.N})", "channels_last": a.channels_last, "batch": a.batch, "image": [H, W], "n_refs": a.refs,
            "eager_ms": timed(eager, a.iters)}
     for fork in (False, True):
-        run = m.make_graphed_forward(x, refs, fork_branches=fork)
+        run = m.make_graphed_forward(x, refs, fork_branches=fork, channels_last=a.channels_last)
         res["graph_forked_ms" if fork else "graph_ms"] = timed(lambda: run(x, refs), a.iters)
     res["kernel_nodes_note"] = "same kernels in all three; the difference is host launch overhead and branch overlap"
     print(json.dumps(res))

@@ -204,3 +204,24 @@ def test_graphed_forward_equals_eager_forward():
     m.train()
     with pytest.raises(RuntimeError):
         m.make_graphed_forward(x, refs)
+
+
+def test_graphed_forward_channels_last_within_conv_roundoff():
+    """channels_last weights / inputs (cuDNN NHWC kernels, no layout-conversion kernels): same rate and distortion
+    as the NCHW forward up to convolution round-off."""
+    from clc_b200.models import CLC
+    from oracle import detfill
+    d = torch.device("cuda:0")
+    m = detfill.fill_(CLC(N=64), seed=0).eval().to(d)
+    x = detfill.det_image((1, 3, 256, 256), 11).to(d)
+    refs = [detfill.det_image((1, 3, 256, 256), 12 + i).to(d) for i in range(3)]
+    with torch.no_grad():
+        want = m(x, refs)
+    bpp_want, psnr_want = _bpp(want, 65536), _psnr(x, want["x_hat"])
+    run = m.make_graphed_forward(x, refs, channels_last=True)
+    got = run(x, refs)
+    torch.cuda.synchronize()
+    assert abs(_bpp(got, 65536) - bpp_want) < 1e-3
+    assert abs(_psnr(x, got["x_hat"]) - psnr_want) < 0.01
+    moved = (got["para"]["y"].round() != want["para"]["y"].round()).float().mean().item()
+    assert moved < 2e-3, moved
