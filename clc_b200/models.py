@@ -200,7 +200,8 @@ class _ChARMBase(CompressionModel):
             st = self._side = torch.cuda.Stream(device=device)
         return st
 
-    def make_graphed_forward(self, *example_inputs, fork_branches=True, channels_last=False, warmup=3):
+    def make_graphed_forward(self, *example_inputs, fork_branches=True, channels_last=False, tf32_matmul=False,
+                             warmup=3):
         """Inference: capture `forward` for these input shapes into ONE CUDA graph and return `run(*inputs) ->
         the same output dict` (tensors are static buffers, overwritten by the next call).  The reference's
         forward is ~1 500 eager launches (SWAtten blocks, the 5-slice ChARM loop with 10 parameter networks),
@@ -209,7 +210,10 @@ class _ChARMBase(CompressionModel):
         converts the weights (in place) and the static inputs to torch.channels_last: cuDNN then runs its NHWC
         kernels without the per-call NCHW<->NHWC conversion kernels (1.4 ms of 12 ms at 256 x 256) and the Swin
         blocks' 'b c h w -> b h w c' rearranges become views; results then differ from the NCHW forward by
-        convolution round-off (other algorithms), not bit for bit."""
+        convolution round-off (other algorithms), not bit for bit.  `tf32_matmul=True` lets the Linear layers of the
+        Swin blocks use TF32 tensor cores while the graph is captured (the convolutions already do, cuDNN's default,
+        as in the reference; the reference's matmuls are fp32, so this is a stated deviation: ~1e-3 relative in the
+        activations)."""
         if self.training:
             raise RuntimeError("make_graphed_forward is for eval mode (training draws fresh noise per step: use "
                                "clc_b200.latent_path.LatentPath for a captured training step)")
@@ -238,6 +242,8 @@ class _ChARMBase(CompressionModel):
         static = [clone(a) for a in example_inputs]
         dev = next(self.parameters()).device
         prev, self.fork_branches = getattr(self, "fork_branches", False), bool(fork_branches)
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32_matmul) or prev_tf32
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -251,6 +257,7 @@ class _ChARMBase(CompressionModel):
                 out = self(*static)
         finally:
             self.fork_branches = prev
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
         def run(*inputs):
             if len(inputs) != len(static):

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--refs", type=int, default=3)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--channels-last", action="store_true", help="weights and images in torch.channels_last")
+    ap.add_argument("--tf32-matmul", action="store_true", help="TF32 tensor cores for the Linear layers (graphs only)")
     a = ap.parse_args()
     from clc_b200.models import CLC
     d = torch.device("cuda:0")
@@ -50,10 +51,11 @@ def main():
         with torch.no_grad():
             return m(x, refs)
 
-    res = {"model": f"CLC(N={a.N})", "channels_last": a.channels_last, "batch": a.batch, "image": [H, W], "n_refs": a.refs,
+    res = {"model": f"CLC(N={a.N})", "channels_last": a.channels_last, "tf32_matmul": a.tf32_matmul, "batch": a.batch, "image": [H, W], "n_refs": a.refs,
            "eager_ms": timed(eager, a.iters)}
     for fork in (False, True):
-        run = m.make_graphed_forward(x, refs, fork_branches=fork, channels_last=a.channels_last)
+        run = m.make_graphed_forward(x, refs, fork_branches=fork, channels_last=a.channels_last,
+                                     tf32_matmul=a.tf32_matmul)
         res["graph_forked_ms" if fork else "graph_ms"] = timed(lambda: run(x, refs), a.iters)
     res["kernel_nodes_note"] = "same kernels in all three; the difference is host launch overhead and branch overlap"
     print(json.dumps(res))

@@ -206,9 +206,11 @@ def test_graphed_forward_equals_eager_forward():
         m.make_graphed_forward(x, refs)
 
 
-def test_graphed_forward_channels_last_within_conv_roundoff():
-    """channels_last weights / inputs (cuDNN NHWC kernels, no layout-conversion kernels): same rate and distortion
-    as the NCHW forward up to convolution round-off."""
+@pytest.mark.parametrize("tf32_matmul", [False, True])
+def test_graphed_forward_channels_last_within_conv_roundoff(tf32_matmul):
+    """channels_last weights / inputs (cuDNN NHWC kernels, no layout-conversion kernels), optionally TF32 tensor
+    cores for the Linear layers: same rate and distortion as the NCHW fp32-matmul forward up to round-off
+    (measured: bpp 4e-4, PSNR 2e-4 dB, 0.007 % of the symbols with TF32 matmuls)."""
     from clc_b200.models import CLC
     from oracle import detfill
     d = torch.device("cuda:0")
@@ -218,10 +220,11 @@ def test_graphed_forward_channels_last_within_conv_roundoff():
     with torch.no_grad():
         want = m(x, refs)
     bpp_want, psnr_want = _bpp(want, 65536), _psnr(x, want["x_hat"])
-    run = m.make_graphed_forward(x, refs, channels_last=True)
+    run = m.make_graphed_forward(x, refs, channels_last=True, tf32_matmul=tf32_matmul)
+    assert torch.backends.cuda.matmul.allow_tf32 is False          # restored after the capture
     got = run(x, refs)
     torch.cuda.synchronize()
-    assert abs(_bpp(got, 65536) - bpp_want) < 1e-3
+    assert abs(_bpp(got, 65536) - bpp_want) < (5e-3 if tf32_matmul else 1e-3)
     assert abs(_psnr(x, got["x_hat"]) - psnr_want) < 0.01
     moved = (got["para"]["y"].round() != want["para"]["y"].round()).float().mean().item()
     assert moved < 2e-3, moved
